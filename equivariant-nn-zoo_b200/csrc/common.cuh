@@ -1,0 +1,53 @@
+// Shared definitions for libe3b200 (sm_100a).  Also compiled by g++ with E3B_HOST_EMU for the
+// CPU emulation of the GENERATED contraction code that tests/ use to check the generator's
+// algebra without a GPU (never linked into the product library).
+#pragma once
+#include <stdint.h>
+
+#include <cmath>
+
+#include "../../include/e3b200.h"
+
+#ifdef E3B_HOST_EMU
+#define __device__
+#define __forceinline__ inline
+#define __restrict__
+template <typename T> static inline T ldg(const T* p) { return *p; }
+static inline float fma_(float a, float b, float c) { return fmaf(a, b, c); }
+static inline double fma_(double a, double b, double c) { return fma(a, b, c); }
+#define E3B_GSH_STORE(ptr, idx, val) do { if (active) (ptr)[idx] += (val); } while (0)
+#define E3B_GSH_ZERO(ptr, idx) do { } while (0)
+#else
+#include <cuda_runtime.h>
+template <typename T> __device__ __forceinline__ T ldg(const T* p) { return __ldg(p); }
+__device__ __forceinline__ float fma_(float a, float b, float c) { return fmaf(a, b, c); }
+__device__ __forceinline__ double fma_(double a, double b, double c) { return fma(a, b, c); }
+template <typename T> __device__ __forceinline__ T warp_sum(T v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+#define E3B_GSH_STORE(ptr, idx, val) do { const T r_ = warp_sum(val); if (lane == 0) (ptr)[idx] = r_; } while (0)
+#define E3B_GSH_ZERO(ptr, idx) do { if (lane == 0) (ptr)[idx] = T(0); } while (0)
+#endif
+
+#define TP_THREADS 128
+
+// Arguments of the tensor-product convolution kernels.  Dims are in scalars per row.
+template <typename T>
+struct TpArgs {
+  const T* x;    // [N, x_dim]   imu layout
+  const T* sh;   // [E, sh_dim]
+  const T* w;    // [E, w_dim]
+  const T* gy;   // [N, y_dim]   (backward)
+  T* y;          // [N, y_dim]
+  T* gx_edge;    // [E, x_dim]   (backward, may be null)
+  T* gsh;        // [E, n_part, sh_dim] (backward, may be null)
+  T* gw;         // [E, w_dim]   (backward)
+  const int64_t* in_ptr;
+  const int32_t* in_nbr;
+  const int32_t* in_eid;
+  int64_t n_nodes;
+  int64_t x_dim, sh_dim, w_dim, y_dim;
+  int32_t mul, n_chunks, n_part;
+};

@@ -1,0 +1,896 @@
+// libe3b200: C ABI + the non-generated kernels (neighbour list, edge geometry, generic tensor
+// product, segmented sums, gate, layout conversion).  sm_100a only.
+#include <cuda_runtime.h>
+#include <stdarg.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <new>
+
+#include "cg_tables.cuh"
+#include "common.cuh"
+#include "tp_fast.h"
+
+// ------------------------------------------------------------------------------------------
+// errors
+static thread_local char g_err[512] = "";
+
+static int fail(int code, const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+  return code;
+}
+
+static int check_launch(const char* what) {
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return fail(E3B_ERR_CUDA, "%s: %s", what, cudaGetErrorString(e));
+  return E3B_OK;
+}
+
+extern "C" int e3b_abi_version(void) { return E3B_ABI_VERSION; }
+extern "C" const char* e3b_last_error(void) { return g_err; }
+
+static inline unsigned blocks_for(int64_t n, int per_block) { return (unsigned)((n + per_block - 1) / per_block); }
+
+#define DISPATCH_DTYPE(dtype, ...)                                  \
+  if ((dtype) == E3B_F32) { typedef float T; __VA_ARGS__ }          \
+  else if ((dtype) == E3B_F64) { typedef double T; __VA_ARGS__ }    \
+  else return fail(E3B_ERR_INVALID, "dtype must be 0 (f32) or 1 (f64)");
+
+// ------------------------------------------------------------------------------------------
+// Neighbour list (data/compute_edge.py:38-113).  One warp per atom a; lanes sweep the atoms b
+// of a's graph in ascending order, so edges come out sorted by (a, b) with ballot/popc
+// compaction -- no atomics, deterministic, bit-exact predicate.
+__device__ __forceinline__ bool within(const float* __restrict__ pos, int64_t stride, float ax, float ay, float az,
+                                       int64_t b, float r_max) {
+  const float dx = __fsub_rn(ax, pos[b * stride + 0]);
+  const float dy = __fsub_rn(ay, pos[b * stride + 1]);
+  const float dz = __fsub_rn(az, pos[b * stride + 2]);
+  // torch.linalg.norm over 3 fp32 elements on CPU == sqrt(fma(z,z,fma(y,y,x*x)))
+  const float d = __fsqrt_rn(__fmaf_rn(dz, dz, __fmaf_rn(dy, dy, __fmul_rn(dx, dx))));
+  return d < r_max;
+}
+
+__device__ __forceinline__ int find_graph(const int64_t* __restrict__ node_ptr, int n_graphs, int64_t a) {
+  int lo = 0, hi = n_graphs;  // node_ptr[lo] <= a < node_ptr[hi]
+  while (hi - lo > 1) {
+    const int mid = (lo + hi) >> 1;
+    if (node_ptr[mid] <= a) lo = mid; else hi = mid;
+  }
+  return lo;
+}
+
+template <bool FILL>
+__global__ void __launch_bounds__(256) radius_graph_kernel(const float* __restrict__ pos, int64_t stride,
+                                                           const int64_t* __restrict__ node_ptr, int n_graphs,
+                                                           int64_t n_nodes, float r_max, int32_t* __restrict__ deg,
+                                                           const int64_t* __restrict__ row_ptr, int64_t n_edges,
+                                                           int64_t* __restrict__ edge_index) {
+  const int lane = threadIdx.x & 31;
+  const int64_t a = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (a >= n_nodes) return;
+  const int g = find_graph(node_ptr, n_graphs, a);
+  const int64_t b0 = node_ptr[g], b1 = node_ptr[g + 1];
+  const float ax = pos[a * stride], ay = pos[a * stride + 1], az = pos[a * stride + 2];
+  int64_t cursor = FILL ? row_ptr[a] : 0;
+  int count = 0;
+  for (int64_t base = b0; base < b1; base += 32) {
+    const int64_t b = base + lane;
+    bool hit = false;
+    if (b < b1 && b != a) hit = within(pos, stride, ax, ay, az, b, r_max);
+    const unsigned m = __ballot_sync(0xffffffffu, hit);
+    if (FILL) {
+      if (hit) {
+        const int64_t p = cursor + __popc(m & ((1u << lane) - 1u));
+        edge_index[p] = a;
+        edge_index[n_edges + p] = b;
+      }
+      cursor += __popc(m);
+    } else {
+      count += __popc(m);
+    }
+  }
+  if (!FILL && lane == 0) deg[a] = count;
+}
+
+// rev[e] = index of the reversed edge (b, a): binary search for a among b's sorted neighbours
+__global__ void reverse_edge_kernel(const int64_t* __restrict__ edge_index, const int64_t* __restrict__ row_ptr,
+                                    int64_t n_edges, int32_t* __restrict__ rev) {
+  const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= n_edges) return;
+  const int64_t a = edge_index[e], b = edge_index[n_edges + e];
+  int64_t lo = row_ptr[b], hi = row_ptr[b + 1] - 1;
+  int64_t found = -1;
+  while (lo <= hi) {
+    const int64_t mid = (lo + hi) >> 1;
+    const int64_t v = edge_index[n_edges + mid];
+    if (v == a) { found = mid; break; }
+    if (v < a) lo = mid + 1; else hi = mid - 1;
+  }
+  rev[e] = (int32_t)found;
+}
+
+extern "C" int e3b_radius_graph_count(const float* pos, int64_t pos_stride, const int64_t* node_ptr, int32_t n_graphs,
+                                      int64_t n_nodes, float r_max, int32_t* deg, void* stream) {
+  if (n_nodes == 0) return E3B_OK;
+  if (!pos || !node_ptr || !deg || n_graphs <= 0) return fail(E3B_ERR_INVALID, "radius_graph_count: null/empty argument");
+  radius_graph_kernel<false><<<blocks_for(n_nodes, 8), 256, 0, (cudaStream_t)stream>>>(
+      pos, pos_stride, node_ptr, n_graphs, n_nodes, r_max, deg, nullptr, 0, nullptr);
+  return check_launch("radius_graph_count");
+}
+
+extern "C" int e3b_radius_graph_fill(const float* pos, int64_t pos_stride, const int64_t* node_ptr, int32_t n_graphs,
+                                     int64_t n_nodes, float r_max, const int64_t* row_ptr, int64_t n_edges,
+                                     int64_t* edge_index, int32_t* rev, void* stream) {
+  if (n_nodes == 0 || n_edges == 0) return E3B_OK;
+  if (!pos || !node_ptr || !row_ptr || !edge_index) return fail(E3B_ERR_INVALID, "radius_graph_fill: null argument");
+  radius_graph_kernel<true><<<blocks_for(n_nodes, 8), 256, 0, (cudaStream_t)stream>>>(
+      pos, pos_stride, node_ptr, n_graphs, n_nodes, r_max, nullptr, row_ptr, n_edges, edge_index);
+  int rc = check_launch("radius_graph_fill");
+  if (rc) return rc;
+  if (rev) {
+    reverse_edge_kernel<<<blocks_for(n_edges, 256), 256, 0, (cudaStream_t)stream>>>(edge_index, row_ptr, n_edges, rev);
+    rc = check_launch("radius_graph_reverse");
+  }
+  return rc;
+}
+
+// Grouped CSR of an arbitrary edge list: node n's segment lists, in ascending edge id, the
+// edges whose `which_row` endpoint is n.  One warp per node sweeps... no: the edge list is
+// unsorted, so: pass 1 scatter with an atomic cursor, pass 2 per-segment sort (ascending id).
+__global__ void csr_scatter_kernel(const int64_t* __restrict__ key, int64_t n_edges, const int64_t* __restrict__ row_ptr,
+                                   int32_t* __restrict__ cursor, int32_t* __restrict__ eid) {
+  const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= n_edges) return;
+  const int64_t n = key[e];
+  const int32_t slot = atomicAdd(&cursor[n], 1);
+  eid[row_ptr[n] + slot] = (int32_t)e;
+}
+
+__global__ void csr_sort_kernel(const int64_t* __restrict__ row_ptr, int64_t n_nodes, int32_t* __restrict__ eid) {
+  const int64_t n = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (n >= n_nodes) return;
+  const int64_t a = row_ptr[n], b = row_ptr[n + 1];
+  // Shell sort (gaps 57, 23, 10, 4, 1): segments are tens to a few hundred entries.
+  const int gaps[5] = {57, 23, 10, 4, 1};
+  for (int gi = 0; gi < 5; ++gi) {
+    const int64_t gap = gaps[gi];
+    for (int64_t i = a + gap; i < b; ++i) {
+      const int32_t v = eid[i];
+      int64_t j = i;
+      while (j - gap >= a && eid[j - gap] > v) { eid[j] = eid[j - gap]; j -= gap; }
+      eid[j] = v;
+    }
+  }
+}
+
+extern "C" int e3b_csr_fill(const int64_t* edge_index, int64_t n_edges, int64_t n_nodes, int which_row,
+                            const int64_t* row_ptr, int32_t* cursor, int32_t* eid, void* stream) {
+  if (n_edges == 0 || n_nodes == 0) return E3B_OK;
+  if (!edge_index || !row_ptr || !cursor || !eid || (which_row != 0 && which_row != 1))
+    return fail(E3B_ERR_INVALID, "csr_fill: bad argument");
+  const int64_t* key = edge_index + (int64_t)which_row * n_edges;
+  csr_scatter_kernel<<<blocks_for(n_edges, 256), 256, 0, (cudaStream_t)stream>>>(key, n_edges, row_ptr, cursor, eid);
+  int rc = check_launch("csr_scatter");
+  if (rc) return rc;
+  csr_sort_kernel<<<blocks_for(n_nodes, 128), 128, 0, (cudaStream_t)stream>>>(row_ptr, n_nodes, eid);
+  return check_launch("csr_sort");
+}
+
+// ------------------------------------------------------------------------------------------
+// Edge vectors (data/compute_edge.py:13-36)
+template <typename T> __device__ __forceinline__ T sqrt_(T v);
+template <> __device__ __forceinline__ float sqrt_<float>(float v) { return sqrtf(v); }
+template <> __device__ __forceinline__ double sqrt_<double>(double v) { return sqrt(v); }
+
+template <typename T>
+__global__ void edge_vectors_fwd_kernel(const T* __restrict__ pos, const int64_t* __restrict__ ei, int64_t n_edges,
+                                        T* __restrict__ vec, T* __restrict__ len) {
+  const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= n_edges) return;
+  const int64_t s = ei[e], d = ei[n_edges + e];
+  const T x = pos[d * 3] - pos[s * 3], y = pos[d * 3 + 1] - pos[s * 3 + 1], z = pos[d * 3 + 2] - pos[s * 3 + 2];
+  vec[e * 3] = x; vec[e * 3 + 1] = y; vec[e * 3 + 2] = z;
+  if (len) len[e] = sqrt_<T>(fma_(z, z, fma_(y, y, x * x)));
+}
+
+template <typename T>
+__global__ void edge_vectors_bwd_kernel(const T* __restrict__ gvec, const T* __restrict__ glen, const T* __restrict__ vec,
+                                        const T* __restrict__ len, int64_t n_nodes, const int64_t* __restrict__ in_ptr,
+                                        const int32_t* __restrict__ in_eid, const int64_t* __restrict__ out_ptr,
+                                        const int32_t* __restrict__ out_eid, T* __restrict__ gpos) {
+  const int64_t n = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (n >= n_nodes) return;
+  T ax = 0, ay = 0, az = 0;
+  for (int pass = 0; pass < 2; ++pass) {
+    const int64_t* ptr = pass == 0 ? in_ptr : out_ptr;
+    const int32_t* ids = pass == 0 ? in_eid : out_eid;
+    const T sgn = pass == 0 ? T(1) : T(-1);  // vec = pos[dst] - pos[src]
+    for (int64_t k = ptr[n]; k < ptr[n + 1]; ++k) {
+      const int64_t e = ids ? (int64_t)ids[k] : k;
+      T gx = 0, gy = 0, gz = 0;
+      if (gvec) { gx = gvec[e * 3]; gy = gvec[e * 3 + 1]; gz = gvec[e * 3 + 2]; }
+      if (glen) {
+        const T l = len[e];
+        const T f = l > T(0) ? glen[e] / l : T(0);
+        gx = fma_(f, vec[e * 3], gx); gy = fma_(f, vec[e * 3 + 1], gy); gz = fma_(f, vec[e * 3 + 2], gz);
+      }
+      ax = fma_(sgn, gx, ax); ay = fma_(sgn, gy, ay); az = fma_(sgn, gz, az);
+    }
+  }
+  gpos[n * 3] = ax; gpos[n * 3 + 1] = ay; gpos[n * 3 + 2] = az;
+}
+
+extern "C" int e3b_edge_vectors_fwd(int dtype, const void* pos, const int64_t* edge_index, int64_t n_edges, void* vec,
+                                    void* len, void* stream) {
+  if (n_edges == 0) return E3B_OK;
+  if (!pos || !edge_index || !vec) return fail(E3B_ERR_INVALID, "edge_vectors_fwd: null argument");
+  DISPATCH_DTYPE(dtype, edge_vectors_fwd_kernel<T><<<blocks_for(n_edges, 256), 256, 0, (cudaStream_t)stream>>>(
+                            (const T*)pos, edge_index, n_edges, (T*)vec, (T*)len);)
+  return check_launch("edge_vectors_fwd");
+}
+
+extern "C" int e3b_edge_vectors_bwd(int dtype, const void* gvec, const void* glen, const void* vec, const void* len,
+                                    int64_t n_nodes, const int64_t* in_ptr, const int32_t* in_eid,
+                                    const int64_t* out_ptr, const int32_t* out_eid, void* gpos, void* stream) {
+  if (n_nodes == 0) return E3B_OK;
+  if (!in_ptr || !out_ptr || !gpos || (glen && (!vec || !len)))
+    return fail(E3B_ERR_INVALID, "edge_vectors_bwd: null argument");
+  DISPATCH_DTYPE(dtype, edge_vectors_bwd_kernel<T><<<blocks_for(n_nodes, 128), 128, 0, (cudaStream_t)stream>>>(
+                            (const T*)gvec, (const T*)glen, (const T*)vec, (const T*)len, n_nodes, in_ptr, in_eid,
+                            out_ptr, out_eid, (T*)gpos);)
+  return check_launch("edge_vectors_bwd");
+}
+
+// ------------------------------------------------------------------------------------------
+// Spherical harmonics, l <= 2, 'component' normalisation (nn/embedding.py:163-165)
+template <typename T>
+__global__ void sh_fwd_kernel(const T* __restrict__ vec, int64_t n, int lmax, int normalize, T* __restrict__ sh) {
+  const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= n) return;
+  T x = vec[e * 3], y = vec[e * 3 + 1], z = vec[e * 3 + 2];
+  if (normalize) {
+    T r = sqrt_<T>(x * x + y * y + z * z);
+    r = r > T(1e-12) ? r : T(1e-12);
+    x /= r; y /= r; z /= r;
+  }
+  const int dim = (lmax + 1) * (lmax + 1);
+  T* o = sh + e * dim;
+  o[0] = T(1);
+  if (lmax >= 1) {
+    const T s3 = T(1.7320508075688772);
+    o[1] = s3 * x; o[2] = s3 * y; o[3] = s3 * z;
+  }
+  if (lmax >= 2) {
+    const T s3 = T(1.7320508075688772), s5 = T(2.23606797749979);
+    o[4] = s5 * s3 * x * z;
+    o[5] = s5 * s3 * x * y;
+    o[6] = s5 * (y * y - T(0.5) * (x * x + z * z));
+    o[7] = s5 * s3 * y * z;
+    o[8] = s5 * (s3 / T(2)) * (z * z - x * x);
+  }
+}
+
+template <typename T>
+__global__ void sh_bwd_kernel(const T* __restrict__ vec, const T* __restrict__ gsh, int64_t n, int lmax, int normalize,
+                              T* __restrict__ gvec) {
+  const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= n) return;
+  T x = vec[e * 3], y = vec[e * 3 + 1], z = vec[e * 3 + 2];
+  T r = T(1);
+  bool clamped = false;
+  if (normalize) {
+    r = sqrt_<T>(x * x + y * y + z * z);
+    if (!(r > T(1e-12))) { r = T(1e-12); clamped = true; }
+    x /= r; y /= r; z /= r;
+  }
+  const int dim = (lmax + 1) * (lmax + 1);
+  const T* g = gsh + e * dim;
+  T gx = 0, gy = 0, gz = 0;
+  if (lmax >= 1) {
+    const T s3 = T(1.7320508075688772);
+    gx += s3 * g[1]; gy += s3 * g[2]; gz += s3 * g[3];
+  }
+  if (lmax >= 2) {
+    const T s3 = T(1.7320508075688772), s5 = T(2.23606797749979);
+    gx += s5 * (s3 * z * g[4] + s3 * y * g[5] - x * g[6] - s3 * x * g[8]);
+    gy += s5 * (s3 * x * g[5] + T(2) * y * g[6] + s3 * z * g[7]);
+    gz += s5 * (s3 * x * g[4] - z * g[6] + s3 * y * g[7] + s3 * z * g[8]);
+  }
+  if (normalize) {
+    if (clamped) {  // n = v / 1e-12: plain scaling
+      gx /= r; gy /= r; gz /= r;
+    } else {        // d(v/|v|): (g - n (n.g)) / |v|
+      const T dot = gx * x + gy * y + gz * z;
+      gx = (gx - x * dot) / r; gy = (gy - y * dot) / r; gz = (gz - z * dot) / r;
+    }
+  }
+  gvec[e * 3] = gx; gvec[e * 3 + 1] = gy; gvec[e * 3 + 2] = gz;
+}
+
+extern "C" int e3b_sh_fwd(int dtype, const void* vec, int64_t n, int lmax, int normalize, void* sh, void* stream) {
+  if (n == 0) return E3B_OK;
+  if (lmax < 0 || lmax > 2) return fail(E3B_ERR_UNSUPPORTED, "sh: lmax %d not supported (0..2)", lmax);
+  if (!vec || !sh) return fail(E3B_ERR_INVALID, "sh_fwd: null argument");
+  DISPATCH_DTYPE(dtype, sh_fwd_kernel<T><<<blocks_for(n, 256), 256, 0, (cudaStream_t)stream>>>((const T*)vec, n, lmax,
+                                                                                              normalize, (T*)sh);)
+  return check_launch("sh_fwd");
+}
+
+extern "C" int e3b_sh_bwd(int dtype, const void* vec, const void* gsh, int64_t n, int lmax, int normalize, void* gvec,
+                          void* stream) {
+  if (n == 0) return E3B_OK;
+  if (lmax < 0 || lmax > 2) return fail(E3B_ERR_UNSUPPORTED, "sh: lmax %d not supported (0..2)", lmax);
+  if (!vec || !gsh || !gvec) return fail(E3B_ERR_INVALID, "sh_bwd: null argument");
+  DISPATCH_DTYPE(dtype, sh_bwd_kernel<T><<<blocks_for(n, 256), 256, 0, (cudaStream_t)stream>>>(
+                            (const T*)vec, (const T*)gsh, n, lmax, normalize, (T*)gvec);)
+  return check_launch("sh_bwd");
+}
+
+// ------------------------------------------------------------------------------------------
+// Radial basis (nn/embedding.py:181-219, 74-127, 26-40)
+template <typename T> __device__ __forceinline__ void sincos_(T a, T* s, T* c);
+template <> __device__ __forceinline__ void sincos_<float>(float a, float* s, float* c) { sincosf(a, s, c); }
+template <> __device__ __forceinline__ void sincos_<double>(double a, double* s, double* c) { sincos(a, s, c); }
+template <typename T> __device__ __forceinline__ T pow_(T a, T b);
+template <> __device__ __forceinline__ float pow_<float>(float a, float b) { return powf(a, b); }
+template <> __device__ __forceinline__ double pow_<double>(double a, double b) { return pow(a, b); }
+
+struct RadialParams {
+  double r_max, r_min, p;
+  int n_basis, one_over_r, cutoff_kind;
+};
+
+template <typename T>
+__device__ __forceinline__ void cutoff_eval(T r, const RadialParams& P, T* c, T* dc) {
+  const T f = T(1.0 / P.r_max);
+  const T x = r * f;
+  if (P.cutoff_kind == 1) {  // symmetricCutoff: (x-1)^2 (x+1)^2 [|x| < 1]
+    if (fabs((double)x) < 1.0) {
+      const T q = (x - T(1)) * (x + T(1));
+      *c = q * q;
+      *dc = T(4) * x * q * f;
+    } else { *c = T(0); *dc = T(0); }
+    return;
+  }
+  if (x < T(1)) {
+    const T p = T(P.p);
+    const T xp = pow_<T>(x, p);          // x^p
+    const T xm = xp / x;                 // x^(p-1)  (x > 0 for distances)
+    *c = T(1) - (p + T(1)) * (p + T(2)) / T(2) * xp + p * (p + T(2)) * xp * x - p * (p + T(1)) / T(2) * xp * x * x;
+    *dc = (x > T(0)) ? f * p * (p + T(1)) * (p + T(2)) / T(2) * (-xm + T(2) * xp - xp * x) : T(0);
+  } else { *c = T(0); *dc = T(0); }
+}
+
+template <typename T>
+__global__ void radial_fwd_kernel(const T* __restrict__ r_in, int64_t n, const T* __restrict__ bw, RadialParams P,
+                                  T* __restrict__ out) {
+  const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= n * P.n_basis) return;
+  const int64_t e = idx / P.n_basis;
+  const int k = (int)(idx - e * P.n_basis);
+  const T r = r_in[e];
+  T c, dc;
+  cutoff_eval<T>(r, P, &c, &dc);
+  const T span = T(P.r_max - P.r_min);
+  T s, co;
+  sincos_<T>(bw[k] * r / span, &s, &co);
+  T b = T(2.0) / span * s;
+  if (P.one_over_r) b = b / r;
+  out[idx] = b * c;
+}
+
+#define RADIAL_BWD_ROWS 256  // edges per block in the backward
+template <typename T>
+__global__ void __launch_bounds__(256) radial_bwd_kernel(const T* __restrict__ r_in, const T* __restrict__ gout,
+                                                         int64_t n, const T* __restrict__ bw, RadialParams P,
+                                                         T* __restrict__ gr, T* __restrict__ gw_partial) {
+  // thread t handles edge blockIdx*256 + t (all basis functions); gw reduced over the block
+  extern __shared__ unsigned char smem_raw[];
+  T* red = reinterpret_cast<T*>(smem_raw);  // [8 warps][n_basis]
+  const int64_t e = (int64_t)blockIdx.x * RADIAL_BWD_ROWS + threadIdx.x;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const bool valid = e < n;
+  T r = valid ? r_in[e] : T(1);
+  T c = 0, dc = 0;
+  if (valid) cutoff_eval<T>(r, P, &c, &dc);
+  const T span = T(P.r_max - P.r_min);
+  const T pref = T(2.0) / span;
+  T g_r = 0;
+  for (int k = 0; k < P.n_basis; ++k) {
+    T gwk = 0;
+    if (valid) {
+      const T a = bw[k] / span;
+      T s, co;
+      sincos_<T>(a * r, &s, &co);
+      const T go = gout[e * P.n_basis + k];
+      T b, db, dbw;
+      if (P.one_over_r) {
+        b = pref * s / r;
+        db = pref * (a * co / r - s / (r * r));
+        dbw = pref * co / span;  // d/dw [sin(w r/span)/r] = cos * (r/span)/r
+      } else {
+        b = pref * s;
+        db = pref * a * co;
+        dbw = pref * co * r / span;
+      }
+      g_r += go * (db * c + b * dc);
+      gwk = go * dbw * c;
+    }
+    gwk = warp_sum(gwk);
+    if (lane == 0) red[warp * P.n_basis + k] = gwk;
+  }
+  if (valid && gr) gr[e] = g_r;
+  __syncthreads();
+  if (gw_partial) {
+    for (int k = threadIdx.x; k < P.n_basis; k += blockDim.x) {
+      T s = 0;
+      for (int w = 0; w < 8; ++w) s += red[w * P.n_basis + k];
+      gw_partial[(int64_t)blockIdx.x * P.n_basis + k] = s;
+    }
+  }
+}
+
+extern "C" int e3b_radial_fwd(int dtype, const void* r, int64_t n, const void* bessel_w, int n_basis, double r_max,
+                              double r_min, int one_over_r, int cutoff_kind, double p, void* out, void* stream) {
+  if (n == 0) return E3B_OK;
+  if (!r || !bessel_w || !out || n_basis <= 0) return fail(E3B_ERR_INVALID, "radial_fwd: bad argument");
+  RadialParams P{r_max, r_min, p, n_basis, one_over_r, cutoff_kind};
+  DISPATCH_DTYPE(dtype, radial_fwd_kernel<T><<<blocks_for(n * n_basis, 256), 256, 0, (cudaStream_t)stream>>>(
+                            (const T*)r, n, (const T*)bessel_w, P, (T*)out);)
+  return check_launch("radial_fwd");
+}
+
+extern "C" int64_t e3b_radial_bwd_blocks(int64_t n) { return (n + RADIAL_BWD_ROWS - 1) / RADIAL_BWD_ROWS; }
+
+extern "C" int e3b_radial_bwd(int dtype, const void* r, const void* gout, int64_t n, const void* bessel_w, int n_basis,
+                              double r_max, double r_min, int one_over_r, int cutoff_kind, double p, void* gr,
+                              void* gw_partial, void* stream) {
+  if (n == 0) return E3B_OK;
+  if (!r || !gout || !bessel_w || n_basis <= 0) return fail(E3B_ERR_INVALID, "radial_bwd: bad argument");
+  RadialParams P{r_max, r_min, p, n_basis, one_over_r, cutoff_kind};
+  const unsigned grid = (unsigned)e3b_radial_bwd_blocks(n);
+  DISPATCH_DTYPE(dtype, radial_bwd_kernel<T><<<grid, 256, 8 * n_basis * sizeof(T), (cudaStream_t)stream>>>(
+                            (const T*)r, (const T*)gout, n, (const T*)bessel_w, P, (T*)gr, (T*)gw_partial);)
+  return check_launch("radial_bwd");
+}
+
+// ------------------------------------------------------------------------------------------
+// Tensor-product convolution: plan + generic kernels (any multiplicities, l <= 3, f32/f64).
+struct e3b_tp_plan {
+  e3b_tp_desc desc;
+  const GenEntry* gen;             // matching generated kernel or null
+  int32_t mul[E3B_MAX_BLOCKS];     // generic: per input block multiplicity (== desc.mul)
+  int64_t x_dim, sh_dim, w_dim, y_dim;
+  int32_t x_off[E3B_MAX_BLOCKS], sh_off[E3B_MAX_BLOCKS];
+  int32_t w_off[E3B_MAX_PATHS], y_off[E3B_MAX_PATHS];
+  float sign[E3B_MAX_PATHS];
+};
+
+struct GenericTp {
+  int32_t n_paths, mul;
+  int32_t l1[E3B_MAX_PATHS], l2[E3B_MAX_PATHS], l3[E3B_MAX_PATHS];
+  int32_t x_off[E3B_MAX_PATHS], sh_off[E3B_MAX_PATHS], w_off[E3B_MAX_PATHS], y_off[E3B_MAX_PATHS];
+  float sign[E3B_MAX_PATHS];
+};
+
+extern "C" int e3b_tp_plan_create(const e3b_tp_desc* d, e3b_tp_plan** out) {
+  if (!d || !out) return fail(E3B_ERR_INVALID, "tp_plan_create: null argument");
+  if (d->mul <= 0 || d->n_in <= 0 || d->n_in > E3B_MAX_BLOCKS || d->n_sh <= 0 || d->n_sh > E3B_MAX_BLOCKS ||
+      d->n_paths <= 0 || d->n_paths > E3B_MAX_PATHS)
+    return fail(E3B_ERR_INVALID, "tp_plan_create: sizes out of range (mul %d, n_in %d, n_sh %d, n_paths %d)", d->mul,
+                d->n_in, d->n_sh, d->n_paths);
+  e3b_tp_plan* p = new (std::nothrow) e3b_tp_plan();
+  if (!p) return fail(E3B_ERR_NOMEM, "tp_plan_create: out of host memory");
+  p->desc = *d;
+  int off = 0;
+  for (int b = 0; b < d->n_in; ++b) {
+    if (d->in_l[b] < 0 || d->in_l[b] > E3B_CG_LMAX) { delete p; return fail(E3B_ERR_UNSUPPORTED, "input l=%d > %d", d->in_l[b], E3B_CG_LMAX); }
+    p->x_off[b] = off;
+    off += 2 * d->in_l[b] + 1;
+  }
+  p->x_dim = (int64_t)off * d->mul;
+  off = 0;
+  for (int s = 0; s < d->n_sh; ++s) {
+    if (d->sh_l[s] < 0 || d->sh_l[s] > E3B_CG_LMAX) { delete p; return fail(E3B_ERR_UNSUPPORTED, "sh l=%d > %d", d->sh_l[s], E3B_CG_LMAX); }
+    p->sh_off[s] = off;
+    off += 2 * d->sh_l[s] + 1;
+  }
+  p->sh_dim = off;
+  p->w_dim = (int64_t)d->n_paths * d->mul;
+  // output blocks by slot
+  int slot_l[E3B_MAX_PATHS];
+  for (int q = 0; q < d->n_paths; ++q) slot_l[q] = -1;
+  for (int q = 0; q < d->n_paths; ++q) {
+    const int b = d->path_in[q], s = d->path_sh[q], l3 = d->path_lout[q], slot = d->path_slot[q];
+    if (b < 0 || b >= d->n_in || s < 0 || s >= d->n_sh || slot < 0 || slot >= d->n_paths || slot_l[slot] != -1 ||
+        l3 > E3B_CG_LMAX || l3 < abs(d->in_l[b] - d->sh_l[s]) || l3 > d->in_l[b] + d->sh_l[s]) {
+      delete p;
+      return fail(E3B_ERR_INVALID, "tp_plan_create: bad path %d (in %d, sh %d, l_out %d, slot %d)", q, b, s, l3, slot);
+    }
+    slot_l[slot] = l3;
+  }
+  int yo[E3B_MAX_PATHS];
+  off = 0;
+  for (int s = 0; s < d->n_paths; ++s) { yo[s] = off; off += 2 * slot_l[s] + 1; }
+  p->y_dim = (int64_t)off * d->mul;
+  const int n = E3B_CG_LMAX + 1;
+  for (int q = 0; q < d->n_paths; ++q) {
+    p->w_off[q] = q;
+    p->y_off[q] = yo[d->path_slot[q]];
+    const int l1 = d->in_l[d->path_in[q]], l2 = d->sh_l[d->path_sh[q]], l3 = d->path_lout[q];
+    p->sign[q] = (d->w3j_sign_preset == 1) ? (float)kCgSign044[(l1 * n + l2) * n + l3] : 1.0f;
+  }
+  p->gen = (d->w3j_sign_preset == 0) ? e3b_find_generated(d) : nullptr;
+  *out = p;
+  return E3B_OK;
+}
+
+extern "C" void e3b_tp_plan_destroy(e3b_tp_plan* p) { delete p; }
+extern "C" int e3b_tp_plan_is_specialized(const e3b_tp_plan* p) { return p && p->gen ? 1 : 0; }
+extern "C" int e3b_tp_plan_dims(const e3b_tp_plan* p, int32_t* x_dim, int32_t* sh_dim, int32_t* w_dim, int32_t* y_dim,
+                                int32_t* n_part_f32) {
+  if (!p) return fail(E3B_ERR_INVALID, "tp_plan_dims: null plan");
+  if (x_dim) *x_dim = (int32_t)p->x_dim;
+  if (sh_dim) *sh_dim = (int32_t)p->sh_dim;
+  if (w_dim) *w_dim = (int32_t)p->w_dim;
+  if (y_dim) *y_dim = (int32_t)p->y_dim;
+  if (n_part_f32) *n_part_f32 = p->gen ? p->gen->n_groups * ((p->desc.mul + 31) / 32) : 1;
+  return E3B_OK;
+}
+
+static GenericTp make_generic(const e3b_tp_plan* p) {
+  GenericTp g;
+  g.n_paths = p->desc.n_paths;
+  g.mul = p->desc.mul;
+  for (int q = 0; q < g.n_paths; ++q) {
+    const int b = p->desc.path_in[q], s = p->desc.path_sh[q];
+    g.l1[q] = p->desc.in_l[b]; g.l2[q] = p->desc.sh_l[s]; g.l3[q] = p->desc.path_lout[q];
+    g.x_off[q] = p->x_off[b]; g.sh_off[q] = p->sh_off[s]; g.w_off[q] = p->w_off[q]; g.y_off[q] = p->y_off[q];
+    g.sign[q] = p->sign[q];
+  }
+  return g;
+}
+
+__device__ __forceinline__ const double* cg_table(int l1, int l2, int l3) {
+  const int n = E3B_CG_LMAX + 1;
+  return kCgData + kCgOffset[(l1 * n + l2) * n + l3];
+}
+
+// one thread per (node, path, channel)
+template <typename T>
+__global__ void __launch_bounds__(128) tp_generic_fwd_kernel(const __grid_constant__ GenericTp g, TpArgs<T> a) {
+  const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int64_t per_node = (int64_t)g.n_paths * g.mul;
+  if (idx >= a.n_nodes * per_node) return;
+  const int64_t node = idx / per_node;
+  const int rem = (int)(idx - node * per_node);
+  const int q = rem / g.mul, u = rem - q * g.mul;
+  const int l1 = g.l1[q], l2 = g.l2[q], l3 = g.l3[q];
+  const int d1 = 2 * l1 + 1, d2 = 2 * l2 + 1, d3 = 2 * l3 + 1;
+  const double* C = cg_table(l1, l2, l3);
+  const T scale = T(sqrt((double)d3)) * T(g.sign[q]);
+  T acc[2 * E3B_CG_LMAX + 1];
+  for (int k = 0; k < d3; ++k) acc[k] = T(0);
+  for (int64_t kk = a.in_ptr[node]; kk < a.in_ptr[node + 1]; ++kk) {
+    const int64_t src = a.in_nbr[kk];
+    const int64_t eid = a.in_eid ? (int64_t)a.in_eid[kk] : kk;
+    const T* xr = a.x + src * a.x_dim + (int64_t)g.x_off[q] * g.mul + u;
+    const T* yr = a.sh + eid * a.sh_dim + g.sh_off[q];
+    const T wv = a.w[eid * a.w_dim + (int64_t)g.w_off[q] * g.mul + u] * scale;
+    for (int i = 0; i < d1; ++i) {
+      const T xi = xr[(int64_t)i * g.mul] * wv;
+      for (int j = 0; j < d2; ++j) {
+        const T xy = xi * yr[j];
+        const double* c = C + (i * d2 + j) * d3;
+        for (int k = 0; k < d3; ++k) acc[k] = fma_(T(c[k]), xy, acc[k]);
+      }
+    }
+  }
+  T* yo = a.y + node * a.y_dim + (int64_t)g.y_off[q] * g.mul + u;
+  for (int k = 0; k < d3; ++k) yo[(int64_t)k * g.mul] = acc[k];
+}
+
+template <typename T>
+__global__ void __launch_bounds__(128) tp_generic_bwd_kernel(const __grid_constant__ GenericTp g, TpArgs<T> a) {
+  const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int64_t per_node = (int64_t)g.n_paths * g.mul;
+  if (idx >= a.n_nodes * per_node) return;
+  const int64_t node = idx / per_node;
+  const int rem = (int)(idx - node * per_node);
+  const int q = rem / g.mul, u = rem - q * g.mul;
+  const int l1 = g.l1[q], l2 = g.l2[q], l3 = g.l3[q];
+  const int d1 = 2 * l1 + 1, d2 = 2 * l2 + 1, d3 = 2 * l3 + 1;
+  const double* C = cg_table(l1, l2, l3);
+  const T scale = T(sqrt((double)d3)) * T(g.sign[q]);
+  T gy[2 * E3B_CG_LMAX + 1];
+  const T* gyr = a.gy + node * a.y_dim + (int64_t)g.y_off[q] * g.mul + u;
+  for (int k = 0; k < d3; ++k) gy[k] = gyr[(int64_t)k * g.mul];
+  for (int64_t kk = a.in_ptr[node]; kk < a.in_ptr[node + 1]; ++kk) {
+    const int64_t src = a.in_nbr[kk];
+    const int64_t eid = a.in_eid ? (int64_t)a.in_eid[kk] : kk;
+    const T* xr = a.x + src * a.x_dim + (int64_t)g.x_off[q] * g.mul + u;
+    const T* yr = a.sh + eid * a.sh_dim + g.sh_off[q];
+    const int64_t wi = eid * a.w_dim + (int64_t)g.w_off[q] * g.mul + u;
+    const T wv = a.w[wi] * scale;
+    T gw = T(0);
+    for (int i = 0; i < d1; ++i) {
+      const T xi = xr[(int64_t)i * g.mul];
+      T gxi = T(0);
+      for (int j = 0; j < d2; ++j) {
+        const double* c = C + (i * d2 + j) * d3;
+        T m = T(0);  // sum_k C_ijk gy_k
+        for (int k = 0; k < d3; ++k) m = fma_(T(c[k]), gy[k], m);
+        const T yj = yr[j];
+        gw = fma_(m, xi * yj, gw);
+        gxi = fma_(m, yj, gxi);
+        if (a.gsh && m != T(0)) atomicAdd(a.gsh + eid * a.sh_dim + g.sh_off[q] + j, m * xi * wv);
+      }
+      if (a.gx_edge) atomicAdd(a.gx_edge + eid * a.x_dim + (int64_t)(g.x_off[q] + i) * g.mul + u, gxi * wv);
+    }
+    a.gw[wi] = gw * scale;
+  }
+}
+
+template <typename T>
+static TpArgs<T> make_args(const e3b_tp_plan* p, int64_t n_nodes, const void* x, const void* sh, const void* w,
+                           const void* gy, const int64_t* in_ptr, const int32_t* in_nbr, const int32_t* in_eid, void* y,
+                           void* gx_edge, void* gsh, void* gw) {
+  TpArgs<T> a;
+  a.x = (const T*)x; a.sh = (const T*)sh; a.w = (const T*)w; a.gy = (const T*)gy;
+  a.y = (T*)y; a.gx_edge = (T*)gx_edge; a.gsh = (T*)gsh; a.gw = (T*)gw;
+  a.in_ptr = in_ptr; a.in_nbr = in_nbr; a.in_eid = in_eid;
+  a.n_nodes = n_nodes;
+  a.x_dim = p->x_dim; a.sh_dim = p->sh_dim; a.w_dim = p->w_dim; a.y_dim = p->y_dim;
+  a.mul = p->desc.mul;
+  a.n_chunks = (p->desc.mul + 31) / 32;
+  a.n_part = p->gen ? p->gen->n_groups * a.n_chunks : 1;
+  return a;
+}
+
+extern "C" int e3b_tpconv_fwd(const e3b_tp_plan* plan, int dtype, int64_t n_nodes, int64_t n_edges, const void* x,
+                              const void* sh, const void* w, const int64_t* in_ptr, const int32_t* in_nbr,
+                              const int32_t* in_eid, void* y, void* stream) {
+  if (!plan) return fail(E3B_ERR_INVALID, "tpconv_fwd: null plan");
+  if (n_nodes == 0) return E3B_OK;
+  if (!x || !in_ptr || !y || (n_edges > 0 && (!sh || !w || !in_nbr)))
+    return fail(E3B_ERR_INVALID, "tpconv_fwd: null argument");
+  cudaStream_t st = (cudaStream_t)stream;
+  if (dtype == E3B_F32 && plan->gen) {
+    TpArgs<float> a = make_args<float>(plan, n_nodes, x, sh, w, nullptr, in_ptr, in_nbr, in_eid, y, nullptr, nullptr, nullptr);
+    const int64_t items = n_nodes * a.n_part;
+    plan->gen->fwd(a, (items + TP_THREADS / 32 - 1) / (TP_THREADS / 32), st);
+    return check_launch("tpconv_fwd (generated)");
+  }
+  const GenericTp g = make_generic(plan);
+  const int64_t threads = n_nodes * g.n_paths * g.mul;
+  DISPATCH_DTYPE(dtype, TpArgs<T> a = make_args<T>(plan, n_nodes, x, sh, w, nullptr, in_ptr, in_nbr, in_eid, y, nullptr,
+                                                   nullptr, nullptr);
+                 tp_generic_fwd_kernel<T><<<blocks_for(threads, 128), 128, 0, st>>>(g, a);)
+  return check_launch("tpconv_fwd (generic)");
+}
+
+extern "C" int e3b_tpconv_bwd(const e3b_tp_plan* plan, int dtype, int64_t n_nodes, int64_t n_edges, const void* x,
+                              const void* sh, const void* w, const void* gy, const int64_t* in_ptr,
+                              const int32_t* in_nbr, const int32_t* in_eid, void* gx_edge, void* gsh, void* gw,
+                              void* stream) {
+  if (!plan) return fail(E3B_ERR_INVALID, "tpconv_bwd: null plan");
+  if (n_nodes == 0 || n_edges == 0) return E3B_OK;
+  if (!x || !sh || !w || !gy || !in_ptr || !in_nbr || !gw) return fail(E3B_ERR_INVALID, "tpconv_bwd: null argument");
+  cudaStream_t st = (cudaStream_t)stream;
+  if (dtype == E3B_F32 && plan->gen) {
+    TpArgs<float> a = make_args<float>(plan, n_nodes, x, sh, w, gy, in_ptr, in_nbr, in_eid, nullptr, gx_edge, gsh, gw);
+    const int64_t items = n_nodes * a.n_part;
+    plan->gen->bwd(a, (items + TP_THREADS / 32 - 1) / (TP_THREADS / 32), st);
+    return check_launch("tpconv_bwd (generated)");
+  }
+  const GenericTp g = make_generic(plan);
+  const int64_t threads = n_nodes * g.n_paths * g.mul;
+  DISPATCH_DTYPE(dtype, TpArgs<T> a = make_args<T>(plan, n_nodes, x, sh, w, gy, in_ptr, in_nbr, in_eid, nullptr, gx_edge,
+                                                   gsh, gw);
+                 tp_generic_bwd_kernel<T><<<blocks_for(threads, 128), 128, 0, st>>>(g, a);)
+  return check_launch("tpconv_bwd (generic)");
+}
+
+// ------------------------------------------------------------------------------------------
+// Segmented row sum (scatter-sum by sorted segments; nn/message_passing.py:109, nn/output.py:69)
+template <typename T>
+__global__ void segment_sum_kernel(const T* __restrict__ src, int64_t width, const int64_t* __restrict__ ptr,
+                                   const int32_t* __restrict__ ids, int64_t n_out, T* __restrict__ out) {
+  const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= n_out * width) return;
+  const int64_t n = idx / width, c = idx - n * width;
+  T acc = T(0);
+  for (int64_t k = ptr[n]; k < ptr[n + 1]; ++k) {
+    const int64_t row = ids ? (int64_t)ids[k] : k;
+    acc += src[row * width + c];
+  }
+  out[idx] = acc;
+}
+
+extern "C" int e3b_segment_sum(int dtype, const void* src, int64_t width, const int64_t* ptr, const int32_t* ids,
+                               int64_t n_out, void* out, void* stream) {
+  if (n_out == 0 || width == 0) return E3B_OK;
+  if (!ptr || !out) return fail(E3B_ERR_INVALID, "segment_sum: null argument");
+  DISPATCH_DTYPE(dtype, segment_sum_kernel<T><<<blocks_for(n_out * width, 256), 256, 0, (cudaStream_t)stream>>>(
+                            (const T*)src, width, ptr, ids, n_out, (T*)out);)
+  return check_launch("segment_sum");
+}
+
+// ------------------------------------------------------------------------------------------
+// Gate (e3nn nn.Gate as wired at nn/message_passing.py:191-207)
+template <typename T> __device__ __forceinline__ T exp_(T v);
+template <> __device__ __forceinline__ float exp_<float>(float v) { return expf(v); }
+template <> __device__ __forceinline__ double exp_<double>(double v) { return exp(v); }
+template <typename T> __device__ __forceinline__ T tanh_(T v);
+template <> __device__ __forceinline__ float tanh_<float>(float v) { return tanhf(v); }
+template <> __device__ __forceinline__ double tanh_<double>(double v) { return tanh(v); }
+template <typename T> __device__ __forceinline__ T log1p_(T v);
+template <> __device__ __forceinline__ float log1p_<float>(float v) { return log1pf(v); }
+template <> __device__ __forceinline__ double log1p_<double>(double v) { return log1p(v); }
+
+template <typename T>
+__device__ __forceinline__ void act_eval(int code, T x, T* f, T* df) {
+  switch (code) {
+    case 1: {  // silu
+      const T s = T(1) / (T(1) + exp_<T>(-x));
+      *f = x * s; *df = s * (T(1) + x * (T(1) - s));
+    } break;
+    case 2: {  // tanh
+      const T t = tanh_<T>(x);
+      *f = t; *df = T(1) - t * t;
+    } break;
+    case 3: {  // shifted softplus (torch softplus threshold 20)
+      const T sp = x > T(20) ? x : log1p_<T>(exp_<T>(x));
+      *f = sp - T(0.6931471805599453);
+      *df = T(1) / (T(1) + exp_<T>(-x));
+    } break;
+    case 4: {  // tanhlu = tanh(x) |x|
+      const T t = tanh_<T>(x), ax = x < T(0) ? -x : x, sg = x > T(0) ? T(1) : (x < T(0) ? T(-1) : T(0));
+      *f = t * ax; *df = (T(1) - t * t) * ax + t * sg;
+    } break;
+    case 5: {  // abs
+      *f = x < T(0) ? -x : x; *df = x > T(0) ? T(1) : (x < T(0) ? T(-1) : T(0));
+    } break;
+    default: *f = x; *df = T(1);
+  }
+}
+
+struct GateLayout {
+  e3b_gate_desc d;
+  int32_t n_scalars, n_gates, in_dim, out_dim;
+};
+
+static GateLayout gate_layout(const e3b_gate_desc* d) {
+  GateLayout L;
+  L.d = *d;
+  L.n_scalars = 0; L.n_gates = 0;
+  int gated = 0;
+  for (int i = 0; i < d->n_scalar_blocks; ++i) L.n_scalars += d->scalar_mul[i];
+  for (int i = 0; i < d->n_gated_blocks; ++i) { L.n_gates += d->gated_mul[i]; gated += d->gated_mul[i] * (2 * d->gated_l[i] + 1); }
+  L.in_dim = L.n_scalars + L.n_gates + gated;
+  L.out_dim = L.n_scalars + gated;
+  return L;
+}
+
+// one thread per output element; BWD recomputes the activation
+template <typename T, bool BWD>
+__global__ void gate_kernel(const __grid_constant__ GateLayout L, const T* __restrict__ in, const T* __restrict__ gout,
+                            int64_t n, T* __restrict__ out, T* __restrict__ gin) {
+  const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= n * L.out_dim) return;
+  const int64_t row = idx / L.out_dim;
+  int c = (int)(idx - row * L.out_dim);
+  const T* xin = in + row * L.in_dim;
+  if (c < L.n_scalars) {
+    int b = 0, o = c;
+    while (o >= L.d.scalar_mul[b]) { o -= L.d.scalar_mul[b]; ++b; }
+    T f, df;
+    act_eval<T>(L.d.scalar_act[b], xin[c], &f, &df);
+    const T cst = T(L.d.scalar_cst[b]);
+    if (BWD) gin[row * L.in_dim + c] = gout[idx] * cst * df;
+    else out[idx] = cst * f;
+    return;
+  }
+  c -= L.n_scalars;
+  int b = 0, goff = 0;  // gated block b; goff = gate index offset
+  int dim = 2 * L.d.gated_l[0] + 1;
+  while (c >= L.d.gated_mul[b] * dim) {
+    c -= L.d.gated_mul[b] * dim;
+    goff += L.d.gated_mul[b];
+    ++b;
+    dim = 2 * L.d.gated_l[b] + 1;
+  }
+  const int u = c / dim;
+  const int in_col = (int)(L.n_scalars + L.n_gates + (idx - row * L.out_dim - L.n_scalars));
+  const T gate_in = xin[L.n_scalars + goff + u];
+  T f, df;
+  act_eval<T>(L.d.gate_act[b], gate_in, &f, &df);
+  const T cst = T(L.d.gate_cst[b]);
+  if (!BWD) {
+    out[idx] = xin[in_col] * (cst * f);
+  } else {
+    const T go = gout[idx];
+    gin[row * L.in_dim + in_col] = go * (cst * f);
+    // d/d gate = sum_m go_m * x_m * cst * f'  -> thread with m == 0 sums the 2l+1 components
+    if (c - u * dim == 0) {
+      T s = T(0);
+      for (int m = 0; m < dim; ++m) s = fma_(gout[idx + m], xin[in_col + m], s);
+      gin[row * L.in_dim + L.n_scalars + goff + u] = s * cst * df;
+    }
+  }
+}
+
+static int gate_check(const e3b_gate_desc* d) {
+  if (!d || d->n_scalar_blocks < 0 || d->n_scalar_blocks > E3B_MAX_BLOCKS || d->n_gated_blocks < 0 ||
+      d->n_gated_blocks > E3B_MAX_BLOCKS)
+    return fail(E3B_ERR_INVALID, "gate: bad descriptor");
+  return E3B_OK;
+}
+
+extern "C" int e3b_gate_fwd(const e3b_gate_desc* desc, int dtype, const void* in, int64_t n, void* out, void* stream) {
+  int rc = gate_check(desc);
+  if (rc) return rc;
+  if (n == 0) return E3B_OK;
+  if (!in || !out) return fail(E3B_ERR_INVALID, "gate_fwd: null argument");
+  const GateLayout L = gate_layout(desc);
+  if (L.out_dim == 0) return E3B_OK;
+  DISPATCH_DTYPE(dtype, gate_kernel<T, false><<<blocks_for(n * L.out_dim, 256), 256, 0, (cudaStream_t)stream>>>(
+                            L, (const T*)in, nullptr, n, (T*)out, nullptr);)
+  return check_launch("gate_fwd");
+}
+
+extern "C" int e3b_gate_bwd(const e3b_gate_desc* desc, int dtype, const void* in, const void* gout, int64_t n,
+                            void* gin, void* stream) {
+  int rc = gate_check(desc);
+  if (rc) return rc;
+  if (n == 0) return E3B_OK;
+  if (!in || !gout || !gin) return fail(E3B_ERR_INVALID, "gate_bwd: null argument");
+  const GateLayout L = gate_layout(desc);
+  if (L.out_dim == 0) return E3B_OK;
+  DISPATCH_DTYPE(dtype, gate_kernel<T, true><<<blocks_for(n * L.out_dim, 256), 256, 0, (cudaStream_t)stream>>>(
+                            L, (const T*)in, (const T*)gout, n, nullptr, (T*)gin);)
+  return check_launch("gate_bwd");
+}
+
+// ------------------------------------------------------------------------------------------
+// mul_ir <-> imu layout conversion
+struct LayoutDesc {
+  int32_t n_blocks, dim;
+  int32_t mul[E3B_MAX_BLOCKS], l[E3B_MAX_BLOCKS], off[E3B_MAX_BLOCKS];
+};
+
+template <typename T>
+__global__ void layout_kernel(const __grid_constant__ LayoutDesc L, const T* __restrict__ in, int64_t n, int to_imu,
+                              T* __restrict__ out) {
+  const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= n * L.dim) return;
+  const int64_t row = idx / L.dim;
+  const int c = (int)(idx - row * L.dim);
+  int b = 0;
+  while (b + 1 < L.n_blocks && c >= L.off[b + 1]) ++b;
+  const int d = 2 * L.l[b] + 1, r = c - L.off[b];
+  // idx addresses the OUTPUT element
+  int src;
+  if (to_imu) { const int m = r / L.mul[b], u = r - m * L.mul[b]; src = L.off[b] + u * d + m; }
+  else        { const int u = r / d, m = r - u * d;               src = L.off[b] + m * L.mul[b] + u; }
+  out[idx] = in[row * L.dim + src];
+}
+
+extern "C" int e3b_layout_convert(int dtype, const void* in, int64_t n, int32_t n_blocks, const int32_t* h_mul,
+                                  const int32_t* h_l, int to_imu, void* out, void* stream) {
+  if (n_blocks <= 0 || n_blocks > E3B_MAX_BLOCKS || !h_mul || !h_l) return fail(E3B_ERR_INVALID, "layout_convert: bad blocks");
+  if (n == 0) return E3B_OK;
+  if (!in || !out) return fail(E3B_ERR_INVALID, "layout_convert: null argument");
+  LayoutDesc L;
+  L.n_blocks = n_blocks;
+  int off = 0;
+  for (int b = 0; b < n_blocks; ++b) { L.mul[b] = h_mul[b]; L.l[b] = h_l[b]; L.off[b] = off; off += h_mul[b] * (2 * h_l[b] + 1); }
+  L.dim = off;
+  if (off == 0) return E3B_OK;
+  DISPATCH_DTYPE(dtype, layout_kernel<T><<<blocks_for(n * L.dim, 256), 256, 0, (cudaStream_t)stream>>>(
+                            L, (const T*)in, n, to_imu, (T*)out);)
+  return check_launch("layout_convert");
+}

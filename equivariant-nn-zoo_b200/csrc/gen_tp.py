@@ -1,0 +1,348 @@
+#!/usr/bin/env python3
+"""Build-time generator for the fully unrolled tensor-product convolution kernels
+(csrc/tp_generated.cuh) and the dense CG tables of the generic kernel (csrc/cg_tables.cuh).
+
+For every TP structure the reference's configs produce (e3b200.plan.reference_structures) it
+emits straight-line CUDA: per warp "group" (a balanced subset of the input blocks) the sparse
+Clebsch-Gordan contraction with the coefficients sqrt(2 l3+1) C_ijk as immediates, the outer
+products x_i * Y_j shared between the paths of one (input block, SH block) pair, accumulators
+in named registers, channel = lane.  Run by __graft_entry__.build(); output is committed too.
+"""
+import os
+import sys
+from math import sqrt
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, os.path.dirname(HERE))
+
+from e3b200 import cg  # noqa: E402
+from e3b200.plan import generated_structures  # noqa: E402
+
+MAX_ACC_PER_GROUP = 56  # accumulator registers per thread (forward)
+
+
+def lit(v):
+    return f"T({float(v)!r})"
+
+
+def coef(l1, l2, l3):
+    return sqrt(2 * l3 + 1) * cg.w3j(l1, l2, l3)
+
+
+def make_groups(st):
+    """Partition input blocks into groups with <= MAX_ACC_PER_GROUP output components, keeping
+    blocks whole and balancing the FMA count.  Returns list of lists of input-block indices."""
+    n_in = len(st.irreps_in)
+    acc = [sum(p.ir_out.dim for p in st.paths if p.i_in == b) for b in range(n_in)]
+    work = [sum((abs(coef(st.irreps_in[p.i_in].ir.l, st.irreps_sh[p.i_sh].ir.l, p.ir_out.l)) > 0).sum()
+                for p in st.paths if p.i_in == b) for b in range(n_in)]
+    total = sum(acc)
+    n_groups = max(1, -(-total // MAX_ACC_PER_GROUP))
+    while True:
+        groups = [[] for _ in range(n_groups)]
+        gacc = [0] * n_groups
+        gwork = [0] * n_groups
+        ok = True
+        for b in sorted(range(n_in), key=lambda b: -work[b]):
+            cands = [g for g in range(n_groups) if gacc[g] + acc[b] <= MAX_ACC_PER_GROUP]
+            if not cands:
+                ok = False
+                break
+            g = min(cands, key=lambda g: gwork[g])
+            groups[g].append(b)
+            gacc[g] += acc[b]
+            gwork[g] += work[b]
+        if ok:
+            return [sorted(g) for g in groups if g]
+        n_groups += 1
+
+
+class Emitter:
+    def __init__(self):
+        self.lines = []
+
+    def __call__(self, s=""):
+        self.lines.append(s)
+
+    def text(self):
+        return "\n".join(self.lines) + "\n"
+
+
+def emit_structure(E, sid, st):
+    groups = make_groups(st)
+    xoff, xdim = st.x_comp_offsets()
+    soff, sdim = st.sh_comp_offsets()
+    yoff, ydim = st.y_comp_offsets()
+    n_paths = len(st.paths)
+    G = len(groups)
+
+    def pairs_of(blocks):
+        """(b, s) pairs in order with their paths"""
+        out = []
+        for b in blocks:
+            for s in range(len(st.irreps_sh)):
+                ps = [pi for pi, p in enumerate(st.paths) if p.i_in == b and p.i_sh == s]
+                if ps:
+                    out.append((b, s, ps))
+        return out
+
+    # ------------------------------------------------------------------ forward
+    for g, blocks in enumerate(groups):
+        E(f"template <typename T> __device__ __forceinline__ void tpf_S{sid}_g{g}(const TpArgs<T>& a, int64_t node, int u, bool active) {{")
+        E("  const int mul = a.mul;")
+        accs = []
+        for pi, p in enumerate(st.paths):
+            if p.i_in in blocks:
+                for k in range(p.ir_out.dim):
+                    accs.append(f"acc_{pi}_{k}")
+        for i in range(0, len(accs), 8):
+            E("  T " + ", ".join(f"{n} = T(0)" for n in accs[i:i + 8]) + ";")
+        E("  const int64_t e0 = a.in_ptr[node], e1 = a.in_ptr[node + 1];")
+        E("  for (int64_t kk = e0; kk < e1; ++kk) {")
+        E("    const int64_t src = a.in_nbr[kk];")
+        E("    const int64_t eid = a.in_eid ? (int64_t)a.in_eid[kk] : kk;")
+        E("    const T* __restrict__ xr = a.x + src * a.x_dim + u;")
+        E("    const T* __restrict__ wr = a.w + eid * a.w_dim + u;")
+        E("    const T* __restrict__ yr = a.sh + eid * a.sh_dim;")
+        for b in blocks:
+            for i in range(st.irreps_in[b].ir.dim):
+                E(f"    const T x_{b}_{i} = ldg(xr + {xoff[b] + i} * mul);")
+        used_s = sorted({s for (b, s, ps) in pairs_of(blocks)})
+        for s in used_s:
+            for j in range(st.irreps_sh[s].ir.dim):
+                E(f"    const T Y_{s}_{j} = ldg(yr + {soff[s] + j});")
+        for pi, p in enumerate(st.paths):
+            if p.i_in in blocks:
+                E(f"    const T w_{pi} = ldg(wr + {pi} * mul);")
+        for (b, s, ps) in pairs_of(blocks):
+            l1, l2 = st.irreps_in[b].ir.l, st.irreps_sh[s].ir.l
+            need = set()
+            for pi in ps:
+                C = coef(l1, l2, st.paths[pi].ir_out.l)
+                for i in range(2 * l1 + 1):
+                    for j in range(2 * l2 + 1):
+                        if abs(C[i, j]).max() > 0:
+                            need.add((i, j))
+            E("    {")
+            for (i, j) in sorted(need):
+                E(f"      const T xy_{i}_{j} = x_{b}_{i} * Y_{s}_{j};")
+            for pi in ps:
+                l3 = st.paths[pi].ir_out.l
+                C = coef(l1, l2, l3)
+                for k in range(2 * l3 + 1):
+                    terms = [(i, j, C[i, j, k]) for i in range(2 * l1 + 1) for j in range(2 * l2 + 1) if C[i, j, k] != 0]
+                    if not terms:
+                        continue
+                    i, j, c = terms[0]
+                    expr = f"{lit(c)} * xy_{i}_{j}"
+                    for (i, j, c) in terms[1:]:
+                        expr = f"fma_({lit(c)}, xy_{i}_{j}, {expr})"
+                    E(f"      acc_{pi}_{k} = fma_(w_{pi}, {expr}, acc_{pi}_{k});")
+            E("    }")
+        E("  }")
+        E("  if (active) {")
+        E("    T* __restrict__ yo = a.y + node * a.y_dim + u;")
+        for pi, p in enumerate(st.paths):
+            if p.i_in in blocks:
+                for k in range(p.ir_out.dim):
+                    E(f"    yo[{yoff[p.slot] + k} * mul] = acc_{pi}_{k};")
+        E("  }")
+        E("}")
+        E()
+
+    # ------------------------------------------------------------------ backward
+    for g, blocks in enumerate(groups):
+        E(f"template <typename T> __device__ __forceinline__ void tpb_S{sid}_g{g}(const TpArgs<T>& a, int64_t node, int u, bool active, int part, int lane) {{")
+        E("  const int mul = a.mul;")
+        E("  const T* __restrict__ gyr = a.gy + node * a.y_dim + u;")
+        for pi, p in enumerate(st.paths):
+            if p.i_in in blocks:
+                for k in range(p.ir_out.dim):
+                    E(f"  const T gy_{pi}_{k} = active ? ldg(gyr + {yoff[p.slot] + k} * mul) : T(0);")
+        E("  const int64_t e0 = a.in_ptr[node], e1 = a.in_ptr[node + 1];")
+        E("  for (int64_t kk = e0; kk < e1; ++kk) {")
+        E("    const int64_t src = a.in_nbr[kk];")
+        E("    const int64_t eid = a.in_eid ? (int64_t)a.in_eid[kk] : kk;")
+        E("    const T* __restrict__ xr = a.x + src * a.x_dim + u;")
+        E("    const T* __restrict__ wr = a.w + eid * a.w_dim + u;")
+        E("    const T* __restrict__ yr = a.sh + eid * a.sh_dim;")
+        E("    T* __restrict__ gwr = a.gw + eid * a.w_dim + u;")
+        used_s = sorted({s for (b, s, ps) in pairs_of(blocks)})
+        for s in used_s:
+            for j in range(st.irreps_sh[s].ir.dim):
+                E(f"    const T Y_{s}_{j} = ldg(yr + {soff[s] + j});")
+                E(f"    T gY_{s}_{j} = T(0);")
+        for b in blocks:
+            d1 = st.irreps_in[b].ir.dim
+            for i in range(d1):
+                E(f"    const T x_{b}_{i} = ldg(xr + {xoff[b] + i} * mul);")
+            for i in range(d1):
+                E(f"    T gx_{b}_{i} = T(0);")
+            for (bb, s, ps) in pairs_of([b]):
+                l1, l2 = st.irreps_in[b].ir.l, st.irreps_sh[s].ir.l
+                need = set()
+                for pi in ps:
+                    C = coef(l1, l2, st.paths[pi].ir_out.l)
+                    for i in range(2 * l1 + 1):
+                        for j in range(2 * l2 + 1):
+                            if abs(C[i, j]).max() > 0:
+                                need.add((i, j))
+                need = sorted(need)
+                E("    {")
+                for (i, j) in need:
+                    E(f"      const T xy_{i}_{j} = x_{b}_{i} * Y_{s}_{j};")
+                    E(f"      T gxy_{i}_{j} = T(0);")
+                for pi in ps:
+                    l3 = st.paths[pi].ir_out.l
+                    C = coef(l1, l2, l3)
+                    E(f"      {{ const T w_p = ldg(wr + {pi} * mul); T gw_p = T(0);")
+                    for k in range(2 * l3 + 1):
+                        terms = [(i, j, C[i, j, k]) for i in range(2 * l1 + 1) for j in range(2 * l2 + 1) if C[i, j, k] != 0]
+                        if not terms:
+                            continue
+                        i, j, c = terms[0]
+                        expr = f"{lit(c)} * xy_{i}_{j}"
+                        for (i, j, c) in terms[1:]:
+                            expr = f"fma_({lit(c)}, xy_{i}_{j}, {expr})"
+                        E(f"        gw_p = fma_(gy_{pi}_{k}, {expr}, gw_p);")
+                        E(f"        {{ const T gt = w_p * gy_{pi}_{k};")
+                        for (i, j, c) in terms:
+                            E(f"          gxy_{i}_{j} = fma_({lit(c)}, gt, gxy_{i}_{j});")
+                        E("        }")
+                    E(f"        if (active) gwr[{pi} * mul] = gw_p; }}")
+                for (i, j) in need:
+                    E(f"      gx_{b}_{i} = fma_(gxy_{i}_{j}, Y_{s}_{j}, gx_{b}_{i});")
+                    E(f"      gY_{s}_{j} = fma_(gxy_{i}_{j}, x_{b}_{i}, gY_{s}_{j});")
+                E("    }")
+            E("    if (a.gx_edge != nullptr && active) {")
+            E("      T* __restrict__ gxr = a.gx_edge + eid * a.x_dim + u;")
+            for i in range(d1):
+                E(f"      gxr[{xoff[b] + i} * mul] = gx_{b}_{i};")
+            E("    }")
+        E("    if (a.gsh != nullptr) {")
+        E("      T* __restrict__ gsr = a.gsh + (eid * a.n_part + part) * a.sh_dim;")
+        for s in range(len(st.irreps_sh)):
+            for j in range(st.irreps_sh[s].ir.dim):
+                if s in used_s:
+                    E(f"      E3B_GSH_STORE(gsr, {soff[s] + j}, gY_{s}_{j});")
+                else:
+                    E(f"      E3B_GSH_ZERO(gsr, {soff[s] + j});")
+        E("    }")
+        E("  }")
+        E("}")
+        E()
+
+    # ------------------------------------------------------------------ kernels
+    E("#ifdef __CUDACC__")
+    for kind in ("f", "b"):
+        extra = ", part, lane" if kind == "b" else ""
+        E(f"template <typename T> __global__ void __launch_bounds__(TP_THREADS) tp{kind}_S{sid}(const TpArgs<T> a) {{")
+        E("  const int lane = threadIdx.x & 31;")
+        E("  const int64_t item = (int64_t)blockIdx.x * (TP_THREADS / 32) + (threadIdx.x >> 5);")
+        E(f"  const int per_node = a.n_chunks * {G};")
+        E("  if (item >= a.n_nodes * per_node) return;")
+        E("  const int64_t node = item / per_node;")
+        E("  const int part = (int)(item - node * per_node);")
+        E(f"  const int chunk = part / {G}, group = part - chunk * {G};")
+        E("  int u = chunk * 32 + lane;")
+        E("  const bool active = u < a.mul;")
+        E("  if (!active) u = a.mul - 1;")
+        E("  switch (group) {")
+        for g in range(G):
+            E(f"    case {g}: tp{kind}_S{sid}_g{g}<T>(a, node, u, active{extra}); break;")
+        E("  }")
+        E("}")
+        E()
+    E("#endif  // __CUDACC__")
+    return G
+
+
+def emit_tables(st_list):
+    E = Emitter()
+    E("// GENERATED by csrc/gen_tp.py -- do not edit.")
+    E("#pragma once")
+    E()
+    Gs = []
+    for sid, st in enumerate(st_list):
+        E(f"// ---- structure S{sid}: in l={[b.ir.l for b in st.irreps_in]} sh l={[b.ir.l for b in st.irreps_sh]} "
+          f"paths={len(st.paths)} out comps={st.y_comp_offsets()[1]}")
+        Gs.append(emit_structure(E, sid, st))
+    E("#ifdef E3B_HOST_EMU")
+    E("// CPU emulation entry (tests only): runs every (node, channel, group) item serially.")
+    E("template <typename T> static int emu_tp(int sid, int bwd, const TpArgs<T>& a) {")
+    E("  for (int64_t node = 0; node < a.n_nodes; ++node)")
+    E("    for (int u = 0; u < a.mul; ++u) {")
+    E("      const int chunk = u / 32, lane = u % 32; (void)lane;")
+    E("      switch (sid) {")
+    for sid in range(len(st_list)):
+        E(f"        case {sid}:")
+        for g in range(Gs[sid]):
+            E(f"          if (bwd) tpb_S{sid}_g{g}<T>(a, node, u, true, chunk * {Gs[sid]} + {g}, lane); else tpf_S{sid}_g{g}<T>(a, node, u, true);")
+        E("          break;")
+    E("        default: return -1;")
+    E("      }")
+    E("    }")
+    E("  return 0;")
+    E("}")
+    E("static const int kEmuGroups[] = {" + ", ".join(str(g) for g in Gs) + "};")
+    E("#endif  // E3B_HOST_EMU")
+    E("#ifdef __CUDACC__")
+    for sid in range(len(st_list)):
+        for kind in ("f", "b"):
+            E(f"static void launch_tp{kind}_S{sid}(const TpArgs<float>& a, int64_t grid, cudaStream_t s) {{ "
+              f"tp{kind}_S{sid}<float><<<(unsigned)grid, TP_THREADS, 0, s>>>(a); }}")
+
+    def arr(v):
+        return "{" + ", ".join(str(int(t)) for t in v) + "}"
+
+    E(f"static const int kNumGenEntries = {len(st_list)};")
+    E("static const GenEntry kGenEntries[] = {")
+    for sid, st in enumerate(st_list):
+        E("  {" + ", ".join([
+            str(len(st.irreps_in)), arr(b.ir.l for b in st.irreps_in),
+            str(len(st.irreps_sh)), arr(b.ir.l for b in st.irreps_sh),
+            str(len(st.paths)), arr(p.i_in for p in st.paths), arr(p.i_sh for p in st.paths),
+            arr(p.ir_out.l for p in st.paths), arr(p.slot for p in st.paths),
+            str(Gs[sid]), f"launch_tpf_S{sid}", f"launch_tpb_S{sid}"]) + "},")
+    E("};")
+    E("#endif  // __CUDACC__")
+    return E.text()
+
+
+def emit_cg_tables(lmax=3):
+    E = Emitter()
+    E("// GENERATED by csrc/gen_tp.py -- dense real Wigner-3j tables (analytic signs), l <= %d." % lmax)
+    E("#pragma once")
+    n = lmax + 1
+    offs, data, signs = [], [], []
+    for l1 in range(n):
+        for l2 in range(n):
+            for l3 in range(n):
+                if abs(l1 - l2) <= l3 <= l1 + l2:
+                    offs.append(len(data))
+                    data.extend(cg.w3j(l1, l2, l3).reshape(-1).tolist())
+                    signs.append(int(cg._preset_sign(l1, l2, l3)))
+                else:
+                    offs.append(-1)
+                    signs.append(1)
+    E(f"#define E3B_CG_LMAX {lmax}")
+    E(f"static __device__ const int kCgOffset[{len(offs)}] = {{" + ", ".join(map(str, offs)) + "};")
+    E(f"static const int kCgSign044[{len(signs)}] = {{" + ", ".join(map(str, signs)) + "};")
+    E(f"static __device__ const double kCgData[{len(data)}] = {{")
+    for i in range(0, len(data), 6):
+        E("  " + ", ".join(repr(v) for v in data[i:i + 6]) + ",")
+    E("};")
+    return E.text()
+
+
+def main():
+    sts = generated_structures()
+    with open(os.path.join(HERE, "tp_generated.cuh"), "w") as f:
+        f.write(emit_tables(sts))
+    with open(os.path.join(HERE, "cg_tables.cuh"), "w") as f:
+        f.write(emit_cg_tables())
+    print(f"generated {len(sts)} structures:", [(len(s.paths), [b.ir.l for b in s.irreps_in]) for s in sts])
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,16 @@
+// Interface between the ABI translation unit and the generated-kernel translation unit.
+#pragma once
+#include <cuda_runtime.h>
+
+#include "common.cuh"
+
+struct GenEntry {
+  int n_in; int in_l[E3B_MAX_BLOCKS]; int n_sh; int sh_l[E3B_MAX_BLOCKS]; int n_paths;
+  int path_in[E3B_MAX_PATHS], path_sh[E3B_MAX_PATHS], path_lout[E3B_MAX_PATHS], path_slot[E3B_MAX_PATHS];
+  int n_groups;
+  void (*fwd)(const TpArgs<float>&, int64_t grid, cudaStream_t);
+  void (*bwd)(const TpArgs<float>&, int64_t grid, cudaStream_t);
+};
+
+// the generated kernel whose structure equals `d` (ignoring mul and parities), or nullptr
+const GenEntry* e3b_find_generated(const e3b_tp_desc* d);

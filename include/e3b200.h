@@ -1,0 +1,201 @@
+/*
+ * e3b200.h -- C ABI of libe3b200.so: the B200 (sm_100a) hot path of Equivariant-NN-Zoo.
+ *
+ * The reference (pure Python on e3nn 0.4.4) has no FFI; the seam this library plugs into is
+ * its Python module protocol.  Each entry point below names the
+ * reference interface it replaces (paths relative to /root/reference).  The host side that
+ * binds these symbols with ctypes is equivariant-nn-zoo_b200/e3b200/_lib.py; the reference-side
+ * binding a maintainer would add is shown in INTEGRATION.md.
+ *
+ * Conventions
+ *   - return 0 on success, a negative e3b_status otherwise; text via e3b_last_error()
+ *     (thread-local, valid until the next call on the same thread);
+ *   - no C++ exceptions cross the boundary;
+ *   - the CALLER allocates every buffer (torch caching allocator); the library never
+ *     allocates device memory and never synchronises;
+ *   - all pointers are DEVICE pointers unless named h_*; functions are asynchronous on the
+ *     supplied stream (a cudaStream_t passed as void*);
+ *   - dtype: 0 = float32, 1 = float64 (the fp64 build of the same templates is the
+ *     1e-10 correctness mode);
+ *   - node feature rows cross this ABI in the library's "channel-fastest" layout
+ *     [block][m][u] ("imu") unless stated otherwise; e3nn's "mul_ir" layout is [block][u][m].
+ *     e3b_layout_convert translates.
+ */
+#ifndef E3B200_H
+#define E3B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define E3B_ABI_VERSION 1
+
+typedef enum {
+  E3B_OK = 0,
+  E3B_ERR_INVALID = -1,     /* bad argument / descriptor            */
+  E3B_ERR_UNSUPPORTED = -2, /* irreps outside what the kernels cover */
+  E3B_ERR_CUDA = -3,        /* launch failed; see e3b_last_error()   */
+  E3B_ERR_NOMEM = -4        /* host allocation for a plan failed     */
+} e3b_status;
+
+#define E3B_F32 0
+#define E3B_F64 1
+
+int e3b_abi_version(void);
+const char* e3b_last_error(void);
+
+/* ---------------------------------------------------------------------------------------
+ * Neighbour list.   Replaces computeEdgeIndex, e3_layers/data/compute_edge.py:38-113
+ * (radius part + self-loop removal; the optional `criteria` edges are OR-ed in by the host
+ * as an extra edge list).  Semantics: per graph g (nodes node_ptr[g]..node_ptr[g+1]) every
+ * ordered pair (a,b), a != b, with  sqrtf(fmaf(dz,dz,fmaf(dy,dy,dx*dx))) < r_max  in fp32
+ * (bit-identical to torch.linalg.norm on the fp32 difference, compute_edge.py:68-70).
+ * Output order = the reference's: lexicographic in (edge_index[0]=a, edge_index[1]=b).
+ * Two phases so that the caller allocates the output:
+ *   count: deg[a] = number of neighbours of a                       (int32 [N])
+ *   (caller: row_ptr = exclusive scan of deg, int64 [N+1]; E = row_ptr[N])
+ *   fill : edge_index int64 [2,E]; optional rev int32 [E] with rev[e] = position of the
+ *          reversed edge (b,a) -- the radius graph is symmetric, so (row_ptr, edge_index[1],
+ *          rev) is also the dst-grouped CSR the convolution consumes.
+ * pos_stride = floats between consecutive rows of pos (3 for a dense [N,3]).
+ */
+int e3b_radius_graph_count(const float* pos, int64_t pos_stride, const int64_t* node_ptr /* [G+1] */,
+                           int32_t n_graphs, int64_t n_nodes, float r_max, int32_t* deg, void* stream);
+int e3b_radius_graph_fill(const float* pos, int64_t pos_stride, const int64_t* node_ptr, int32_t n_graphs,
+                          int64_t n_nodes, float r_max, const int64_t* row_ptr, int64_t n_edges,
+                          int64_t* edge_index /* [2,E] */, int32_t* rev /* [E] or NULL */, void* stream);
+
+/* Dst-grouped CSR of an arbitrary edge list (any order, e.g. with `criteria` edges or a
+ * user-supplied edge_index).  The caller passes row_ptr = exclusive scan of the in-degree
+ * (int64 [N+1]) and a zeroed int32 cursor[N]; the kernel fills, per destination node, the
+ * edge ids of its incoming edges in ASCENDING edge id (deterministic).              */
+int e3b_csr_fill(const int64_t* edge_index, int64_t n_edges, int64_t n_nodes, int which_row /*0|1*/,
+                 const int64_t* row_ptr, int32_t* cursor /* [N], zeroed */, int32_t* eid /* [E] */, void* stream);
+
+/* ---------------------------------------------------------------------------------------
+ * Edge geometry.  Replaces computeEdgeVector (data/compute_edge.py:13-36),
+ * SphericalEncoding (nn/embedding.py:130-178; e3nn o3.SphericalHarmonics, normalize=True,
+ * 'component', l <= 2 -- every in-scope config uses 1x0e+1x1o+1x2e) and RadialBasisEncoding (nn/embedding.py:181-219: Bessel x polynomial
+ * cutoff p, or the symmetric cutoff of :26-29 when cutoff_kind = 1).
+ */
+int e3b_edge_vectors_fwd(int dtype, const void* pos, const int64_t* edge_index, int64_t n_edges,
+                         void* vec /* [E,3] */, void* len /* [E] or NULL */, void* stream);
+/* gpos[n] += sum_{e: dst=n} g[e] - sum_{e: src=n} g[e]  via the two CSR views, no atomics.
+ * g = gvec + glen * vec/len (either may be NULL). */
+int e3b_edge_vectors_bwd(int dtype, const void* gvec, const void* glen, const void* vec, const void* len,
+                         int64_t n_nodes, const int64_t* in_ptr, const int32_t* in_eid,
+                         const int64_t* out_ptr, const int32_t* out_eid, void* gpos /* [N,3] */, void* stream);
+
+int e3b_sh_fwd(int dtype, const void* vec, int64_t n, int lmax, int normalize, void* sh /* [n,(lmax+1)^2] */,
+               void* stream);
+int e3b_sh_bwd(int dtype, const void* vec, const void* gsh, int64_t n, int lmax, int normalize,
+               void* gvec /* [n,3] */, void* stream);
+
+int e3b_radial_fwd(int dtype, const void* r, int64_t n, const void* bessel_w, int n_basis, double r_max,
+                   double r_min, int one_over_r, int cutoff_kind, double p, void* out /* [n,n_basis] */,
+                   void* stream);
+/* gr [n]; gw_partial [n_blocks, n_basis] partial sums of d/d bessel_w (caller sums rows;
+ * n_blocks = e3b_radial_bwd_blocks(n)). */
+int64_t e3b_radial_bwd_blocks(int64_t n);
+int e3b_radial_bwd(int dtype, const void* r, const void* gout, int64_t n, const void* bessel_w, int n_basis,
+                   double r_max, double r_min, int one_over_r, int cutoff_kind, double p, void* gr,
+                   void* gw_partial, void* stream);
+
+/* ---------------------------------------------------------------------------------------
+ * Fused tensor-product convolution.  Replaces, in FactorizedConvolution.forward
+ * (nn/message_passing.py:104-109): x[edge_src] gather, TensorProductExpansion.tp
+ * (o3.TensorProduct 'uvu', external per-edge weights, nn/pointwise.py:61-85,98) and
+ * scatter(edge_features, edge_dst) -- with the post-TP o3.Linear (pointwise.py:99) moved
+ * AFTER the reduction by linearity.
+ *
+ *   y[n, p, k, u] = sum_{e in in(n)} w[e, p, u] * sqrt(2 l3+1) *
+ *                   sum_{ij} C^{l1 l2 l3}_{ijk} x[src(e), b1(p), i, u] * Y[e, b2(p), j]
+ *
+ * A plan fixes the irreps: input blocks (l, parity) all with multiplicity `mul`, SH blocks,
+ * and the path list in e3nn instruction order (weight layout) with each path's slot in the
+ * sorted output (irreps_mid).  Layouts: x [N][sum_b (2l_b+1)][mul]; Y [E][sum (2l+1)];
+ * w [E][n_paths][mul] (== e3nn's weight layout for uvu with mul_in2 = 1);
+ * y [N][sum_p (2l3_p+1) in sorted-slot order][mul].
+ */
+#define E3B_MAX_BLOCKS 16
+#define E3B_MAX_PATHS 96
+
+typedef struct {
+  int32_t mul;                       /* common multiplicity of every input block        */
+  int32_t n_in;
+  int32_t in_l[E3B_MAX_BLOCKS];      /* l of input block b                              */
+  int32_t in_p[E3B_MAX_BLOCKS];      /* parity (+1/-1), informational                   */
+  int32_t n_sh;
+  int32_t sh_l[E3B_MAX_BLOCKS];
+  int32_t n_paths;
+  int32_t path_in[E3B_MAX_PATHS];    /* input block index                               */
+  int32_t path_sh[E3B_MAX_PATHS];    /* SH block index                                  */
+  int32_t path_lout[E3B_MAX_PATHS];  /* l3                                              */
+  int32_t path_slot[E3B_MAX_PATHS];  /* position of this path's output block in y       */
+  int32_t w3j_sign_preset;           /* 0 = analytic (e3nn >= 0.5), 1 = e3nn044 (R1)    */
+} e3b_tp_desc;
+
+typedef struct e3b_tp_plan e3b_tp_plan;
+
+int e3b_tp_plan_create(const e3b_tp_desc* desc, e3b_tp_plan** out);
+void e3b_tp_plan_destroy(e3b_tp_plan* plan);
+/* 1 if a generated (fully unrolled) kernel matches this plan, 0 if the generic one runs */
+int e3b_tp_plan_is_specialized(const e3b_tp_plan* plan);
+/* row widths in scalars, and n_part = number of partial rows per edge the f32 backward writes
+ * into gsh (1 for the generic kernel, which accumulates with atomics into a ZEROED buffer) */
+int e3b_tp_plan_dims(const e3b_tp_plan* plan, int32_t* x_dim, int32_t* sh_dim, int32_t* w_dim, int32_t* y_dim,
+                     int32_t* n_part_f32);
+
+/* in_ptr/in_nbr/in_eid: dst-grouped CSR (in_nbr[k] = source node, in_eid[k] = row of w / Y;
+ * in_eid may be NULL when the edge arrays are already in CSR order).                        */
+int e3b_tpconv_fwd(const e3b_tp_plan* plan, int dtype, int64_t n_nodes, int64_t n_edges, const void* x,
+                   const void* sh, const void* w, const int64_t* in_ptr, const int32_t* in_nbr,
+                   const int32_t* in_eid, void* y, void* stream);
+/* First-order backward.  gx_edge [E, x_dim] receives the per-edge contribution to d/dx[src]
+ * (row = edge id); the caller reduces it by source with e3b_segment_sum over the src-grouped
+ * CSR (deterministic, no atomics).  gw [E, w_dim] is written directly.  gsh is
+ * [E, n_part, sh_dim]: each warp role writes its own partial row (caller sums over n_part).
+ * When the plan is not specialized (or dtype is f64) the generic kernel runs: gx_edge and gsh
+ * must then be ZERO-filled by the caller (it accumulates with atomics, n_part = 1).
+ * gx_edge and gsh may be NULL when those gradients are not needed.                         */
+int e3b_tpconv_bwd(const e3b_tp_plan* plan, int dtype, int64_t n_nodes, int64_t n_edges, const void* x,
+                   const void* sh, const void* w, const void* gy, const int64_t* in_ptr, const int32_t* in_nbr,
+                   const int32_t* in_eid, void* gx_edge, void* gsh, void* gw, void* stream);
+
+/* out[n, :] = sum_{k in [ptr[n], ptr[n+1])} src[ids ? ids[k] : k, :]  (rows of `width` scalars).
+ * Replaces torch_runstats scatter at nn/message_passing.py:109 / nn/output.py:69 (Pooling). */
+int e3b_segment_sum(int dtype, const void* src, int64_t width, const int64_t* ptr, const int32_t* ids,
+                    int64_t n_out, void* out, void* stream);
+
+/* ---------------------------------------------------------------------------------------
+ * Gate non-linearity.  Replaces e3nn nn.Gate as built at nn/message_passing.py:191-207:
+ * input [scalars | gates | gated] in mul_ir layout; act codes: 0 identity, 1 silu, 2 tanh,
+ * 3 ssp, 4 tanhlu, 5 abs; each multiplied by its normalize2mom constant `cst`.
+ */
+typedef struct {
+  int32_t n_scalar_blocks;
+  int32_t scalar_mul[E3B_MAX_BLOCKS];
+  int32_t scalar_act[E3B_MAX_BLOCKS];
+  double scalar_cst[E3B_MAX_BLOCKS];
+  int32_t n_gated_blocks;
+  int32_t gated_mul[E3B_MAX_BLOCKS];
+  int32_t gated_l[E3B_MAX_BLOCKS];
+  int32_t gate_act[E3B_MAX_BLOCKS];
+  double gate_cst[E3B_MAX_BLOCKS];
+} e3b_gate_desc;
+
+int e3b_gate_fwd(const e3b_gate_desc* desc, int dtype, const void* in, int64_t n, void* out, void* stream);
+int e3b_gate_bwd(const e3b_gate_desc* desc, int dtype, const void* in, const void* gout, int64_t n, void* gin,
+                 void* stream);
+
+/* mul_ir <-> imu layout conversion of feature rows (blocks: mul, l). to_imu = 1: [u][m]->[m][u] */
+int e3b_layout_convert(int dtype, const void* in, int64_t n, int32_t n_blocks, const int32_t* mul,
+                       const int32_t* l, int to_imu, void* out, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* E3B200_H */
