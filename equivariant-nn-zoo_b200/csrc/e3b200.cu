@@ -465,14 +465,14 @@ struct e3b_tp_plan {
   int32_t mul[E3B_MAX_BLOCKS];     // generic: per input block multiplicity (== desc.mul)
   int64_t x_dim, sh_dim, w_dim, y_dim;
   int32_t x_off[E3B_MAX_BLOCKS], sh_off[E3B_MAX_BLOCKS];
-  int32_t w_off[E3B_MAX_PATHS], y_off[E3B_MAX_PATHS];
+  int32_t w_off[E3B_MAX_PATHS], y_off[E3B_MAX_PATHS], y_kstride[E3B_MAX_PATHS];
   float sign[E3B_MAX_PATHS];
 };
 
 struct GenericTp {
   int32_t n_paths, mul;
   int32_t l1[E3B_MAX_PATHS], l2[E3B_MAX_PATHS], l3[E3B_MAX_PATHS];
-  int32_t x_off[E3B_MAX_PATHS], sh_off[E3B_MAX_PATHS], w_off[E3B_MAX_PATHS], y_off[E3B_MAX_PATHS];
+  int32_t x_off[E3B_MAX_PATHS], sh_off[E3B_MAX_PATHS], w_off[E3B_MAX_PATHS], y_off[E3B_MAX_PATHS], y_kstride[E3B_MAX_PATHS];
   float sign[E3B_MAX_PATHS];
 };
 
@@ -500,8 +500,9 @@ extern "C" int e3b_tp_plan_create(const e3b_tp_desc* d, e3b_tp_plan** out) {
   }
   p->sh_dim = off;
   p->w_dim = (int64_t)d->n_paths * d->mul;
-  // output blocks by slot
-  int slot_l[E3B_MAX_PATHS];
+  // output blocks by slot; consecutive slots with the same (l, parity) form one group laid out
+  // [k][slot-in-group][u]
+  int slot_l[E3B_MAX_PATHS], slot_p[E3B_MAX_PATHS];
   for (int q = 0; q < d->n_paths; ++q) slot_l[q] = -1;
   for (int q = 0; q < d->n_paths; ++q) {
     const int b = d->path_in[q], s = d->path_sh[q], l3 = d->path_lout[q], slot = d->path_slot[q];
@@ -511,19 +512,27 @@ extern "C" int e3b_tp_plan_create(const e3b_tp_desc* d, e3b_tp_plan** out) {
       return fail(E3B_ERR_INVALID, "tp_plan_create: bad path %d (in %d, sh %d, l_out %d, slot %d)", q, b, s, l3, slot);
     }
     slot_l[slot] = l3;
+    slot_p[slot] = d->in_p[b] * d->sh_p[s];
   }
-  int yo[E3B_MAX_PATHS];
+  int ybase[E3B_MAX_PATHS], ykst[E3B_MAX_PATHS];
   off = 0;
-  for (int s = 0; s < d->n_paths; ++s) { yo[s] = off; off += 2 * slot_l[s] + 1; }
+  for (int s = 0; s < d->n_paths;) {
+    int e = s;
+    while (e < d->n_paths && slot_l[e] == slot_l[s] && slot_p[e] == slot_p[s]) ++e;
+    for (int t = s; t < e; ++t) { ybase[t] = off + (t - s); ykst[t] = e - s; }
+    off += (e - s) * (2 * slot_l[s] + 1);
+    s = e;
+  }
   p->y_dim = (int64_t)off * d->mul;
   const int n = E3B_CG_LMAX + 1;
   for (int q = 0; q < d->n_paths; ++q) {
     p->w_off[q] = q;
-    p->y_off[q] = yo[d->path_slot[q]];
+    p->y_off[q] = ybase[d->path_slot[q]];
+    p->y_kstride[q] = ykst[d->path_slot[q]];
     const int l1 = d->in_l[d->path_in[q]], l2 = d->sh_l[d->path_sh[q]], l3 = d->path_lout[q];
     p->sign[q] = (d->w3j_sign_preset == 1) ? (float)kCgSign044[(l1 * n + l2) * n + l3] : 1.0f;
   }
-  p->gen = (d->w3j_sign_preset == 0) ? e3b_find_generated(d) : nullptr;
+  p->gen = (d->w3j_sign_preset == 0) ? e3b_find_generated(d, p->y_off, p->y_kstride) : nullptr;
   *out = p;
   return E3B_OK;
 }
@@ -548,7 +557,7 @@ static GenericTp make_generic(const e3b_tp_plan* p) {
   for (int q = 0; q < g.n_paths; ++q) {
     const int b = p->desc.path_in[q], s = p->desc.path_sh[q];
     g.l1[q] = p->desc.in_l[b]; g.l2[q] = p->desc.sh_l[s]; g.l3[q] = p->desc.path_lout[q];
-    g.x_off[q] = p->x_off[b]; g.sh_off[q] = p->sh_off[s]; g.w_off[q] = p->w_off[q]; g.y_off[q] = p->y_off[q];
+    g.x_off[q] = p->x_off[b]; g.sh_off[q] = p->sh_off[s]; g.w_off[q] = p->w_off[q]; g.y_off[q] = p->y_off[q]; g.y_kstride[q] = p->y_kstride[q];
     g.sign[q] = p->sign[q];
   }
   return g;
@@ -590,7 +599,7 @@ __global__ void __launch_bounds__(128) tp_generic_fwd_kernel(const __grid_consta
     }
   }
   T* yo = a.y + node * a.y_dim + (int64_t)g.y_off[q] * g.mul + u;
-  for (int k = 0; k < d3; ++k) yo[(int64_t)k * g.mul] = acc[k];
+  for (int k = 0; k < d3; ++k) yo[(int64_t)k * g.y_kstride[q] * g.mul] = acc[k];
 }
 
 template <typename T>
@@ -607,7 +616,7 @@ __global__ void __launch_bounds__(128) tp_generic_bwd_kernel(const __grid_consta
   const T scale = T(sqrt((double)d3)) * T(g.sign[q]);
   T gy[2 * E3B_CG_LMAX + 1];
   const T* gyr = a.gy + node * a.y_dim + (int64_t)g.y_off[q] * g.mul + u;
-  for (int k = 0; k < d3; ++k) gy[k] = gyr[(int64_t)k * g.mul];
+  for (int k = 0; k < d3; ++k) gy[k] = gyr[(int64_t)k * g.y_kstride[q] * g.mul];
   for (int64_t kk = a.in_ptr[node]; kk < a.in_ptr[node + 1]; ++kk) {
     const int64_t src = a.in_nbr[kk];
     const int64_t eid = a.in_eid ? (int64_t)a.in_eid[kk] : kk;

@@ -72,7 +72,7 @@ def emit_structure(E, sid, st):
     groups = make_groups(st)
     xoff, xdim = st.x_comp_offsets()
     soff, sdim = st.sh_comp_offsets()
-    yoff, ydim = st.y_comp_offsets()
+    ybase, ykst, ydim = st.y_layout()
     n_paths = len(st.paths)
     G = len(groups)
 
@@ -145,7 +145,7 @@ def emit_structure(E, sid, st):
         for pi, p in enumerate(st.paths):
             if p.i_in in blocks:
                 for k in range(p.ir_out.dim):
-                    E(f"    yo[{yoff[p.slot] + k} * mul] = acc_{pi}_{k};")
+                    E(f"    yo[{ybase[p.slot] + k * ykst[p.slot]} * mul] = acc_{pi}_{k};")
         E("  }")
         E("}")
         E()
@@ -158,7 +158,7 @@ def emit_structure(E, sid, st):
         for pi, p in enumerate(st.paths):
             if p.i_in in blocks:
                 for k in range(p.ir_out.dim):
-                    E(f"  const T gy_{pi}_{k} = active ? ldg(gyr + {yoff[p.slot] + k} * mul) : T(0);")
+                    E(f"  const T gy_{pi}_{k} = active ? ldg(gyr + {ybase[p.slot] + k * ykst[p.slot]} * mul) : T(0);")
         E("  const int64_t e0 = a.in_ptr[node], e1 = a.in_ptr[node + 1];")
         E("  for (int64_t kk = e0; kk < e1; ++kk) {")
         E("    const int64_t src = a.in_nbr[kk];")
@@ -265,7 +265,7 @@ def emit_tables(st_list):
     Gs = []
     for sid, st in enumerate(st_list):
         E(f"// ---- structure S{sid}: in l={[b.ir.l for b in st.irreps_in]} sh l={[b.ir.l for b in st.irreps_sh]} "
-          f"paths={len(st.paths)} out comps={st.y_comp_offsets()[1]}")
+          f"paths={len(st.paths)} out comps={st.y_layout()[2]}")
         Gs.append(emit_structure(E, sid, st))
     E("#ifdef E3B_HOST_EMU")
     E("// CPU emulation entry (tests only): runs every (node, channel, group) item serially.")
@@ -303,6 +303,7 @@ def emit_tables(st_list):
             str(len(st.irreps_sh)), arr(b.ir.l for b in st.irreps_sh),
             str(len(st.paths)), arr(p.i_in for p in st.paths), arr(p.i_sh for p in st.paths),
             arr(p.ir_out.l for p in st.paths), arr(p.slot for p in st.paths),
+            arr(st.y_layout()[0][p.slot] for p in st.paths), arr(st.y_layout()[1][p.slot] for p in st.paths),
             str(Gs[sid]), f"launch_tpf_S{sid}", f"launch_tpb_S{sid}"]) + "},")
     E("};")
     E("#endif  // __CUDACC__")

@@ -7,10 +7,11 @@
 struct GenEntry {
   int n_in; int in_l[E3B_MAX_BLOCKS]; int n_sh; int sh_l[E3B_MAX_BLOCKS]; int n_paths;
   int path_in[E3B_MAX_PATHS], path_sh[E3B_MAX_PATHS], path_lout[E3B_MAX_PATHS], path_slot[E3B_MAX_PATHS];
+  int path_ybase[E3B_MAX_PATHS], path_ykstride[E3B_MAX_PATHS];  // output layout the kernel was generated for
   int n_groups;
   void (*fwd)(const TpArgs<float>&, int64_t grid, cudaStream_t);
   void (*bwd)(const TpArgs<float>&, int64_t grid, cudaStream_t);
 };
 
 // the generated kernel whose structure equals `d` (ignoring mul and parities), or nullptr
-const GenEntry* e3b_find_generated(const e3b_tp_desc* d);
+const GenEntry* e3b_find_generated(const e3b_tp_desc* d, const int32_t* y_base, const int32_t* y_kstride);

@@ -1,0 +1,73 @@
+"""Layer protocol and the sequential graph network (reference ``e3_layers/nn/sequential.py``).
+
+Every layer is ``forward(data: dict, attrs: dict) -> (new_data, new_attrs)``; irreps arguments
+are ``irreps | (irreps, custom_key)`` and the runner renames keys on the way in and out."""
+from collections import OrderedDict
+
+import torch
+from torch.profiler import record_function
+
+from e3b200.irreps import Irreps
+
+from ..data import Batch
+from ..utils import ConfigDict, build, keyMap
+
+
+class Module(torch.nn.Module):
+    def init_irreps(self, output_keys=(), **kwargs):
+        outs = {output_keys} if isinstance(output_keys, str) else set(output_keys)
+        self.irreps_in, self.irreps_out = {}, {}
+        self.input_key_mapping, self.output_key_mapping = {}, {}
+        for name, spec in kwargs.items():
+            if spec is None:
+                continue
+            if isinstance(spec, (str, Irreps)):
+                irreps, custom = spec, name
+            else:
+                irreps, custom = spec
+            if name in outs:
+                self.irreps_out[name] = irreps
+                self.output_key_mapping[name] = custom
+            else:
+                self.irreps_in[name] = irreps
+                self.input_key_mapping[custom] = name
+
+    def inputKeyMap(self, obj):
+        return keyMap(obj, self.input_key_mapping)
+
+    def outputKeyMap(self, obj):
+        return keyMap(obj, self.output_key_mapping)
+
+
+class SequentialGraphNetwork(torch.nn.Sequential):
+    """Runs (key, layer) pairs over one shared dict; a layer is a ``Module`` built from a config
+    node or any callable ``f(data, attrs)``.  ``jit`` in the config is accepted and ignored (the
+    kernels are already compiled)."""
+
+    def __init__(self, **config):
+        built, self.layers = OrderedDict(), []
+        for key, node in config["layers"]:
+            if isinstance(node, (dict, ConfigDict)):
+                layer = build(node)
+                built[key] = layer
+            elif callable(node):
+                layer = node
+            else:
+                raise TypeError("invalid config node")
+            self.layers.append((key, layer))
+        self.layer_configs = config["layers"]
+        super().__init__(built)
+
+    def forward(self, batch):
+        data, attrs = batch.data, batch.attrs
+        for key, layer in self.layers:
+            with record_function(key):
+                mapped = isinstance(layer, Module)
+                d = layer.inputKeyMap(data) if mapped else data
+                a = layer.inputKeyMap(attrs) if mapped else attrs
+                d, a = layer(d, a)
+                if mapped:
+                    d, a = layer.outputKeyMap(d), layer.outputKeyMap(a)
+                data.update(d)
+                attrs.update(a)
+        return Batch(attrs, **data)

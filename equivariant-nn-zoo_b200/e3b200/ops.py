@@ -1,0 +1,368 @@
+"""torch.autograd bindings of the libe3b200 kernels.  PyTorch here is plumbing (device memory,
+streams, autograd tape); every op below launches hand-written sm_100a kernels through the C ABI
+and raises if the library or a CUDA device is missing."""
+import ctypes
+
+import torch
+from torch.autograd.function import once_differentiable
+
+from . import _lib
+from ._lib import check, count_launch, dtype_code, ptr, require_cuda, stream
+
+
+# ------------------------------------------------------------------------------------------
+# graph structure
+class GraphCSR:
+    """Both groupings of an edge list edge_index [2, E] over N nodes (reference convention:
+    edge_index[0] = source, edge_index[1] = destination, ``nn/message_passing.py:96-97``).
+
+    in_*  : grouped by destination (what the convolution forward walks)
+    out_* : grouped by source      (what d/dx and d/dpos reductions walk)
+    *_eid[k] is the edge id (column of edge_index) in slot k; None means identity."""
+
+    def __init__(self, n_nodes, n_edges, in_ptr, in_nbr, in_eid, out_ptr, out_eid):
+        self.n_nodes, self.n_edges = n_nodes, n_edges
+        self.in_ptr, self.in_nbr, self.in_eid = in_ptr, in_nbr, in_eid
+        self.out_ptr, self.out_eid = out_ptr, out_eid
+
+
+def _exclusive_scan(deg, n):
+    ptr_ = torch.zeros(n + 1, dtype=torch.int64, device=deg.device)
+    if n:
+        torch.cumsum(deg, 0, out=ptr_[1:])
+    return ptr_
+
+
+def _group(edge_index, n_nodes, which_row):
+    lib = _lib.load()
+    E = edge_index.shape[1]
+    key = edge_index[which_row]
+    deg = torch.bincount(key, minlength=n_nodes) if E else torch.zeros(n_nodes, dtype=torch.int64, device=key.device)
+    row_ptr = _exclusive_scan(deg, n_nodes)
+    eid = torch.empty(E, dtype=torch.int32, device=key.device)
+    cursor = torch.zeros(max(n_nodes, 1), dtype=torch.int32, device=key.device)
+    check(lib.e3b_csr_fill(ptr(edge_index), E, n_nodes, which_row, ptr(row_ptr), ptr(cursor), ptr(eid), stream()))
+    count_launch(2)
+    return row_ptr, eid
+
+
+def build_csr(edge_index, n_nodes):
+    """CSR views of an arbitrary edge list (kernels e3b_csr_fill)."""
+    require_cuda(edge_index)
+    edge_index = edge_index.contiguous()
+    E = edge_index.shape[1]
+    in_ptr, in_eid = _group(edge_index, n_nodes, 1)
+    out_ptr, out_eid = _group(edge_index, n_nodes, 0)
+    in_nbr = edge_index[0][in_eid.long()].to(torch.int32) if E else torch.empty(0, dtype=torch.int32, device=edge_index.device)
+    return GraphCSR(n_nodes, E, in_ptr, in_nbr, in_eid, out_ptr, out_eid)
+
+
+def graph_of(edge_index, n_nodes):
+    """CSR views cached on the edge_index tensor object (it travels through the layer dict)."""
+    g = getattr(edge_index, "_e3b_csr", None)
+    if g is None or g.n_nodes != n_nodes or g.n_edges != edge_index.shape[1]:
+        g = build_csr(edge_index, n_nodes)
+        edge_index._e3b_csr = g
+    return g
+
+
+def radius_graph(pos, n_nodes_per_graph, r_max):
+    """Neighbour list in the reference's order plus its CSR views.
+    pos [N,3] float32 (cuda), n_nodes_per_graph int64 [G].  -> edge_index int64 [2,E], n_edges [G], GraphCSR"""
+    lib = _lib.load()
+    require_cuda(pos)
+    if pos.dtype != torch.float32:
+        pos = pos.float()  # the reference predicate is evaluated in the default dtype (fp32)
+    pos = pos.contiguous()
+    N = pos.shape[0]
+    counts = n_nodes_per_graph.reshape(-1).to(device=pos.device, dtype=torch.int64)
+    G = counts.numel()
+    node_ptr = _exclusive_scan(counts, G)
+    deg = torch.zeros(max(N, 1), dtype=torch.int32, device=pos.device)
+    check(lib.e3b_radius_graph_count(ptr(pos), 3, ptr(node_ptr), G, N, float(r_max), ptr(deg), stream()))
+    row_ptr = _exclusive_scan(deg[:N].long(), N)
+    E = int(row_ptr[-1].item()) if N else 0   # the one host sync: the caller must size edge_index
+    edge_index = torch.empty(2, E, dtype=torch.int64, device=pos.device)
+    rev = torch.empty(E, dtype=torch.int32, device=pos.device)
+    check(lib.e3b_radius_graph_fill(ptr(pos), 3, ptr(node_ptr), G, N, float(r_max), ptr(row_ptr), E,
+                                    ptr(edge_index), ptr(rev), stream()))
+    count_launch(3)
+    # symmetric graph: in-edges of n are the reversed out-edges; slot k of node n holds the
+    # edge (nbr -> n) whose id is rev[k]; out-grouping is the identity (edges sorted by source)
+    csr = GraphCSR(N, E, row_ptr, edge_index[1].to(torch.int32), rev, row_ptr, None)
+    edge_index._e3b_csr = csr
+    graph_ptr_edges = row_ptr[node_ptr]
+    n_edges = (graph_ptr_edges[1:] - graph_ptr_edges[:-1]).view(-1, 1)
+    return edge_index, n_edges, csr
+
+
+# ------------------------------------------------------------------------------------------
+class _EdgeVectors(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, pos, edge_index, csr):
+        lib = _lib.load()
+        require_cuda(pos, edge_index)
+        pos = pos.contiguous()
+        E = edge_index.shape[1]
+        vec = torch.empty(E, 3, dtype=pos.dtype, device=pos.device)
+        length = torch.empty(E, dtype=pos.dtype, device=pos.device)
+        check(lib.e3b_edge_vectors_fwd(dtype_code(pos), ptr(pos), ptr(edge_index), E, ptr(vec), ptr(length), stream()))
+        count_launch()
+        ctx.csr = csr
+        ctx.save_for_backward(vec, length)
+        ctx.n = pos.shape[0]
+        return vec, length
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, gvec, glen):
+        lib = _lib.load()
+        vec, length = ctx.saved_tensors
+        g = ctx.csr
+        gpos = torch.empty(ctx.n, 3, dtype=vec.dtype, device=vec.device)
+        gvec = gvec.contiguous() if gvec is not None else None
+        glen = glen.contiguous() if glen is not None else None
+        check(lib.e3b_edge_vectors_bwd(dtype_code(vec), ptr(gvec), ptr(glen), ptr(vec), ptr(length), ctx.n,
+                                       ptr(g.in_ptr), ptr(g.in_eid), ptr(g.out_ptr), ptr(g.out_eid), ptr(gpos), stream()))
+        count_launch()
+        return gpos, None, None
+
+
+def edge_vectors(pos, edge_index, csr):
+    return _EdgeVectors.apply(pos, edge_index.contiguous(), csr)
+
+
+class _SphericalHarmonics(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, vec, lmax, normalize):
+        lib = _lib.load()
+        require_cuda(vec)
+        vec = vec.contiguous()
+        n = vec.shape[0]
+        sh = torch.empty(n, (lmax + 1) ** 2, dtype=vec.dtype, device=vec.device)
+        check(lib.e3b_sh_fwd(dtype_code(vec), ptr(vec), n, lmax, int(normalize), ptr(sh), stream()))
+        count_launch()
+        ctx.save_for_backward(vec)
+        ctx.lmax, ctx.normalize = lmax, int(normalize)
+        return sh
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, gsh):
+        lib = _lib.load()
+        (vec,) = ctx.saved_tensors
+        gvec = torch.empty_like(vec)
+        check(lib.e3b_sh_bwd(dtype_code(vec), ptr(vec), ptr(gsh.contiguous()), vec.shape[0], ctx.lmax, ctx.normalize,
+                             ptr(gvec), stream()))
+        count_launch()
+        return gvec, None, None
+
+
+def spherical_harmonics(vec, lmax, normalize=True):
+    """[n,3] -> [n,(lmax+1)^2], e3nn 'component' normalisation, l <= 2"""
+    return _SphericalHarmonics.apply(vec, lmax, normalize)
+
+
+class _Radial(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, r, bessel_w, r_max, r_min, one_over_r, cutoff_kind, p):
+        lib = _lib.load()
+        require_cuda(r, bessel_w)
+        r = r.contiguous().reshape(-1)
+        bw = bessel_w.to(r.dtype).contiguous()
+        n, nb = r.shape[0], bw.shape[0]
+        out = torch.empty(n, nb, dtype=r.dtype, device=r.device)
+        check(lib.e3b_radial_fwd(dtype_code(r), ptr(r), n, ptr(bw), nb, r_max, r_min, int(one_over_r), cutoff_kind,
+                                 float(p), ptr(out), stream()))
+        count_launch()
+        ctx.save_for_backward(r, bw)
+        ctx.params = (r_max, r_min, int(one_over_r), cutoff_kind, float(p))
+        ctx.w_dtype = bessel_w.dtype
+        return out
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, gout):
+        lib = _lib.load()
+        r, bw = ctx.saved_tensors
+        r_max, r_min, one_over_r, cutoff_kind, p = ctx.params
+        n, nb = r.shape[0], bw.shape[0]
+        gr = torch.empty_like(r)
+        nblk = lib.e3b_radial_bwd_blocks(n)
+        part = torch.empty(nblk, nb, dtype=r.dtype, device=r.device)
+        check(lib.e3b_radial_bwd(dtype_code(r), ptr(r), ptr(gout.contiguous()), n, ptr(bw), nb, r_max, r_min, one_over_r,
+                                 cutoff_kind, p, ptr(gr), ptr(part), stream()))
+        count_launch()
+        gw = part.sum(0).to(ctx.w_dtype) if ctx.needs_input_grad[1] else None
+        return gr, gw, None, None, None, None, None
+
+
+def radial_basis(r, bessel_w, r_max, r_min=0.0, one_over_r=True, cutoff_kind=0, p=6.0):
+    """Bessel x cutoff embedding of distances r [n] -> [n, n_basis]"""
+    return _Radial.apply(r, bessel_w, float(r_max), float(r_min), one_over_r, int(cutoff_kind), p)
+
+
+# ------------------------------------------------------------------------------------------
+class TPPlan:
+    """Owns an e3b_tp_plan (immutable after creation, shareable across streams)."""
+
+    def __init__(self, structure, w3j_sign_preset=0):
+        lib = _lib.load()
+        mul = structure.uniform_mul
+        if mul is None:
+            raise RuntimeError("libe3b200 tensor-product plans need one common multiplicity for all input blocks "
+                               f"and mul-1 spherical harmonics, got {structure.irreps_in} x {structure.irreps_sh}")
+        d = _lib.TpDesc()
+        d.mul = mul
+        d.n_in = len(structure.irreps_in)
+        for b, blk in enumerate(structure.irreps_in):
+            d.in_l[b], d.in_p[b] = blk.ir.l, blk.ir.p
+        d.n_sh = len(structure.irreps_sh)
+        for s, blk in enumerate(structure.irreps_sh):
+            d.sh_l[s], d.sh_p[s] = blk.ir.l, blk.ir.p
+        d.n_paths = len(structure.paths)
+        for q, path in enumerate(structure.paths):
+            d.path_in[q], d.path_sh[q], d.path_lout[q], d.path_slot[q] = path.i_in, path.i_sh, path.ir_out.l, path.slot
+        d.w3j_sign_preset = w3j_sign_preset
+        handle = ctypes.c_void_p()
+        check(lib.e3b_tp_plan_create(ctypes.byref(d), ctypes.byref(handle)))
+        self.handle = handle
+        dims = [ctypes.c_int32() for _ in range(5)]
+        check(lib.e3b_tp_plan_dims(handle, *[ctypes.byref(v) for v in dims]))
+        self.x_dim, self.sh_dim, self.w_dim, self.y_dim, self.n_part_f32 = [v.value for v in dims]
+        self.specialized = bool(lib.e3b_tp_plan_is_specialized(handle))
+        self.structure = structure
+
+    def __del__(self):
+        try:
+            if self.handle:
+                _lib.load().e3b_tp_plan_destroy(self.handle)
+                self.handle = None
+        except Exception:
+            pass
+
+
+class _TPConv(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, sh, w, plan, csr):
+        lib = _lib.load()
+        require_cuda(x, sh, w)
+        x, sh, w = x.contiguous(), sh.contiguous(), w.contiguous()
+        N, E = x.shape[0], sh.shape[0]
+        assert x.shape[1] == plan.x_dim and sh.shape[1] == plan.sh_dim and w.shape == (E, plan.w_dim), \
+            (x.shape, sh.shape, w.shape, plan.x_dim, plan.sh_dim, plan.w_dim)
+        assert csr.n_nodes == N and csr.n_edges == E
+        y = torch.empty(N, plan.y_dim, dtype=x.dtype, device=x.device)
+        check(lib.e3b_tpconv_fwd(plan.handle, dtype_code(x), N, E, ptr(x), ptr(sh), ptr(w), ptr(csr.in_ptr),
+                                 ptr(csr.in_nbr), ptr(csr.in_eid), ptr(y), stream()))
+        count_launch()
+        ctx.plan, ctx.csr = plan, csr
+        ctx.save_for_backward(x, sh, w)
+        return y
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, gy):
+        lib = _lib.load()
+        x, sh, w = ctx.saved_tensors
+        plan, csr = ctx.plan, ctx.csr
+        N, E = x.shape[0], sh.shape[0]
+        fast = plan.specialized and x.dtype == torch.float32
+        alloc = torch.empty if fast else torch.zeros
+        n_part = plan.n_part_f32 if fast else 1
+        need_x, need_sh = ctx.needs_input_grad[0], ctx.needs_input_grad[1]
+        gx_edge = alloc(E, plan.x_dim, dtype=x.dtype, device=x.device) if need_x else None
+        gsh_part = alloc(E, n_part, plan.sh_dim, dtype=x.dtype, device=x.device) if need_sh else None
+        gw = torch.empty_like(w)
+        if E:
+            check(lib.e3b_tpconv_bwd(plan.handle, dtype_code(x), N, E, ptr(x), ptr(sh), ptr(w), ptr(gy.contiguous()),
+                                     ptr(csr.in_ptr), ptr(csr.in_nbr), ptr(csr.in_eid), ptr(gx_edge), ptr(gsh_part),
+                                     ptr(gw), stream()))
+            count_launch()
+        gx = None
+        if need_x:
+            gx = torch.empty_like(x)
+            check(lib.e3b_segment_sum(dtype_code(x), ptr(gx_edge), plan.x_dim, ptr(csr.out_ptr), ptr(csr.out_eid), N,
+                                      ptr(gx), stream()))
+            count_launch()
+        gsh = None
+        if need_sh:
+            gsh = gsh_part.sum(1) if n_part > 1 else gsh_part.view(E, plan.sh_dim)
+        return gx, gsh, gw, None, None
+
+
+def tp_conv(x_imu, sh, w, plan, csr):
+    """y[n] = sum over incoming edges of the weighted uvu tensor product (imu layouts)."""
+    return _TPConv.apply(x_imu, sh, w, plan, csr)
+
+
+# ------------------------------------------------------------------------------------------
+class _SegmentSum(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, src, seg_ptr, seg_index, n_out):
+        lib = _lib.load()
+        require_cuda(src)
+        src2 = src.contiguous().reshape(src.shape[0], -1)
+        out = torch.empty(n_out, src2.shape[1], dtype=src.dtype, device=src.device)
+        check(lib.e3b_segment_sum(dtype_code(src2), ptr(src2), src2.shape[1], ptr(seg_ptr), None, n_out, ptr(out), stream()))
+        count_launch()
+        ctx.save_for_backward(seg_index)
+        return out.reshape(n_out, *src.shape[1:])
+
+    @staticmethod
+    def backward(ctx, g):
+        (seg_index,) = ctx.saved_tensors
+        return g[seg_index], None, None, None
+
+
+def segment_sum(src, seg_ptr, seg_index, n_out):
+    """rows of src are grouped in consecutive segments (seg_ptr [n_out+1]); seg_index [rows]
+    is the segment of each row (used by the backward gather)."""
+    return _SegmentSum.apply(src, seg_ptr, seg_index, n_out)
+
+
+# ------------------------------------------------------------------------------------------
+ACT_CODES = {None: 0, "silu": 1, "tanh": 2, "ssp": 3, "tanhlu": 4, "abs": 5}
+
+
+class _Gate(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, desc, out_dim):
+        lib = _lib.load()
+        require_cuda(x)
+        x = x.contiguous()
+        out = torch.empty(x.shape[0], out_dim, dtype=x.dtype, device=x.device)
+        check(lib.e3b_gate_fwd(ctypes.byref(desc), dtype_code(x), ptr(x), x.shape[0], ptr(out), stream()))
+        count_launch()
+        ctx.desc = desc
+        ctx.save_for_backward(x)
+        return out
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, gout):
+        lib = _lib.load()
+        (x,) = ctx.saved_tensors
+        gin = torch.empty_like(x)
+        check(lib.e3b_gate_bwd(ctypes.byref(ctx.desc), dtype_code(x), ptr(x), ptr(gout.contiguous()), x.shape[0],
+                               ptr(gin), stream()))
+        count_launch()
+        return gin, None, None
+
+
+def gate(x, desc, out_dim):
+    return _Gate.apply(x, desc, out_dim)
+
+
+def layout_convert(x, irreps, to_imu):
+    """kernel-side mul_ir <-> imu conversion (no autograd; used for buffers/tests)"""
+    lib = _lib.load()
+    require_cuda(x)
+    x = x.contiguous()
+    nb = len(irreps)
+    mul = (ctypes.c_int32 * nb)(*[b.mul for b in irreps])
+    ls = (ctypes.c_int32 * nb)(*[b.ir.l for b in irreps])
+    out = torch.empty_like(x)
+    check(lib.e3b_layout_convert(dtype_code(x), ptr(x), x.shape[0], nb, mul, ls, int(to_imu), ptr(out), stream()))
+    count_launch()
+    return out

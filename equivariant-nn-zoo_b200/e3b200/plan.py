@@ -38,8 +38,9 @@ class TPStructure:
 
     def key(self):
         """Arithmetic signature (independent of mul and of parities)."""
+        base, kstride, _ = self.y_layout()
         return (tuple(b.ir.l for b in self.irreps_in), tuple(b.ir.l for b in self.irreps_sh),
-                tuple((p.i_in, p.i_sh, p.ir_out.l, p.slot) for p in self.paths))
+                tuple((p.i_in, p.i_sh, p.ir_out.l, p.slot, base[p.slot], kstride[p.slot]) for p in self.paths))
 
     # layouts in units of `mul` scalars (imu layout: [component][channel])
     def x_comp_offsets(self):
@@ -56,13 +57,23 @@ class TPStructure:
             o += b.ir.dim
         return out, o
 
-    def y_comp_offsets(self):
-        """offset of the output block of slot s, and total number of components"""
-        out, o = [], 0
-        for b in self.irreps_mid:
-            out.append(o)
-            o += b.ir.dim
-        return out, o
+    def y_layout(self):
+        """Output row layout, in units of `mul` scalars.  Slots (sorted irreps_mid blocks) with
+        the same irrep form one group laid out [k][slot-in-group][u] -- exactly the imu layout
+        of the SIMPLIFIED irreps_mid block the post-linear consumes.
+        -> (base[slot], kstride[slot], total components)"""
+        base, kstride = [0] * len(self.irreps_mid), [0] * len(self.irreps_mid)
+        o, s = 0, 0
+        while s < len(self.irreps_mid):
+            e = s
+            while e < len(self.irreps_mid) and self.irreps_mid[e].ir == self.irreps_mid[s].ir:
+                e += 1
+            n = e - s
+            for t in range(s, e):
+                base[t], kstride[t] = o + (t - s), n
+            o += n * self.irreps_mid[s].ir.dim
+            s = e
+        return base, kstride, o
 
 
 def reference_structures(l_max_features, sh="1x0e+1x1o+1x2e", n_layers=6):

@@ -32,6 +32,7 @@ extern "C" {
 #endif
 
 #define E3B_ABI_VERSION 1
+#define E3B_API __attribute__((visibility("default")))
 
 typedef enum {
   E3B_OK = 0,
@@ -44,8 +45,8 @@ typedef enum {
 #define E3B_F32 0
 #define E3B_F64 1
 
-int e3b_abi_version(void);
-const char* e3b_last_error(void);
+E3B_API int e3b_abi_version(void);
+E3B_API const char* e3b_last_error(void);
 
 /* ---------------------------------------------------------------------------------------
  * Neighbour list.   Replaces computeEdgeIndex, e3_layers/data/compute_edge.py:38-113
@@ -62,9 +63,9 @@ const char* e3b_last_error(void);
  *          rev) is also the dst-grouped CSR the convolution consumes.
  * pos_stride = floats between consecutive rows of pos (3 for a dense [N,3]).
  */
-int e3b_radius_graph_count(const float* pos, int64_t pos_stride, const int64_t* node_ptr /* [G+1] */,
+E3B_API int e3b_radius_graph_count(const float* pos, int64_t pos_stride, const int64_t* node_ptr /* [G+1] */,
                            int32_t n_graphs, int64_t n_nodes, float r_max, int32_t* deg, void* stream);
-int e3b_radius_graph_fill(const float* pos, int64_t pos_stride, const int64_t* node_ptr, int32_t n_graphs,
+E3B_API int e3b_radius_graph_fill(const float* pos, int64_t pos_stride, const int64_t* node_ptr, int32_t n_graphs,
                           int64_t n_nodes, float r_max, const int64_t* row_ptr, int64_t n_edges,
                           int64_t* edge_index /* [2,E] */, int32_t* rev /* [E] or NULL */, void* stream);
 
@@ -72,7 +73,7 @@ int e3b_radius_graph_fill(const float* pos, int64_t pos_stride, const int64_t* n
  * user-supplied edge_index).  The caller passes row_ptr = exclusive scan of the in-degree
  * (int64 [N+1]) and a zeroed int32 cursor[N]; the kernel fills, per destination node, the
  * edge ids of its incoming edges in ASCENDING edge id (deterministic).              */
-int e3b_csr_fill(const int64_t* edge_index, int64_t n_edges, int64_t n_nodes, int which_row /*0|1*/,
+E3B_API int e3b_csr_fill(const int64_t* edge_index, int64_t n_edges, int64_t n_nodes, int which_row /*0|1*/,
                  const int64_t* row_ptr, int32_t* cursor /* [N], zeroed */, int32_t* eid /* [E] */, void* stream);
 
 /* ---------------------------------------------------------------------------------------
@@ -81,26 +82,26 @@ int e3b_csr_fill(const int64_t* edge_index, int64_t n_edges, int64_t n_nodes, in
  * 'component', l <= 2 -- every in-scope config uses 1x0e+1x1o+1x2e) and RadialBasisEncoding (nn/embedding.py:181-219: Bessel x polynomial
  * cutoff p, or the symmetric cutoff of :26-29 when cutoff_kind = 1).
  */
-int e3b_edge_vectors_fwd(int dtype, const void* pos, const int64_t* edge_index, int64_t n_edges,
+E3B_API int e3b_edge_vectors_fwd(int dtype, const void* pos, const int64_t* edge_index, int64_t n_edges,
                          void* vec /* [E,3] */, void* len /* [E] or NULL */, void* stream);
 /* gpos[n] += sum_{e: dst=n} g[e] - sum_{e: src=n} g[e]  via the two CSR views, no atomics.
  * g = gvec + glen * vec/len (either may be NULL). */
-int e3b_edge_vectors_bwd(int dtype, const void* gvec, const void* glen, const void* vec, const void* len,
+E3B_API int e3b_edge_vectors_bwd(int dtype, const void* gvec, const void* glen, const void* vec, const void* len,
                          int64_t n_nodes, const int64_t* in_ptr, const int32_t* in_eid,
                          const int64_t* out_ptr, const int32_t* out_eid, void* gpos /* [N,3] */, void* stream);
 
-int e3b_sh_fwd(int dtype, const void* vec, int64_t n, int lmax, int normalize, void* sh /* [n,(lmax+1)^2] */,
+E3B_API int e3b_sh_fwd(int dtype, const void* vec, int64_t n, int lmax, int normalize, void* sh /* [n,(lmax+1)^2] */,
                void* stream);
-int e3b_sh_bwd(int dtype, const void* vec, const void* gsh, int64_t n, int lmax, int normalize,
+E3B_API int e3b_sh_bwd(int dtype, const void* vec, const void* gsh, int64_t n, int lmax, int normalize,
                void* gvec /* [n,3] */, void* stream);
 
-int e3b_radial_fwd(int dtype, const void* r, int64_t n, const void* bessel_w, int n_basis, double r_max,
+E3B_API int e3b_radial_fwd(int dtype, const void* r, int64_t n, const void* bessel_w, int n_basis, double r_max,
                    double r_min, int one_over_r, int cutoff_kind, double p, void* out /* [n,n_basis] */,
                    void* stream);
 /* gr [n]; gw_partial [n_blocks, n_basis] partial sums of d/d bessel_w (caller sums rows;
  * n_blocks = e3b_radial_bwd_blocks(n)). */
-int64_t e3b_radial_bwd_blocks(int64_t n);
-int e3b_radial_bwd(int dtype, const void* r, const void* gout, int64_t n, const void* bessel_w, int n_basis,
+E3B_API int64_t e3b_radial_bwd_blocks(int64_t n);
+E3B_API int e3b_radial_bwd(int dtype, const void* r, const void* gout, int64_t n, const void* bessel_w, int n_basis,
                    double r_max, double r_min, int one_over_r, int cutoff_kind, double p, void* gr,
                    void* gw_partial, void* stream);
 
@@ -118,7 +119,8 @@ int e3b_radial_bwd(int dtype, const void* r, const void* gout, int64_t n, const 
  * and the path list in e3nn instruction order (weight layout) with each path's slot in the
  * sorted output (irreps_mid).  Layouts: x [N][sum_b (2l_b+1)][mul]; Y [E][sum (2l+1)];
  * w [E][n_paths][mul] (== e3nn's weight layout for uvu with mul_in2 = 1);
- * y [N][sum_p (2l3_p+1) in sorted-slot order][mul].
+ * y [N][...][mul]: output slots sorted by irrep; the slots of one irrep (l3, parity) form a
+ * group stored [k][slot-in-group][u], i.e. the imu layout of the simplified irreps_mid block.
  */
 #define E3B_MAX_BLOCKS 16
 #define E3B_MAX_PATHS 96
@@ -127,9 +129,10 @@ typedef struct {
   int32_t mul;                       /* common multiplicity of every input block        */
   int32_t n_in;
   int32_t in_l[E3B_MAX_BLOCKS];      /* l of input block b                              */
-  int32_t in_p[E3B_MAX_BLOCKS];      /* parity (+1/-1), informational                   */
+  int32_t in_p[E3B_MAX_BLOCKS];      /* parity (+1/-1); only used to group output slots  */
   int32_t n_sh;
   int32_t sh_l[E3B_MAX_BLOCKS];
+  int32_t sh_p[E3B_MAX_BLOCKS];      /* parity of SH block (output parity = in_p * sh_p)  */
   int32_t n_paths;
   int32_t path_in[E3B_MAX_PATHS];    /* input block index                               */
   int32_t path_sh[E3B_MAX_PATHS];    /* SH block index                                  */
@@ -140,18 +143,18 @@ typedef struct {
 
 typedef struct e3b_tp_plan e3b_tp_plan;
 
-int e3b_tp_plan_create(const e3b_tp_desc* desc, e3b_tp_plan** out);
-void e3b_tp_plan_destroy(e3b_tp_plan* plan);
+E3B_API int e3b_tp_plan_create(const e3b_tp_desc* desc, e3b_tp_plan** out);
+E3B_API void e3b_tp_plan_destroy(e3b_tp_plan* plan);
 /* 1 if a generated (fully unrolled) kernel matches this plan, 0 if the generic one runs */
-int e3b_tp_plan_is_specialized(const e3b_tp_plan* plan);
+E3B_API int e3b_tp_plan_is_specialized(const e3b_tp_plan* plan);
 /* row widths in scalars, and n_part = number of partial rows per edge the f32 backward writes
  * into gsh (1 for the generic kernel, which accumulates with atomics into a ZEROED buffer) */
-int e3b_tp_plan_dims(const e3b_tp_plan* plan, int32_t* x_dim, int32_t* sh_dim, int32_t* w_dim, int32_t* y_dim,
+E3B_API int e3b_tp_plan_dims(const e3b_tp_plan* plan, int32_t* x_dim, int32_t* sh_dim, int32_t* w_dim, int32_t* y_dim,
                      int32_t* n_part_f32);
 
 /* in_ptr/in_nbr/in_eid: dst-grouped CSR (in_nbr[k] = source node, in_eid[k] = row of w / Y;
  * in_eid may be NULL when the edge arrays are already in CSR order).                        */
-int e3b_tpconv_fwd(const e3b_tp_plan* plan, int dtype, int64_t n_nodes, int64_t n_edges, const void* x,
+E3B_API int e3b_tpconv_fwd(const e3b_tp_plan* plan, int dtype, int64_t n_nodes, int64_t n_edges, const void* x,
                    const void* sh, const void* w, const int64_t* in_ptr, const int32_t* in_nbr,
                    const int32_t* in_eid, void* y, void* stream);
 /* First-order backward.  gx_edge [E, x_dim] receives the per-edge contribution to d/dx[src]
@@ -161,13 +164,13 @@ int e3b_tpconv_fwd(const e3b_tp_plan* plan, int dtype, int64_t n_nodes, int64_t 
  * When the plan is not specialized (or dtype is f64) the generic kernel runs: gx_edge and gsh
  * must then be ZERO-filled by the caller (it accumulates with atomics, n_part = 1).
  * gx_edge and gsh may be NULL when those gradients are not needed.                         */
-int e3b_tpconv_bwd(const e3b_tp_plan* plan, int dtype, int64_t n_nodes, int64_t n_edges, const void* x,
+E3B_API int e3b_tpconv_bwd(const e3b_tp_plan* plan, int dtype, int64_t n_nodes, int64_t n_edges, const void* x,
                    const void* sh, const void* w, const void* gy, const int64_t* in_ptr, const int32_t* in_nbr,
                    const int32_t* in_eid, void* gx_edge, void* gsh, void* gw, void* stream);
 
 /* out[n, :] = sum_{k in [ptr[n], ptr[n+1])} src[ids ? ids[k] : k, :]  (rows of `width` scalars).
  * Replaces torch_runstats scatter at nn/message_passing.py:109 / nn/output.py:69 (Pooling). */
-int e3b_segment_sum(int dtype, const void* src, int64_t width, const int64_t* ptr, const int32_t* ids,
+E3B_API int e3b_segment_sum(int dtype, const void* src, int64_t width, const int64_t* ptr, const int32_t* ids,
                     int64_t n_out, void* out, void* stream);
 
 /* ---------------------------------------------------------------------------------------
@@ -187,12 +190,12 @@ typedef struct {
   double gate_cst[E3B_MAX_BLOCKS];
 } e3b_gate_desc;
 
-int e3b_gate_fwd(const e3b_gate_desc* desc, int dtype, const void* in, int64_t n, void* out, void* stream);
-int e3b_gate_bwd(const e3b_gate_desc* desc, int dtype, const void* in, const void* gout, int64_t n, void* gin,
+E3B_API int e3b_gate_fwd(const e3b_gate_desc* desc, int dtype, const void* in, int64_t n, void* out, void* stream);
+E3B_API int e3b_gate_bwd(const e3b_gate_desc* desc, int dtype, const void* in, const void* gout, int64_t n, void* gin,
                  void* stream);
 
 /* mul_ir <-> imu layout conversion of feature rows (blocks: mul, l). to_imu = 1: [u][m]->[m][u] */
-int e3b_layout_convert(int dtype, const void* in, int64_t n, int32_t n_blocks, const int32_t* mul,
+E3B_API int e3b_layout_convert(int dtype, const void* in, int64_t n, int32_t n_blocks, const int32_t* mul,
                        const int32_t* l, int to_imu, void* out, void* stream);
 
 #ifdef __cplusplus

@@ -1,0 +1,139 @@
+"""TEST-ONLY stand-ins for the libe3b200 kernels, written with differentiable torch ops, so that
+the host-side composition of the product (e3_layers mirror, dense contractions, imu layouts,
+config builders, weight layouts) can be checked against the golden fixtures on a machine WITHOUT
+a GPU.  ``patch()`` swaps them into ``e3b200.ops``; nothing in the product imports this file and
+the product itself has no CPU path (it raises)."""
+import math
+
+import torch
+
+from e3b200 import cg, ops
+from e3b200.ops import GraphCSR
+from oracle import ref_layers, wigner
+
+
+def _csr(edge_index, n_nodes):
+    src, dst = edge_index[0], edge_index[1]
+    E = edge_index.shape[1]
+    in_eid = torch.argsort(dst, stable=True)
+    out_eid = torch.argsort(src, stable=True)
+    in_ptr = torch.zeros(n_nodes + 1, dtype=torch.long)
+    in_ptr[1:] = torch.bincount(dst, minlength=n_nodes).cumsum(0)
+    out_ptr = torch.zeros(n_nodes + 1, dtype=torch.long)
+    out_ptr[1:] = torch.bincount(src, minlength=n_nodes).cumsum(0)
+    return GraphCSR(n_nodes, E, in_ptr, src[in_eid].int(), in_eid.int(), out_ptr, out_eid.int())
+
+
+def graph_of(edge_index, n_nodes):
+    g = getattr(edge_index, "_e3b_csr", None)
+    if g is None:
+        g = _csr(edge_index, n_nodes)
+        edge_index._e3b_csr = g
+    return g
+
+
+def radius_graph(pos, n_nodes_per_graph, r_max):
+    data = {"pos": pos.float(), "_n_nodes": n_nodes_per_graph.reshape(-1, 1)}
+    d, _ = ref_layers.computeEdgeIndex(data, {}, r_max=r_max)
+    ei = d["edge_index"]
+    return ei, data["_n_edges"], graph_of(ei, pos.shape[0])
+
+
+def edge_vectors(pos, edge_index, csr):
+    vec = pos[edge_index[1]] - pos[edge_index[0]]
+    return vec, torch.linalg.norm(vec, dim=-1)
+
+
+def spherical_harmonics(vec, lmax, normalize=True):
+    return wigner.spherical_harmonics(list(range(lmax + 1)), vec, normalize, "component")
+
+
+def radial_basis(r, bessel_w, r_max, r_min=0.0, one_over_r=True, cutoff_kind=0, p=6.0):
+    r = r.reshape(-1)
+    b = (2.0 / (r_max - r_min)) * torch.sin(bessel_w * r.unsqueeze(-1) / (r_max - r_min))
+    if one_over_r:
+        b = b / r.unsqueeze(-1)
+    cut = ref_layers.symmetricCutoff if cutoff_kind == 1 else ref_layers._poly_cutoff
+    return b * cut(r, 1.0 / r_max, p)[:, None]
+
+
+class TPPlan:
+    def __init__(self, structure, w3j_sign_preset=0):
+        self.structure = structure
+        self.specialized = False
+
+
+def tp_conv(x_imu, sh, w, plan, csr):
+    st = plan.structure
+    mul = st.uniform_mul
+    N = x_imu.shape[0]
+    xo, _ = st.x_comp_offsets()
+    so, _ = st.sh_comp_offsets()
+    ybase, ykst, ydim = st.y_layout()
+    src = csr.in_nbr.long()
+    eid = csr.in_eid.long() if csr.in_eid is not None else torch.arange(csr.n_edges)
+    dst = torch.repeat_interleave(torch.arange(N), csr.in_ptr[1:] - csr.in_ptr[:-1])
+    xs = x_imu[src].view(len(src), -1, mul)           # [E, comp, mul]
+    Y = sh[eid]
+    W = w[eid].view(len(src), len(st.paths), mul)
+    y = x_imu.new_zeros(N, ydim, mul)
+    for q, p in enumerate(st.paths):
+        l1, l2, l3 = st.irreps_in[p.i_in].ir.l, st.irreps_sh[p.i_sh].ir.l, p.ir_out.l
+        C = torch.tensor(cg.w3j(l1, l2, l3), dtype=x_imu.dtype) * math.sqrt(2 * l3 + 1)
+        xb = xs[:, xo[p.i_in]:xo[p.i_in] + 2 * l1 + 1]                 # [E, i, u]
+        Yb = Y[:, so[p.i_sh]:so[p.i_sh] + 2 * l2 + 1]                  # [E, j]
+        t = torch.einsum("ijk,eiu,ej,eu->eku", C, xb, Yb, W[:, q])     # [E, k, u]
+        rows = ybase[p.slot] + ykst[p.slot] * torch.arange(2 * l3 + 1)
+        contrib = x_imu.new_zeros(N, 2 * l3 + 1, mul).index_add_(0, dst, t)
+        y = y.index_add(1, rows, contrib)
+    return y.reshape(N, ydim * mul)
+
+
+def segment_sum(src, seg_ptr, seg_index, n_out):
+    out = src.new_zeros((n_out,) + tuple(src.shape[1:]))
+    return out.index_add_(0, seg_index, src)
+
+
+_ACTS = {0: lambda x: x, 1: torch.nn.functional.silu, 2: torch.tanh, 3: ref_layers.ShiftedSoftPlus,
+         4: ref_layers.tanhlu, 5: torch.abs}
+
+
+def gate(x, desc, out_dim):
+    cols, off = [], 0
+    ns = sum(desc.scalar_mul[i] for i in range(desc.n_scalar_blocks))
+    ng = sum(desc.gated_mul[i] for i in range(desc.n_gated_blocks))
+    for i in range(desc.n_scalar_blocks):
+        m = desc.scalar_mul[i]
+        cols.append(desc.scalar_cst[i] * _ACTS[desc.scalar_act[i]](x[:, off:off + m]))
+        off += m
+    goff, doff = ns, ns + ng
+    for i in range(desc.n_gated_blocks):
+        m, d = desc.gated_mul[i], 2 * desc.gated_l[i] + 1
+        g = desc.gate_cst[i] * _ACTS[desc.gate_act[i]](x[:, goff:goff + m])
+        cols.append((x[:, doff:doff + m * d].view(-1, m, d) * g.unsqueeze(-1)).reshape(-1, m * d))
+        goff += m
+        doff += m * d
+    return torch.cat(cols, dim=1)
+
+
+_NAMES = ["graph_of", "radius_graph", "edge_vectors", "spherical_harmonics", "radial_basis", "TPPlan", "tp_conv",
+          "segment_sum", "gate"]
+
+
+def patch(monkeypatch):
+    import e3_layers.data.compute_edge as ce
+
+    for n in _NAMES:
+        monkeypatch.setattr(ops, n, globals()[n])
+    # the product's computeEdgeIndex refuses CPU tensors; lift that guard for the emulation only
+    orig = ce.computeEdgeIndex
+
+    def compute_edge_index_cpu(data, attrs, r_max=None, key="pos", criteria=None):
+        assert criteria is None
+        ei, n_edges, _ = radius_graph(data[key], data["_n_nodes"].reshape(-1), r_max)
+        attrs["_n_edges"] = ("graph", "1x0e")
+        data["_n_edges"] = n_edges
+        return {"edge_index": ei}, attrs
+
+    monkeypatch.setattr(ce, "computeEdgeIndex", compute_edge_index_cpu)
+    return orig
