@@ -1,0 +1,287 @@
+#!/usr/bin/env python3
+"""Benchmark of the B200 hot path (BASELINE.json metric: energy+force atoms/s; fused TP-conv
+edges/s and % of the HBM roofline).
+
+A "step" = one energy+force evaluation of the reference's ``config_energy_force`` model
+(n_dim 64, l_max 2, 5 interaction blocks, r_max 5) on one batch of 512 synthetic QM9-shaped
+molecules per GPU (workload W2): neighbour list + forward + position-gradient
+backward, through the public ``e3_layers`` API (``GradientOutput.forward``).
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+
+N > 1 is launched by the driver with torchrun (one rank per GPU); ranks hold different batches
+(graphs shard naturally, no data-path collective; "weak" scaling).  ``--impl reference`` times
+the CPU oracle (the reference's dataflow restated; the genuine reference cannot be installed:
+e3nn is not in the wheelhouse) on the host cores, on a bounded sample of the same workload.
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+for p in (ROOT, os.path.join(ROOT, "tests"), os.path.join(ROOT, "equivariant-nn-zoo_b200")):
+    if p not in sys.path:
+        sys.path.insert(0, p)
+
+import torch  # noqa: E402
+
+GRAPHS_PER_GPU = 512
+CPU_SAMPLE_GRAPHS = 32
+METRIC = "energy+force atoms/s"
+META = {"config": "config_energy_force", "seed": 0}
+
+
+def peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler(threading.Thread):
+    """samples nvidia-smi clocks / throttle reasons during the timed region"""
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.rows, self._stop = index, [], threading.Event()
+
+    def run(self):
+        while not self._stop.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                      "-i", str(self.index)], capture_output=True, text=True, timeout=5).stdout
+                parts = [x.strip() for x in out.strip().split(",")]
+                if len(parts) == 6:
+                    self.rows.append(parts)
+            except Exception:
+                pass
+            self._stop.wait(0.2)
+
+    def stop(self):
+        self._stop.set()
+        self.join(timeout=3)
+        if not self.rows:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": []}
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for i, n in enumerate(names) if any(r[2 + i].lower().startswith("active") for r in self.rows)]
+        sm = [float(r[0]) for r in self.rows]
+        return {"sm_mhz": statistics.median(sm), "sm_max_mhz": float(self.rows[0][1]), "reasons": reasons,
+                "samples": len(sm)}
+
+
+# ---------------------------------------------------------------------------------------------
+def run_reference(args):
+    """CPU arm: the oracle port of the reference's path, all host threads, bounded sample."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    import harness
+    from e3b200 import synthetic
+
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    inputs = synthetic.qm9_like(CPU_SAMPLE_GRAPHS, seed=0)
+    model = harness.build_oracle(META, torch.float32)
+    n_atoms = inputs["pos"].shape[0]
+    n_edges = None
+    for _ in range(args.warmup):
+        out = harness.run_oracle(model, inputs, torch.float32, pre_edge={"r_max": 5.0})
+        n_edges = out["edge_index"].shape[1]
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        out = harness.run_oracle(model, inputs, torch.float32, pre_edge={"r_max": 5.0})
+        n_edges = out["edge_index"].shape[1]
+    dt = time.perf_counter() - t0
+    value = n_atoms * args.steps / dt
+    sample = (f"{CPU_SAMPLE_GRAPHS} of the {GRAPHS_PER_GPU} W2 molecules ({n_atoms} atoms, {n_edges} edges) per step, "
+              f"neighbour list + forward + autograd forces, fp32")
+    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": "atoms/s", "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": "W2 config_energy_force energy+force, QM9-shaped molecules (bounded CPU sample)",
+                       "model": "config_energy_force n_dim=64 l_max=2 layers=5 r_max=5.0"},
+            "cpu_baseline": {"value": value, "unit": "atoms/s", "cores": cores, "kind": "port", "sample": sample},
+            "e2e": {"value": value, "unit": "atoms/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line), flush=True)
+
+
+# ---------------------------------------------------------------------------------------------
+def tp_bytes(E, N, st_mul_dims):
+    W, D_in, D_mid = st_mul_dims
+    return E * (4 * W + 4) + (N + 1) * 8 + N * (12 + 4 * D_in + 4 * D_mid)
+
+
+def run_ours(args):
+    import torch.distributed as dist
+
+    import product_harness
+    from e3_layers.data import Batch, computeEdgeIndex
+    from e3b200 import _lib, ops, synthetic
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise RuntimeError("bench.py (impl=ours) needs a CUDA device: the B200 path has no CPU fallback")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    _lib.load()
+    model = product_harness.build_product(META, torch.float32, dev)
+    host = synthetic.qm9_like(GRAPHS_PER_GPU, seed=rank)       # each rank its own molecules
+    attrs = {"pos": ("node", "1x1o"), "species": ("node", "1x0e"), "_n_nodes": ("graph", "1x0e")}
+    pinned = {k: v.pin_memory() for k, v in host.items()}
+    n_atoms = host["pos"].shape[0]
+    resident = {k: v.to(dev) for k, v in host.items()}
+
+    def step(tensors):
+        batch = Batch(dict(attrs), **{k: v for k, v in tensors.items()})
+        d, a = computeEdgeIndex(batch.data, batch.attrs, r_max=5.0)
+        batch.update(d)
+        batch.attrs.update(a)
+        batch = Batch(batch.attrs, **batch.data)
+        return model(batch)
+
+    def sync_all():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    # ---- device-resident throughput ("value") -------------------------------------------------
+    for _ in range(args.warmup):
+        out = step({k: v.clone() for k, v in resident.items()})
+    n_edges = out["edge_index"].shape[1]
+    sync_all()
+    sampler = ClockSampler(local)
+    sampler.start()
+    ops.TIMING = []            # (tag, start_event, end_event) per fused TP-conv launch
+    launches0 = _lib.launch_count
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record()
+    for _ in range(args.steps):
+        out = step({k: v.clone() for k, v in resident.items()})
+    ev1.record()
+    sync_all()
+    ms = ev0.elapsed_time(ev1)
+    launches = _lib.launch_count - launches0
+    timing, ops.TIMING = ops.TIMING, None
+    clocks = sampler.stop()
+    t = torch.tensor([ms], device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms = float(t.item())
+    atoms_all = torch.tensor([float(n_atoms)], device=dev)
+    if world > 1:
+        dist.all_reduce(atoms_all)
+    value = float(atoms_all.item()) * args.steps / (ms * 1e-3)
+
+    # ---- end to end through the public API with HOST buffers ("e2e") -----------------------------
+    def e2e_step():
+        dev_in = {k: v.to(dev, non_blocking=True) for k, v in pinned.items()}
+        o = step(dev_in)
+        return o["energy"].cpu(), o["forces"].cpu()
+
+    for _ in range(max(1, args.warmup // 2)):
+        e2e_step()
+    sync_all()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        e_host, f_host = e2e_step()
+    sync_all()
+    e2e_s = time.perf_counter() - t0
+    t = torch.tensor([e2e_s], device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    e2e_value = float(atoms_all.item()) * args.steps / float(t.item())
+    h2d = sum(v.numel() * v.element_size() for v in pinned.values())
+    d2h = e_host.numel() * e_host.element_size() + f_host.numel() * f_host.element_size()
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    # ---- roofline of the dominant kernel: fused TP-conv forward of a full (30-path) layer ----------
+    peak, peak_src = peaks()
+    full = [(s.elapsed_time(e), tag) for tag, s, e in timing if tag[0] == "fwd" and tag[1] == 30]
+    bwd = [(s.elapsed_time(e), tag) for tag, s, e in timing if tag[0] == "bwd" and tag[1] == 30]
+    roof = None
+    if full:
+        t_ms = statistics.mean(x[0] for x in full)
+        _, n_paths, mul, x_dim, y_dim, N, E = full[0][1]
+        alg = tp_bytes(E, N, (n_paths * mul, x_dim, y_dim))
+        ach = alg / (t_ms * 1e-3) / 1e9
+        roof = {"kernel": "tpf_S3<float> (fused gather + uvu CG tensor product + segmented sum, 30 paths, mul 64)",
+                "bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": None,
+                "peak_source": peak_src, "algorithmic_bytes_per_launch": alg, "avg_launch_ms": t_ms,
+                "launches_timed": len(full), "edges_per_s": E / (t_ms * 1e-3),
+                "bwd_avg_launch_ms": statistics.mean(x[0] for x in bwd) if bwd else None}
+
+    # ---- CPU baseline beside it (rank 0, N = 1 only): oracle on a bounded sample ------------------------
+    cpu = None
+    if world == 1 and not args.no_cpu_baseline:
+        import harness
+
+        cores = os.cpu_count() or 1
+        torch.set_num_threads(cores)
+        sample_in = synthetic.qm9_like(CPU_SAMPLE_GRAPHS, seed=0)
+        oracle = harness.build_oracle(META, torch.float32)
+        harness.run_oracle(oracle, sample_in, torch.float32, pre_edge={"r_max": 5.0})   # warm-up
+        reps, t0 = 0, time.perf_counter()
+        while reps < 3 or (time.perf_counter() - t0 < 10 and reps < 20):
+            o = harness.run_oracle(oracle, sample_in, torch.float32, pre_edge={"r_max": 5.0})
+            reps += 1
+        dt = time.perf_counter() - t0
+        cpu = {"value": sample_in["pos"].shape[0] * reps / dt, "unit": "atoms/s", "cores": cores, "kind": "port",
+               "sample": f"{CPU_SAMPLE_GRAPHS} of the {GRAPHS_PER_GPU} W2 molecules ({sample_in['pos'].shape[0]} atoms, "
+                         f"{o['edge_index'].shape[1]} edges) x {reps} evaluations, oracle (reference dataflow) fp32"}
+
+    line = {"metric": METRIC, "value": value, "unit": "atoms/s", "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": "W2: config_energy_force energy+force evaluation (neighbour list + forward + "
+                                   "position-gradient backward), 512 synthetic QM9-shaped molecules per GPU",
+                       "model": "config_energy_force n_dim=64 l_max=2 layers=5 r_max=5.0",
+                       "atoms_per_gpu": n_atoms, "edges_per_gpu": n_edges, "graphs_per_gpu": GRAPHS_PER_GPU,
+                       "parallelism": f"graphs sharded over {world} rank(s), no data-path collective",
+                       "l2": "no explicit flush: per-layer per-edge weights are E*W*4 B = %.2f GB >> 126 MB L2"
+                             % (n_edges * 1920 * 4 / 1e9)},
+            "e2e": {"value": e2e_value, "unit": "atoms/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
+            "gpu_launches": launches, "clocks": clocks, "roofline": roof, "cpu_baseline": cpu}
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--no-cpu-baseline", dest="no_cpu_baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        if args.gpus > 1 and "RANK" not in os.environ:
+            # convenience: re-launch under torchrun when called directly with --gpus N
+            cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={args.gpus}",
+                   "--master-addr", "127.0.0.1", "--master-port", "29531", os.path.abspath(__file__)] + sys.argv[1:]
+            sys.exit(subprocess.call(cmd))
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

