@@ -32,6 +32,41 @@ template <typename T> __device__ __forceinline__ T warp_sum(T v) {
 #endif
 
 #define TP_THREADS 128
+#define TPP_STAGES 3     // shared-memory ring depth of the pipelined forward kernel
+#define TPP_MAXSEG 256   // edges of one destination segment staged per index chunk
+
+#if defined(__CUDACC__) && !defined(E3B_HOST_EMU)
+// ---- mbarrier + TMA bulk-copy primitives (sm_90+; SASS: SYNCS / UBLKCP) ---------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void fence_mbar_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "WAIT_%=:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+      "@p bra DONE_%=;\n\t"
+      "bra WAIT_%=;\n\t"
+      "DONE_%=:\n\t}" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                   smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+// one edge -> one ring stage: [weight row | source feature row]
+__device__ __forceinline__ void tpp_issue(float* stage, uint64_t* bar, const float* w_row, int row_w,
+                                          const float* x_row, int row_x) {
+  mbar_expect_tx(bar, (uint32_t)(row_w + row_x) * 4u);
+  bulk_g2s(stage, w_row, (uint32_t)row_w * 4u, bar);
+  bulk_g2s(stage + row_w, x_row, (uint32_t)row_x * 4u, bar);
+}
+bool e3b_tp_pipelined_enabled();
+#endif
 
 // Arguments of the tensor-product convolution kernels.  Dims are in scalars per row.
 template <typename T>

@@ -88,8 +88,9 @@ def emit_structure(E, sid, st):
 
     # ------------------------------------------------------------------ forward
     for g, blocks in enumerate(groups):
-        E(f"template <typename T> __device__ __forceinline__ void tpf_S{sid}_g{g}(const TpArgs<T>& a, int64_t node, int u, bool active) {{")
-        E("  const int mul = a.mul;")
+        E(f"template <typename T, int MUL> __device__ __forceinline__ void tpf_S{sid}_g{g}(const TpArgs<T>& a, int64_t node, int u, bool active) {{")
+        E("  const int mul = MUL > 0 ? MUL : a.mul;")
+        E(f"  const int64_t x_dim = (int64_t){xdim} * mul, w_dim = (int64_t){n_paths} * mul, y_dim = (int64_t){ydim} * mul;")
         accs = []
         for pi, p in enumerate(st.paths):
             if p.i_in in blocks:
@@ -97,25 +98,41 @@ def emit_structure(E, sid, st):
                     accs.append(f"acc_{pi}_{k}")
         for i in range(0, len(accs), 8):
             E("  T " + ", ".join(f"{n} = T(0)" for n in accs[i:i + 8]) + ";")
-        E("  const int64_t e0 = a.in_ptr[node], e1 = a.in_ptr[node + 1];")
-        E("  for (int64_t kk = e0; kk < e1; ++kk) {")
-        E("    const int64_t src = a.in_nbr[kk];")
-        E("    const int64_t eid = a.in_eid ? (int64_t)a.in_eid[kk] : kk;")
-        E("    const T* __restrict__ xr = a.x + src * a.x_dim + u;")
-        E("    const T* __restrict__ wr = a.w + eid * a.w_dim + u;")
-        E("    const T* __restrict__ yr = a.sh + eid * a.sh_dim;")
-        for b in blocks:
-            for i in range(st.irreps_in[b].ir.dim):
-                E(f"    const T x_{b}_{i} = ldg(xr + {xoff[b] + i} * mul);")
-        used_s = sorted({s for (b, s, ps) in pairs_of(blocks)})
-        for s in used_s:
-            for j in range(st.irreps_sh[s].ir.dim):
-                E(f"    const T Y_{s}_{j} = ldg(yr + {soff[s] + j});")
+        used_s = sorted({s_ for (b_, s_, ps_) in pairs_of(blocks)})
+        names = []          # (register name, load expression given pointers xr/wr/yr)
+        for b_ in blocks:
+            for i in range(st.irreps_in[b_].ir.dim):
+                names.append((f"x_{b_}_{i}", f"ldg(xr + {xoff[b_] + i} * mul)"))
+        for s_ in used_s:
+            for j in range(st.irreps_sh[s_].ir.dim):
+                names.append((f"Y_{s_}_{j}", f"ldg(yr + {soff[s_] + j})"))
         for pi, p in enumerate(st.paths):
             if p.i_in in blocks:
-                E(f"    const T w_{pi} = ldg(wr + {pi} * mul);")
-        for (b, s, ps) in pairs_of(blocks):
-            l1, l2 = st.irreps_in[b].ir.l, st.irreps_sh[s].ir.l
+                names.append((f"w_{pi}", f"ldg(wr + {pi} * mul)"))
+        E("  const int64_t e0 = a.in_ptr[node], e1 = a.in_ptr[node + 1];")
+        E("  if (e0 < e1) {")
+        E("    int64_t src = a.in_nbr[e0];")
+        E("    int64_t eid = a.in_eid ? (int64_t)a.in_eid[e0] : e0;")
+        E("    int64_t nsrc = src, neid = eid;")
+        E("    if (e0 + 1 < e1) { nsrc = a.in_nbr[e0 + 1]; neid = a.in_eid ? (int64_t)a.in_eid[e0 + 1] : e0 + 1; }")
+        E("    const T* __restrict__ xr = a.x + src * x_dim + u;")
+        E("    const T* __restrict__ wr = a.w + eid * w_dim + u;")
+        E("    const T* __restrict__ yr = a.sh + eid * a.sh_dim;")
+        for n, ex in names:
+            E(f"    T {n} = {ex};")
+        E("    for (int64_t kk = e0; kk < e1; ++kk) {")
+        E("      // software pipeline: issue the loads of edge kk+1 (and the indices of kk+2) before the math of kk")
+        E("      const bool has_next = kk + 1 < e1;")
+        for n, ex in names:
+            E(f"      T n{n} = {n};")
+        E("      if (has_next) {")
+        E("        xr = a.x + nsrc * x_dim + u; wr = a.w + neid * w_dim + u; yr = a.sh + neid * a.sh_dim;")
+        for n, ex in names:
+            E(f"        n{n} = {ex};")
+        E("        if (kk + 2 < e1) { nsrc = a.in_nbr[kk + 2]; neid = a.in_eid ? (int64_t)a.in_eid[kk + 2] : kk + 2; }")
+        E("      }")
+        for (b_, s_, ps) in pairs_of(blocks):
+            l1, l2 = st.irreps_in[b_].ir.l, st.irreps_sh[s_].ir.l
             need = set()
             for pi in ps:
                 C = coef(l1, l2, st.paths[pi].ir_out.l)
@@ -123,9 +140,9 @@ def emit_structure(E, sid, st):
                     for j in range(2 * l2 + 1):
                         if abs(C[i, j]).max() > 0:
                             need.add((i, j))
-            E("    {")
+            E("      {")
             for (i, j) in sorted(need):
-                E(f"      const T xy_{i}_{j} = x_{b}_{i} * Y_{s}_{j};")
+                E(f"        const T xy_{i}_{j} = x_{b_}_{i} * Y_{s_}_{j};")
             for pi in ps:
                 l3 = st.paths[pi].ir_out.l
                 C = coef(l1, l2, l3)
@@ -137,11 +154,14 @@ def emit_structure(E, sid, st):
                     expr = f"{lit(c)} * xy_{i}_{j}"
                     for (i, j, c) in terms[1:]:
                         expr = f"fma_({lit(c)}, xy_{i}_{j}, {expr})"
-                    E(f"      acc_{pi}_{k} = fma_(w_{pi}, {expr}, acc_{pi}_{k});")
-            E("    }")
+                    E(f"        acc_{pi}_{k} = fma_(w_{pi}, {expr}, acc_{pi}_{k});")
+            E("      }")
+        for n, ex in names:
+            E(f"      {n} = n{n};")
+        E("    }")
         E("  }")
         E("  if (active) {")
-        E("    T* __restrict__ yo = a.y + node * a.y_dim + u;")
+        E("    T* __restrict__ yo = a.y + node * y_dim + u;")
         for pi, p in enumerate(st.paths):
             if p.i_in in blocks:
                 for k in range(p.ir_out.dim):
@@ -152,9 +172,10 @@ def emit_structure(E, sid, st):
 
     # ------------------------------------------------------------------ backward
     for g, blocks in enumerate(groups):
-        E(f"template <typename T> __device__ __forceinline__ void tpb_S{sid}_g{g}(const TpArgs<T>& a, int64_t node, int u, bool active, int part, int lane) {{")
-        E("  const int mul = a.mul;")
-        E("  const T* __restrict__ gyr = a.gy + node * a.y_dim + u;")
+        E(f"template <typename T, int MUL> __device__ __forceinline__ void tpb_S{sid}_g{g}(const TpArgs<T>& a, int64_t node, int u, bool active, int part, int lane) {{")
+        E("  const int mul = MUL > 0 ? MUL : a.mul;")
+        E(f"  const int64_t x_dim = (int64_t){xdim} * mul, w_dim = (int64_t){n_paths} * mul, y_dim = (int64_t){ydim} * mul;")
+        E("  const T* __restrict__ gyr = a.gy + node * y_dim + u;")
         for pi, p in enumerate(st.paths):
             if p.i_in in blocks:
                 for k in range(p.ir_out.dim):
@@ -163,10 +184,10 @@ def emit_structure(E, sid, st):
         E("  for (int64_t kk = e0; kk < e1; ++kk) {")
         E("    const int64_t src = a.in_nbr[kk];")
         E("    const int64_t eid = a.in_eid ? (int64_t)a.in_eid[kk] : kk;")
-        E("    const T* __restrict__ xr = a.x + src * a.x_dim + u;")
-        E("    const T* __restrict__ wr = a.w + eid * a.w_dim + u;")
+        E("    const T* __restrict__ xr = a.x + src * x_dim + u;")
+        E("    const T* __restrict__ wr = a.w + eid * w_dim + u;")
         E("    const T* __restrict__ yr = a.sh + eid * a.sh_dim;")
-        E("    T* __restrict__ gwr = a.gw + eid * a.w_dim + u;")
+        E("    T* __restrict__ gwr = a.gw + eid * w_dim + u;")
         used_s = sorted({s for (b, s, ps) in pairs_of(blocks)})
         for s in used_s:
             for j in range(st.irreps_sh[s].ir.dim):
@@ -215,7 +236,7 @@ def emit_structure(E, sid, st):
                     E(f"      gY_{s}_{j} = fma_(gxy_{i}_{j}, x_{b}_{i}, gY_{s}_{j});")
                 E("    }")
             E("    if (a.gx_edge != nullptr && active) {")
-            E("      T* __restrict__ gxr = a.gx_edge + eid * a.x_dim + u;")
+            E("      T* __restrict__ gxr = a.gx_edge + eid * x_dim + u;")
             for i in range(d1):
                 E(f"      gxr[{xoff[b] + i} * mul] = gx_{b}_{i};")
             E("    }")
@@ -232,11 +253,123 @@ def emit_structure(E, sid, st):
         E("}")
         E()
 
+    # ------------------------------------------------------------------ pipelined forward (TMA bulk copies)
+    # One CTA per destination node.  An elected thread streams, per incoming edge, the edge's
+    # weight row and the source node's feature row into a TPP_STAGES-deep shared-memory ring with
+    # cp.async.bulk (TMA engine, completion on an mbarrier); the warps (group x channel-chunk)
+    # consume from shared memory, so no registers are tied up by loads in flight.
+    E("#ifdef __CUDACC__")
+    E(f"template <int MUL> __global__ void __launch_bounds__(32 * {G} * (MUL / 32)) tpfp_S{sid}(const TpArgs<float> a) {{")
+    E("  typedef float T;")
+    E(f"  constexpr int G = {G}, ROW_W = {n_paths} * MUL, ROW_X = {xdim} * MUL, STAGE = ROW_W + ROW_X, SH_DIM = {sdim};")
+    E("  constexpr int NT = 32 * G * (MUL / 32);")
+    E("  extern __shared__ __align__(128) unsigned char tpp_smem[];")
+    E("  float* stages = reinterpret_cast<float*>(tpp_smem);")
+    E("  int* s_src = reinterpret_cast<int*>(stages + TPP_STAGES * STAGE);")
+    E("  int* s_eid = s_src + TPP_MAXSEG;")
+    E("  uint64_t* full = reinterpret_cast<uint64_t*>(s_eid + TPP_MAXSEG);")
+    E("  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;")
+    E("  const int64_t node = blockIdx.x;")
+    E(f"  const int chunk = warp / G, group = warp - chunk * G;")
+    E("  const int u = chunk * 32 + lane;")
+    E("  if (tid == 0) {")
+    E("    for (int s = 0; s < TPP_STAGES; ++s) mbar_init(&full[s], 1);")
+    E("    fence_mbar_init();")
+    E("  }")
+    E("  const int64_t e0 = a.in_ptr[node], e1 = a.in_ptr[node + 1];")
+    accs_all = []
+    for pi, p in enumerate(st.paths):
+        for k in range(p.ir_out.dim):
+            accs_all.append(f"acc_{pi}_{k}")
+    # accumulators: each warp only uses its group's, the compiler keeps one live set per branch
+    E("  uint32_t it = 0;  // running edge counter -> ring stage and mbarrier phase")
+    E("  switch (group) {")
+    for g, blocks in enumerate(groups):
+        E(f"  case {g}: {{")
+        accs = [f"acc_{pi}_{k}" for pi, p in enumerate(st.paths) if p.i_in in blocks for k in range(p.ir_out.dim)]
+        for i in range(0, len(accs), 8):
+            E("    T " + ", ".join(f"{n} = T(0)" for n in accs[i:i + 8]) + ";")
+        E("    for (int64_t c0 = e0; c0 < e1; c0 += TPP_MAXSEG) {")
+        E("      const int n = (int)((e1 - c0) < TPP_MAXSEG ? (e1 - c0) : TPP_MAXSEG);")
+        E("      __syncthreads();   // previous chunk fully consumed (also orders the barrier init)")
+        E("      for (int i = tid; i < n; i += NT) {")
+        E("        s_src[i] = a.in_nbr[c0 + i];")
+        E("        s_eid[i] = a.in_eid ? a.in_eid[c0 + i] : (int)(c0 + i);")
+        E("      }")
+        E("      __syncthreads();")
+        E("      if (tid == 0) {")
+        E("        const int pre = n < TPP_STAGES ? n : TPP_STAGES;")
+        E("        for (int j = 0; j < pre; ++j) {")
+        E("          const uint32_t s = (it + j) % TPP_STAGES;")
+        E("          tpp_issue(stages + s * STAGE, &full[s], a.w + (int64_t)s_eid[j] * ROW_W, ROW_W, a.x + (int64_t)s_src[j] * ROW_X, ROW_X);")
+        E("        }")
+        E("      }")
+        E("      T Ycur = (lane < SH_DIM) ? ldg(a.sh + (int64_t)s_eid[0] * SH_DIM + lane) : T(0);")
+        E("      for (int i = 0; i < n; ++i, ++it) {")
+        E("        const uint32_t s = it % TPP_STAGES, ph = (it / TPP_STAGES) & 1u;")
+        E("        T Ynext = T(0);")
+        E("        if (i + 1 < n && lane < SH_DIM) Ynext = ldg(a.sh + (int64_t)s_eid[i + 1] * SH_DIM + lane);")
+        E("        mbar_wait(&full[s], ph);")
+        E("        const T* __restrict__ sw = stages + s * STAGE + u;")
+        E("        const T* __restrict__ sx = sw + ROW_W;")
+        used_s = sorted({s_ for (b_, s_, ps_) in pairs_of(blocks)})
+        for s_ in used_s:
+            for j in range(st.irreps_sh[s_].ir.dim):
+                E(f"        const T Y_{s_}_{j} = __shfl_sync(0xffffffffu, Ycur, {soff[s_] + j});")
+        for b_ in blocks:
+            for i in range(st.irreps_in[b_].ir.dim):
+                E(f"        const T x_{b_}_{i} = sx[{xoff[b_] + i} * MUL];")
+        for (b_, s_, ps) in pairs_of(blocks):
+            l1, l2 = st.irreps_in[b_].ir.l, st.irreps_sh[s_].ir.l
+            need = set()
+            for pi in ps:
+                C = coef(l1, l2, st.paths[pi].ir_out.l)
+                for i in range(2 * l1 + 1):
+                    for j in range(2 * l2 + 1):
+                        if abs(C[i, j]).max() > 0:
+                            need.add((i, j))
+            E("        {")
+            for (i, j) in sorted(need):
+                E(f"          const T xy_{i}_{j} = x_{b_}_{i} * Y_{s_}_{j};")
+            for pi in ps:
+                l3 = st.paths[pi].ir_out.l
+                C = coef(l1, l2, l3)
+                E(f"          {{ const T w_p = sw[{pi} * MUL];")
+                for k in range(2 * l3 + 1):
+                    terms = [(i, j, C[i, j, k]) for i in range(2 * l1 + 1) for j in range(2 * l2 + 1) if C[i, j, k] != 0]
+                    if not terms:
+                        continue
+                    i, j, c = terms[0]
+                    expr = f"{lit(c)} * xy_{i}_{j}"
+                    for (i, j, c) in terms[1:]:
+                        expr = f"fma_({lit(c)}, xy_{i}_{j}, {expr})"
+                    E(f"            acc_{pi}_{k} = fma_(w_p, {expr}, acc_{pi}_{k});")
+                E("          }")
+            E("        }")
+        E("        Ycur = Ynext;")
+        E("        __syncthreads();   // every warp is done with stage s")
+        E("        if (tid == 0 && i + TPP_STAGES < n)")
+        E("          tpp_issue(stages + s * STAGE, &full[s], a.w + (int64_t)s_eid[i + TPP_STAGES] * ROW_W, ROW_W,")
+        E("                    a.x + (int64_t)s_src[i + TPP_STAGES] * ROW_X, ROW_X);")
+        E("      }")
+        E("    }")
+        E(f"    T* __restrict__ yo = a.y + node * ({ydim} * MUL) + u;")
+        for pi, p in enumerate(st.paths):
+            if p.i_in in blocks:
+                for k in range(p.ir_out.dim):
+                    E(f"    yo[{ybase[p.slot] + k * ykst[p.slot]} * MUL] = acc_{pi}_{k};")
+        E("  } break;")
+    E("  }")
+    E("}")
+    E(f"static size_t tpfp_smem_S{sid}(int mul) {{ return (size_t)TPP_STAGES * ({n_paths} + {xdim}) * mul * 4 + 2 * TPP_MAXSEG * 4 + TPP_STAGES * 8; }}")
+    E("#endif  // __CUDACC__")
+    E()
+
     # ------------------------------------------------------------------ kernels
     E("#ifdef __CUDACC__")
     for kind in ("f", "b"):
         extra = ", part, lane" if kind == "b" else ""
-        E(f"template <typename T> __global__ void __launch_bounds__(TP_THREADS) tp{kind}_S{sid}(const TpArgs<T> a) {{")
+        E(f"template <typename T, int MUL> __global__ void __launch_bounds__(TP_THREADS) tp{kind}_S{sid}(const TpArgs<T> a) {{")
         E("  const int lane = threadIdx.x & 31;")
         E("  const int64_t item = (int64_t)blockIdx.x * (TP_THREADS / 32) + (threadIdx.x >> 5);")
         E(f"  const int per_node = a.n_chunks * {G};")
@@ -249,7 +382,7 @@ def emit_structure(E, sid, st):
         E("  if (!active) u = a.mul - 1;")
         E("  switch (group) {")
         for g in range(G):
-            E(f"    case {g}: tp{kind}_S{sid}_g{g}<T>(a, node, u, active{extra}); break;")
+            E(f"    case {g}: tp{kind}_S{sid}_g{g}<T, MUL>(a, node, u, active{extra}); break;")
         E("  }")
         E("}")
         E()
@@ -277,7 +410,7 @@ def emit_tables(st_list):
     for sid in range(len(st_list)):
         E(f"        case {sid}:")
         for g in range(Gs[sid]):
-            E(f"          if (bwd) tpb_S{sid}_g{g}<T>(a, node, u, true, chunk * {Gs[sid]} + {g}, lane); else tpf_S{sid}_g{g}<T>(a, node, u, true);")
+            E(f"          if (bwd) tpb_S{sid}_g{g}<T, 0>(a, node, u, true, chunk * {Gs[sid]} + {g}, lane); else tpf_S{sid}_g{g}<T, 0>(a, node, u, true);")
         E("          break;")
     E("        default: return -1;")
     E("      }")
@@ -289,8 +422,20 @@ def emit_tables(st_list):
     E("#ifdef __CUDACC__")
     for sid in range(len(st_list)):
         for kind in ("f", "b"):
-            E(f"static void launch_tp{kind}_S{sid}(const TpArgs<float>& a, int64_t grid, cudaStream_t s) {{ "
-              f"tp{kind}_S{sid}<float><<<(unsigned)grid, TP_THREADS, 0, s>>>(a); }}")
+            E(f"static void launch_tp{kind}_S{sid}(const TpArgs<float>& a, int64_t grid, cudaStream_t s) {{")
+            if kind == "f":
+                E(f"  if ((a.mul == 64 || a.mul == 32) && e3b_tp_pipelined_enabled()) {{")
+                E(f"    const size_t smem = tpfp_smem_S{sid}(a.mul);")
+                E(f"    if (a.mul == 64) {{ if (smem > 48 * 1024) cudaFuncSetAttribute(tpfp_S{sid}<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);")
+                E(f"      tpfp_S{sid}<64><<<(unsigned)a.n_nodes, 32 * {Gs[sid]} * 2, smem, s>>>(a); }}")
+                E(f"    else {{ if (smem > 48 * 1024) cudaFuncSetAttribute(tpfp_S{sid}<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);")
+                E(f"      tpfp_S{sid}<32><<<(unsigned)a.n_nodes, 32 * {Gs[sid]}, smem, s>>>(a); }}")
+                E("    return;")
+                E("  }")
+            E(f"  if (a.mul == 64) tp{kind}_S{sid}<float, 64><<<(unsigned)grid, TP_THREADS, 0, s>>>(a);")
+            E(f"  else if (a.mul == 32) tp{kind}_S{sid}<float, 32><<<(unsigned)grid, TP_THREADS, 0, s>>>(a);")
+            E(f"  else tp{kind}_S{sid}<float, 0><<<(unsigned)grid, TP_THREADS, 0, s>>>(a);")
+            E("}")
 
     def arr(v):
         return "{" + ", ".join(str(int(t)) for t in v) + "}"

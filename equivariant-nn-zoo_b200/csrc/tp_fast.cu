@@ -1,6 +1,14 @@
 // Translation unit of the GENERATED tensor-product convolution kernels (tp_generated.cuh).
 #include "tp_fast.h"
 
+#include <cstdlib>
+
+// E3B_TP_PIPELINED=0 selects the direct-load kernels (A/B comparison and bisection)
+bool e3b_tp_pipelined_enabled() {
+  static const int on = [] { const char* v = getenv("E3B_TP_PIPELINED"); return (v && v[0] == '0') ? 0 : 1; }();
+  return on != 0;
+}
+
 #include "tp_generated.cuh"
 
 const GenEntry* e3b_find_generated(const e3b_tp_desc* d, const int32_t* y_base, const int32_t* y_kstride) {
