@@ -86,6 +86,70 @@ def emit_structure(E, sid, st):
                     out.append((b, s, ps))
         return out
 
+    def emit_bwd_body(blocks, xl, wl, yl):
+            used_s = sorted({s for (b, s, ps) in pairs_of(blocks)})
+            for s in used_s:
+                for j in range(st.irreps_sh[s].ir.dim):
+                    E(f"    const T Y_{s}_{j} = {yl(s, j)};")
+                    E(f"    T gY_{s}_{j} = T(0);")
+            for b in blocks:
+                d1 = st.irreps_in[b].ir.dim
+                for i in range(d1):
+                    E(f"    const T x_{b}_{i} = {xl(b, i)};")
+                for i in range(d1):
+                    E(f"    T gx_{b}_{i} = T(0);")
+                for (bb, s, ps) in pairs_of([b]):
+                    l1, l2 = st.irreps_in[b].ir.l, st.irreps_sh[s].ir.l
+                    need = set()
+                    for pi in ps:
+                        C = coef(l1, l2, st.paths[pi].ir_out.l)
+                        for i in range(2 * l1 + 1):
+                            for j in range(2 * l2 + 1):
+                                if abs(C[i, j]).max() > 0:
+                                    need.add((i, j))
+                    need = sorted(need)
+                    E("    {")
+                    for (i, j) in need:
+                        E(f"      const T xy_{i}_{j} = x_{b}_{i} * Y_{s}_{j};")
+                        E(f"      T gxy_{i}_{j} = T(0);")
+                    for pi in ps:
+                        l3 = st.paths[pi].ir_out.l
+                        C = coef(l1, l2, l3)
+                        E(f"      {{ const T w_p = {wl(pi)}; T gw_p = T(0);")
+                        for k in range(2 * l3 + 1):
+                            terms = [(i, j, C[i, j, k]) for i in range(2 * l1 + 1) for j in range(2 * l2 + 1) if C[i, j, k] != 0]
+                            if not terms:
+                                continue
+                            i, j, c = terms[0]
+                            expr = f"{lit(c)} * xy_{i}_{j}"
+                            for (i, j, c) in terms[1:]:
+                                expr = f"fma_({lit(c)}, xy_{i}_{j}, {expr})"
+                            E(f"        gw_p = fma_(gy_{pi}_{k}, {expr}, gw_p);")
+                            E(f"        {{ const T gt = w_p * gy_{pi}_{k};")
+                            for (i, j, c) in terms:
+                                E(f"          gxy_{i}_{j} = fma_({lit(c)}, gt, gxy_{i}_{j});")
+                            E("        }")
+                        E(f"        if (active) gwr[{pi} * mul] = gw_p; }}")
+                    for (i, j) in need:
+                        E(f"      gx_{b}_{i} = fma_(gxy_{i}_{j}, Y_{s}_{j}, gx_{b}_{i});")
+                        E(f"      gY_{s}_{j} = fma_(gxy_{i}_{j}, x_{b}_{i}, gY_{s}_{j});")
+                    E("    }")
+                E("    if (a.gx_edge != nullptr && active) {")
+                E("      T* __restrict__ gxr = a.gx_edge + eid * x_dim + u;")
+                for i in range(d1):
+                    E(f"      gxr[{xoff[b] + i} * mul] = gx_{b}_{i};")
+                E("    }")
+            E("    if (a.gsh != nullptr) {")
+            E("      T* __restrict__ gsr = a.gsh + (eid * a.n_part + part) * a.sh_dim;")
+            for s in range(len(st.irreps_sh)):
+                for j in range(st.irreps_sh[s].ir.dim):
+                    if s in used_s:
+                        E(f"      E3B_GSH_STORE(gsr, {soff[s] + j}, gY_{s}_{j});")
+                    else:
+                        E(f"      E3B_GSH_ZERO(gsr, {soff[s] + j});")
+            E("    }")
+
+
     # ------------------------------------------------------------------ forward
     for g, blocks in enumerate(groups):
         E(f"template <typename T, int MUL> __device__ __forceinline__ void tpf_S{sid}_g{g}(const TpArgs<T>& a, int64_t node, int u, bool active) {{")
@@ -188,67 +252,8 @@ def emit_structure(E, sid, st):
         E("    const T* __restrict__ wr = a.w + eid * w_dim + u;")
         E("    const T* __restrict__ yr = a.sh + eid * a.sh_dim;")
         E("    T* __restrict__ gwr = a.gw + eid * w_dim + u;")
-        used_s = sorted({s for (b, s, ps) in pairs_of(blocks)})
-        for s in used_s:
-            for j in range(st.irreps_sh[s].ir.dim):
-                E(f"    const T Y_{s}_{j} = ldg(yr + {soff[s] + j});")
-                E(f"    T gY_{s}_{j} = T(0);")
-        for b in blocks:
-            d1 = st.irreps_in[b].ir.dim
-            for i in range(d1):
-                E(f"    const T x_{b}_{i} = ldg(xr + {xoff[b] + i} * mul);")
-            for i in range(d1):
-                E(f"    T gx_{b}_{i} = T(0);")
-            for (bb, s, ps) in pairs_of([b]):
-                l1, l2 = st.irreps_in[b].ir.l, st.irreps_sh[s].ir.l
-                need = set()
-                for pi in ps:
-                    C = coef(l1, l2, st.paths[pi].ir_out.l)
-                    for i in range(2 * l1 + 1):
-                        for j in range(2 * l2 + 1):
-                            if abs(C[i, j]).max() > 0:
-                                need.add((i, j))
-                need = sorted(need)
-                E("    {")
-                for (i, j) in need:
-                    E(f"      const T xy_{i}_{j} = x_{b}_{i} * Y_{s}_{j};")
-                    E(f"      T gxy_{i}_{j} = T(0);")
-                for pi in ps:
-                    l3 = st.paths[pi].ir_out.l
-                    C = coef(l1, l2, l3)
-                    E(f"      {{ const T w_p = ldg(wr + {pi} * mul); T gw_p = T(0);")
-                    for k in range(2 * l3 + 1):
-                        terms = [(i, j, C[i, j, k]) for i in range(2 * l1 + 1) for j in range(2 * l2 + 1) if C[i, j, k] != 0]
-                        if not terms:
-                            continue
-                        i, j, c = terms[0]
-                        expr = f"{lit(c)} * xy_{i}_{j}"
-                        for (i, j, c) in terms[1:]:
-                            expr = f"fma_({lit(c)}, xy_{i}_{j}, {expr})"
-                        E(f"        gw_p = fma_(gy_{pi}_{k}, {expr}, gw_p);")
-                        E(f"        {{ const T gt = w_p * gy_{pi}_{k};")
-                        for (i, j, c) in terms:
-                            E(f"          gxy_{i}_{j} = fma_({lit(c)}, gt, gxy_{i}_{j});")
-                        E("        }")
-                    E(f"        if (active) gwr[{pi} * mul] = gw_p; }}")
-                for (i, j) in need:
-                    E(f"      gx_{b}_{i} = fma_(gxy_{i}_{j}, Y_{s}_{j}, gx_{b}_{i});")
-                    E(f"      gY_{s}_{j} = fma_(gxy_{i}_{j}, x_{b}_{i}, gY_{s}_{j});")
-                E("    }")
-            E("    if (a.gx_edge != nullptr && active) {")
-            E("      T* __restrict__ gxr = a.gx_edge + eid * x_dim + u;")
-            for i in range(d1):
-                E(f"      gxr[{xoff[b] + i} * mul] = gx_{b}_{i};")
-            E("    }")
-        E("    if (a.gsh != nullptr) {")
-        E("      T* __restrict__ gsr = a.gsh + (eid * a.n_part + part) * a.sh_dim;")
-        for s in range(len(st.irreps_sh)):
-            for j in range(st.irreps_sh[s].ir.dim):
-                if s in used_s:
-                    E(f"      E3B_GSH_STORE(gsr, {soff[s] + j}, gY_{s}_{j});")
-                else:
-                    E(f"      E3B_GSH_ZERO(gsr, {soff[s] + j});")
-        E("    }")
+        emit_bwd_body(blocks, lambda b, i: f"ldg(xr + {xoff[b] + i} * mul)", lambda pi: f"ldg(wr + {pi} * mul)",
+                      lambda s_, j: f"ldg(yr + {soff[s_] + j})")
         E("  }")
         E("}")
         E()
@@ -362,6 +367,76 @@ def emit_structure(E, sid, st):
     E("  }")
     E("}")
     E(f"static size_t tpfp_smem_S{sid}(int mul) {{ return (size_t)TPP_STAGES * ({n_paths} + {xdim}) * mul * 4 + 2 * TPP_MAXSEG * 4 + TPP_STAGES * 8; }}")
+    # ---- pipelined backward: same ring; gy of the node lives in registers, gw / gx_edge / gsh
+    # partials are stored directly (fire-and-forget)
+    E(f"template <int MUL> __global__ void __launch_bounds__(32 * {G} * (MUL / 32)) tpbp_S{sid}(const TpArgs<float> a) {{")
+    E("  typedef float T;")
+    E(f"  constexpr int G = {G}, ROW_W = {n_paths} * MUL, ROW_X = {xdim} * MUL, STAGE = ROW_W + ROW_X, SH_DIM = {sdim};")
+    E("  constexpr int NT = 32 * G * (MUL / 32);")
+    E("  constexpr int mul = MUL; constexpr bool active = true;")
+    E("  constexpr int64_t x_dim = ROW_X, w_dim = ROW_W;")
+    E("  extern __shared__ __align__(128) unsigned char tpp_smem[];")
+    E("  float* stages = reinterpret_cast<float*>(tpp_smem);")
+    E("  int* s_src = reinterpret_cast<int*>(stages + TPP_STAGES * STAGE);")
+    E("  int* s_eid = s_src + TPP_MAXSEG;")
+    E("  uint64_t* full = reinterpret_cast<uint64_t*>(s_eid + TPP_MAXSEG);")
+    E("  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;")
+    E("  const int64_t node = blockIdx.x;")
+    E(f"  const int chunk = warp / G, group = warp - chunk * G, part = warp;")
+    E("  const int u = chunk * 32 + lane;")
+    E("  if (tid == 0) {")
+    E("    for (int s = 0; s < TPP_STAGES; ++s) mbar_init(&full[s], 1);")
+    E("    fence_mbar_init();")
+    E("  }")
+    E("  const int64_t e0 = a.in_ptr[node], e1 = a.in_ptr[node + 1];")
+    E(f"  const T* __restrict__ gyr = a.gy + node * ({ydim} * MUL) + u;")
+    E("  uint32_t it = 0;")
+    E("  switch (group) {")
+    for g, blocks in enumerate(groups):
+        E(f"  case {g}: {{")
+        for pi, p in enumerate(st.paths):
+            if p.i_in in blocks:
+                for k in range(p.ir_out.dim):
+                    E(f"    const T gy_{pi}_{k} = ldg(gyr + {ybase[p.slot] + k * ykst[p.slot]} * MUL);")
+        E("    for (int64_t c0 = e0; c0 < e1; c0 += TPP_MAXSEG) {")
+        E("      const int n = (int)((e1 - c0) < TPP_MAXSEG ? (e1 - c0) : TPP_MAXSEG);")
+        E("      __syncthreads();")
+        E("      for (int i = tid; i < n; i += NT) {")
+        E("        s_src[i] = a.in_nbr[c0 + i];")
+        E("        s_eid[i] = a.in_eid ? a.in_eid[c0 + i] : (int)(c0 + i);")
+        E("      }")
+        E("      __syncthreads();")
+        E("      if (tid == 0) {")
+        E("        const int pre = n < TPP_STAGES ? n : TPP_STAGES;")
+        E("        for (int j = 0; j < pre; ++j) {")
+        E("          const uint32_t s = (it + j) % TPP_STAGES;")
+        E("          tpp_issue(stages + s * STAGE, &full[s], a.w + (int64_t)s_eid[j] * ROW_W, ROW_W, a.x + (int64_t)s_src[j] * ROW_X, ROW_X);")
+        E("        }")
+        E("      }")
+        E("      T Ycur = (lane < SH_DIM) ? ldg(a.sh + (int64_t)s_eid[0] * SH_DIM + lane) : T(0);")
+        E("      for (int i = 0; i < n; ++i, ++it) {")
+        E("        const uint32_t s = it % TPP_STAGES, ph = (it / TPP_STAGES) & 1u;")
+        E("        const int64_t eid = s_eid[i];")
+        E("        T Ynext = T(0);")
+        E("        if (i + 1 < n && lane < SH_DIM) Ynext = ldg(a.sh + (int64_t)s_eid[i + 1] * SH_DIM + lane);")
+        E("        mbar_wait(&full[s], ph);")
+        E("        const T* __restrict__ sw = stages + s * STAGE + u;")
+        E("        const T* __restrict__ sx = sw + ROW_W;")
+        E("        T* __restrict__ gwr = a.gw + eid * w_dim + u;")
+        E("        {")
+        emit_bwd_body(blocks, lambda b, i: f"sx[{xoff[b] + i} * MUL]", lambda pi: f"sw[{pi} * MUL]",
+                      lambda s_, j: f"__shfl_sync(0xffffffffu, Ycur, {soff[s_] + j})")
+        E("        }")
+        E("        Ycur = Ynext;")
+        E("        __syncthreads();")
+        E("        if (tid == 0 && i + TPP_STAGES < n)")
+        E("          tpp_issue(stages + s * STAGE, &full[s], a.w + (int64_t)s_eid[i + TPP_STAGES] * ROW_W, ROW_W,")
+        E("                    a.x + (int64_t)s_src[i + TPP_STAGES] * ROW_X, ROW_X);")
+        E("      }")
+        E("    }")
+        E("  } break;")
+    E("  }")
+    E("}")
     E("#endif  // __CUDACC__")
     E()
 
@@ -423,6 +498,15 @@ def emit_tables(st_list):
     for sid in range(len(st_list)):
         for kind in ("f", "b"):
             E(f"static void launch_tp{kind}_S{sid}(const TpArgs<float>& a, int64_t grid, cudaStream_t s) {{")
+            if kind == "b":
+                E(f"  if ((a.mul == 64 || a.mul == 32) && e3b_tp_pipelined_enabled()) {{")
+                E(f"    const size_t smem = tpfp_smem_S{sid}(a.mul);")
+                E(f"    if (a.mul == 64) {{ if (smem > 48 * 1024) cudaFuncSetAttribute(tpbp_S{sid}<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);")
+                E(f"      tpbp_S{sid}<64><<<(unsigned)a.n_nodes, 32 * {Gs[sid]} * 2, smem, s>>>(a); }}")
+                E(f"    else {{ if (smem > 48 * 1024) cudaFuncSetAttribute(tpbp_S{sid}<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);")
+                E(f"      tpbp_S{sid}<32><<<(unsigned)a.n_nodes, 32 * {Gs[sid]}, smem, s>>>(a); }}")
+                E("    return;")
+                E("  }")
             if kind == "f":
                 E(f"  if ((a.mul == 64 || a.mul == 32) && e3b_tp_pipelined_enabled()) {{")
                 E(f"    const size_t smem = tpfp_smem_S{sid}(a.mul);")
