@@ -23,6 +23,15 @@ static int fail(int code, const char* fmt, ...) {
   return code;
 }
 
+// shared with the other translation units of the library (hidden visibility)
+int e3b_fail(int code, const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+  return code;
+}
+
 static int check_launch(const char* what) {
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return fail(E3B_ERR_CUDA, "%s: %s", what, cudaGetErrorString(e));

@@ -55,6 +55,8 @@ SIGNATURES = {
     "e3b_segment_sum": (c_int, [c_int, c_vp, c_i64, c_vp, c_vp, c_i64, c_vp, c_vp]),
     "e3b_gate_fwd": (c_int, [ctypes.POINTER(GateDesc), c_int, c_vp, c_i64, c_vp, c_vp]),
     "e3b_gate_bwd": (c_int, [ctypes.POINTER(GateDesc), c_int, c_vp, c_vp, c_i64, c_vp, c_vp]),
+    "e3b_gemm_tf32x3": (c_int, [c_vp, c_i64, c_i64, c_i32, c_vp, c_i64, c_vp, c_i64, c_i64, c_i32, c_i64, c_i32, c_i32,
+                                c_i32, c_f32, c_i32, c_vp, c_i64, c_i32, c_i32, c_vp]),
     "e3b_layout_convert": (c_int, [c_int, c_vp, c_i64, c_i32, c_vp, c_vp, c_int, c_vp, c_vp]),
 }
 

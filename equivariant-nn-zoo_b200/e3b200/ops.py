@@ -388,3 +388,29 @@ def layout_convert(x, irreps, to_imu):
     check(lib.e3b_layout_convert(dtype_code(x), ptr(x), x.shape[0], nb, mul, ls, int(to_imu), ptr(out), stream()))
     count_launch()
     return out
+
+
+# ------------------------------------------------------------------------------------------
+def gemm_tf32x3(A, B, C, M, N, K, a_rows=None, c_rows=None, c_col_stride=1, alpha=1.0, reduce_aux=None, aux_d=1):
+    """C[r, n] = alpha * sum_k A[r, k] B[n, k] on the tcgen05 tensor cores (3xTF32, fp32 accumulate).
+
+    A, B, C are fp32 CUDA tensors used as raw storage: ``a_rows`` / ``c_rows`` = (s1, s2, d) give the
+    affine row addressing  base + (r // d) * s1 + (r % d) * s2  (default: dense rows of width K / N).
+    B is [N, K] row-major (row stride = B.stride(0)).  With ``reduce_aux`` ([*, V], V in {16, 32}) the
+    epilogue contracts every group of V accumulator columns with aux[r // aux_d] (self-connection)."""
+    lib = _lib.load()
+    require_cuda(A, B, C)
+    assert A.dtype == B.dtype == C.dtype == torch.float32
+    a_s1, a_s2, a_d = a_rows if a_rows is not None else (K, 0, 1)
+    n_out = N if reduce_aux is None else N // reduce_aux.shape[1]
+    c_s1, c_s2, c_d = c_rows if c_rows is not None else (n_out * c_col_stride, 0, 1)
+    ldb = B.stride(0) if B.dim() == 2 else K
+    if reduce_aux is not None:
+        assert reduce_aux.is_contiguous() and reduce_aux.dtype == torch.float32
+        epi, aux_p, aux_ld, V = 1, reduce_aux.data_ptr(), reduce_aux.stride(0), reduce_aux.shape[1]
+    else:
+        epi, aux_p, aux_ld, V = 0, None, 0, 0
+    check(lib.e3b_gemm_tf32x3(A.data_ptr(), a_s1, a_s2, a_d, B.data_ptr(), ldb, C.data_ptr(), c_s1, c_s2, c_d,
+                              c_col_stride, M, N, K, float(alpha), epi, aux_p, aux_ld, aux_d, V, stream()))
+    count_launch()
+    return C

@@ -194,6 +194,23 @@ E3B_API int e3b_gate_fwd(const e3b_gate_desc* desc, int dtype, const void* in, i
 E3B_API int e3b_gate_bwd(const e3b_gate_desc* desc, int dtype, const void* in, const void* gout, int64_t n, void* gin,
                  void* stream);
 
+/* ---------------------------------------------------------------------------------------
+ * Dense contractions on the tcgen05 tensor cores, fp32-faithful (3xTF32 split, fp32 TMEM
+ * accumulators).  Replaces the cuBLAS/einsum calls behind e3nn o3.Linear
+ * (nn/message_passing.py:58-63,102; nn/pointwise.py:87-92,99), nn.FullyConnectedNet
+ * (nn/message_passing.py:74-79,93) and o3.FullyConnectedTensorProduct (message_passing.py:83-87).
+ *
+ *   epilogue 0:  C[r, n]  = alpha * sum_k A[r, k] B[n, k]
+ *   epilogue 1:  C[r, oc] = alpha * sum_{v < V} aux[(r / aux_d) * aux_ld + v] * acc[r, oc * V + v]
+ *                (the self-connection: B rows ordered (w, v), v fastest; N = n_out * V)
+ * Row r of A starts at A + (r / a_d) * a_s1 + (r % a_d) * a_s2 (k contiguous); element (r, n) of
+ * C is at C + (r / c_d) * c_s1 + (r % c_d) * c_s2 + n * c_s3; row n of B at B + n * ldb.
+ * K, the row strides of A/B and the bases of A/B must be multiples of 4 floats.              */
+E3B_API int e3b_gemm_tf32x3(const float* A, int64_t a_s1, int64_t a_s2, int32_t a_d, const float* B, int64_t ldb,
+                            float* C, int64_t c_s1, int64_t c_s2, int32_t c_d, int64_t c_s3, int32_t M, int32_t N,
+                            int32_t K, float alpha, int32_t epilogue, const float* aux, int64_t aux_ld,
+                            int32_t aux_d, int32_t V, void* stream);
+
 /* mul_ir <-> imu layout conversion of feature rows (blocks: mul, l). to_imu = 1: [u][m]->[m][u] */
 E3B_API int e3b_layout_convert(int dtype, const void* in, int64_t n, int32_t n_blocks, const int32_t* mul,
                        const int32_t* l, int to_imu, void* out, void* stream);
