@@ -40,6 +40,15 @@ static int check_launch(const char* what) {
 
 extern "C" int e3b_abi_version(void) { return E3B_ABI_VERSION; }
 extern "C" const char* e3b_last_error(void) { return g_err; }
+extern "C" int64_t e3b_struct_size(int which) {
+  switch (which) {
+    case 0: return (int64_t)sizeof(e3b_tp_desc);
+    case 1: return (int64_t)sizeof(e3b_gate_desc);
+    case 2: return (int64_t)sizeof(e3b_gemm_problem);
+    case 3: return (int64_t)sizeof(e3b_gemm_pack_desc);
+    default: return -1;
+  }
+}
 
 static inline unsigned blocks_for(int64_t n, int per_block) { return (unsigned)((n + per_block - 1) / per_block); }
 

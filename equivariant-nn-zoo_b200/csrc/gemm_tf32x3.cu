@@ -1,21 +1,28 @@
 // fp32-faithful dense contractions on the 5th-generation tensor cores (tcgen05, sm_100a).
 //
-//   C[r, n] = epilogue( sum_k A[r, k] * B[n, k] )          A, B, C fp32 in HBM
+//   C[r, n] = epilogue( sum_k A[r, k] * B[n, k] )          A, C fp32 in HBM, B a (small) weight
 //
-// Each fp32 operand is split in registers into a TF32 "hi" part (top 19 bits) and a TF32 "lo"
-// part (the exactly representable remainder, truncated), written to shared memory in the UMMA
-// canonical K-major / no-swizzle layout, and three tcgen05.mma.kind::tf32 products
-// (hi*hi + hi*lo + lo*hi) accumulate in TMEM in fp32 -- "3xTF32", relative error ~1e-6, which
-// the 1e-5 parity budget of the interaction block needs (plain TF32 gives ~1e-3).
+// 3xTF32: every fp32 operand is split into a TF32 "hi" part and a TF32 "lo" part (the rounded
+// remainder) and three tcgen05.mma.kind::tf32 products (lo*hi + hi*lo + hi*hi) accumulate in
+// TMEM in fp32 -- relative error ~1e-6, which the 1e-5 parity budget of the interaction block
+// needs (plain TF32 gives ~1e-3).
 //
-// One CTA = 128 threads = one 128-row tile; it walks its column tiles (BN columns each) and the
-// K chunks (32 floats) synchronously: cooperative global->register->(split)->shared stores,
-// fence.proxy.async, one elected thread issues the MMAs and commits to an mbarrier, then the
-// four warps drain their 32 TMEM lanes with tcgen05.ld and run the epilogue.  Latency is hidden
-// by co-resident CTAs (64 KB shared memory and <= 128 TMEM columns per CTA -> 3 per SM).
+// B is a weight: it is split and laid out ONCE by e3b_gemm_pack into the UMMA canonical K-major /
+// no-swizzle layout, tile by tile, so that the kernel fetches a whole (hi | lo) B chunk with one
+// TMA bulk copy.  A is an activation: converter warps stream it with cp.async (16 B per thread,
+// affine row addressing so the irreps layouts are read in place), split it in registers and
+// write the canonical layout to shared memory.
 //
-// Row addressing of A and C is affine in (r / d, r % d) so that the irreps layouts of the
-// interaction block ([node][component][channel] rows) are read and written in place.
+// One persistent CTA = 10 warps, warp-specialised:
+//   warps 0-3  epilogue   TMEM -> registers (tcgen05.ld) -> epilogue math -> global
+//   warps 4-7  converter  global -(cp.async)-> raw ring -> split hi/lo -> canonical A ring
+//   warp  8    producer   TMA bulk copies of packed B chunks into the B ring
+//   warp  9    MMA        one elected thread issues tcgen05.mma and commits to the mbarriers
+// Three pipelines (mbarrier full/empty pairs): A ring, B ring, two TMEM accumulators.  When the
+// whole K extent of a row tile fits the A ring it stays RESIDENT across the column tiles.
+// The tensor core accumulates with truncation, so an unbroken chain over a long K drifts
+// (1.5e-5 at K = 1920, measured): chains are cut every 64 floats of K and the partial sums are
+// added in fp32 registers by the epilogue warps while the next chain runs in the other buffer.
 #include <cuda_runtime.h>
 #include <stdint.h>
 
@@ -25,40 +32,38 @@ int e3b_fail(int code, const char* fmt, ...);  // e3b200.cu
 
 namespace {
 
-struct GemmArgs {
-  const float* A;
-  const float* B;
-  float* C;
-  const float* aux;
-  int64_t a_s1, a_s2;
-  int64_t ldb;
-  int64_t c_s1, c_s2, c_s3;
-  int64_t aux_ld;
-  int32_t a_d, c_d, aux_d;
-  int32_t M, N, K;
-  int32_t epilogue, V;
-  float alpha;
-};
+constexpr int BM = 128;     // UMMA M
+constexpr int BK = 32;      // floats per K chunk = 4 MMA K-steps of 8 = 8 sixteen-byte columns
+constexpr int KSEG = 2;     // chunks per accumulation chain (64 floats of K)
+constexpr int NTHREADS = 320;
+constexpr int CVT0 = 128;   // first converter thread
+constexpr int MAXG = E3B_GEMM_MAX_GROUP;
 
-constexpr int BM = 128;   // UMMA M
-constexpr int BK = 32;    // floats per K chunk = 4 MMA K-steps of 8
-constexpr int NTHREADS = 128;
+struct Problem {
+  e3b_gemm_problem p;
+  int32_t m_tiles, n_tiles, k_chunks;
+  int32_t gx, gy;        // CTA grid of this problem: row tiles bx, bx+gx, ..; column tiles by, by+gy, ..
+  int32_t cta_begin;     // first CTA (blockIdx.x) of this problem
+  uint64_t a_mul;        // ceil(2^40 / a_d): r / a_d == (r * a_mul) >> 40 for r < 2^31, a_d < 512
+};
+struct Batch {
+  Problem pr[MAXG];
+  int32_t n;
+};
 
 __device__ __forceinline__ uint32_t smem_addr(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
 // UMMA shared-memory descriptor, K-major, SWIZZLE_NONE: core matrix = 8 rows x 16 B (128 B
-// contiguous); LBO = bytes between the two 16-byte K chunks of one MMA, SBO = bytes between
+// contiguous); LBO = bytes between the two 16-byte K columns of one MMA, SBO = bytes between
 // consecutive 8-row groups; both encoded >> 4; bits 46-47 = 1 (Blackwell descriptor version).
 __device__ __forceinline__ uint64_t umma_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
   return (uint64_t)((saddr >> 4) & 0x3FFFu) | ((uint64_t)((lbo_bytes >> 4) & 0x3FFFu) << 16) |
          ((uint64_t)((sbo_bytes >> 4) & 0x3FFFu) << 32) | (1ull << 46);
 }
-
-// instruction descriptor: D = F32, A = B = TF32, both K-major, M = 128, N = BN
+// instruction descriptor: D = F32, A = B = TF32, both K-major, M = 128, N = n
 __host__ __device__ constexpr uint32_t umma_idesc(int n) {
   return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
 }
-
 __device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t idesc, uint32_t accumulate) {
   asm volatile(
       "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
@@ -66,16 +71,19 @@ __device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t da, uint64_t
       ::"r"(tmem_d), "l"(da), "l"(db), "r"(idesc), "r"(accumulate)
       : "memory");
 }
-
 __device__ __forceinline__ void umma_commit(uint64_t* bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_addr(bar)) : "memory");
 }
-
-__device__ __forceinline__ void mbar_init1(uint64_t* bar) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_addr(bar)) : "memory");
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_addr(bar)), "r"(count) : "memory");
 }
-
-__device__ __forceinline__ void mbar_wait_parity(uint64_t* bar, uint32_t parity) {
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_addr(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_addr(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   asm volatile(
       "{\n\t.reg .pred p;\n\t"
       "W_%=:\n\t"
@@ -84,6 +92,18 @@ __device__ __forceinline__ void mbar_wait_parity(uint64_t* bar, uint32_t parity)
       "bra W_%=;\n\t"
       "D_%=:\n\t}" ::"r"(smem_addr(bar)), "r"(parity) : "memory");
 }
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                   smem_addr(dst)), "l"(src), "r"(bytes), "r"(smem_addr(bar)) : "memory");
+}
+// 16-byte asynchronous copy; src_bytes = 0 zero-fills the destination
+__device__ __forceinline__ void cp_async16(void* dst, const void* src, uint32_t src_bytes) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(smem_addr(dst)), "l"(src), "r"(src_bytes) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 
 __device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32]) {
   uint32_t r[32];
@@ -103,12 +123,15 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32]) {
 
 // fp32 -> (tf32 hi, tf32 lo) with round-to-nearest (cvt.rna): hi has its low 13 bits cleared, so
 // the tensor core sees it exactly whether it truncates or rounds; lo = rna(x - hi) (x - hi is
-// exact in fp32).  Rounding (not masking) keeps the residual unbiased -- with truncation the
-// error grows linearly in K.
-__device__ __forceinline__ float rna_tf32(float x) {
+// exact in fp32).  Rounding (not masking) keeps the residual unbiased.
+__host__ __device__ __forceinline__ float rna_tf32(float x) {
+#ifdef __CUDA_ARCH__
   uint32_t u;
   asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(x));
   return __uint_as_float(u);
+#else
+  return x;
+#endif
 }
 __device__ __forceinline__ void split4(const float4 x, float4* hi, float4* lo) {
   hi->x = rna_tf32(x.x); hi->y = rna_tf32(x.y); hi->z = rna_tf32(x.z); hi->w = rna_tf32(x.w);
@@ -116,213 +139,493 @@ __device__ __forceinline__ void split4(const float4 x, float4* hi, float4* lo) {
   lo->z = rna_tf32(x.z - hi->z); lo->w = rna_tf32(x.w - hi->w);
 }
 
-// stage rows x BK fp32 (row pointers via `row_ptr(r)`, nullptr = zero row) into the canonical
-// layout [16-byte chunk c (8)][row][16 B]; lanes take consecutive rows -> conflict-free STS.128
-template <int ROWS, typename RowPtr>
-__device__ __forceinline__ void stage_operand(float* s_hi, float* s_lo, RowPtr row_ptr, int k0, int K) {
-  for (int idx = threadIdx.x; idx < ROWS * (BK / 4); idx += NTHREADS) {
-    const int r = idx % ROWS, c = idx / ROWS;
-    const int k = k0 + 4 * c;
-    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-    const float* p = row_ptr(r);
-    if (p != nullptr && k < K) v = __ldg(reinterpret_cast<const float4*>(p + k));
-    float4 hi, lo;
-    split4(v, &hi, &lo);
-    reinterpret_cast<float4*>(s_hi)[c * ROWS + r] = hi;
-    reinterpret_cast<float4*>(s_lo)[c * ROWS + r] = lo;
+// ShiftedSoftPlus pieces (e3nn nn.FullyConnectedNet activation): ssp(z) = softplus(z) - ln 2
+__device__ __forceinline__ float ssp_f(float z) { return (z > 20.f ? z : log1pf(expf(z))) - 0.6931471805599453f; }
+// d/dz [cst * ssp(z)] expressed through the stored output h = cst * ssp(z):
+// sigmoid(z) = 1 - exp(-softplus(z)) = 1 - 0.5 * exp(-h / cst)
+__device__ __forceinline__ float dssp_from_out(float h, float cst) { return cst * (1.f - 0.5f * expf(-h / cst)); }
+
+template <int BN, int SA, int PRAW, int SB>
+struct Smem {
+  static constexpr int A_STAGE = 2 * BM * BK;      // floats: hi | lo
+  static constexpr int B_STAGE = 2 * BN * BK;
+  static constexpr int RAW_STAGE = BM * BK;
+  static constexpr int EPI_STAGE = 32 * 36;       // per epilogue warp: 32 rows x (32 + 4 pad) floats
+  static constexpr size_t BYTES = (size_t)(SA * A_STAGE + SB * B_STAGE + PRAW * RAW_STAGE + 4 * EPI_STAGE) * 4 + 128 /*align slack*/;
+};
+
+struct EpiCtx {
+  const Problem* P;
+  uint64_t* acc_full;
+  uint64_t* acc_empty;
+  float* stg;            // warp-private staging tile [32][36]
+  uint32_t tmem_base;
+  int bx, by, k_chunks;
+};
+
+template <int EPI> __device__ __forceinline__ float epi_apply(float o, float h, float cst) {
+  if (EPI == 2) return cst * ssp_f(o);
+  if (EPI == 3) return o * dssp_from_out(h, cst);
+  return o;
+}
+
+// Epilogue warps: thread = one accumulator row (TMEM lane).  DENSE outputs (unit column stride,
+// N % 4 == 0) are transposed through a warp-private staging tile so that every store instruction
+// writes whole 128-byte lines (4 rows x 128 B per warp instruction) instead of 32 partial sectors.
+template <int BN, bool MULTI, int EPI, bool DENSE>
+__device__ __forceinline__ void epilogue_role(const EpiCtx& c) {
+  const Problem& P = *c.P;
+  const e3b_gemm_problem& g = P.p;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int n_seg = (c.k_chunks + KSEG - 1) / KSEG;
+  uint32_t acc_it = 0;
+  const uint32_t t_lane = c.tmem_base + ((uint32_t)(warp * 32) << 16);
+  const int t_row = lane >> 3, t_c4 = (lane & 7) * 4;     // transposed role: rows t_row + 4 i, columns t_c4..+3
+  const float alpha = g.alpha, cst = g.act_cst;
+  const bool accumulate = g.accumulate != 0;
+  for (int m = c.bx; m < P.m_tiles; m += P.gx) {
+    const int row = m * BM + tid;
+    const bool row_ok = row < g.M;
+    float* c_row = nullptr;
+    const float* h_row = nullptr;
+    if (row_ok && !DENSE) {
+      c_row = g.C + (int64_t)(row / g.c_d) * g.c_s1 + (int64_t)(row % g.c_d) * g.c_s2;
+      if (EPI == 3) h_row = g.H + (int64_t)row * g.h_ld;
+    }
+    float aux[EPI == 1 ? 32 : 1];
+    if (EPI == 1) {
+#pragma unroll
+      for (int v = 0; v < (EPI == 1 ? 32 : 1); ++v)
+        aux[v] = (row_ok && v < g.V) ? __ldg(g.aux + (int64_t)(row / g.aux_d) * g.aux_ld + v) : 0.f;
+    }
+    // DENSE: rows of this warp's quarter tile handled by this lane after the transposition
+    const int r_base = m * BM + warp * 32 + t_row;
+    for (int n = c.by; n < P.n_tiles; n += P.gy) {
+      const int n0 = n * BN;
+      float racc[MULTI ? BN : 1];
+      if (MULTI) {
+#pragma unroll
+        for (int i = 0; i < (MULTI ? BN : 1); ++i) racc[i] = 0.f;
+      }
+      for (int seg = 0; seg < (MULTI ? n_seg : 1); ++seg, ++acc_it) {
+        const uint32_t buf = acc_it & 1u;
+        mbar_wait(&c.acc_full[buf], (acc_it >> 1) & 1u);
+        tc_fence_after();
+        const bool last = !MULTI || seg == n_seg - 1;
+#pragma unroll
+        for (int cb = 0; cb < BN; cb += 32) {
+          float v[32];
+          tmem_ld32(t_lane + buf * BN + (uint32_t)cb, v);
+          if (MULTI) {
+#pragma unroll
+            for (int i = 0; i < 32; ++i) { racc[(MULTI ? cb : 0) + (MULTI ? i : 0)] += v[i]; v[i] = racc[(MULTI ? cb : 0) + (MULTI ? i : 0)]; }
+          }
+          const int nb = n0 + cb;
+          if (!last || nb >= g.N) continue;
+          if (DENSE) {
+            __syncwarp();
+#pragma unroll
+            for (int i = 0; i < 8; ++i)
+              *reinterpret_cast<float4*>(c.stg + lane * 36 + 4 * i) =
+                  make_float4(alpha * v[4 * i], alpha * v[4 * i + 1], alpha * v[4 * i + 2], alpha * v[4 * i + 3]);
+            __syncwarp();
+            const int col = nb + t_c4;
+            if (col < g.N) {
+              float* dst = g.C + (int64_t)r_base * g.c_s1 + col;
+              const float* hp = EPI == 3 ? g.H + (int64_t)r_base * g.h_ld + col : nullptr;
+#pragma unroll
+              for (int i = 0; i < 8; ++i) {
+                if (r_base + 4 * i < g.M) {
+                  float4 o = *reinterpret_cast<const float4*>(c.stg + (t_row + 4 * i) * 36 + t_c4);
+                  float4 h = make_float4(0.f, 0.f, 0.f, 0.f);
+                  if (EPI == 3) h = __ldg(reinterpret_cast<const float4*>(hp + (int64_t)(4 * i) * g.h_ld));
+                  o.x = epi_apply<EPI>(o.x, h.x, cst); o.y = epi_apply<EPI>(o.y, h.y, cst);
+                  o.z = epi_apply<EPI>(o.z, h.z, cst); o.w = epi_apply<EPI>(o.w, h.w, cst);
+                  float4* d4 = reinterpret_cast<float4*>(dst + (int64_t)(4 * i) * g.c_s1);
+                  if (accumulate) { const float4 old = *d4; o.x += old.x; o.y += old.y; o.z += old.z; o.w += old.w; }
+                  *d4 = o;
+                }
+              }
+            }
+          } else if (EPI == 1) {
+            // weighted reduction over groups of V accumulator columns (self-connection)
+            if (row_ok) {
+              if (g.V == 16) {
+                float s0 = 0.f, s1 = 0.f;
+#pragma unroll
+                for (int t = 0; t < 16; ++t) { s0 = fmaf(aux[EPI == 1 ? t : 0], v[t], s0); s1 = fmaf(aux[EPI == 1 ? t : 0], v[16 + t], s1); }
+                const int oc = nb / 16;
+                float* c0 = c_row + (int64_t)oc * g.c_s3;
+                *c0 = alpha * s0 + (accumulate ? *c0 : 0.f);
+                if ((oc + 1) * 16 < g.N) {
+                  float* c1 = c0 + g.c_s3;
+                  *c1 = alpha * s1 + (accumulate ? *c1 : 0.f);
+                }
+              } else {
+                float s0 = 0.f;
+#pragma unroll
+                for (int t = 0; t < 32; ++t) s0 = fmaf(aux[EPI == 1 ? t : 0], v[t], s0);
+                float* c0 = c_row + (int64_t)(nb / 32) * g.c_s3;
+                *c0 = alpha * s0 + (accumulate ? *c0 : 0.f);
+              }
+            }
+          } else {
+            // generic (strided) output: one scalar store per element
+            if (row_ok) {
+#pragma unroll
+              for (int i = 0; i < 32; ++i)
+                if (nb + i < g.N) {
+                  const float o = epi_apply<EPI>(alpha * v[i], EPI == 3 ? __ldg(h_row + nb + i) : 0.f, cst);
+                  float* cp = c_row + (int64_t)(nb + i) * g.c_s3;
+                  *cp = o + (accumulate ? *cp : 0.f);
+                }
+            }
+          }
+        }
+        tc_fence_before();
+        mbar_arrive(&c.acc_empty[buf]);
+      }
+    }
   }
 }
 
-// MULTI: K is long -> the TMEM accumulation chain is cut every KACC floats and the partial sums
-// are added in fp32 registers (round-to-nearest).  The tensor core accumulates with truncation,
-// so an unbroken chain over K = 1920 drifts by ~1.5e-5 (measured); chains of 64 stay below 2e-6.
-constexpr int KACC = 64;
-
-template <int BN, bool MULTI>
-__global__ void __launch_bounds__(NTHREADS) gemm_tf32x3_kernel(const GemmArgs g) {
-  extern __shared__ __align__(1024) unsigned char smem_raw[];
-  float* sA_hi = reinterpret_cast<float*>(smem_raw);
-  float* sA_lo = sA_hi + BM * BK;
-  float* sB_hi = sA_lo + BM * BK;
-  float* sB_lo = sB_hi + BN * BK;
-  __shared__ uint64_t mma_bar;
+// the tile walk every role repeats:  for (m = bx; m < m_tiles; m += gx) for (n = by; n < n_tiles; n += gy)
+template <int BN, bool MULTI, int SA, int PRAW, int SB>
+__global__ void __launch_bounds__(NTHREADS, 1) gemm_tf32x3_kernel(const __grid_constant__ Batch batch) {
+  using L = Smem<BN, SA, PRAW, SB>;
+  extern __shared__ unsigned char smem_dyn[];
+  float* smem = reinterpret_cast<float*>((reinterpret_cast<uintptr_t>(smem_dyn) + 127) & ~(uintptr_t)127);
+  float* sA = smem;                                   // [SA][hi|lo][c(8)][row(128)][4]
+  float* sB = sA + SA * L::A_STAGE;                   // [SB][hi|lo][c(8)][row(BN)][4]
+  float* sRaw = sB + SB * L::B_STAGE;                 // [PRAW][slot(8)][thread(128)][4]
+  float* sEpi = sRaw + PRAW * L::RAW_STAGE;           // [4 warps][32 rows][36]
+  __shared__ uint64_t a_full[SA], a_empty[SA], b_full[SB], b_empty[SB], acc_full[2], acc_empty[2];
   __shared__ uint32_t tmem_base_smem;
 
-  const int tid = threadIdx.x, warp = tid >> 5;
-  const int m0 = blockIdx.x * BM;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
 
-  if (warp == 0) {  // TMEM allocation is warp-collective; the same warp frees it
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_addr(&tmem_base_smem)), "r"((uint32_t)BN) : "memory");
+  // which problem of the group does this CTA work on
+  int gi = 0;
+#pragma unroll 1
+  for (int i = 1; i < batch.n; ++i)
+    if ((int)blockIdx.x >= batch.pr[i].cta_begin) gi = i;
+  const Problem& P = batch.pr[gi];
+  const e3b_gemm_problem& g = P.p;
+  const int local = (int)blockIdx.x - P.cta_begin;
+  const int bx = local % P.gx, by = local / P.gx;
+  const int k_chunks = P.k_chunks;
+  const bool resident = k_chunks <= SA;
+  const int n_count = by < P.n_tiles ? (P.n_tiles - by + P.gy - 1) / P.gy : 0;   // column tiles of this CTA
+
+  if (warp == 9) {  // TMEM allocation is warp-collective; the same warp frees it
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_addr(&tmem_base_smem)), "r"((uint32_t)(2 * BN)) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
   if (tid == 0) {
-    mbar_init1(&mma_bar);
+    for (int s = 0; s < SA; ++s) { mbar_init(&a_full[s], 128); mbar_init(&a_empty[s], 1); }
+    for (int s = 0; s < SB; ++s) { mbar_init(&b_full[s], 1); mbar_init(&b_empty[s], 1); }
+    for (int s = 0; s < 2; ++s) { mbar_init(&acc_full[s], 1); mbar_init(&acc_empty[s], 128); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  tc_fence_before();
   __syncthreads();
-  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  tc_fence_after();
   const uint32_t tmem_base = tmem_base_smem;
 
-  // this thread's output row (TMEM lane = 32 * warp + lane)
-  const int row = m0 + tid;
-  const bool row_ok = row < g.M;
-  float* c_row = nullptr;
-  if (row_ok) c_row = g.C + (int64_t)(row / g.c_d) * g.c_s1 + (int64_t)(row % g.c_d) * g.c_s2;
-  float aux[32];
-  if (g.epilogue == 1) {
+  if (n_count > 0 && bx < P.m_tiles) {
+    if (warp >= 4 && warp < 8) {
+      // =============================== A converter ===============================
+      // thread -> one 16-byte column `col` of the chunk and the 8 rows row0 + 16 i: a quarter-warp
+      // covers 8 consecutive rows of one column = 128 contiguous bytes of the canonical layout
+      // (conflict-free STS.128) and 64 contiguous bytes of each source row (full sectors).
+      const int ct = tid - CVT0;                 // 0..127
+      const int cw = ct >> 5;
+      const int col = (cw & 1) * 4 + (lane >> 3);
+      const int row0 = 8 * (cw >> 1) + (lane & 7);
+      const int reps = resident ? 1 : n_count;
+      const int m_count = (P.m_tiles - bx + P.gx - 1) / P.gx;
+      const int total = m_count * reps * k_chunks;
+      // issue stream state (runs PRAW - 1 jobs ahead of the conversion)
+      int64_t roff[8];
+      uint32_t rbytes[8];
+      auto load_rows = [&](int m_tile) {
 #pragma unroll
-    for (int v = 0; v < 32; ++v) aux[v] = (row_ok && v < g.V) ? __ldg(g.aux + (int64_t)(row / g.aux_d) * g.aux_ld + v) : 0.f;
+        for (int i = 0; i < 8; ++i) {
+          const int r = m_tile * BM + row0 + 16 * i;
+          const int q = (int)(((uint64_t)(uint32_t)r * P.a_mul) >> 40);
+          roff[i] = (int64_t)q * g.a_s1 + (int64_t)(r - q * g.a_d) * g.a_s2;
+          rbytes[i] = r < g.M ? 16u : 0u;
+          if (r >= g.M) roff[i] = 0;
+        }
+      };
+      int i_m = bx, i_rep = 0, i_kc = 0, i_slot = 0, i_left = total;
+      load_rows(i_m);
+      auto issue = [&]() {
+        if (i_left > 0) {
+          --i_left;
+          const int k = i_kc * BK + col * 4;
+          const bool kok = k < g.K;
+          float* dst = sRaw + (size_t)i_slot * L::RAW_STAGE + ct * 4;
+#pragma unroll
+          for (int i = 0; i < 8; ++i)
+            cp_async16(dst + i * (128 * 4), g.A + roff[i] + (kok ? k : 0), kok ? rbytes[i] : 0u);
+          if (++i_kc == k_chunks) {
+            i_kc = 0;
+            if (++i_rep == reps) {
+              i_rep = 0;
+              i_m += P.gx;
+              if (i_left > 0) load_rows(i_m);
+            }
+          }
+        }
+        if (++i_slot == PRAW) i_slot = 0;
+        cp_async_commit();
+      };
+#pragma unroll 1
+      for (int j = 0; j < PRAW - 1; ++j) issue();
+      int st = 0, slot = 0;
+      uint32_t par = 1;                          // parity to wait on a_empty: first pass through the ring is free
+#pragma unroll 1
+      for (int j = 0; j < total; ++j) {
+        issue();
+        cp_async_wait<PRAW - 1>();               // this thread's copies of job j have landed
+        mbar_wait(&a_empty[st], par);
+        const float4* raw = reinterpret_cast<const float4*>(sRaw + (size_t)slot * L::RAW_STAGE) + ct;
+        float4* hi = reinterpret_cast<float4*>(sA + (size_t)st * L::A_STAGE) + col * BM + row0;
+        float4* lo = hi + BM * (BK / 4);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          float4 h, l;
+          split4(raw[i * 128], &h, &l);
+          hi[16 * i] = h;
+          lo[16 * i] = l;
+        }
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy stores -> tensor-core reads
+        mbar_arrive(&a_full[st]);
+        if (++st == SA) { st = 0; par ^= 1u; }
+        if (++slot == PRAW) slot = 0;
+      }
+      cp_async_wait<0>();
+    } else if (warp == 8) {
+      // =============================== B producer (TMA) ===============================
+      if (lane == 0) {
+        uint32_t it = 0;
+        constexpr uint32_t bytes = (uint32_t)L::B_STAGE * 4u;
+        for (int m = bx; m < P.m_tiles; m += P.gx)
+          for (int n = by; n < P.n_tiles; n += P.gy)
+            for (int kc = 0; kc < k_chunks; ++kc, ++it) {
+              const int st = it % SB;
+              mbar_wait(&b_empty[st], ((it / SB) & 1u) ^ 1u);
+              mbar_expect_tx(&b_full[st], bytes);
+              bulk_g2s(sB + (size_t)st * L::B_STAGE, g.B_packed + ((size_t)n * k_chunks + kc) * L::B_STAGE, bytes, &b_full[st]);
+            }
+      }
+    } else if (warp == 9) {
+      // =============================== MMA issuer ===============================
+      if (lane == 0) {
+        const uint32_t idesc = umma_idesc(BN);
+        uint32_t a_it = 0, b_it = 0, acc_it = 0;
+        for (int m = bx; m < P.m_tiles; m += P.gx) {
+          int ni = 0;
+          for (int n = by; n < P.n_tiles; n += P.gy, ++ni) {
+            uint32_t buf = 0;
+            for (int kc = 0; kc < k_chunks; ++kc) {
+              const bool seg_first = (kc % KSEG) == 0;
+              if (seg_first) {
+                buf = acc_it & 1u;
+                mbar_wait(&acc_empty[buf], ((acc_it >> 1) & 1u) ^ 1u);
+              }
+              const uint32_t a_idx = resident ? a_it + (uint32_t)kc : a_it;
+              const int sa = a_idx % SA, sb = b_it % SB;
+              if (!resident || ni == 0) mbar_wait(&a_full[sa], (a_idx / SA) & 1u);
+              mbar_wait(&b_full[sb], (b_it / SB) & 1u);
+              tc_fence_after();
+              const uint32_t a_hi = smem_addr(sA + (size_t)sa * L::A_STAGE), a_lo = a_hi + BM * BK * 4;
+              const uint32_t b_hi = smem_addr(sB + (size_t)sb * L::B_STAGE), b_lo = b_hi + BN * BK * 4;
+              const uint32_t d = tmem_base + buf * BN;
+#pragma unroll
+              for (int j = 0; j < BK / 8; ++j) {   // one MMA covers K = 8 tf32 = two 16-byte columns
+                const uint32_t offA = (uint32_t)(2 * j) * BM * 16, offB = (uint32_t)(2 * j) * BN * 16;
+                const uint64_t dAh = umma_desc(a_hi + offA, BM * 16, 128), dAl = umma_desc(a_lo + offA, BM * 16, 128);
+                const uint64_t dBh = umma_desc(b_hi + offB, BN * 16, 128), dBl = umma_desc(b_lo + offB, BN * 16, 128);
+                umma_tf32(d, dAl, dBh, idesc, (seg_first && j == 0) ? 0u : 1u);
+                umma_tf32(d, dAh, dBl, idesc, 1u);
+                umma_tf32(d, dAh, dBh, idesc, 1u);
+              }
+              umma_commit(&b_empty[sb]);
+              if (!resident || ni == n_count - 1) umma_commit(&a_empty[sa]);
+              if ((kc % KSEG) == KSEG - 1 || kc == k_chunks - 1) { umma_commit(&acc_full[buf]); ++acc_it; }
+              ++b_it;
+              if (!resident) ++a_it;
+            }
+          }
+          if (resident) a_it += (uint32_t)k_chunks;
+        }
+      }
+    } else if (warp < 4) {
+      // =============================== epilogue ===============================
+      const bool dense = g.c_s3 == 1 && g.c_d == 1 && (g.c_s1 & 3) == 0 && (g.N & 3) == 0 &&
+                         (reinterpret_cast<uintptr_t>(g.C) & 15) == 0 && (g.epilogue != 3 || (g.h_ld & 3) == 0);
+      EpiCtx c{&P, acc_full, acc_empty, sEpi + warp * L::EPI_STAGE, tmem_base, bx, by, k_chunks};
+      if (g.epilogue == 1) epilogue_role<BN, MULTI, 1, false>(c);
+      else if (g.epilogue == 0) { if (dense) epilogue_role<BN, MULTI, 0, true>(c); else epilogue_role<BN, MULTI, 0, false>(c); }
+      else if (g.epilogue == 2) { if (dense) epilogue_role<BN, MULTI, 2, true>(c); else epilogue_role<BN, MULTI, 2, false>(c); }
+      else { if (dense) epilogue_role<BN, MULTI, 3, true>(c); else epilogue_role<BN, MULTI, 3, false>(c); }
+    }
   }
 
-  const uint32_t idesc = umma_idesc(BN);
-  uint32_t phase = 0;
-  const int n_tiles = (g.N + BN - 1) / BN;
-  const int n_chunks = (g.K + BK - 1) / BK;
-
-  const uint32_t t_row = tmem_base + ((uint32_t)(warp * 32) << 16);
-  for (int tile = blockIdx.y; tile < n_tiles; tile += gridDim.y) {
-    const int n0 = tile * BN;
-    float racc[MULTI ? BN : 1];
-    if (MULTI) {
-#pragma unroll
-      for (int i = 0; i < (MULTI ? BN : 1); ++i) racc[i] = 0.f;
-    }
-    for (int kc = 0; kc < n_chunks; ++kc) {
-      const int k0 = kc * BK;
-      stage_operand<BM>(sA_hi, sA_lo, [&](int r) -> const float* {
-        const int rr = m0 + r;
-        return rr < g.M ? g.A + (int64_t)(rr / g.a_d) * g.a_s1 + (int64_t)(rr % g.a_d) * g.a_s2 : nullptr;
-      }, k0, g.K);
-      stage_operand<BN>(sB_hi, sB_lo, [&](int r) -> const float* {
-        const int nn = n0 + r;
-        return nn < g.N ? g.B + (int64_t)nn * g.ldb : nullptr;
-      }, k0, g.K);
-      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy stores -> tensor-core reads
-      __syncthreads();
-      if (tid == 0) {
-        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        const uint32_t a_hi = smem_addr(sA_hi), a_lo = smem_addr(sA_lo), b_hi = smem_addr(sB_hi), b_lo = smem_addr(sB_lo);
-#pragma unroll
-        for (int j = 0; j < BK / 8; ++j) {   // one MMA covers K = 8 tf32 = two 16-byte chunks
-          const uint32_t offA = (uint32_t)(2 * j) * BM * 16, offB = (uint32_t)(2 * j) * BN * 16;
-          const uint64_t dAh = umma_desc(a_hi + offA, BM * 16, 128), dAl = umma_desc(a_lo + offA, BM * 16, 128);
-          const uint64_t dBh = umma_desc(b_hi + offB, BN * 16, 128), dBl = umma_desc(b_lo + offB, BN * 16, 128);
-          const bool first = MULTI ? ((kc % (KACC / BK)) | j) == 0 : (kc | j) == 0;
-          umma_tf32(tmem_base, dAl, dBh, idesc, first ? 0u : 1u);
-          umma_tf32(tmem_base, dAh, dBl, idesc, 1u);
-          umma_tf32(tmem_base, dAh, dBh, idesc, 1u);
-        }
-        umma_commit(&mma_bar);   // arrives when the MMAs above have finished reading smem / writing TMEM
-      }
-      mbar_wait_parity(&mma_bar, phase);
-      phase ^= 1u;
-      if (MULTI && ((kc % (KACC / BK)) == KACC / BK - 1 || kc == n_chunks - 1)) {
-        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-#pragma unroll
-        for (int cb = 0; cb < (MULTI ? BN : 0); cb += 32) {
-          float v[32];
-          tmem_ld32(t_row + (uint32_t)cb, v);
-#pragma unroll
-          for (int i = 0; i < 32; ++i) racc[cb + i] += v[i];
-        }
-        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-      }
-    }
-    // ---- epilogue: TMEM (or the register partial sums) -> global
-    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-#pragma unroll
-    for (int cb = 0; cb < BN; cb += 32) {
-      float v[32];
-      if (MULTI) {
-#pragma unroll
-        for (int i = 0; i < 32; ++i) v[i] = racc[(MULTI ? cb : 0) + (MULTI ? i : 0)];
-      } else {
-        tmem_ld32(t_row + (uint32_t)cb, v);
-      }
-      if (!row_ok) continue;
-      if (g.epilogue == 0) {
-        const int nb = n0 + cb;
-        if (g.c_s3 == 1 && nb + 32 <= g.N && ((reinterpret_cast<uintptr_t>(c_row + nb) & 15) == 0)) {
-#pragma unroll
-          for (int i = 0; i < 32; i += 4)
-            *reinterpret_cast<float4*>(c_row + nb + i) =
-                make_float4(g.alpha * v[i], g.alpha * v[i + 1], g.alpha * v[i + 2], g.alpha * v[i + 3]);
-        } else {
-#pragma unroll
-          for (int i = 0; i < 32; ++i)
-            if (nb + i < g.N) c_row[(int64_t)(nb + i) * g.c_s3] = g.alpha * v[i];
-        }
-      } else {
-        // weighted reduction over groups of V accumulator columns: out col = (n0 + cb) / V (+1)
-        if (g.V == 16) {
-          float s0 = 0.f, s1 = 0.f;
-#pragma unroll
-          for (int t = 0; t < 16; ++t) { s0 = fmaf(aux[t], v[t], s0); s1 = fmaf(aux[t], v[16 + t], s1); }
-          const int oc = (n0 + cb) / 16;
-          if (oc * 16 < g.N) c_row[(int64_t)oc * g.c_s3] = g.alpha * s0;
-          if ((oc + 1) * 16 < g.N) c_row[(int64_t)(oc + 1) * g.c_s3] = g.alpha * s1;
-        } else {
-          float s0 = 0.f;
-#pragma unroll
-          for (int t = 0; t < 32; ++t) s0 = fmaf(aux[t], v[t], s0);
-          const int oc = (n0 + cb) / 32;
-          if (oc * 32 < g.N) c_row[(int64_t)oc * g.c_s3] = g.alpha * s0;
-        }
-      }
-    }
-    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-    __syncthreads();   // all TMEM reads retired before the next tile's MMAs overwrite the accumulator
-  }
-
-  if (warp == 0) {
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)BN) : "memory");
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 9) {
+    __syncwarp();
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)(2 * BN)) : "memory");
   }
 }
 
-template <int BN, bool MULTI>
-int launch(const GemmArgs& g, cudaStream_t st) {
-  const size_t smem = (size_t)(2 * BM * BK + 2 * BN * BK) * sizeof(float);
+// ---- packing: weight B[n, k] (n = n1 * d + n2 at src + n1 * s1 + n2 * s2 + k * sk) -> tiles
+// [n_tile][k_chunk][hi | lo][c (8)][row (BN)][4], zero padded
+struct PackBatch {
+  e3b_gemm_pack_desc d[MAXG];
+  int32_t bn[MAXG];
+  int64_t begin[MAXG + 1];   // first float4 slot of each descriptor in the flat index space
+  int32_t n;
+};
+
+__global__ void gemm_pack_kernel(const __grid_constant__ PackBatch pb) {
+  const int64_t total = pb.begin[pb.n];
+  for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (int64_t)gridDim.x * blockDim.x) {
+    int gi = 0;
+    for (int i = 1; i < pb.n; ++i)
+      if (idx >= pb.begin[i]) gi = i;
+    const e3b_gemm_pack_desc& d = pb.d[gi];
+    const int BN = pb.bn[gi];
+    const int64_t q = idx - pb.begin[gi];          // float4 slot: [n_tile][k_chunk][c][row]
+    const int k_chunks = (d.K + BK - 1) / BK;
+    const int row = (int)(q % BN);
+    const int c = (int)((q / BN) % 8);
+    const int kc = (int)((q / (BN * 8)) % k_chunks);
+    const int nt = (int)(q / ((int64_t)BN * 8 * k_chunks));
+    const int n = nt * BN + row;
+    float x[4];
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const int k = kc * BK + c * 4 + e;
+      x[e] = (n < d.N && k < d.K) ? __ldg(d.src + (int64_t)(n / d.d) * d.s1 + (int64_t)(n % d.d) * d.s2 + (int64_t)k * d.sk) : 0.f;
+    }
+    float4 hi, lo;
+    split4(make_float4(x[0], x[1], x[2], x[3]), &hi, &lo);
+    float4* tile = reinterpret_cast<float4*>(d.dst) + ((int64_t)nt * k_chunks + kc) * (2 * BN * 8);
+    tile[c * BN + row] = hi;
+    tile[BN * 8 + c * BN + row] = lo;
+  }
+}
+
+template <int BN, bool MULTI, int SA, int PRAW, int SB>
+cudaError_t launch(const Batch& b, int ctas, cudaStream_t st) {
+  using L = Smem<BN, SA, PRAW, SB>;
   static bool attr_set = false;
   if (!attr_set) {
-    cudaFuncSetAttribute(gemm_tf32x3_kernel<BN, MULTI>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaError_t e = cudaFuncSetAttribute(gemm_tf32x3_kernel<BN, MULTI, SA, PRAW, SB>,
+                                         cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L::BYTES);
+    if (e != cudaSuccess) return e;
     attr_set = true;
   }
-  const int m_tiles = (g.M + BM - 1) / BM;
-  const int n_tiles = (g.N + BN - 1) / BN;
-  // enough CTAs to fill the machine: split the column tiles when there are few row tiles
-  int ny = 1;
-  while (m_tiles * ny < 3 * 148 && ny < n_tiles) ++ny;
-  dim3 grid((unsigned)m_tiles, (unsigned)ny);
-  gemm_tf32x3_kernel<BN, MULTI><<<grid, NTHREADS, smem, st>>>(g);
-  return 0;
+  gemm_tf32x3_kernel<BN, MULTI, SA, PRAW, SB><<<ctas, NTHREADS, L::BYTES, st>>>(b);
+  return cudaGetLastError();
 }
+
+int tile_n(int N, int K) { return (K <= KSEG * BK && N > 64) ? 128 : 64; }
 
 }  // namespace
 
-extern "C" int e3b_gemm_tf32x3(const float* A, int64_t a_s1, int64_t a_s2, int32_t a_d, const float* B, int64_t ldb,
-                               float* C, int64_t c_s1, int64_t c_s2, int32_t c_d, int64_t c_s3, int32_t M, int32_t N,
-                               int32_t K, float alpha, int32_t epilogue, const float* aux, int64_t aux_ld,
-                               int32_t aux_d, int32_t V, void* stream) {
-  if (M == 0 || N == 0) return E3B_OK;
-  if (!A || !B || !C || M < 0 || N < 0 || K <= 0 || a_d <= 0 || c_d <= 0)
-    return e3b_fail(E3B_ERR_INVALID, "gemm_tf32x3: bad argument");
-  if ((K & 3) || (a_s1 & 3) || (a_s2 & 3) || (ldb & 3) || (reinterpret_cast<uintptr_t>(A) & 15) ||
-      (reinterpret_cast<uintptr_t>(B) & 15))
-    return e3b_fail(E3B_ERR_UNSUPPORTED, "gemm_tf32x3: K, row strides and bases must be multiples of 4 floats (16 B)");
-  if (epilogue == 1 && (!aux || (V != 16 && V != 32) || aux_d <= 0 || (N % V) != 0))
-    return e3b_fail(E3B_ERR_INVALID, "gemm_tf32x3: reduce epilogue needs aux, V in {16, 32} and N %% V == 0");
-  if (epilogue != 0 && epilogue != 1) return e3b_fail(E3B_ERR_INVALID, "gemm_tf32x3: unknown epilogue %d", epilogue);
-  GemmArgs g;
-  g.A = A; g.B = B; g.C = C; g.aux = aux;
-  g.a_s1 = a_s1; g.a_s2 = a_s2; g.a_d = a_d; g.ldb = ldb;
-  g.c_s1 = c_s1; g.c_s2 = c_s2; g.c_d = c_d; g.c_s3 = c_s3;
-  g.aux_ld = aux_ld; g.aux_d = aux_d > 0 ? aux_d : 1;
-  g.M = M; g.N = N; g.K = K; g.epilogue = epilogue; g.V = V > 0 ? V : 32; g.alpha = alpha;
-  if (K > KACC) launch<64, true>(g, (cudaStream_t)stream);        // long K: 64-column tiles, register partial sums
-  else if (N <= 64) launch<64, false>(g, (cudaStream_t)stream);
-  else launch<128, false>(g, (cudaStream_t)stream);
+extern "C" int e3b_gemm_tile_n(int32_t N, int32_t K) { return tile_n(N, K); }
+
+extern "C" int64_t e3b_gemm_packed_floats(int32_t N, int32_t K) {
+  const int bn = tile_n(N, K);
+  return (int64_t)((N + bn - 1) / bn) * ((K + BK - 1) / BK) * 2 * bn * BK;
+}
+
+extern "C" int e3b_gemm_pack(const e3b_gemm_pack_desc* descs, int32_t n, void* stream) {
+  if (n <= 0) return E3B_OK;
+  if (!descs || n > MAXG) return e3b_fail(E3B_ERR_INVALID, "gemm_pack: 1..%d descriptors", MAXG);
+  PackBatch pb;
+  pb.n = n;
+  pb.begin[0] = 0;
+  for (int i = 0; i < n; ++i) {
+    const e3b_gemm_pack_desc& d = descs[i];
+    if (!d.src || !d.dst || d.N <= 0 || d.K <= 0 || d.d <= 0) return e3b_fail(E3B_ERR_INVALID, "gemm_pack: bad descriptor %d", i);
+    if (reinterpret_cast<uintptr_t>(d.dst) & 127) return e3b_fail(E3B_ERR_INVALID, "gemm_pack: dst must be 128-byte aligned");
+    pb.d[i] = d;
+    pb.bn[i] = tile_n(d.N, d.K);
+    pb.begin[i + 1] = pb.begin[i] + e3b_gemm_packed_floats(d.N, d.K) / 8;   // one float4 slot feeds hi and lo
+  }
+  const int64_t total = pb.begin[n];
+  const int blocks = (int)((total + 255) / 256 < 148 * 8 ? (total + 255) / 256 : 148 * 8);
+  gemm_pack_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(pb);
   cudaError_t e = cudaGetLastError();
-  if (e != cudaSuccess) return e3b_fail(E3B_ERR_CUDA, "gemm_tf32x3: %s", cudaGetErrorString(e));
+  if (e != cudaSuccess) return e3b_fail(E3B_ERR_CUDA, "gemm_pack: %s", cudaGetErrorString(e));
+  return E3B_OK;
+}
+
+extern "C" int e3b_gemm_run(const e3b_gemm_problem* problems, int32_t n, void* stream) {
+  if (n <= 0) return E3B_OK;
+  if (!problems || n > MAXG) return e3b_fail(E3B_ERR_INVALID, "gemm_run: 1..%d problems per launch", MAXG);
+  Batch b;
+  b.n = 0;
+  int bn = 0;
+  bool multi = false;
+  double work[MAXG], total_work = 0;
+  for (int i = 0; i < n; ++i) {
+    const e3b_gemm_problem& p = problems[i];
+    if (p.M == 0 || p.N == 0) continue;
+    if (!p.A || !p.B_packed || !p.C || p.M < 0 || p.N < 0 || p.K <= 0 || p.a_d <= 0 || p.c_d <= 0)
+      return e3b_fail(E3B_ERR_INVALID, "gemm_run: bad argument in problem %d", i);
+    if ((p.K & 3) || (p.a_s1 & 3) || (p.a_s2 & 3) || (reinterpret_cast<uintptr_t>(p.A) & 15) ||
+        (reinterpret_cast<uintptr_t>(p.B_packed) & 127))
+      return e3b_fail(E3B_ERR_UNSUPPORTED, "gemm_run: K, the row strides and the base of A must be multiples of 4 floats");
+    if (p.epilogue < 0 || p.epilogue > 3) return e3b_fail(E3B_ERR_INVALID, "gemm_run: unknown epilogue %d", p.epilogue);
+    if (p.epilogue == 1 && (!p.aux || (p.V != 16 && p.V != 32) || p.aux_d <= 0 || (p.N % p.V) != 0))
+      return e3b_fail(E3B_ERR_INVALID, "gemm_run: reduce epilogue needs aux, V in {16, 32} and N %% V == 0");
+    if (p.epilogue == 3 && !p.H) return e3b_fail(E3B_ERR_INVALID, "gemm_run: epilogue 3 needs H");
+    const int t = tile_n(p.N, p.K);
+    const bool mu = p.K > KSEG * BK;
+    if (b.n == 0) { bn = t; multi = mu; }
+    else if (bn != t || multi != mu)
+      return e3b_fail(E3B_ERR_UNSUPPORTED, "gemm_run: the problems of one launch must share the tile shape "
+                      "(K <= 64 or not; N <= 64 or not)");
+    Problem& P = b.pr[b.n];
+    P.p = p;
+    P.m_tiles = (p.M + BM - 1) / BM;
+    P.n_tiles = (p.N + t - 1) / t;
+    P.k_chunks = (p.K + BK - 1) / BK;
+    if (p.a_d >= 512) return e3b_fail(E3B_ERR_UNSUPPORTED, "gemm_run: a_d must be < 512");
+    P.a_mul = ((1ull << 40) + (uint64_t)p.a_d - 1) / (uint64_t)p.a_d;
+    work[b.n] = (double)P.m_tiles * P.n_tiles * (P.k_chunks + 2);
+    total_work += work[b.n];
+    ++b.n;
+  }
+  if (b.n == 0) return E3B_OK;
+  // CTAs per problem proportional to its work; one CTA per SM is resident (persistent tile walk)
+  const int target = b.n == 1 ? 148 : 296;
+  int ctas = 0;
+  for (int i = 0; i < b.n; ++i) {
+    Problem& P = b.pr[i];
+    int64_t want = (int64_t)(target * work[i] / total_work + 0.5);
+    const int64_t tiles = (int64_t)P.m_tiles * P.n_tiles;
+    if (want < 1) want = 1;
+    if (want > tiles) want = tiles;
+    P.gx = (int)(want < P.m_tiles ? want : P.m_tiles);
+    P.gy = (int)(want / P.gx);
+    if (P.gy < 1) P.gy = 1;
+    if (P.gy > P.n_tiles) P.gy = P.n_tiles;
+    P.cta_begin = ctas;
+    ctas += P.gx * P.gy;
+  }
+  cudaError_t e;
+  if (multi) e = launch<64, true, 3, 3, 4>(b, ctas, (cudaStream_t)stream);
+  else if (bn == 64) e = launch<64, false, 3, 3, 4>(b, ctas, (cudaStream_t)stream);
+  else e = launch<128, false, 4, 1, 2>(b, ctas, (cudaStream_t)stream);
+  if (e != cudaSuccess) return e3b_fail(E3B_ERR_CUDA, "gemm_run: %s", cudaGetErrorString(e));
   return E3B_OK;
 }

@@ -32,10 +32,25 @@ class GateDesc(ctypes.Structure):
                 ("gate_act", c_i32 * E3B_MAX_BLOCKS), ("gate_cst", c_f64 * E3B_MAX_BLOCKS)]
 
 
+class GemmProblem(ctypes.Structure):
+    _fields_ = [("A", c_vp), ("a_s1", c_i64), ("a_s2", c_i64), ("a_d", c_i32), ("B_packed", c_vp), ("C", c_vp),
+                ("c_s1", c_i64), ("c_s2", c_i64), ("c_s3", c_i64), ("c_d", c_i32), ("aux", c_vp), ("aux_ld", c_i64),
+                ("aux_d", c_i32), ("V", c_i32), ("H", c_vp), ("h_ld", c_i64), ("M", c_i32), ("N", c_i32), ("K", c_i32),
+                ("epilogue", c_i32), ("accumulate", c_i32), ("alpha", c_f32), ("act_cst", c_f32)]
+
+
+class GemmPackDesc(ctypes.Structure):
+    _fields_ = [("src", c_vp), ("s1", c_i64), ("s2", c_i64), ("sk", c_i64), ("d", c_i32), ("N", c_i32), ("K", c_i32),
+                ("dst", c_vp)]
+
+
+E3B_GEMM_MAX_GROUP = 8
+
 # name -> (restype, argtypes); must list EVERY symbol include/e3b200.h declares
 SIGNATURES = {
     "e3b_abi_version": (c_int, []),
     "e3b_last_error": (ctypes.c_char_p, []),
+    "e3b_struct_size": (c_i64, [c_int]),
     "e3b_radius_graph_count": (c_int, [c_vp, c_i64, c_vp, c_i32, c_i64, c_f32, c_vp, c_vp]),
     "e3b_radius_graph_fill": (c_int, [c_vp, c_i64, c_vp, c_i32, c_i64, c_f32, c_vp, c_i64, c_vp, c_vp, c_vp]),
     "e3b_csr_fill": (c_int, [c_vp, c_i64, c_i64, c_int, c_vp, c_vp, c_vp, c_vp]),
@@ -55,8 +70,10 @@ SIGNATURES = {
     "e3b_segment_sum": (c_int, [c_int, c_vp, c_i64, c_vp, c_vp, c_i64, c_vp, c_vp]),
     "e3b_gate_fwd": (c_int, [ctypes.POINTER(GateDesc), c_int, c_vp, c_i64, c_vp, c_vp]),
     "e3b_gate_bwd": (c_int, [ctypes.POINTER(GateDesc), c_int, c_vp, c_vp, c_i64, c_vp, c_vp]),
-    "e3b_gemm_tf32x3": (c_int, [c_vp, c_i64, c_i64, c_i32, c_vp, c_i64, c_vp, c_i64, c_i64, c_i32, c_i64, c_i32, c_i32,
-                                c_i32, c_f32, c_i32, c_vp, c_i64, c_i32, c_i32, c_vp]),
+    "e3b_gemm_tile_n": (c_int, [c_i32, c_i32]),
+    "e3b_gemm_packed_floats": (c_i64, [c_i32, c_i32]),
+    "e3b_gemm_pack": (c_int, [ctypes.POINTER(GemmPackDesc), c_i32, c_vp]),
+    "e3b_gemm_run": (c_int, [ctypes.POINTER(GemmProblem), c_i32, c_vp]),
     "e3b_layout_convert": (c_int, [c_int, c_vp, c_i64, c_i32, c_vp, c_vp, c_int, c_vp, c_vp]),
 }
 
@@ -78,6 +95,9 @@ def load():
             fn.argtypes = args
         if lib.e3b_abi_version() != 1:
             raise RuntimeError("libe3b200.so ABI version mismatch")
+        for which, st in enumerate((TpDesc, GateDesc, GemmProblem, GemmPackDesc)):
+            if lib.e3b_struct_size(which) != ctypes.sizeof(st):
+                raise RuntimeError(f"libe3b200.so struct layout mismatch for {st.__name__}")
         _lib = lib
     return _lib
 

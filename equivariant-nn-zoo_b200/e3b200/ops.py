@@ -391,26 +391,92 @@ def layout_convert(x, irreps, to_imu):
 
 
 # ------------------------------------------------------------------------------------------
-def gemm_tf32x3(A, B, C, M, N, K, a_rows=None, c_rows=None, c_col_stride=1, alpha=1.0, reduce_aux=None, aux_d=1):
-    """C[r, n] = alpha * sum_k A[r, k] B[n, k] on the tcgen05 tensor cores (3xTF32, fp32 accumulate).
+class PackedWeight:
+    """A weight in the form the tcgen05 GEMM consumes (TF32 hi/lo split, UMMA canonical tiles)."""
 
-    A, B, C are fp32 CUDA tensors used as raw storage: ``a_rows`` / ``c_rows`` = (s1, s2, d) give the
-    affine row addressing  base + (r // d) * s1 + (r % d) * s2  (default: dense rows of width K / N).
-    B is [N, K] row-major (row stride = B.stride(0)).  With ``reduce_aux`` ([*, V], V in {16, 32}) the
-    epilogue contracts every group of V accumulator columns with aux[r // aux_d] (self-connection)."""
+    def __init__(self, N, K, device):
+        lib = _lib.load()
+        self.N, self.K = int(N), int(K)
+        self.tile_n = lib.e3b_gemm_tile_n(self.N, self.K)
+        self.buf = torch.empty(lib.e3b_gemm_packed_floats(self.N, self.K), dtype=torch.float32, device=device)
+
+
+def gemm_pack(views):
+    """views: list of (src fp32 CUDA tensor, element offset, s1, s2, sk, d, N, K): element (n, k),
+    n = n1 * d + n2, is src.flat[offset + n1 * s1 + n2 * s2 + k * sk].  -> list of PackedWeight
+    (one kernel launch per E3B_GEMM_MAX_GROUP views)."""
     lib = _lib.load()
+    out = []
+    for lo in range(0, len(views), _lib.E3B_GEMM_MAX_GROUP):
+        chunk = views[lo:lo + _lib.E3B_GEMM_MAX_GROUP]
+        descs = (_lib.GemmPackDesc * len(chunk))()
+        for i, (src, off, s1, s2, sk, d, N, K) in enumerate(chunk):
+            require_cuda(src)
+            assert src.dtype == torch.float32
+            pw = PackedWeight(N, K, src.device)
+            out.append(pw)
+            descs[i].src, descs[i].dst = src.data_ptr() + 4 * off, pw.buf.data_ptr()
+            descs[i].s1, descs[i].s2, descs[i].sk, descs[i].d, descs[i].N, descs[i].K = s1, s2, sk, d, N, K
+        check(lib.e3b_gemm_pack(descs, len(chunk), stream()))
+        count_launch()
+    return out
+
+
+def gemm_problem(A, Bp, C, M, a_off=0, a_rows=None, c_off=0, c_rows=None, c_col_stride=1, alpha=1.0, epilogue=0,
+                 accumulate=False, aux=None, aux_d=1, H=None, act_cst=1.0):
+    """One problem of a grouped launch: C[r, n] = epilogue(sum_k A[r, k] B[n, k]).  A / C are fp32 CUDA
+    tensors used as raw storage (element offsets a_off / c_off); ``a_rows`` / ``c_rows`` = (s1, s2, d)
+    give the affine row addressing base + (r // d) * s1 + (r % d) * s2 (default: dense rows)."""
+    N, K = Bp.N, Bp.K
+    g = _lib.GemmProblem()
+    a_s1, a_s2, a_d = a_rows if a_rows is not None else (K, 0, 1)
+    n_out = N if epilogue != 1 else N // aux.shape[1]
+    c_s1, c_s2, c_d = c_rows if c_rows is not None else (n_out * c_col_stride, 0, 1)
+    g.A, g.a_s1, g.a_s2, g.a_d = A.data_ptr() + 4 * a_off, a_s1, a_s2, a_d
+    g.B_packed = Bp.buf.data_ptr()
+    g.C, g.c_s1, g.c_s2, g.c_s3, g.c_d = C.data_ptr() + 4 * c_off, c_s1, c_s2, c_col_stride, c_d
+    if aux is not None:
+        assert aux.is_contiguous() and aux.dtype == torch.float32
+        g.aux, g.aux_ld, g.aux_d, g.V = aux.data_ptr(), aux.stride(0), aux_d, aux.shape[1]
+    else:
+        g.aux, g.aux_ld, g.aux_d, g.V = None, 0, 1, 0
+    if H is not None:
+        assert H.dtype == torch.float32 and H.stride(1) == 1
+        g.H, g.h_ld = H.data_ptr(), H.stride(0)
+    else:
+        g.H, g.h_ld = None, 0
+    g.M, g.N, g.K = M, N, K
+    g.epilogue, g.accumulate, g.alpha, g.act_cst = epilogue, int(bool(accumulate)), float(alpha), float(act_cst)
+    return g
+
+
+def gemm_run(problems):
+    """launches the problems (built by gemm_problem) grouped by tile shape, <= 8 per kernel"""
+    lib = _lib.load()
+    classes = {}
+    for g in problems:
+        if g.M == 0 or g.N == 0:
+            continue
+        classes.setdefault((g.K <= 64, lib.e3b_gemm_tile_n(g.N, g.K)), []).append(g)
+    for group in classes.values():
+        for lo in range(0, len(group), _lib.E3B_GEMM_MAX_GROUP):
+            chunk = group[lo:lo + _lib.E3B_GEMM_MAX_GROUP]
+            arr = (_lib.GemmProblem * len(chunk))(*chunk)
+            check(lib.e3b_gemm_run(arr, len(chunk), stream()))
+            count_launch()
+
+
+def gemm_tf32x3(A, B, C, M, N, K, a_rows=None, c_rows=None, c_col_stride=1, alpha=1.0, reduce_aux=None, aux_d=1,
+                epilogue=None, H=None, act_cst=1.0, accumulate=False):
+    """C[r, n] = alpha * sum_k A[r, k] B[n, k] on the tcgen05 tensor cores (3xTF32, fp32 accumulate);
+    B is [N, K] (row stride B.stride(0)) and is packed here -- convenience form of
+    gemm_pack + gemm_problem + gemm_run.  With ``reduce_aux`` ([*, V], V in {16, 32}) the epilogue
+    contracts every group of V accumulator columns with aux[r // aux_d] (self-connection)."""
     require_cuda(A, B, C)
     assert A.dtype == B.dtype == C.dtype == torch.float32
-    a_s1, a_s2, a_d = a_rows if a_rows is not None else (K, 0, 1)
-    n_out = N if reduce_aux is None else N // reduce_aux.shape[1]
-    c_s1, c_s2, c_d = c_rows if c_rows is not None else (n_out * c_col_stride, 0, 1)
-    ldb = B.stride(0) if B.dim() == 2 else K
-    if reduce_aux is not None:
-        assert reduce_aux.is_contiguous() and reduce_aux.dtype == torch.float32
-        epi, aux_p, aux_ld, V = 1, reduce_aux.data_ptr(), reduce_aux.stride(0), reduce_aux.shape[1]
-    else:
-        epi, aux_p, aux_ld, V = 0, None, 0, 0
-    check(lib.e3b_gemm_tf32x3(A.data_ptr(), a_s1, a_s2, a_d, B.data_ptr(), ldb, C.data_ptr(), c_s1, c_s2, c_d,
-                              c_col_stride, M, N, K, float(alpha), epi, aux_p, aux_ld, aux_d, V, stream()))
-    count_launch()
+    (Bp,) = gemm_pack([(B, 0, B.stride(0), 0, B.stride(1) if B.dim() == 2 else 1, 1, N, K)])
+    if epilogue is None:
+        epilogue = 1 if reduce_aux is not None else 0
+    gemm_run([gemm_problem(A, Bp, C, M, a_rows=a_rows, c_rows=c_rows, c_col_stride=c_col_stride, alpha=alpha,
+                           epilogue=epilogue, aux=reduce_aux, aux_d=aux_d, H=H, act_cst=act_cst, accumulate=accumulate)])
     return C

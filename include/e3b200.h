@@ -47,6 +47,9 @@ typedef enum {
 
 E3B_API int e3b_abi_version(void);
 E3B_API const char* e3b_last_error(void);
+/* sizeof of the ABI structs as compiled (0 e3b_tp_desc, 1 e3b_gate_desc, 2 e3b_gemm_problem,
+ * 3 e3b_gemm_pack_desc) so that a binding can verify its own struct layout; -1 otherwise */
+E3B_API int64_t e3b_struct_size(int which);
 
 /* ---------------------------------------------------------------------------------------
  * Neighbour list.   Replaces computeEdgeIndex, e3_layers/data/compute_edge.py:38-113
@@ -196,20 +199,62 @@ E3B_API int e3b_gate_bwd(const e3b_gate_desc* desc, int dtype, const void* in, c
 
 /* ---------------------------------------------------------------------------------------
  * Dense contractions on the tcgen05 tensor cores, fp32-faithful (3xTF32 split, fp32 TMEM
- * accumulators).  Replaces the cuBLAS/einsum calls behind e3nn o3.Linear
- * (nn/message_passing.py:58-63,102; nn/pointwise.py:87-92,99), nn.FullyConnectedNet
- * (nn/message_passing.py:74-79,93) and o3.FullyConnectedTensorProduct (message_passing.py:83-87).
+ * accumulators, accumulation chains cut every 64 floats of K).  Replaces the cuBLAS/einsum
+ * calls behind e3nn o3.Linear (nn/message_passing.py:58-63,102; nn/pointwise.py:87-92,99),
+ * nn.FullyConnectedNet (nn/message_passing.py:74-79,93) and o3.FullyConnectedTensorProduct
+ * (nn/message_passing.py:83-87), forward and data-gradient backward.
  *
- *   epilogue 0:  C[r, n]  = alpha * sum_k A[r, k] B[n, k]
+ *   acc[r, n] = sum_k A[r, k] B[n, k]             A: activation (HBM), B: weight (packed once)
+ *   epilogue 0:  C[r, n]  = alpha * acc
  *   epilogue 1:  C[r, oc] = alpha * sum_{v < V} aux[(r / aux_d) * aux_ld + v] * acc[r, oc * V + v]
  *                (the self-connection: B rows ordered (w, v), v fastest; N = n_out * V)
+ *   epilogue 2:  C[r, n]  = act_cst * ssp(alpha * acc)          (radial MLP hidden layer, forward)
+ *   epilogue 3:  C[r, n]  = alpha * acc * d/dz[act_cst * ssp](z) (radial MLP backward), the
+ *                derivative evaluated from the stored forward output H[r * h_ld + n]
+ *   accumulate != 0: the value is ADDED to what C holds.
  * Row r of A starts at A + (r / a_d) * a_s1 + (r % a_d) * a_s2 (k contiguous); element (r, n) of
- * C is at C + (r / c_d) * c_s1 + (r % c_d) * c_s2 + n * c_s3; row n of B at B + n * ldb.
- * K, the row strides of A/B and the bases of A/B must be multiples of 4 floats.              */
-E3B_API int e3b_gemm_tf32x3(const float* A, int64_t a_s1, int64_t a_s2, int32_t a_d, const float* B, int64_t ldb,
-                            float* C, int64_t c_s1, int64_t c_s2, int32_t c_d, int64_t c_s3, int32_t M, int32_t N,
-                            int32_t K, float alpha, int32_t epilogue, const float* aux, int64_t aux_ld,
-                            int32_t aux_d, int32_t V, void* stream);
+ * C is at C + (r / c_d) * c_s1 + (r % c_d) * c_s2 + n * c_s3.  K, a_s1, a_s2 and the base of A
+ * must be multiples of 4 floats.
+ *
+ * B is consumed in a packed form (TF32 hi/lo split, UMMA canonical tiles) produced by
+ * e3b_gemm_pack from any strided view of the weight: element (n, k), n = n1 * d + n2, is read
+ * from src[n1 * s1 + n2 * s2 + k * sk].  dst needs e3b_gemm_packed_floats(N, K) floats,
+ * 128-byte aligned; repack only when the weight changes.
+ * e3b_gemm_run launches up to E3B_GEMM_MAX_GROUP independent problems (e.g. the irreps blocks
+ * of one o3.Linear) as ONE persistent kernel; they must share the tile shape, i.e. agree on
+ * (K <= 64) and on (N <= 64 or K > 64)  [e3b_gemm_tile_n returns the column-tile width].     */
+#define E3B_GEMM_MAX_GROUP 8
+
+typedef struct {
+  const float* A;
+  int64_t a_s1, a_s2;
+  int32_t a_d;
+  const float* B_packed;
+  float* C;
+  int64_t c_s1, c_s2, c_s3;
+  int32_t c_d;
+  const float* aux;      /* epilogue 1 */
+  int64_t aux_ld;
+  int32_t aux_d, V;
+  const float* H;        /* epilogue 3 */
+  int64_t h_ld;
+  int32_t M, N, K;
+  int32_t epilogue, accumulate;
+  float alpha, act_cst;
+} e3b_gemm_problem;
+
+typedef struct {
+  const float* src;
+  int64_t s1, s2, sk;
+  int32_t d;
+  int32_t N, K;
+  float* dst;
+} e3b_gemm_pack_desc;
+
+E3B_API int e3b_gemm_tile_n(int32_t N, int32_t K);
+E3B_API int64_t e3b_gemm_packed_floats(int32_t N, int32_t K);
+E3B_API int e3b_gemm_pack(const e3b_gemm_pack_desc* descs, int32_t n, void* stream);
+E3B_API int e3b_gemm_run(const e3b_gemm_problem* problems, int32_t n, void* stream);
 
 /* mul_ir <-> imu layout conversion of feature rows (blocks: mul, l). to_imu = 1: [u][m]->[m][u] */
 E3B_API int e3b_layout_convert(int dtype, const void* in, int64_t n, int32_t n_blocks, const int32_t* mul,

@@ -38,6 +38,10 @@ def test_struct_sizes_match_header():
     # TpDesc: 1 + 1 + 16*2 + 1 + 16*2 + 1 + 96*4 + 1 int32
     assert ctypes.sizeof(_lib.TpDesc) == 4 * (2 + 32 + 1 + 32 + 1 + 384 + 1)
     assert ctypes.sizeof(_lib.GateDesc) % 8 == 0
+    lib = _lib.load()
+    for which, st in enumerate((_lib.TpDesc, _lib.GateDesc, _lib.GemmProblem, _lib.GemmPackDesc)):
+        assert lib.e3b_struct_size(which) == ctypes.sizeof(st), st.__name__
+    assert lib.e3b_struct_size(99) == -1
 
 
 def test_product_refuses_cpu_tensors():

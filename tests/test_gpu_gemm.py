@@ -53,3 +53,73 @@ def test_gemm_reduce_epilogue(V):
     C = torch.zeros(Z * d, Wn, device=DEV)
     ops.gemm_tf32x3(x.to(DEV), Bm.to(DEV), C, Z * d, Wn * V, U, reduce_aux=a.to(DEV), aux_d=d)
     assert _rel(C, ref) < 2e-6
+
+
+def _ssp(z):
+    return torch.nn.functional.softplus(z) - 0.6931471805599453
+
+
+def test_gemm_activation_epilogues_and_accumulate():
+    """epilogue 2: c * ssp(alpha * acc); epilogue 3: alpha * acc * d/dz[c ssp](z) from the stored output;
+    accumulate adds to C"""
+    g = torch.Generator().manual_seed(5)
+    M, N, K, c = 700, 64, 64, 1.8782
+    A = torch.randn(M, K, generator=g)
+    B = torch.randn(N, K, generator=g)
+    z = 0.125 * (A.double() @ B.double().T)
+    ref2 = c * _ssp(z)
+    C = torch.empty(M, N, device=DEV)
+    ops.gemm_tf32x3(A.to(DEV), B.to(DEV), C, M, N, K, alpha=0.125, epilogue=2, act_cst=c)
+    assert _rel(C, ref2) < 2e-6
+    # backward through the activation, derivative taken from the stored forward output
+    G = torch.randn(M, 96, generator=g)
+    W = torch.randn(N, 96, generator=g)
+    ref3 = 0.3 * (G.double() @ W.double().T) * (c * torch.sigmoid(z))
+    D = torch.empty(M, N, device=DEV)
+    ops.gemm_tf32x3(G.to(DEV), W.to(DEV), D, M, N, 96, alpha=0.3, epilogue=3, H=C, act_cst=c)
+    assert _rel(D, ref3) < 5e-6
+    base = torch.randn(M, N, generator=g)
+    D2 = base.to(DEV)
+    ops.gemm_tf32x3(G.to(DEV), W.to(DEV), D2, M, N, 96, alpha=0.3, accumulate=True)
+    assert _rel(D2, base.double() + 0.3 * (G.double() @ W.double().T)) < 2e-6
+
+
+@pytest.mark.parametrize("K,N", [(64, 64), (64, 320), (192, 64), (384, 320)])
+def test_gemm_grouped_launch(K, N):
+    """several independent problems (irreps blocks with their own weights) in one kernel"""
+    g = torch.Generator().manual_seed(K + N)
+    Z, D = 777, 9 * K
+    X = torch.randn(Z, D, generator=g)
+    Xd = X.to(DEV)
+    dims = [1, 3, 5]
+    offs = [0, K, 4 * K]
+    Ws = [torch.randn(N, K, generator=g) for _ in dims]
+    packed = ops.gemm_pack([(w.to(DEV), 0, K, 0, 1, 1, N, K) for w in Ws])
+    out = torch.zeros(Z, 9 * N, device=DEV)
+    probs = []
+    for d, off, pw in zip(dims, offs, packed):
+        o_off = off // K * N
+        probs.append(ops.gemm_problem(Xd, pw, out, Z * d, a_off=off, a_rows=(D, K, d), c_off=o_off, c_rows=(9 * N, N, d)))
+    ops.gemm_run(probs)
+    for d, off, w in zip(dims, offs, Ws):
+        a = X[:, off:off + d * K].reshape(Z * d, K)
+        ref = (a.double() @ w.double().T).reshape(Z, d * N)
+        o_off = off // K * N
+        assert _rel(out[:, o_off:o_off + d * N], ref) < 2e-6
+
+
+def test_gemm_many_row_tiles_long_k():
+    """more row tiles than CTAs and a long K (ring wrap-around, chained accumulation)"""
+    g = torch.Generator().manual_seed(11)
+    M, N, K = 40000, 64, 1920
+    A = torch.randn(M, K, generator=g)
+    B = torch.randn(N, K, generator=g)
+    C = torch.empty(M, N, device=DEV)
+    ops.gemm_tf32x3(A.to(DEV), B.to(DEV), C, M, N, K)
+    assert _rel(C, A.double() @ B.double().T) < 2e-6
+    M, N, K = 30000, 1920, 64
+    A = torch.randn(M, K, generator=g)
+    B = torch.randn(N, K, generator=g)
+    C = torch.empty(M, N, device=DEV)
+    ops.gemm_tf32x3(A.to(DEV), B.to(DEV), C, M, N, K)
+    assert _rel(C, A.double() @ B.double().T) < 2e-6
