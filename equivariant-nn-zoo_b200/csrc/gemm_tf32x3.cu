@@ -13,18 +13,19 @@
 // affine row addressing so the irreps layouts are read in place), split it in registers and
 // write the canonical layout to shared memory.
 //
-// One persistent CTA = 10 warps, warp-specialised:
+// One persistent CTA = 14 warps, warp-specialised:
 //   warps 0-3  epilogue   TMEM -> registers (tcgen05.ld) -> epilogue math -> global
-//   warps 4-7  converter  global -(cp.async)-> raw ring -> split hi/lo -> canonical A ring
-//   warp  8    producer   TMA bulk copies of packed B chunks into the B ring
-//   warp  9    MMA        one elected thread issues tcgen05.mma and commits to the mbarriers
+//   warps 4-11 converter  global -(cp.async)-> raw ring -> split hi/lo -> canonical A ring
+//   warp  12   producer   TMA bulk copies of packed B chunks into the B ring
+//   warp  13   MMA        one elected thread issues tcgen05.mma and commits to the mbarriers
 // Three pipelines (mbarrier full/empty pairs): A ring, B ring, two TMEM accumulators.  When the
 // whole K extent of a row tile fits the A ring it stays RESIDENT across the column tiles.
 // The tensor core accumulates with truncation, so an unbroken chain over a long K drifts
-// (1.5e-5 at K = 1920, measured): chains are cut every 64 floats of K and the partial sums are
+// (1.5e-5 at K = 1920, measured): chains are cut every 128 floats of K and the partial sums are
 // added in fp32 registers by the epilogue warps while the next chain runs in the other buffer.
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <stdlib.h>
 
 #include "../../include/e3b200.h"
 
@@ -34,8 +35,10 @@ namespace {
 
 constexpr int BM = 128;     // UMMA M
 constexpr int BK = 32;      // floats per K chunk = 4 MMA K-steps of 8 = 8 sixteen-byte columns
-constexpr int KSEG = 2;     // chunks per accumulation chain (64 floats of K)
-constexpr int NTHREADS = 320;
+constexpr int KSEG = 4;     // chunks per accumulation chain (128 floats of K)
+constexpr int NACC = 4;     // TMEM accumulator buffers
+constexpr int NTHREADS = 448;
+constexpr int NCVT = 256;    // converter threads (warps 4-11)
 constexpr int CVT0 = 128;   // first converter thread
 constexpr int MAXG = E3B_GEMM_MAX_GROUP;
 
@@ -45,6 +48,7 @@ struct Problem {
   int32_t gx, gy;        // CTA grid of this problem: row tiles bx, bx+gx, ..; column tiles by, by+gy, ..
   int32_t cta_begin;     // first CTA (blockIdx.x) of this problem
   uint64_t a_mul;        // ceil(2^40 / a_d): r / a_d == (r * a_mul) >> 40 for r < 2^31, a_d < 512
+  int32_t dbg;           // E3B_GEMM_DEBUG bisection bits: 1 skip A load+convert, 2 skip MMA, 4 skip B loads, 8 skip stores
 };
 struct Batch {
   Problem pr[MAXG];
@@ -102,6 +106,11 @@ __device__ __forceinline__ void cp_async16(void* dst, const void* src, uint32_t 
 }
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
+  return pred != 0;
+}
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 
@@ -208,8 +217,8 @@ __device__ __forceinline__ void epilogue_role(const EpiCtx& c) {
         for (int i = 0; i < (MULTI ? BN : 1); ++i) racc[i] = 0.f;
       }
       for (int seg = 0; seg < (MULTI ? n_seg : 1); ++seg, ++acc_it) {
-        const uint32_t buf = acc_it & 1u;
-        mbar_wait(&c.acc_full[buf], (acc_it >> 1) & 1u);
+        const uint32_t buf = acc_it % NACC;
+        mbar_wait(&c.acc_full[buf], (acc_it / NACC) & 1u);
         tc_fence_after();
         const bool last = !MULTI || seg == n_seg - 1;
 #pragma unroll
@@ -221,7 +230,7 @@ __device__ __forceinline__ void epilogue_role(const EpiCtx& c) {
             for (int i = 0; i < 32; ++i) { racc[(MULTI ? cb : 0) + (MULTI ? i : 0)] += v[i]; v[i] = racc[(MULTI ? cb : 0) + (MULTI ? i : 0)]; }
           }
           const int nb = n0 + cb;
-          if (!last || nb >= g.N) continue;
+          if (!last || nb >= g.N || (P.dbg & 8)) continue;
           if (DENSE) {
             __syncwarp();
 #pragma unroll
@@ -297,9 +306,9 @@ __global__ void __launch_bounds__(NTHREADS, 1) gemm_tf32x3_kernel(const __grid_c
   float* smem = reinterpret_cast<float*>((reinterpret_cast<uintptr_t>(smem_dyn) + 127) & ~(uintptr_t)127);
   float* sA = smem;                                   // [SA][hi|lo][c(8)][row(128)][4]
   float* sB = sA + SA * L::A_STAGE;                   // [SB][hi|lo][c(8)][row(BN)][4]
-  float* sRaw = sB + SB * L::B_STAGE;                 // [PRAW][slot(8)][thread(128)][4]
+  float* sRaw = sB + SB * L::B_STAGE;                 // [PRAW][slot(4)][thread(256)][4]
   float* sEpi = sRaw + PRAW * L::RAW_STAGE;           // [4 warps][32 rows][36]
-  __shared__ uint64_t a_full[SA], a_empty[SA], b_full[SB], b_empty[SB], acc_full[2], acc_empty[2];
+  __shared__ uint64_t a_full[SA], a_empty[SA], b_full[SB], b_empty[SB], acc_full[NACC], acc_empty[NACC];
   __shared__ uint32_t tmem_base_smem;
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -317,14 +326,14 @@ __global__ void __launch_bounds__(NTHREADS, 1) gemm_tf32x3_kernel(const __grid_c
   const bool resident = k_chunks <= SA;
   const int n_count = by < P.n_tiles ? (P.n_tiles - by + P.gy - 1) / P.gy : 0;   // column tiles of this CTA
 
-  if (warp == 9) {  // TMEM allocation is warp-collective; the same warp frees it
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_addr(&tmem_base_smem)), "r"((uint32_t)(2 * BN)) : "memory");
+  if (warp == 13) {  // TMEM allocation is warp-collective; the same warp frees it
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_addr(&tmem_base_smem)), "r"((uint32_t)(NACC * BN)) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
   if (tid == 0) {
-    for (int s = 0; s < SA; ++s) { mbar_init(&a_full[s], 128); mbar_init(&a_empty[s], 1); }
+    for (int s = 0; s < SA; ++s) { mbar_init(&a_full[s], NCVT); mbar_init(&a_empty[s], 1); }
     for (int s = 0; s < SB; ++s) { mbar_init(&b_full[s], 1); mbar_init(&b_empty[s], 1); }
-    for (int s = 0; s < 2; ++s) { mbar_init(&acc_full[s], 1); mbar_init(&acc_empty[s], 128); }
+    for (int s = 0; s < NACC; ++s) { mbar_init(&acc_full[s], 1); mbar_init(&acc_empty[s], 128); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   tc_fence_before();
@@ -333,25 +342,25 @@ __global__ void __launch_bounds__(NTHREADS, 1) gemm_tf32x3_kernel(const __grid_c
   const uint32_t tmem_base = tmem_base_smem;
 
   if (n_count > 0 && bx < P.m_tiles) {
-    if (warp >= 4 && warp < 8) {
+    if (warp >= 4 && warp < 12) {
       // =============================== A converter ===============================
-      // thread -> one 16-byte column `col` of the chunk and the 8 rows row0 + 16 i: a quarter-warp
+      // thread -> one 16-byte column `col` of the chunk and the 4 rows row0 + 32 i: a quarter-warp
       // covers 8 consecutive rows of one column = 128 contiguous bytes of the canonical layout
       // (conflict-free STS.128) and 64 contiguous bytes of each source row (full sectors).
-      const int ct = tid - CVT0;                 // 0..127
+      const int ct = tid - CVT0;                 // 0..255
       const int cw = ct >> 5;
       const int col = (cw & 1) * 4 + (lane >> 3);
-      const int row0 = 8 * (cw >> 1) + (lane & 7);
+      const int row0 = 8 * (cw >> 1) + (lane & 7);      // rows row0 + 32 i, i = 0..3
       const int reps = resident ? 1 : n_count;
       const int m_count = (P.m_tiles - bx + P.gx - 1) / P.gx;
       const int total = m_count * reps * k_chunks;
       // issue stream state (runs PRAW - 1 jobs ahead of the conversion)
-      int64_t roff[8];
-      uint32_t rbytes[8];
+      int64_t roff[4];
+      uint32_t rbytes[4];
       auto load_rows = [&](int m_tile) {
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          const int r = m_tile * BM + row0 + 16 * i;
+        for (int i = 0; i < 4; ++i) {
+          const int r = m_tile * BM + row0 + 32 * i;
           const int q = (int)(((uint64_t)(uint32_t)r * P.a_mul) >> 40);
           roff[i] = (int64_t)q * g.a_s1 + (int64_t)(r - q * g.a_d) * g.a_s2;
           rbytes[i] = r < g.M ? 16u : 0u;
@@ -361,14 +370,14 @@ __global__ void __launch_bounds__(NTHREADS, 1) gemm_tf32x3_kernel(const __grid_c
       int i_m = bx, i_rep = 0, i_kc = 0, i_slot = 0, i_left = total;
       load_rows(i_m);
       auto issue = [&]() {
-        if (i_left > 0) {
+        if (i_left > 0 && !(P.dbg & 1)) {
           --i_left;
           const int k = i_kc * BK + col * 4;
           const bool kok = k < g.K;
           float* dst = sRaw + (size_t)i_slot * L::RAW_STAGE + ct * 4;
 #pragma unroll
-          for (int i = 0; i < 8; ++i)
-            cp_async16(dst + i * (128 * 4), g.A + roff[i] + (kok ? k : 0), kok ? rbytes[i] : 0u);
+          for (int i = 0; i < 4; ++i)
+            cp_async16(dst + i * (NCVT * 4), g.A + roff[i] + (kok ? k : 0), kok ? rbytes[i] : 0u);
           if (++i_kc == k_chunks) {
             i_kc = 0;
             if (++i_rep == reps) {
@@ -393,12 +402,14 @@ __global__ void __launch_bounds__(NTHREADS, 1) gemm_tf32x3_kernel(const __grid_c
         const float4* raw = reinterpret_cast<const float4*>(sRaw + (size_t)slot * L::RAW_STAGE) + ct;
         float4* hi = reinterpret_cast<float4*>(sA + (size_t)st * L::A_STAGE) + col * BM + row0;
         float4* lo = hi + BM * (BK / 4);
+        if (!(P.dbg & 1)) {
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          float4 h, l;
-          split4(raw[i * 128], &h, &l);
-          hi[16 * i] = h;
-          lo[16 * i] = l;
+          for (int i = 0; i < 4; ++i) {
+            float4 h, l;
+            split4(raw[i * NCVT], &h, &l);
+            hi[32 * i] = h;
+            lo[32 * i] = l;
+          }
         }
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy stores -> tensor-core reads
         mbar_arrive(&a_full[st]);
@@ -406,7 +417,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) gemm_tf32x3_kernel(const __grid_c
         if (++slot == PRAW) slot = 0;
       }
       cp_async_wait<0>();
-    } else if (warp == 8) {
+    } else if (warp == 12) {
       // =============================== B producer (TMA) ===============================
       if (lane == 0) {
         uint32_t it = 0;
@@ -416,51 +427,60 @@ __global__ void __launch_bounds__(NTHREADS, 1) gemm_tf32x3_kernel(const __grid_c
             for (int kc = 0; kc < k_chunks; ++kc, ++it) {
               const int st = it % SB;
               mbar_wait(&b_empty[st], ((it / SB) & 1u) ^ 1u);
+              if (P.dbg & 4) { mbar_arrive(&b_full[st]); continue; }
               mbar_expect_tx(&b_full[st], bytes);
               bulk_g2s(sB + (size_t)st * L::B_STAGE, g.B_packed + ((size_t)n * k_chunks + kc) * L::B_STAGE, bytes, &b_full[st]);
             }
       }
-    } else if (warp == 9) {
+    } else if (warp == 13) {
       // =============================== MMA issuer ===============================
-      if (lane == 0) {
-        const uint32_t idesc = umma_idesc(BN);
-        uint32_t a_it = 0, b_it = 0, acc_it = 0;
-        for (int m = bx; m < P.m_tiles; m += P.gx) {
-          int ni = 0;
-          for (int n = by; n < P.n_tiles; n += P.gy, ++ni) {
-            uint32_t buf = 0;
-            for (int kc = 0; kc < k_chunks; ++kc) {
-              const bool seg_first = (kc % KSEG) == 0;
-              if (seg_first) {
-                buf = acc_it & 1u;
-                mbar_wait(&acc_empty[buf], ((acc_it >> 1) & 1u) ^ 1u);
-              }
-              const uint32_t a_idx = resident ? a_it + (uint32_t)kc : a_it;
-              const int sa = a_idx % SA, sb = b_it % SB;
-              if (!resident || ni == 0) mbar_wait(&a_full[sa], (a_idx / SA) & 1u);
-              mbar_wait(&b_full[sb], (b_it / SB) & 1u);
-              tc_fence_after();
-              const uint32_t a_hi = smem_addr(sA + (size_t)sa * L::A_STAGE), a_lo = a_hi + BM * BK * 4;
-              const uint32_t b_hi = smem_addr(sB + (size_t)sb * L::B_STAGE), b_lo = b_hi + BN * BK * 4;
+      // The whole warp walks the tiles (uniform control flow, so addresses and descriptors live in
+      // uniform registers); one elected lane issues the MMAs of a chunk and the commits.
+      const uint32_t idesc = umma_idesc(BN);
+      const uint32_t sA_u = smem_addr(sA), sB_u = smem_addr(sB);
+      // descriptor templates: LBO / SBO / version bits fixed, 14-bit start address added per use
+      const uint64_t tmplA = umma_desc(0, BM * 16, 128), tmplB = umma_desc(0, BN * 16, 128);
+      uint32_t a_it = 0, b_it = 0, acc_it = 0;
+      for (int m = bx; m < P.m_tiles; m += P.gx) {
+        int ni = 0;
+        for (int n = by; n < P.n_tiles; n += P.gy, ++ni) {
+          uint32_t buf = 0;
+          for (int kc = 0; kc < k_chunks; ++kc) {
+            const bool seg_first = (kc % KSEG) == 0;
+            if (seg_first) {
+              buf = acc_it % NACC;
+              mbar_wait(&acc_empty[buf], ((acc_it / NACC) & 1u) ^ 1u);
+            }
+            const uint32_t a_idx = resident ? a_it + (uint32_t)kc : a_it;
+            const uint32_t sa = a_idx % SA, sb = b_it % SB;
+            if (!resident || ni == 0) mbar_wait(&a_full[sa], (a_idx / SA) & 1u);
+            mbar_wait(&b_full[sb], (b_it / SB) & 1u);
+            tc_fence_after();
+            const bool seg_last = (kc % KSEG) == KSEG - 1 || kc == k_chunks - 1;
+            if (elect_one()) {
+              const uint64_t dAh = tmplA | (uint64_t)(((sA_u + sa * (uint32_t)(L::A_STAGE * 4)) >> 4) & 0x3FFFu);
+              const uint64_t dAl = dAh + (uint64_t)((BM * BK * 4) >> 4);
+              const uint64_t dBh = tmplB | (uint64_t)(((sB_u + sb * (uint32_t)(L::B_STAGE * 4)) >> 4) & 0x3FFFu);
+              const uint64_t dBl = dBh + (uint64_t)((BN * BK * 4) >> 4);
               const uint32_t d = tmem_base + buf * BN;
 #pragma unroll
-              for (int j = 0; j < BK / 8; ++j) {   // one MMA covers K = 8 tf32 = two 16-byte columns
-                const uint32_t offA = (uint32_t)(2 * j) * BM * 16, offB = (uint32_t)(2 * j) * BN * 16;
-                const uint64_t dAh = umma_desc(a_hi + offA, BM * 16, 128), dAl = umma_desc(a_lo + offA, BM * 16, 128);
-                const uint64_t dBh = umma_desc(b_hi + offB, BN * 16, 128), dBl = umma_desc(b_lo + offB, BN * 16, 128);
-                umma_tf32(d, dAl, dBh, idesc, (seg_first && j == 0) ? 0u : 1u);
-                umma_tf32(d, dAh, dBl, idesc, 1u);
-                umma_tf32(d, dAh, dBh, idesc, 1u);
+              for (int j = 0; j < ((P.dbg & 2) ? 0 : BK / 8); ++j) {   // one MMA covers K = 8 tf32 = two 16-byte columns
+                const uint64_t oA = (uint64_t)((2 * j * BM * 16) >> 4), oB = (uint64_t)((2 * j * BN * 16) >> 4);
+                umma_tf32(d, dAl + oA, dBh + oB, idesc, (seg_first && j == 0) ? 0u : 1u);
+                umma_tf32(d, dAh + oA, dBl + oB, idesc, 1u);
+                umma_tf32(d, dAh + oA, dBh + oB, idesc, 1u);
               }
               umma_commit(&b_empty[sb]);
               if (!resident || ni == n_count - 1) umma_commit(&a_empty[sa]);
-              if ((kc % KSEG) == KSEG - 1 || kc == k_chunks - 1) { umma_commit(&acc_full[buf]); ++acc_it; }
-              ++b_it;
-              if (!resident) ++a_it;
+              if (seg_last) umma_commit(&acc_full[buf]);
             }
+            __syncwarp();
+            if (seg_last) ++acc_it;
+            ++b_it;
+            if (!resident) ++a_it;
           }
-          if (resident) a_it += (uint32_t)k_chunks;
         }
+        if (resident) a_it += (uint32_t)k_chunks;
       }
     } else if (warp < 4) {
       // =============================== epilogue ===============================
@@ -476,10 +496,10 @@ __global__ void __launch_bounds__(NTHREADS, 1) gemm_tf32x3_kernel(const __grid_c
 
   tc_fence_before();
   __syncthreads();
-  if (warp == 9) {
+  if (warp == 13) {
     __syncwarp();
     tc_fence_after();
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)(2 * BN)) : "memory");
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)(NACC * BN)) : "memory");
   }
 }
 
@@ -593,13 +613,14 @@ extern "C" int e3b_gemm_run(const e3b_gemm_problem* problems, int32_t n, void* s
     if (b.n == 0) { bn = t; multi = mu; }
     else if (bn != t || multi != mu)
       return e3b_fail(E3B_ERR_UNSUPPORTED, "gemm_run: the problems of one launch must share the tile shape "
-                      "(K <= 64 or not; N <= 64 or not)");
+                      "(K <= 128 or not; N <= 64 or not)");
     Problem& P = b.pr[b.n];
     P.p = p;
     P.m_tiles = (p.M + BM - 1) / BM;
     P.n_tiles = (p.N + t - 1) / t;
     P.k_chunks = (p.K + BK - 1) / BK;
     if (p.a_d >= 512) return e3b_fail(E3B_ERR_UNSUPPORTED, "gemm_run: a_d must be < 512");
+    { static const int dbg = [] { const char* v = getenv("E3B_GEMM_DEBUG"); return v ? atoi(v) : 0; }(); P.dbg = dbg; }
     P.a_mul = ((1ull << 40) + (uint64_t)p.a_d - 1) / (uint64_t)p.a_d;
     work[b.n] = (double)P.m_tiles * P.n_tiles * (P.k_chunks + 2);
     total_work += work[b.n];
@@ -623,8 +644,8 @@ extern "C" int e3b_gemm_run(const e3b_gemm_problem* problems, int32_t n, void* s
     ctas += P.gx * P.gy;
   }
   cudaError_t e;
-  if (multi) e = launch<64, true, 3, 3, 4>(b, ctas, (cudaStream_t)stream);
-  else if (bn == 64) e = launch<64, false, 3, 3, 4>(b, ctas, (cudaStream_t)stream);
+  if (multi) e = launch<64, true, 2, 7, 2>(b, ctas, (cudaStream_t)stream);
+  else if (bn == 64) e = launch<64, false, 3, 4, 2>(b, ctas, (cudaStream_t)stream);
   else e = launch<128, false, 4, 1, 2>(b, ctas, (cudaStream_t)stream);
   if (e != cudaSuccess) return e3b_fail(E3B_ERR_CUDA, "gemm_run: %s", cudaGetErrorString(e));
   return E3B_OK;
