@@ -205,7 +205,7 @@ __device__ __forceinline__ void epilogue_role(const EpiCtx& c) {
     if (EPI == 1) {
 #pragma unroll
       for (int v = 0; v < (EPI == 1 ? 32 : 1); ++v)
-        aux[v] = (row_ok && v < g.V) ? __ldg(g.aux + (int64_t)(row / g.aux_d) * g.aux_ld + v) : 0.f;
+        aux[v] = (row_ok && v < (g.aux_cols > 0 ? g.aux_cols : g.V)) ? __ldg(g.aux + (int64_t)(row / g.aux_d) * g.aux_ld + v) : 0.f;
     }
     // DENSE: rows of this warp's quarter tile handled by this lane after the transposition
     const int r_base = m * BM + warp * 32 + t_row;
@@ -531,7 +531,7 @@ __global__ void gemm_pack_kernel(const __grid_constant__ PackBatch pb) {
 #pragma unroll
     for (int e = 0; e < 4; ++e) {
       const int k = kc * BK + c * 4 + e;
-      x[e] = (n < d.N && k < d.K) ? __ldg(d.src + (int64_t)(n / d.d) * d.s1 + (int64_t)(n % d.d) * d.s2 + (int64_t)k * d.sk) : 0.f;
+      x[e] = (n < d.N && k < d.K && (d.n2_valid <= 0 || (n % d.d) < d.n2_valid)) ? __ldg(d.src + (int64_t)(n / d.d) * d.s1 + (int64_t)(n % d.d) * d.s2 + (int64_t)k * d.sk) : 0.f;
     }
     float4 hi, lo;
     split4(make_float4(x[0], x[1], x[2], x[3]), &hi, &lo);

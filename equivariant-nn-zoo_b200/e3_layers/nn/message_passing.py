@@ -11,7 +11,7 @@ import math
 
 import torch
 
-from e3b200 import _lib, dense, ops
+from e3b200 import _lib, dense, interaction, ops
 from e3b200.irreps import Irreps
 
 from ..utils import activation_name, build, tp_path_exists
@@ -113,14 +113,30 @@ class MessagePassing(Module):
         self.resnet = bool(resnet and (scalars + gated).simplify() == prev)
         self.conv = build(convolution, input_features=input_features, output_features=conv_out, node_attrs=node_attrs,
                           edge_radial=edge_radial, edge_spherical=edge_spherical)
+        self._fused = None
         self.normalize = normalize
         if normalize:
             self.norm = LayerNormalization(self.irreps_out["output_features"], self.irreps_out["output_features"])
 
+    @property
+    def fused(self):
+        """description of this block for the single-node fp32 path (e3b200.interaction)"""
+        if self._fused is None:
+            self._fused = interaction.FusedInteraction(self)
+        return self._fused
+
     def forward(self, data, attrs):
         skip = data["input_features"]
-        out = self.conv(data, attrs)[0]["output_features"]
-        out = self.equivariant_nonlin(out)
+        if skip.dtype == torch.float32 and skip.is_cuda and self.fused.reason is None:
+            edge_index = data["edge_index"]
+            csr = ops.graph_of(edge_index, skip.shape[0])
+            out, out_imu = interaction.interaction(self.fused, skip, data["node_attrs"], data["edge_radial"],
+                                                   data["edge_spherical"], csr)
+            out._e3b_imu = out_imu       # the next block gathers from the channel-fastest twin
+        else:
+            # fp64 correctness mode / irregular irreps: the same kernels composed op by op
+            out = self.conv(data, attrs)[0]["output_features"]
+            out = self.equivariant_nonlin(out)
         if self.resnet:
             out = skip + out
         if self.normalize:

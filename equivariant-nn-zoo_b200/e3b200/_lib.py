@@ -35,13 +35,13 @@ class GateDesc(ctypes.Structure):
 class GemmProblem(ctypes.Structure):
     _fields_ = [("A", c_vp), ("a_s1", c_i64), ("a_s2", c_i64), ("a_d", c_i32), ("B_packed", c_vp), ("C", c_vp),
                 ("c_s1", c_i64), ("c_s2", c_i64), ("c_s3", c_i64), ("c_d", c_i32), ("aux", c_vp), ("aux_ld", c_i64),
-                ("aux_d", c_i32), ("V", c_i32), ("H", c_vp), ("h_ld", c_i64), ("M", c_i32), ("N", c_i32), ("K", c_i32),
+                ("aux_d", c_i32), ("V", c_i32), ("aux_cols", c_i32), ("H", c_vp), ("h_ld", c_i64), ("M", c_i32), ("N", c_i32), ("K", c_i32),
                 ("epilogue", c_i32), ("accumulate", c_i32), ("alpha", c_f32), ("act_cst", c_f32)]
 
 
 class GemmPackDesc(ctypes.Structure):
-    _fields_ = [("src", c_vp), ("s1", c_i64), ("s2", c_i64), ("sk", c_i64), ("d", c_i32), ("N", c_i32), ("K", c_i32),
-                ("dst", c_vp)]
+    _fields_ = [("src", c_vp), ("s1", c_i64), ("s2", c_i64), ("sk", c_i64), ("d", c_i32), ("n2_valid", c_i32), ("N", c_i32),
+                ("K", c_i32), ("dst", c_vp)]
 
 
 E3B_GEMM_MAX_GROUP = 8
@@ -70,6 +70,8 @@ SIGNATURES = {
     "e3b_segment_sum": (c_int, [c_int, c_vp, c_i64, c_vp, c_vp, c_i64, c_vp, c_vp]),
     "e3b_gate_fwd": (c_int, [ctypes.POINTER(GateDesc), c_int, c_vp, c_i64, c_vp, c_vp]),
     "e3b_gate_bwd": (c_int, [ctypes.POINTER(GateDesc), c_int, c_vp, c_vp, c_i64, c_vp, c_vp]),
+    "e3b_gate_imu_fwd": (c_int, [ctypes.POINTER(GateDesc), c_int, c_vp, c_i64, c_vp, c_vp, c_vp]),
+    "e3b_gate_imu_bwd": (c_int, [ctypes.POINTER(GateDesc), c_int, c_vp, c_vp, c_vp, c_i64, c_vp, c_vp]),
     "e3b_gemm_tile_n": (c_int, [c_i32, c_i32]),
     "e3b_gemm_packed_floats": (c_i64, [c_i32, c_i32]),
     "e3b_gemm_pack": (c_int, [ctypes.POINTER(GemmPackDesc), c_i32, c_vp]),

@@ -1,0 +1,392 @@
+"""One interaction block (reference ``MessagePassing.forward``, ``nn/message_passing.py:242-262`` around
+``FactorizedConvolution.forward`` ``:91-124``) as ONE autograd node on the fp32 B200 path.
+
+Forward, per layer (every step is a libe3b200 kernel; feature rows stay in the channel-fastest
+"imu" layout between the kernels, so no transposes or concatenations are materialised):
+
+    x_l   = linear_1(x)                               grouped tcgen05 GEMM (irreps blocks = problems)
+    h, w  = radial MLP(edge_radial)                   tcgen05 GEMMs, ssp fused in the epilogue
+    mid   = sum_{e -> n} w_e * (x_l[src] (x) Y_e)     fused gather / CG product / segmented sum
+    conv  = linear(mid) / sqrt(avg_num_neighbors)     grouped tcgen05 GEMM (after the reduction)
+    conv += sc(x, node_attrs)                         grouped tcgen05 GEMM, attribute contraction in the epilogue
+    out   = gate(conv)                                written in both layouts (mul_ir for the caller,
+                                                      imu for the next block)
+
+Backward (first order) runs the transposed GEMMs from the same parameter tensors (packed per
+role), the backward tensor-product kernel and the activation-derivative epilogues.  Parameter
+gradients, needed only when training, are plain library GEMMs on the saved activations."""
+import ctypes
+import math
+
+import torch
+from torch.autograd.function import once_differentiable
+
+from . import _lib, dense, ops
+from ._lib import check, count_launch, ptr, stream
+from .irreps import Irreps
+
+
+def _offsets(irreps):
+    out, o = [], 0
+    for b in irreps:
+        out.append(o)
+        o += b.dim
+    return out, o
+
+
+class FusedInteraction:
+    """Static description of one MessagePassing layer + its packed weights (cached per parameter version)."""
+
+    def __init__(self, mp):
+        conv = mp.conv
+        self.mp, self.conv = mp, conv
+        self.feat_in = Irreps(conv.irreps_in["input_features"])
+        self.conv_out = Irreps(conv.irreps_out["output_features"])
+        self.attrs = Irreps(conv.irreps_in["node_attrs"])
+        self.structure = conv.tp.tp.structure
+        self.mid = self.structure.irreps_mid.simplify()
+        self.x_off, self.Din = _offsets(self.feat_in)
+        self.c_off, self.Dconv = _offsets(self.conv_out)
+        self.m_off, self.Dmid = _offsets(self.mid)
+        self.gate = mp.equivariant_nonlin
+        self.Dout = self.gate.irreps_out.dim
+        self.inv_sqrt_avg = 1.0 / math.sqrt(conv.avg_num_neighbors) if conv.avg_num_neighbors is not None else 1.0
+        self.all_scalar_in = all(b.ir.l == 0 for b in self.feat_in)
+        self.fc = conv.fc
+        self.hs = list(conv.fc.hs)
+        self.V = self.attrs.dim
+        self.Vg = 16 if self.V <= 16 else 32           # epilogue group width (attributes zero-extended)
+        self._cache = {}
+        self.reason = self._unsupported()
+
+    # -- which layers take the fused path -------------------------------------------------------
+    def _unsupported(self):
+        c = self.conv
+        if self.structure.uniform_mul is None:
+            return "input blocks of different multiplicity"
+        if c.sc is None:
+            return "no self-connection"
+        if len(self.attrs) != 1 or not self.attrs[0].ir.is_scalar() or self.V > 32:
+            return "node_attrs must be one block of <= 32 scalars"
+        if any(h % 4 for h in self.hs[:-1]) or any(b.mul % 4 for b in self.feat_in) or any(b.mul % 4 for b in self.conv_out):
+            return "widths must be multiples of 4"
+        return None
+
+    # -- packed weights -------------------------------------------------------------------------
+    def _params(self):
+        c = self.conv
+        return [getattr(c.fc, f"layer{i}").weight for i in range(c.fc.n_layers)] + [c.linear_1.weight, c.tp.linear.weight,
+                                                                                   c.sc.weight]
+
+    def packs(self, role):
+        """role 'fwd' | 'bwd' -> dict of PackedWeight lists, repacked only when a parameter changed"""
+        key = tuple((p.data_ptr(), p._version) for p in self._params())
+        hit = self._cache.get(role)
+        if hit is not None and hit[0] == key:
+            return hit[1]
+        c = self.conv
+        views, names = [], []
+        fwd = role == "fwd"
+        for i in range(c.fc.n_layers):                                   # radial MLP: W[h_in, h_out]
+            W = getattr(c.fc, f"layer{i}").weight
+            hi, ho = W.shape
+            views.append((W, 0, 1, 0, ho, 1, 0, ho, hi) if fwd else (W, 0, ho, 0, 1, 1, 0, hi, ho))
+            names.append(("fc", i))
+        lin1 = c.linear_1
+        for q, (i, o, off, _) in enumerate(lin1.paths):                   # W[u, w]
+            mi, mo = lin1.irreps_in[i].mul, lin1.irreps_out[o].mul
+            views.append((lin1.weight, off, 1, 0, mo, 1, 0, mo, mi) if fwd else (lin1.weight, off, mo, 0, 1, 1, 0, mi, mo))
+            names.append(("lin1", q))
+        post = c.tp.linear
+        for q, (i, o, off, _) in enumerate(post.paths):                   # W[kk, w]
+            mi, mo = post.irreps_in[i].mul, post.irreps_out[o].mul
+            views.append((post.weight, off, 1, 0, mo, 1, 0, mo, mi) if fwd else (post.weight, off, mo, 0, 1, 1, 0, mi, mo))
+            names.append(("post", q))
+        sc, V, Vg = c.sc, self.V, self.Vg
+        for q, (i1, i2, o, off, _) in enumerate(sc.paths):                # W[u, v, w]
+            m1, mo = sc.irreps_in1[i1].mul, sc.irreps_out[o].mul
+            if fwd:   # rows (w, v), v fastest, K = u
+                views.append((sc.weight, off, 1, mo, V * mo, Vg, V, mo * Vg, m1))
+            else:     # rows (u, v), v fastest, K = w
+                views.append((sc.weight, off, V * mo, mo, 1, Vg, V, m1 * Vg, mo))
+            names.append(("sc", q))
+        packed = ops.gemm_pack(views)
+        out = {"fc": [], "lin1": [], "post": [], "sc": []}
+        for (kind, _), pw in zip(names, packed):
+            out[kind].append(pw)
+        self._cache[role] = (key, out)
+        return out
+
+
+def _waves(problems_with_target):
+    """[(problem, target block id)] -> launches such that accumulating problems run after the first
+    writer of their block; sets .accumulate accordingly.  `written` blocks are tracked by the caller."""
+    waves = []
+    depth = {}
+    for g, tgt, pre_written in problems_with_target:
+        d = depth.get(tgt, 1 if pre_written else 0)
+        g.accumulate = 1 if d > 0 else 0
+        while len(waves) <= d:
+            waves.append([])
+        waves[d].append(g)
+        depth[tgt] = d + 1
+    return [w for w in waves if w]
+
+
+class _Interaction(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x_mi, x_imu, attrs, er, Y, fi, csr, *params):
+        lib = _lib.load()
+        ctx.set_materialize_grads(False)
+        conv = fi.conv
+        src_is_imu = x_imu is not None
+        if x_imu is None:
+            x_imu = x_mi.contiguous() if fi.all_scalar_in else ops.layout_convert(x_mi, fi.feat_in, True)
+        x_imu, attrs, er, Y = x_imu.contiguous(), attrs.contiguous(), er.contiguous(), Y.contiguous()
+        N, E = x_imu.shape[0], er.shape[0]
+        dev = x_imu.device
+        P = fi.packs("fwd")
+        new = lambda *s: torch.empty(*s, dtype=torch.float32, device=dev)
+        # ---- linear_1 (imu -> imu)
+        lin1 = conv.linear_1
+        xl = new(N, fi.Din)
+        probs, written = [], set()
+        for q, (i, o, off, alpha) in enumerate(lin1.paths):
+            bi, bo = fi.feat_in[i], fi.feat_in[o]
+            probs.append((ops.gemm_problem(x_imu, P["lin1"][q], xl, N * bi.ir.dim, a_off=fi.x_off[i],
+                                           a_rows=(fi.Din, bi.mul, bi.ir.dim), c_off=fi.x_off[o],
+                                           c_rows=(fi.Din, bo.mul, bo.ir.dim), alpha=alpha), o, False))
+            written.add(o)
+        if len(written) < len(fi.feat_in):
+            xl.zero_()
+        for wave in _waves(probs):
+            ops.gemm_run(wave)
+        # ---- radial MLP
+        hs = fi.hs
+        h = [er]
+        for i in range(conv.fc.n_layers):
+            last = i == conv.fc.n_layers - 1
+            out = new(E, hs[i + 1])
+            ops.gemm_run([ops.gemm_problem(h[-1], P["fc"][i], out, E, a_rows=(h[-1].stride(0), 0, 1),
+                                           alpha=1.0 / math.sqrt(hs[i]), epilogue=0 if last else 2, act_cst=conv.fc.cst)])
+            h.append(out)
+        w = h[-1]
+        # ---- fused gather + CG tensor product + segmented sum
+        plan = conv.tp.plan
+        mid = new(N, plan.y_dim)
+        end = ops._timed(("fwd", len(plan.structure.paths), plan.structure.uniform_mul, plan.x_dim, plan.y_dim, N, E))
+        check(lib.e3b_tpconv_fwd(plan.handle, 0, N, E, ptr(xl), ptr(Y), ptr(w), ptr(csr.in_ptr), ptr(csr.in_nbr),
+                                 ptr(csr.in_eid), ptr(mid), stream()))
+        if end is not None:
+            end.record()
+        count_launch()
+        # ---- post-reduction linear (scaled by 1/sqrt(avg_num_neighbors)) + self-connection, both into conv (imu)
+        post, sc = conv.tp.linear, conv.sc
+        cv = new(N, fi.Dconv)
+        probs, written = [], set()
+        for q, (i, o, off, alpha) in enumerate(post.paths):
+            bi, bo = fi.mid[i], fi.conv_out[o]
+            probs.append((ops.gemm_problem(mid, P["post"][q], cv, N * bi.ir.dim, a_off=fi.m_off[i],
+                                           a_rows=(fi.Dmid, bi.mul, bi.ir.dim), c_off=fi.c_off[o],
+                                           c_rows=(fi.Dconv, bo.mul, bo.ir.dim), alpha=alpha * fi.inv_sqrt_avg), o, False))
+            written.add(o)
+        sc_probs = []
+        for q, (i1, i2, o, off, alpha) in enumerate(sc.paths):
+            bi, bo = fi.feat_in[i1], fi.conv_out[o]
+            g = ops.gemm_problem(x_imu, P["sc"][q], cv, N * bi.ir.dim, a_off=fi.x_off[i1],
+                                 a_rows=(fi.Din, bi.mul, bi.ir.dim), c_off=fi.c_off[o],
+                                 c_rows=(fi.Dconv, bo.mul, bo.ir.dim), alpha=alpha, epilogue=1, aux=attrs,
+                                 aux_d=bi.ir.dim, aux_group=fi.Vg)
+            sc_probs.append((g, o, o in written))
+        all_written = written | {o for _, o, _ in sc_probs}
+        if len(all_written) < len(fi.conv_out):
+            cv.zero_()
+        for wave in _waves(probs):
+            ops.gemm_run(wave)
+        for wave in _waves(sc_probs):
+            ops.gemm_run(wave)
+        # ---- gate, in both layouts
+        out_mi, out_imu = new(N, fi.Dout), new(N, fi.Dout)
+        check(lib.e3b_gate_imu_fwd(ctypes.byref(fi.gate.desc), 0, ptr(cv), N, ptr(out_mi), ptr(out_imu), stream()))
+        count_launch()
+        ctx.fi, ctx.csr, ctx.src_is_imu = fi, csr, src_is_imu
+        # parameter gradients are produced in training mode only (module.train()): an energy+force
+        # evaluation differentiates with respect to positions alone and must not pay for them
+        ctx.want_params = bool(fi.mp.training and any(p.requires_grad for p in params))
+        ctx.save_for_backward(x_imu, attrs, Y, xl, cv, *h, mid if ctx.want_params else None)
+        ctx.n_h = len(h)
+        return out_mi, out_imu
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, g_mi, g_imu):
+        lib = _lib.load()
+        fi, csr = ctx.fi, ctx.csr
+        conv = fi.conv
+        saved = ctx.saved_tensors
+        x_imu, attrs, Y, xl, cv = saved[:5]
+        h = list(saved[5:5 + ctx.n_h])
+        mid = saved[5 + ctx.n_h]
+        er, w = h[0], h[-1]
+        N, E = x_imu.shape[0], er.shape[0]
+        dev = x_imu.device
+        new = lambda *s: torch.empty(*s, dtype=torch.float32, device=dev)
+        need_x = ctx.needs_input_grad[0] or ctx.needs_input_grad[1]
+        need_attrs, need_er, need_Y = ctx.needs_input_grad[2], ctx.needs_input_grad[3], ctx.needs_input_grad[4]
+        need_params = ctx.want_params and any(ctx.needs_input_grad[7:])
+        need_attrs = need_attrs and ctx.want_params
+        if g_mi is None and g_imu is None:
+            return (None,) * (7 + len(ctx.needs_input_grad[7:]))
+        P = fi.packs("bwd")
+        # ---- gate
+        g_cv = new(N, fi.Dconv)
+        check(lib.e3b_gate_imu_bwd(ctypes.byref(fi.gate.desc), 0, ptr(cv), ptr(g_mi.contiguous()) if g_mi is not None else None,
+                                   ptr(g_imu.contiguous()) if g_imu is not None else None, N, ptr(g_cv), stream()))
+        count_launch()
+        # ---- post linear, transposed: g_mid[z, k, kk] = alpha sum_w W[kk, w] g_cv[z, k, w]
+        post, sc, lin1 = conv.tp.linear, conv.sc, conv.linear_1
+        plan = conv.tp.plan
+        g_mid = new(N, plan.y_dim)
+        probs, written = [], set()
+        for q, (i, o, off, alpha) in enumerate(post.paths):
+            bi, bo = fi.mid[i], fi.conv_out[o]
+            probs.append((ops.gemm_problem(g_cv, P["post"][q], g_mid, N * bi.ir.dim, a_off=fi.c_off[o],
+                                           a_rows=(fi.Dconv, bo.mul, bo.ir.dim), c_off=fi.m_off[i],
+                                           c_rows=(fi.Dmid, bi.mul, bi.ir.dim), alpha=alpha * fi.inv_sqrt_avg), i, False))
+            written.add(i)
+        if len(written) < len(fi.mid):
+            g_mid.zero_()
+        for wave in _waves(probs):
+            ops.gemm_run(wave)
+        # ---- tensor-product convolution backward
+        fast = plan.specialized
+        alloc = torch.empty if fast else torch.zeros
+        n_part = plan.n_part_f32 if fast else 1
+        gx_edge = alloc(E, plan.x_dim, dtype=torch.float32, device=dev) if need_x else None
+        gsh_part = alloc(E, n_part, plan.sh_dim, dtype=torch.float32, device=dev) if need_Y else None
+        gw = new(E, plan.w_dim)
+        if E:
+            end = ops._timed(("bwd", len(plan.structure.paths), plan.structure.uniform_mul, plan.x_dim, plan.y_dim, N, E))
+            check(lib.e3b_tpconv_bwd(plan.handle, 0, N, E, ptr(xl), ptr(Y), ptr(w), ptr(g_mid), ptr(csr.in_ptr),
+                                     ptr(csr.in_nbr), ptr(csr.in_eid), ptr(gx_edge), ptr(gsh_part), ptr(gw), stream()))
+            if end is not None:
+                end.record()
+            count_launch()
+        g_Y = None
+        if need_Y:
+            g_Y = gsh_part.sum(1) if n_part > 1 else gsh_part.view(E, plan.sh_dim)
+        # ---- radial MLP backward (data path): g_z_i = (g_z_{i+1} W_i^T) * act'(z_i), derivative from the stored h_i
+        hs = fi.hs
+        gz = [None] * (conv.fc.n_layers + 1)       # gz[i] = gradient wrt the INPUT of layer i (after its activation derivative)
+        gz[conv.fc.n_layers] = gw
+        lo = 0 if need_er else 1
+        for i in range(conv.fc.n_layers - 1, lo - 1, -1):
+            if not (need_er or need_params):
+                break
+            out = new(E, hs[i])
+            ops.gemm_run([ops.gemm_problem(gz[i + 1], P["fc"][i], out, E, alpha=1.0 / math.sqrt(hs[i]),
+                                           epilogue=3 if i > 0 else 0, H=h[i] if i > 0 else None, act_cst=conv.fc.cst)])
+            gz[i] = out
+        g_er = gz[0] if need_er else None
+        # ---- d/dx: linear_1 transposed on the reduced edge gradient + self-connection transposed
+        g_x = g_xl = None
+        if need_x:
+            g_xl = new(N, fi.Din)
+            check(lib.e3b_segment_sum(0, ptr(gx_edge), plan.x_dim, ptr(csr.out_ptr), ptr(csr.out_eid), N, ptr(g_xl), stream()))
+            count_launch()
+            g_x = new(N, fi.Din)
+            probs, written = [], set()
+            for q, (i, o, off, alpha) in enumerate(lin1.paths):
+                bi, bo = fi.feat_in[i], fi.feat_in[o]
+                probs.append((ops.gemm_problem(g_xl, P["lin1"][q], g_x, N * bi.ir.dim, a_off=fi.x_off[o],
+                                               a_rows=(fi.Din, bo.mul, bo.ir.dim), c_off=fi.x_off[i],
+                                               c_rows=(fi.Din, bi.mul, bi.ir.dim), alpha=alpha), i, False))
+                written.add(i)
+            sc_probs = []
+            for q, (i1, i2, o, off, alpha) in enumerate(sc.paths):
+                bi, bo = fi.feat_in[i1], fi.conv_out[o]
+                g = ops.gemm_problem(g_cv, P["sc"][q], g_x, N * bi.ir.dim, a_off=fi.c_off[o],
+                                     a_rows=(fi.Dconv, bo.mul, bo.ir.dim), c_off=fi.x_off[i1],
+                                     c_rows=(fi.Din, bi.mul, bi.ir.dim), alpha=alpha, epilogue=1, aux=attrs,
+                                     aux_d=bi.ir.dim, aux_group=fi.Vg)
+                sc_probs.append((g, i1, i1 in written))
+            if len(written | {t for _, t, _ in sc_probs}) < len(fi.feat_in):
+                g_x.zero_()
+            for wave in _waves(probs):
+                ops.gemm_run(wave)
+            # several self-connection paths may feed from one input block (0e -> scalars and gates)
+            for wave in _waves(sc_probs):
+                ops.gemm_run(wave)
+        # ---- parameter / attribute gradients (training only): library GEMMs on the saved activations
+        g_params = [None] * len(ctx.needs_input_grad[7:])
+        g_attrs = None
+        if need_params or need_attrs:
+            g_params, g_attrs = _param_grads(fi, ctx.needs_input_grad, x_imu, attrs, h, gz, mid, g_cv, g_xl, need_attrs)
+        g_x_mi = g_x_imu = None
+        if need_x:
+            if ctx.src_is_imu:
+                g_x_imu = g_x
+            else:
+                g_x_mi = g_x if fi.all_scalar_in else ops.layout_convert(g_x, fi.feat_in, False)
+        return (g_x_mi, g_x_imu, g_attrs, g_er, g_Y, None, None, *g_params)
+
+
+def _param_grads(fi, needs, x_imu, attrs, h, gz, mid, g_cv, g_xl, need_attrs):
+    conv = fi.conv
+    n_fc = conv.fc.n_layers
+    out = []
+    N = x_imu.shape[0]
+    for i in range(n_fc):
+        out.append((h[i].t() @ gz[i + 1]) * (1.0 / math.sqrt(fi.hs[i])) if needs[7 + i] else None)
+    # linear_1: dW[u, w] = alpha sum_{z, m} x[z, m, u] g_xl[z, m, w]
+    lin1 = conv.linear_1
+    g = None
+    if needs[7 + n_fc] and g_xl is not None:
+        g = torch.zeros_like(lin1.weight)
+        for i, o, off, alpha in lin1.paths:
+            bi, bo = fi.feat_in[i], fi.feat_in[o]
+            a = x_imu[:, fi.x_off[i]:fi.x_off[i] + bi.dim].reshape(-1, bi.mul)
+            b = g_xl[:, fi.x_off[o]:fi.x_off[o] + bo.dim].reshape(-1, bo.mul)
+            g[off:off + bi.mul * bo.mul] += (alpha * (a.t() @ b)).reshape(-1)
+    elif needs[7 + n_fc]:
+        g = torch.zeros_like(lin1.weight)
+    out.append(g)
+    # post linear: dW[kk, w] = alpha' sum_{z, k} mid[z, k, kk] g_cv[z, k, w]
+    post = conv.tp.linear
+    g = None
+    if needs[8 + n_fc]:
+        g = torch.zeros_like(post.weight)
+        for i, o, off, alpha in post.paths:
+            bi, bo = fi.mid[i], fi.conv_out[o]
+            a = mid[:, fi.m_off[i]:fi.m_off[i] + bi.dim].reshape(-1, bi.mul)
+            b = g_cv[:, fi.c_off[o]:fi.c_off[o] + bo.dim].reshape(-1, bo.mul)
+            g[off:off + bi.mul * bo.mul] += (alpha * fi.inv_sqrt_avg * (a.t() @ b)).reshape(-1)
+    out.append(g)
+    # self-connection: dW[u, v, w] = alpha sum_{z, m} x[z, m, u] a[z, v] g[z, m, w];  da[z, v] likewise
+    sc = conv.sc
+    g = torch.zeros_like(sc.weight) if needs[9 + n_fc] else None
+    g_attrs = torch.zeros_like(attrs) if need_attrs else None
+    if g is not None or g_attrs is not None:
+        V = fi.V
+        for i1, i2, o, off, alpha in sc.paths:
+            bi, bo = fi.feat_in[i1], fi.conv_out[o]
+            xa = x_imu[:, fi.x_off[i1]:fi.x_off[i1] + bi.dim].reshape(N, bi.ir.dim, bi.mul)
+            gb = g_cv[:, fi.c_off[o]:fi.c_off[o] + bo.dim].reshape(N, bi.ir.dim, bo.mul)
+            t = torch.einsum("zmu,zmw->zuw", xa, gb)                     # [z, u, w]
+            if g is not None:
+                g[off:off + bi.mul * V * bo.mul] += (alpha * torch.einsum("zuw,zv->uvw", t, attrs)).reshape(-1)
+            if g_attrs is not None:
+                W = sc.weight[off:off + bi.mul * V * bo.mul].reshape(bi.mul, V, bo.mul)
+                g_attrs += alpha * torch.einsum("zuw,uvw->zv", t, W)
+    out.append(g)
+    return out, g_attrs
+
+
+def interaction(fi, x, attrs, er, Y, csr):
+    """-> (out mul_ir, out imu).  `x` is the mul_ir feature tensor; if it carries the imu twin written by the
+    previous block's gate (attribute ``_e3b_imu``) that one is consumed instead, so no layout pass runs."""
+    twin = getattr(x, "_e3b_imu", None)
+    params = fi._params()
+    if twin is not None:
+        return _Interaction.apply(None, twin, attrs, er, Y, fi, csr, *params)
+    return _Interaction.apply(x, None, attrs, er, Y, fi, csr, *params)

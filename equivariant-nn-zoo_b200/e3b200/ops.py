@@ -402,44 +402,47 @@ class PackedWeight:
 
 
 def gemm_pack(views):
-    """views: list of (src fp32 CUDA tensor, element offset, s1, s2, sk, d, N, K): element (n, k),
-    n = n1 * d + n2, is src.flat[offset + n1 * s1 + n2 * s2 + k * sk].  -> list of PackedWeight
+    """views: list of (src fp32 CUDA tensor, element offset, s1, s2, sk, d, n2_valid, N, K): element (n, k),
+    n = n1 * d + n2, is src.flat[offset + n1 * s1 + n2 * s2 + k * sk] (zero for n2 >= n2_valid > 0).
+    -> list of PackedWeight
     (one kernel launch per E3B_GEMM_MAX_GROUP views)."""
     lib = _lib.load()
     out = []
     for lo in range(0, len(views), _lib.E3B_GEMM_MAX_GROUP):
         chunk = views[lo:lo + _lib.E3B_GEMM_MAX_GROUP]
         descs = (_lib.GemmPackDesc * len(chunk))()
-        for i, (src, off, s1, s2, sk, d, N, K) in enumerate(chunk):
+        for i, (src, off, s1, s2, sk, d, n2_valid, N, K) in enumerate(chunk):
             require_cuda(src)
             assert src.dtype == torch.float32
             pw = PackedWeight(N, K, src.device)
             out.append(pw)
             descs[i].src, descs[i].dst = src.data_ptr() + 4 * off, pw.buf.data_ptr()
             descs[i].s1, descs[i].s2, descs[i].sk, descs[i].d, descs[i].N, descs[i].K = s1, s2, sk, d, N, K
+            descs[i].n2_valid = n2_valid
         check(lib.e3b_gemm_pack(descs, len(chunk), stream()))
         count_launch()
     return out
 
 
 def gemm_problem(A, Bp, C, M, a_off=0, a_rows=None, c_off=0, c_rows=None, c_col_stride=1, alpha=1.0, epilogue=0,
-                 accumulate=False, aux=None, aux_d=1, H=None, act_cst=1.0):
+                 accumulate=False, aux=None, aux_d=1, aux_group=None, H=None, act_cst=1.0):
     """One problem of a grouped launch: C[r, n] = epilogue(sum_k A[r, k] B[n, k]).  A / C are fp32 CUDA
     tensors used as raw storage (element offsets a_off / c_off); ``a_rows`` / ``c_rows`` = (s1, s2, d)
     give the affine row addressing base + (r // d) * s1 + (r % d) * s2 (default: dense rows)."""
     N, K = Bp.N, Bp.K
     g = _lib.GemmProblem()
     a_s1, a_s2, a_d = a_rows if a_rows is not None else (K, 0, 1)
-    n_out = N if epilogue != 1 else N // aux.shape[1]
+    V = (aux_group or aux.shape[1]) if aux is not None else 0
+    n_out = N if epilogue != 1 else N // V
     c_s1, c_s2, c_d = c_rows if c_rows is not None else (n_out * c_col_stride, 0, 1)
     g.A, g.a_s1, g.a_s2, g.a_d = A.data_ptr() + 4 * a_off, a_s1, a_s2, a_d
     g.B_packed = Bp.buf.data_ptr()
     g.C, g.c_s1, g.c_s2, g.c_s3, g.c_d = C.data_ptr() + 4 * c_off, c_s1, c_s2, c_col_stride, c_d
     if aux is not None:
         assert aux.is_contiguous() and aux.dtype == torch.float32
-        g.aux, g.aux_ld, g.aux_d, g.V = aux.data_ptr(), aux.stride(0), aux_d, aux.shape[1]
+        g.aux, g.aux_ld, g.aux_d, g.V, g.aux_cols = aux.data_ptr(), aux.stride(0), aux_d, V, aux.shape[1]
     else:
-        g.aux, g.aux_ld, g.aux_d, g.V = None, 0, 1, 0
+        g.aux, g.aux_ld, g.aux_d, g.V, g.aux_cols = None, 0, 1, 0, 0
     if H is not None:
         assert H.dtype == torch.float32 and H.stride(1) == 1
         g.H, g.h_ld = H.data_ptr(), H.stride(0)
@@ -474,7 +477,7 @@ def gemm_tf32x3(A, B, C, M, N, K, a_rows=None, c_rows=None, c_col_stride=1, alph
     contracts every group of V accumulator columns with aux[r // aux_d] (self-connection)."""
     require_cuda(A, B, C)
     assert A.dtype == B.dtype == C.dtype == torch.float32
-    (Bp,) = gemm_pack([(B, 0, B.stride(0), 0, B.stride(1) if B.dim() == 2 else 1, 1, N, K)])
+    (Bp,) = gemm_pack([(B, 0, B.stride(0), 0, B.stride(1) if B.dim() == 2 else 1, 1, 0, N, K)])
     if epilogue is None:
         epilogue = 1 if reduce_aux is not None else 0
     gemm_run([gemm_problem(A, Bp, C, M, a_rows=a_rows, c_rows=c_rows, c_col_stride=c_col_stride, alpha=alpha,

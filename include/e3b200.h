@@ -197,6 +197,15 @@ E3B_API int e3b_gate_fwd(const e3b_gate_desc* desc, int dtype, const void* in, i
 E3B_API int e3b_gate_bwd(const e3b_gate_desc* desc, int dtype, const void* in, const void* gout, int64_t n, void* gin,
                  void* stream);
 
+/* The same gate on the library's channel-fastest layout: `in` is [scalars | gates | gated] with the
+ * gated blocks stored [m][u]; the result is written in the imu layout (out_imu) and / or e3nn's
+ * mul_ir layout (out_mul_ir); either may be NULL.  The backward accepts the gradient in either or
+ * both layouts (summed) and returns d/d in in the imu layout.                                  */
+E3B_API int e3b_gate_imu_fwd(const e3b_gate_desc* desc, int dtype, const void* in, int64_t n, void* out_mul_ir,
+                             void* out_imu, void* stream);
+E3B_API int e3b_gate_imu_bwd(const e3b_gate_desc* desc, int dtype, const void* in, const void* gout_mul_ir,
+                             const void* gout_imu, int64_t n, void* gin, void* stream);
+
 /* ---------------------------------------------------------------------------------------
  * Dense contractions on the tcgen05 tensor cores, fp32-faithful (3xTF32 split, fp32 TMEM
  * accumulators, accumulation chains cut every 128 floats of K).  Replaces the cuBLAS/einsum
@@ -218,7 +227,7 @@ E3B_API int e3b_gate_bwd(const e3b_gate_desc* desc, int dtype, const void* in, c
  *
  * B is consumed in a packed form (TF32 hi/lo split, UMMA canonical tiles) produced by
  * e3b_gemm_pack from any strided view of the weight: element (n, k), n = n1 * d + n2, is read
- * from src[n1 * s1 + n2 * s2 + k * sk].  dst needs e3b_gemm_packed_floats(N, K) floats,
+ * from src[n1 * s1 + n2 * s2 + k * sk] (zero when n2 >= n2_valid > 0).  dst needs e3b_gemm_packed_floats(N, K) floats,
  * 128-byte aligned; repack only when the weight changes.
  * e3b_gemm_run launches up to E3B_GEMM_MAX_GROUP independent problems (e.g. the irreps blocks
  * of one o3.Linear) as ONE persistent kernel; they must share the tile shape, i.e. agree on
@@ -236,6 +245,7 @@ typedef struct {
   const float* aux;      /* epilogue 1 */
   int64_t aux_ld;
   int32_t aux_d, V;
+  int32_t aux_cols;      /* valid columns of aux (<= V; 0 means V): narrower attributes are zero-extended */
   const float* H;        /* epilogue 3 */
   int64_t h_ld;
   int32_t M, N, K;
@@ -247,6 +257,7 @@ typedef struct {
   const float* src;
   int64_t s1, s2, sk;
   int32_t d;
+  int32_t n2_valid;      /* rows with n2 >= n2_valid are zero (0 means all valid): pads a group to V */
   int32_t N, K;
   float* dst;
 } e3b_gemm_pack_desc;

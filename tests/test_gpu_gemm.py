@@ -94,7 +94,7 @@ def test_gemm_grouped_launch(K, N):
     dims = [1, 3, 5]
     offs = [0, K, 4 * K]
     Ws = [torch.randn(N, K, generator=g) for _ in dims]
-    packed = ops.gemm_pack([(w.to(DEV), 0, K, 0, 1, 1, N, K) for w in Ws])
+    packed = ops.gemm_pack([(w.to(DEV), 0, K, 0, 1, 1, 0, N, K) for w in Ws])
     out = torch.zeros(Z, 9 * N, device=DEV)
     probs = []
     for d, off, pw in zip(dims, offs, packed):

@@ -40,7 +40,7 @@ for name, M, N, K in SHAPES:
     A = torch.randn(M, K, device=dev)
     B = torch.randn(N, K, device=dev)
     C = torch.empty(M, N, device=dev)
-    (Bp,) = ops.gemm_pack([(B, 0, K, 0, 1, 1, N, K)])
+    (Bp,) = ops.gemm_pack([(B, 0, K, 0, 1, 1, 0, N, K)])
     prob = [ops.gemm_problem(A, Bp, C, M)]
     t = timeit(lambda: ops.gemm_run(prob))
     torch.backends.cuda.matmul.allow_tf32 = False

@@ -7,7 +7,7 @@ from e3b200 import ops
 dev = torch.device("cuda"); E = 149452
 for name, M, N, K in [("s1", E, 1920, 64), ("s2", E, 64, 1920)]:
     A = torch.randn(M, K, device=dev); B = torch.randn(N, K, device=dev); C = torch.empty(M, N, device=dev)
-    (Bp,) = ops.gemm_pack([(B, 0, K, 0, 1, 1, N, K)])
+    (Bp,) = ops.gemm_pack([(B, 0, K, 0, 1, 1, 0, N, K)])
     prob = [ops.gemm_problem(A, Bp, C, M)]
     for _ in range(3): ops.gemm_run(prob)
     torch.cuda.synchronize()

@@ -18,7 +18,7 @@ for w in which:
     A = torch.randn(M, K, device=dev)
     B = torch.randn(N, K, device=dev)
     C = torch.empty(M, N, device=dev)
-    (Bp,) = ops.gemm_pack([(B, 0, K, 0, 1, 1, N, K)])
+    (Bp,) = ops.gemm_pack([(B, 0, K, 0, 1, 1, 0, N, K)])
     prob = [ops.gemm_problem(A, Bp, C, M)]
     for _ in range(3):
         ops.gemm_run(prob)
