@@ -21,7 +21,7 @@
 // Three pipelines (mbarrier full/empty pairs): A ring, B ring, two TMEM accumulators.  When the
 // whole K extent of a row tile fits the A ring it stays RESIDENT across the column tiles.
 // The tensor core accumulates with truncation, so an unbroken chain over a long K drifts
-// (1.5e-5 at K = 1920, measured): chains are cut every 128 floats of K and the partial sums are
+// (1.5e-5 at K = 1920, measured): chains are cut every 64 floats of K and the partial sums are
 // added in fp32 registers by the epilogue warps while the next chain runs in the other buffer.
 #include <cuda_runtime.h>
 #include <stdint.h>
@@ -35,7 +35,7 @@ namespace {
 
 constexpr int BM = 128;     // UMMA M
 constexpr int BK = 32;      // floats per K chunk = 4 MMA K-steps of 8 = 8 sixteen-byte columns
-constexpr int KSEG = 4;     // chunks per accumulation chain (128 floats of K)
+constexpr int KSEG = 2;     // chunks per accumulation chain (64 floats of K)
 constexpr int NACC = 4;     // TMEM accumulator buffers
 constexpr int NTHREADS = 448;
 constexpr int NCVT = 256;    // converter threads (warps 4-11)
@@ -45,7 +45,8 @@ constexpr int MAXG = E3B_GEMM_MAX_GROUP;
 struct Problem {
   e3b_gemm_problem p;
   int32_t m_tiles, n_tiles, k_chunks;
-  int32_t gx, gy;        // CTA grid of this problem: row tiles bx, bx+gx, ..; column tiles by, by+gy, ..
+  int32_t n_ctas;        // CTAs of this problem; CTA i walks the tiles [i * T / n, (i + 1) * T / n), T = m_tiles * n_tiles,
+                         // in row-major order (tile t = row tile t / n_tiles, column tile t % n_tiles)
   int32_t cta_begin;     // first CTA (blockIdx.x) of this problem
   uint64_t a_mul;        // ceil(2^40 / a_d): r / a_d == (r * a_mul) >> 40 for r < 2^31, a_d < 512
   int32_t dbg;           // E3B_GEMM_DEBUG bisection bits: 1 skip A load+convert, 2 skip MMA, 4 skip B loads, 8 skip stores
@@ -169,7 +170,7 @@ struct EpiCtx {
   uint64_t* acc_empty;
   float* stg;            // warp-private staging tile [32][36]
   uint32_t tmem_base;
-  int bx, by, k_chunks;
+  int t0, t1, k_chunks;
 };
 
 template <int EPI> __device__ __forceinline__ float epi_apply(float o, float h, float cst) {
@@ -192,30 +193,38 @@ __device__ __forceinline__ void epilogue_role(const EpiCtx& c) {
   const int t_row = lane >> 3, t_c4 = (lane & 7) * 4;     // transposed role: rows t_row + 4 i, columns t_c4..+3
   const float alpha = g.alpha, cst = g.act_cst;
   const bool accumulate = g.accumulate != 0;
-  for (int m = c.bx; m < P.m_tiles; m += P.gx) {
+  int m_cur = -1;
+  bool row_ok = false;
+  float* c_row = nullptr;
+  const float* h_row = nullptr;
+  float aux[EPI == 1 ? 32 : 1];
+  int r_base = 0;
+  for (int t = c.t0; t < c.t1; ++t) {
+    const int m = t / P.n_tiles, n = t - m * P.n_tiles;
+    if (m != m_cur) {
+    m_cur = m;
     const int row = m * BM + tid;
-    const bool row_ok = row < g.M;
-    float* c_row = nullptr;
-    const float* h_row = nullptr;
+    row_ok = row < g.M;
     if (row_ok && !DENSE) {
       c_row = g.C + (int64_t)(row / g.c_d) * g.c_s1 + (int64_t)(row % g.c_d) * g.c_s2;
       if (EPI == 3) h_row = g.H + (int64_t)row * g.h_ld;
     }
-    float aux[EPI == 1 ? 32 : 1];
     if (EPI == 1) {
 #pragma unroll
       for (int v = 0; v < (EPI == 1 ? 32 : 1); ++v)
         aux[v] = (row_ok && v < (g.aux_cols > 0 ? g.aux_cols : g.V)) ? __ldg(g.aux + (int64_t)(row / g.aux_d) * g.aux_ld + v) : 0.f;
     }
     // DENSE: rows of this warp's quarter tile handled by this lane after the transposition
-    const int r_base = m * BM + warp * 32 + t_row;
-    for (int n = c.by; n < P.n_tiles; n += P.gy) {
+    r_base = m * BM + warp * 32 + t_row;
+    }
+    {
       const int n0 = n * BN;
       float racc[MULTI ? BN : 1];
       if (MULTI) {
 #pragma unroll
         for (int i = 0; i < (MULTI ? BN : 1); ++i) racc[i] = 0.f;
       }
+      float red[EPI == 1 ? BN / 16 : 1];   // epilogue 1: the reduced outputs of this column tile
       for (int seg = 0; seg < (MULTI ? n_seg : 1); ++seg, ++acc_it) {
         const uint32_t buf = acc_it % NACC;
         mbar_wait(&c.acc_full[buf], (acc_it / NACC) & 1u);
@@ -258,25 +267,17 @@ __device__ __forceinline__ void epilogue_role(const EpiCtx& c) {
             }
           } else if (EPI == 1) {
             // weighted reduction over groups of V accumulator columns (self-connection)
-            if (row_ok) {
-              if (g.V == 16) {
-                float s0 = 0.f, s1 = 0.f;
+            if (g.V == 16) {
+              float s0 = 0.f, s1 = 0.f;
 #pragma unroll
-                for (int t = 0; t < 16; ++t) { s0 = fmaf(aux[EPI == 1 ? t : 0], v[t], s0); s1 = fmaf(aux[EPI == 1 ? t : 0], v[16 + t], s1); }
-                const int oc = nb / 16;
-                float* c0 = c_row + (int64_t)oc * g.c_s3;
-                *c0 = alpha * s0 + (accumulate ? *c0 : 0.f);
-                if ((oc + 1) * 16 < g.N) {
-                  float* c1 = c0 + g.c_s3;
-                  *c1 = alpha * s1 + (accumulate ? *c1 : 0.f);
-                }
-              } else {
-                float s0 = 0.f;
+              for (int t = 0; t < 16; ++t) { s0 = fmaf(aux[EPI == 1 ? t : 0], v[t], s0); s1 = fmaf(aux[EPI == 1 ? t : 0], v[16 + t], s1); }
+              red[EPI == 1 ? cb / 16 : 0] = alpha * s0;
+              red[EPI == 1 ? cb / 16 + 1 : 0] = alpha * s1;
+            } else {
+              float s0 = 0.f;
 #pragma unroll
-                for (int t = 0; t < 32; ++t) s0 = fmaf(aux[EPI == 1 ? t : 0], v[t], s0);
-                float* c0 = c_row + (int64_t)(nb / 32) * g.c_s3;
-                *c0 = alpha * s0 + (accumulate ? *c0 : 0.f);
-              }
+              for (int t = 0; t < 32; ++t) s0 = fmaf(aux[EPI == 1 ? t : 0], v[t], s0);
+              red[EPI == 1 ? cb / 32 : 0] = alpha * s0;
             }
           } else {
             // generic (strided) output: one scalar store per element
@@ -293,12 +294,35 @@ __device__ __forceinline__ void epilogue_role(const EpiCtx& c) {
         }
         tc_fence_before();
         mbar_arrive(&c.acc_empty[buf]);
+        if (EPI == 1 && last && row_ok) {
+          // outputs of this tile: columns n0 / V .. of the row; whole sectors when the row is contiguous
+          const int per = BN / g.V, oc0 = n0 / g.V, n_out = g.N / g.V;
+          float* c0 = c_row + (int64_t)oc0 * g.c_s3;
+          if (g.c_s3 == 1 && (per & 3) == 0 && oc0 + per <= n_out && (reinterpret_cast<uintptr_t>(c0) & 15) == 0) {
+#pragma unroll
+            for (int i = 0; i < (EPI == 1 ? BN / 16 : 1); i += 4) {
+              if (i < per) {
+                float4 o = make_float4(red[EPI == 1 ? i : 0], red[EPI == 1 ? i + 1 : 0], red[EPI == 1 ? i + 2 : 0], red[EPI == 1 ? i + 3 : 0]);
+                float4* d4 = reinterpret_cast<float4*>(c0 + i);
+                if (accumulate) { const float4 old = *d4; o.x += old.x; o.y += old.y; o.z += old.z; o.w += old.w; }
+                *d4 = o;
+              }
+            }
+          } else {
+#pragma unroll
+            for (int i = 0; i < (EPI == 1 ? BN / 16 : 1); ++i)
+              if (i < per && oc0 + i < n_out) {
+                float* cp = c0 + (int64_t)i * g.c_s3;
+                *cp = red[EPI == 1 ? i : 0] + (accumulate ? *cp : 0.f);
+              }
+          }
+        }
       }
     }
   }
 }
 
-// the tile walk every role repeats:  for (m = bx; m < m_tiles; m += gx) for (n = by; n < n_tiles; n += gy)
+// every role repeats the same walk over this CTA's tile range [t0, t1)
 template <int BN, bool MULTI, int SA, int PRAW, int SB>
 __global__ void __launch_bounds__(NTHREADS, 1) gemm_tf32x3_kernel(const __grid_constant__ Batch batch) {
   using L = Smem<BN, SA, PRAW, SB>;
@@ -321,10 +345,10 @@ __global__ void __launch_bounds__(NTHREADS, 1) gemm_tf32x3_kernel(const __grid_c
   const Problem& P = batch.pr[gi];
   const e3b_gemm_problem& g = P.p;
   const int local = (int)blockIdx.x - P.cta_begin;
-  const int bx = local % P.gx, by = local / P.gx;
+  const int n_all = P.m_tiles * P.n_tiles;
+  const int t0 = (int)((int64_t)local * n_all / P.n_ctas), t1 = (int)((int64_t)(local + 1) * n_all / P.n_ctas);
   const int k_chunks = P.k_chunks;
   const bool resident = k_chunks <= SA;
-  const int n_count = by < P.n_tiles ? (P.n_tiles - by + P.gy - 1) / P.gy : 0;   // column tiles of this CTA
 
   if (warp == 13) {  // TMEM allocation is warp-collective; the same warp frees it
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_addr(&tmem_base_smem)), "r"((uint32_t)(NACC * BN)) : "memory");
@@ -341,7 +365,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) gemm_tf32x3_kernel(const __grid_c
   tc_fence_after();
   const uint32_t tmem_base = tmem_base_smem;
 
-  if (n_count > 0 && bx < P.m_tiles) {
+  if (t1 > t0) {
     if (warp >= 4 && warp < 12) {
       // =============================== A converter ===============================
       // thread -> one 16-byte column `col` of the chunk and the 4 rows row0 + 32 i: a quarter-warp
@@ -351,9 +375,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) gemm_tf32x3_kernel(const __grid_c
       const int cw = ct >> 5;
       const int col = (cw & 1) * 4 + (lane >> 3);
       const int row0 = 8 * (cw >> 1) + (lane & 7);      // rows row0 + 32 i, i = 0..3
-      const int reps = resident ? 1 : n_count;
-      const int m_count = (P.m_tiles - bx + P.gx - 1) / P.gx;
-      const int total = m_count * reps * k_chunks;
+      // jobs: one per K chunk of every tile (streaming) or of every distinct row tile (resident A)
+      const int total = (resident ? (t1 - 1) / P.n_tiles - t0 / P.n_tiles + 1 : t1 - t0) * k_chunks;
       // issue stream state (runs PRAW - 1 jobs ahead of the conversion)
       int64_t roff[4];
       uint32_t rbytes[4];
@@ -367,8 +390,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) gemm_tf32x3_kernel(const __grid_c
           if (r >= g.M) roff[i] = 0;
         }
       };
-      int i_m = bx, i_rep = 0, i_kc = 0, i_slot = 0, i_left = total;
-      load_rows(i_m);
+      int i_t = t0, i_kc = 0, i_slot = 0, i_left = total;
+      load_rows(i_t / P.n_tiles);
       auto issue = [&]() {
         if (i_left > 0 && !(P.dbg & 1)) {
           --i_left;
@@ -380,11 +403,9 @@ __global__ void __launch_bounds__(NTHREADS, 1) gemm_tf32x3_kernel(const __grid_c
             cp_async16(dst + i * (NCVT * 4), g.A + roff[i] + (kok ? k : 0), kok ? rbytes[i] : 0u);
           if (++i_kc == k_chunks) {
             i_kc = 0;
-            if (++i_rep == reps) {
-              i_rep = 0;
-              i_m += P.gx;
-              if (i_left > 0) load_rows(i_m);
-            }
+            const int m_old = i_t / P.n_tiles;
+            i_t = resident ? (m_old + 1) * P.n_tiles : i_t + 1;
+            if (i_left > 0 && i_t / P.n_tiles != m_old) load_rows(i_t / P.n_tiles);
           }
         }
         if (++i_slot == PRAW) i_slot = 0;
@@ -422,8 +443,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) gemm_tf32x3_kernel(const __grid_c
       if (lane == 0) {
         uint32_t it = 0;
         constexpr uint32_t bytes = (uint32_t)L::B_STAGE * 4u;
-        for (int m = bx; m < P.m_tiles; m += P.gx)
-          for (int n = by; n < P.n_tiles; n += P.gy)
+        for (int t = t0; t < t1; ++t) {
+          const int n = t % P.n_tiles;
             for (int kc = 0; kc < k_chunks; ++kc, ++it) {
               const int st = it % SB;
               mbar_wait(&b_empty[st], ((it / SB) & 1u) ^ 1u);
@@ -431,6 +452,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) gemm_tf32x3_kernel(const __grid_c
               mbar_expect_tx(&b_full[st], bytes);
               bulk_g2s(sB + (size_t)st * L::B_STAGE, g.B_packed + ((size_t)n * k_chunks + kc) * L::B_STAGE, bytes, &b_full[st]);
             }
+        }
       }
     } else if (warp == 13) {
       // =============================== MMA issuer ===============================
@@ -441,9 +463,10 @@ __global__ void __launch_bounds__(NTHREADS, 1) gemm_tf32x3_kernel(const __grid_c
       // descriptor templates: LBO / SBO / version bits fixed, 14-bit start address added per use
       const uint64_t tmplA = umma_desc(0, BM * 16, 128), tmplB = umma_desc(0, BN * 16, 128);
       uint32_t a_it = 0, b_it = 0, acc_it = 0;
-      for (int m = bx; m < P.m_tiles; m += P.gx) {
-        int ni = 0;
-        for (int n = by; n < P.n_tiles; n += P.gy, ++ni) {
+      for (int t = t0; t < t1; ++t) {
+        const int n = t % P.n_tiles;
+        const bool first_m = t == t0 || n == 0, last_m = t == t1 - 1 || n == P.n_tiles - 1;
+        {
           uint32_t buf = 0;
           for (int kc = 0; kc < k_chunks; ++kc) {
             const bool seg_first = (kc % KSEG) == 0;
@@ -453,7 +476,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) gemm_tf32x3_kernel(const __grid_c
             }
             const uint32_t a_idx = resident ? a_it + (uint32_t)kc : a_it;
             const uint32_t sa = a_idx % SA, sb = b_it % SB;
-            if (!resident || ni == 0) mbar_wait(&a_full[sa], (a_idx / SA) & 1u);
+            if (!resident || first_m) mbar_wait(&a_full[sa], (a_idx / SA) & 1u);
             mbar_wait(&b_full[sb], (b_it / SB) & 1u);
             tc_fence_after();
             const bool seg_last = (kc % KSEG) == KSEG - 1 || kc == k_chunks - 1;
@@ -471,7 +494,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) gemm_tf32x3_kernel(const __grid_c
                 umma_tf32(d, dAh + oA, dBh + oB, idesc, 1u);
               }
               umma_commit(&b_empty[sb]);
-              if (!resident || ni == n_count - 1) umma_commit(&a_empty[sa]);
+              if (!resident || last_m) umma_commit(&a_empty[sa]);
               if (seg_last) umma_commit(&acc_full[buf]);
             }
             __syncwarp();
@@ -480,13 +503,13 @@ __global__ void __launch_bounds__(NTHREADS, 1) gemm_tf32x3_kernel(const __grid_c
             if (!resident) ++a_it;
           }
         }
-        if (resident) a_it += (uint32_t)k_chunks;
+        if (resident && last_m) a_it += (uint32_t)k_chunks;
       }
     } else if (warp < 4) {
       // =============================== epilogue ===============================
       const bool dense = g.c_s3 == 1 && g.c_d == 1 && (g.c_s1 & 3) == 0 && (g.N & 3) == 0 &&
                          (reinterpret_cast<uintptr_t>(g.C) & 15) == 0 && (g.epilogue != 3 || (g.h_ld & 3) == 0);
-      EpiCtx c{&P, acc_full, acc_empty, sEpi + warp * L::EPI_STAGE, tmem_base, bx, by, k_chunks};
+      EpiCtx c{&P, acc_full, acc_empty, sEpi + warp * L::EPI_STAGE, tmem_base, t0, t1, k_chunks};
       if (g.epilogue == 1) epilogue_role<BN, MULTI, 1, false>(c);
       else if (g.epilogue == 0) { if (dense) epilogue_role<BN, MULTI, 0, true>(c); else epilogue_role<BN, MULTI, 0, false>(c); }
       else if (g.epilogue == 2) { if (dense) epilogue_role<BN, MULTI, 2, true>(c); else epilogue_role<BN, MULTI, 2, false>(c); }
@@ -613,7 +636,7 @@ extern "C" int e3b_gemm_run(const e3b_gemm_problem* problems, int32_t n, void* s
     if (b.n == 0) { bn = t; multi = mu; }
     else if (bn != t || multi != mu)
       return e3b_fail(E3B_ERR_UNSUPPORTED, "gemm_run: the problems of one launch must share the tile shape "
-                      "(K <= 128 or not; N <= 64 or not)");
+                      "(K <= 64 or not; N <= 64 or not)");
     Problem& P = b.pr[b.n];
     P.p = p;
     P.m_tiles = (p.M + BM - 1) / BM;
@@ -627,21 +650,38 @@ extern "C" int e3b_gemm_run(const e3b_gemm_problem* problems, int32_t n, void* s
     ++b.n;
   }
   if (b.n == 0) return E3B_OK;
-  // CTAs per problem proportional to its work; one CTA per SM is resident (persistent tile walk)
-  const int target = b.n == 1 ? 148 : 296;
+  // one persistent CTA per SM in total: CTAs per problem proportional to its work (>= 1, <= its tiles)
+  const int target = 148;
+  int want[MAXG], sum = 0;
+  for (int i = 0; i < b.n; ++i) {
+    const int64_t tiles = (int64_t)b.pr[i].m_tiles * b.pr[i].n_tiles;
+    int64_t w = (int64_t)(target * work[i] / total_work);
+    if (w < 1) w = 1;
+    if (w > tiles) w = tiles;
+    want[i] = (int)w;
+    sum += want[i];
+  }
+  for (bool moved = true; moved && sum != target;) {   // hand out / take back the rounding remainder
+    moved = false;
+    int best = -1;
+    double best_v = 0;
+    for (int i = 0; i < b.n; ++i) {
+      const int64_t tiles = (int64_t)b.pr[i].m_tiles * b.pr[i].n_tiles;
+      if (sum < target && want[i] < tiles) {
+        const double v = work[i] / want[i];                 // most loaded CTAs get help first
+        if (best < 0 || v > best_v) { best = i; best_v = v; }
+      } else if (sum > target && want[i] > 1) {
+        const double v = -work[i] / (want[i] - 1);          // cheapest to shrink
+        if (best < 0 || v > best_v) { best = i; best_v = v; }
+      }
+    }
+    if (best >= 0) { want[best] += sum < target ? 1 : -1; sum += sum < target ? 1 : -1; moved = true; }
+  }
   int ctas = 0;
   for (int i = 0; i < b.n; ++i) {
-    Problem& P = b.pr[i];
-    int64_t want = (int64_t)(target * work[i] / total_work + 0.5);
-    const int64_t tiles = (int64_t)P.m_tiles * P.n_tiles;
-    if (want < 1) want = 1;
-    if (want > tiles) want = tiles;
-    P.gx = (int)(want < P.m_tiles ? want : P.m_tiles);
-    P.gy = (int)(want / P.gx);
-    if (P.gy < 1) P.gy = 1;
-    if (P.gy > P.n_tiles) P.gy = P.n_tiles;
-    P.cta_begin = ctas;
-    ctas += P.gx * P.gy;
+    b.pr[i].n_ctas = want[i];
+    b.pr[i].cta_begin = ctas;
+    ctas += want[i];
   }
   cudaError_t e;
   if (multi) e = launch<64, true, 2, 7, 2>(b, ctas, (cudaStream_t)stream);

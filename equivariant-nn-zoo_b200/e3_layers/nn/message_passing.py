@@ -8,6 +8,7 @@ self-connection.  ``MessagePassing`` adds the gate non-linearity (kernel), optio
 LayerNormalization.  Constructor kwargs, forward protocol and parameter names follow the reference."""
 import ctypes
 import math
+import os
 
 import torch
 
@@ -17,6 +18,10 @@ from e3b200.irreps import Irreps
 from ..utils import activation_name, build, tp_path_exists
 from .pointwise import LayerNormalization, TensorProductExpansion
 from .sequential import Module
+
+
+# E3B_FUSED=0 composes the block op by op (A/B comparison of the two fp32 paths; both are CUDA kernels)
+FUSED_BLOCKS = os.environ.get("E3B_FUSED", "1") != "0"
 
 
 class FactorizedConvolution(Module):
@@ -127,7 +132,7 @@ class MessagePassing(Module):
 
     def forward(self, data, attrs):
         skip = data["input_features"]
-        if skip.dtype == torch.float32 and skip.is_cuda and self.fused.reason is None:
+        if skip.dtype == torch.float32 and skip.is_cuda and self.fused.reason is None and FUSED_BLOCKS:
             edge_index = data["edge_index"]
             csr = ops.graph_of(edge_index, skip.shape[0])
             out, out_imu = interaction.interaction(self.fused, skip, data["node_attrs"], data["edge_radial"],

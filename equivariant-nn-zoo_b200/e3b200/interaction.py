@@ -183,27 +183,29 @@ class _Interaction(torch.autograd.Function):
         # ---- post-reduction linear (scaled by 1/sqrt(avg_num_neighbors)) + self-connection, both into conv (imu)
         post, sc = conv.tp.linear, conv.sc
         cv = new(N, fi.Dconv)
-        probs, written = [], set()
-        for q, (i, o, off, alpha) in enumerate(post.paths):
-            bi, bo = fi.mid[i], fi.conv_out[o]
-            probs.append((ops.gemm_problem(mid, P["post"][q], cv, N * bi.ir.dim, a_off=fi.m_off[i],
-                                           a_rows=(fi.Dmid, bi.mul, bi.ir.dim), c_off=fi.c_off[o],
-                                           c_rows=(fi.Dconv, bo.mul, bo.ir.dim), alpha=alpha * fi.inv_sqrt_avg), o, False))
-            written.add(o)
-        sc_probs = []
+        # (the self-connection writes first: its reducing epilogue stores whole sectors without reading;
+        #  the dense epilogue of the linear map then accumulates with coalesced read-modify-writes)
+        sc_probs, written = [], set()
         for q, (i1, i2, o, off, alpha) in enumerate(sc.paths):
             bi, bo = fi.feat_in[i1], fi.conv_out[o]
             g = ops.gemm_problem(x_imu, P["sc"][q], cv, N * bi.ir.dim, a_off=fi.x_off[i1],
                                  a_rows=(fi.Din, bi.mul, bi.ir.dim), c_off=fi.c_off[o],
                                  c_rows=(fi.Dconv, bo.mul, bo.ir.dim), alpha=alpha, epilogue=1, aux=attrs,
                                  aux_d=bi.ir.dim, aux_group=fi.Vg)
-            sc_probs.append((g, o, o in written))
-        all_written = written | {o for _, o, _ in sc_probs}
-        if len(all_written) < len(fi.conv_out):
+            sc_probs.append((g, o, False))
+            written.add(o)
+        probs = []
+        for q, (i, o, off, alpha) in enumerate(post.paths):
+            bi, bo = fi.mid[i], fi.conv_out[o]
+            probs.append((ops.gemm_problem(mid, P["post"][q], cv, N * bi.ir.dim, a_off=fi.m_off[i],
+                                           a_rows=(fi.Dmid, bi.mul, bi.ir.dim), c_off=fi.c_off[o],
+                                           c_rows=(fi.Dconv, bo.mul, bo.ir.dim), alpha=alpha * fi.inv_sqrt_avg),
+                          o, o in written))
+        if len(written | {o for _, o, _ in probs}) < len(fi.conv_out):
             cv.zero_()
-        for wave in _waves(probs):
-            ops.gemm_run(wave)
         for wave in _waves(sc_probs):
+            ops.gemm_run(wave)
+        for wave in _waves(probs):
             ops.gemm_run(wave)
         # ---- gate, in both layouts
         out_mi, out_imu = new(N, fi.Dout), new(N, fi.Dout)

@@ -460,7 +460,7 @@ def gemm_run(problems):
     for g in problems:
         if g.M == 0 or g.N == 0:
             continue
-        classes.setdefault((g.K <= 128, lib.e3b_gemm_tile_n(g.N, g.K)), []).append(g)
+        classes.setdefault((g.K <= 64, lib.e3b_gemm_tile_n(g.N, g.K)), []).append(g)
     for group in classes.values():
         for lo in range(0, len(group), _lib.E3B_GEMM_MAX_GROUP):
             chunk = group[lo:lo + _lib.E3B_GEMM_MAX_GROUP]

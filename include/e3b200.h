@@ -208,7 +208,7 @@ E3B_API int e3b_gate_imu_bwd(const e3b_gate_desc* desc, int dtype, const void* i
 
 /* ---------------------------------------------------------------------------------------
  * Dense contractions on the tcgen05 tensor cores, fp32-faithful (3xTF32 split, fp32 TMEM
- * accumulators, accumulation chains cut every 128 floats of K).  Replaces the cuBLAS/einsum
+ * accumulators, accumulation chains cut every 64 floats of K).  Replaces the cuBLAS/einsum
  * calls behind e3nn o3.Linear (nn/message_passing.py:58-63,102; nn/pointwise.py:87-92,99),
  * nn.FullyConnectedNet (nn/message_passing.py:74-79,93) and o3.FullyConnectedTensorProduct
  * (nn/message_passing.py:83-87), forward and data-gradient backward.
@@ -231,7 +231,7 @@ E3B_API int e3b_gate_imu_bwd(const e3b_gate_desc* desc, int dtype, const void* i
  * 128-byte aligned; repack only when the weight changes.
  * e3b_gemm_run launches up to E3B_GEMM_MAX_GROUP independent problems (e.g. the irreps blocks
  * of one o3.Linear) as ONE persistent kernel; they must share the tile shape, i.e. agree on
- * (K <= 128) and on (N <= 64 or K > 128)  [e3b_gemm_tile_n returns the column-tile width].   */
+ * (K <= 64) and on (N <= 64 or K > 64)  [e3b_gemm_tile_n returns the column-tile width].     */
 #define E3B_GEMM_MAX_GROUP 8
 
 typedef struct {
