@@ -10,12 +10,14 @@
 // B is a weight: it is split and laid out ONCE by e3b_gemm_pack into the UMMA canonical K-major /
 // no-swizzle layout, tile by tile, so that the kernel fetches a whole (hi | lo) B chunk with one
 // TMA bulk copy.  A is an activation: converter warps stream it with cp.async (16 B per thread,
-// affine row addressing so the irreps layouts are read in place), split it in registers and
-// write the canonical layout to shared memory.
+// coalesced, affine row addressing so the irreps layouts are read in place) into a padded raw
+// ring, read their own accumulator row back, split it in registers and store the hi / lo parts
+// straight into TENSOR MEMORY (tcgen05.st); the MMAs take A from TMEM, so of the operands only B
+// crosses shared memory (the kernel was bound by shared-memory bandwidth with A staged there).
 //
 // One persistent CTA = 14 warps, warp-specialised:
 //   warps 0-3  epilogue   TMEM -> registers (tcgen05.ld) -> epilogue math -> global
-//   warps 4-11 converter  global -(cp.async)-> raw ring -> split hi/lo -> canonical A ring
+//   warps 4-11 converter  global -(cp.async)-> raw ring -> split hi/lo -> A ring in TMEM
 //   warp  12   producer   TMA bulk copies of packed B chunks into the B ring
 //   warp  13   MMA        one elected thread issues tcgen05.mma and commits to the mbarriers
 // Three pipelines (mbarrier full/empty pairs): A ring, B ring, two TMEM accumulators.  When the
@@ -36,7 +38,7 @@ namespace {
 constexpr int BM = 128;     // UMMA M
 constexpr int BK = 32;      // floats per K chunk = 4 MMA K-steps of 8 = 8 sixteen-byte columns
 constexpr int KSEG = 2;     // chunks per accumulation chain (64 floats of K)
-constexpr int NACC = 4;     // TMEM accumulator buffers
+constexpr int A_COLS = 2 * BK;   // TMEM columns of one A stage: 32 hi | 32 lo
 constexpr int NTHREADS = 448;
 constexpr int NCVT = 256;    // converter threads (warps 4-11)
 constexpr int CVT0 = 128;   // first converter thread
@@ -69,11 +71,22 @@ __device__ __forceinline__ uint64_t umma_desc(uint32_t saddr, uint32_t lbo_bytes
 __host__ __device__ constexpr uint32_t umma_idesc(int n) {
   return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
 }
-__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t idesc, uint32_t accumulate) {
+// A operand from tensor memory (lane = row, one tf32 per 32-bit column), B from shared memory
+__device__ __forceinline__ void umma_tf32_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t db, uint32_t idesc, uint32_t accumulate) {
   asm volatile(
       "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
-      ::"r"(tmem_d), "l"(da), "l"(db), "r"(idesc), "r"(accumulate)
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "r"(tmem_a), "l"(db), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_st16(uint32_t taddr, const float (&v)[16]) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};"
+      ::"r"(taddr), "r"(__float_as_uint(v[0])), "r"(__float_as_uint(v[1])), "r"(__float_as_uint(v[2])),
+        "r"(__float_as_uint(v[3])), "r"(__float_as_uint(v[4])), "r"(__float_as_uint(v[5])), "r"(__float_as_uint(v[6])),
+        "r"(__float_as_uint(v[7])), "r"(__float_as_uint(v[8])), "r"(__float_as_uint(v[9])), "r"(__float_as_uint(v[10])),
+        "r"(__float_as_uint(v[11])), "r"(__float_as_uint(v[12])), "r"(__float_as_uint(v[13])), "r"(__float_as_uint(v[14])),
+        "r"(__float_as_uint(v[15]))
       : "memory");
 }
 __device__ __forceinline__ void umma_commit(uint64_t* bar) {
@@ -155,13 +168,13 @@ __device__ __forceinline__ float ssp_f(float z) { return (z > 20.f ? z : log1pf(
 // sigmoid(z) = 1 - exp(-softplus(z)) = 1 - 0.5 * exp(-h / cst)
 __device__ __forceinline__ float dssp_from_out(float h, float cst) { return cst * (1.f - 0.5f * expf(-h / cst)); }
 
-template <int BN, int SA, int PRAW, int SB>
+template <int BN, int PRAW, int SB>
 struct Smem {
-  static constexpr int A_STAGE = 2 * BM * BK;      // floats: hi | lo
-  static constexpr int B_STAGE = 2 * BN * BK;
-  static constexpr int RAW_STAGE = BM * BK;
-  static constexpr int EPI_STAGE = 32 * 36;       // per epilogue warp: 32 rows x (32 + 4 pad) floats
-  static constexpr size_t BYTES = (size_t)(SA * A_STAGE + SB * B_STAGE + PRAW * RAW_STAGE + 4 * EPI_STAGE) * 4 + 128 /*align slack*/;
+  static constexpr int B_STAGE = 2 * BN * BK;      // floats: hi | lo
+  static constexpr int RAW_ROW = BK + 4;           // padded row (144 B): conflict-free row-per-lane reads
+  static constexpr int RAW_STAGE = BM * RAW_ROW;
+  static constexpr int EPI_STAGE = 32 * 36;        // per epilogue warp: 32 rows x (32 + 4 pad) floats
+  static constexpr size_t BYTES = (size_t)(SB * B_STAGE + PRAW * RAW_STAGE + 4 * EPI_STAGE) * 4 + 128 /*align slack*/;
 };
 
 struct EpiCtx {
@@ -182,7 +195,7 @@ template <int EPI> __device__ __forceinline__ float epi_apply(float o, float h, 
 // Epilogue warps: thread = one accumulator row (TMEM lane).  DENSE outputs (unit column stride,
 // N % 4 == 0) are transposed through a warp-private staging tile so that every store instruction
 // writes whole 128-byte lines (4 rows x 128 B per warp instruction) instead of 32 partial sectors.
-template <int BN, bool MULTI, int EPI, bool DENSE>
+template <int BN, bool MULTI, int NACC, int EPI, bool DENSE>
 __device__ __forceinline__ void epilogue_role(const EpiCtx& c) {
   const Problem& P = *c.P;
   const e3b_gemm_problem& g = P.p;
@@ -323,14 +336,15 @@ __device__ __forceinline__ void epilogue_role(const EpiCtx& c) {
 }
 
 // every role repeats the same walk over this CTA's tile range [t0, t1)
-template <int BN, bool MULTI, int SA, int PRAW, int SB>
+// TMEM map (512 columns): [NACC accumulators of BN columns][SA stages of A: 32 hi | 32 lo columns]
+template <int BN, bool MULTI, int NACC, int SA, int PRAW, int SB>
 __global__ void __launch_bounds__(NTHREADS, 1) gemm_tf32x3_kernel(const __grid_constant__ Batch batch) {
-  using L = Smem<BN, SA, PRAW, SB>;
+  using L = Smem<BN, PRAW, SB>;
+  static_assert(NACC * BN + SA * A_COLS <= 512 && PRAW >= 2, "TMEM / ring configuration");
   extern __shared__ unsigned char smem_dyn[];
   float* smem = reinterpret_cast<float*>((reinterpret_cast<uintptr_t>(smem_dyn) + 127) & ~(uintptr_t)127);
-  float* sA = smem;                                   // [SA][hi|lo][c(8)][row(128)][4]
-  float* sB = sA + SA * L::A_STAGE;                   // [SB][hi|lo][c(8)][row(BN)][4]
-  float* sRaw = sB + SB * L::B_STAGE;                 // [PRAW][slot(4)][thread(256)][4]
+  float* sB = smem;                                   // [SB][hi|lo][c(8)][row(BN)][4]
+  float* sRaw = sB + SB * L::B_STAGE;                 // [PRAW][row(128)][36]
   float* sEpi = sRaw + PRAW * L::RAW_STAGE;           // [4 warps][32 rows][36]
   __shared__ uint64_t a_full[SA], a_empty[SA], b_full[SB], b_empty[SB], acc_full[NACC], acc_empty[NACC];
   __shared__ uint32_t tmem_base_smem;
@@ -351,7 +365,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) gemm_tf32x3_kernel(const __grid_c
   const bool resident = k_chunks <= SA;
 
   if (warp == 13) {  // TMEM allocation is warp-collective; the same warp frees it
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_addr(&tmem_base_smem)), "r"((uint32_t)(NACC * BN)) : "memory");
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_addr(&tmem_base_smem)), "r"(512u) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
   if (tid == 0) {
@@ -364,17 +378,21 @@ __global__ void __launch_bounds__(NTHREADS, 1) gemm_tf32x3_kernel(const __grid_c
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = tmem_base_smem;
+  const uint32_t tmem_a0 = tmem_base + NACC * BN;     // first A stage
 
   if (t1 > t0) {
     if (warp >= 4 && warp < 12) {
       // =============================== A converter ===============================
-      // thread -> one 16-byte column `col` of the chunk and the 4 rows row0 + 32 i: a quarter-warp
-      // covers 8 consecutive rows of one column = 128 contiguous bytes of the canonical layout
-      // (conflict-free STS.128) and 64 contiguous bytes of each source row (full sectors).
+      // load role : thread -> one 16-byte column `col` of the chunk and the 4 rows row0 + 32 i (a warp
+      //             instruction reads 64 contiguous bytes of 8 rows: whole sectors);
+      // split role: thread -> ITS accumulator row (TMEM lane 32 * (warp % 4) + lane) and one half of the
+      //             chunk's 32 columns; the padded raw rows make the row-per-lane reads conflict-free.
       const int ct = tid - CVT0;                 // 0..255
       const int cw = ct >> 5;
       const int col = (cw & 1) * 4 + (lane >> 3);
-      const int row0 = 8 * (cw >> 1) + (lane & 7);      // rows row0 + 32 i, i = 0..3
+      const int row0 = 8 * (cw >> 1) + (lane & 7);
+      const int my_row = 32 * (cw & 3) + lane, half = cw >> 2;
+      const uint32_t t_mine = tmem_a0 + ((uint32_t)(32 * (cw & 3)) << 16) + 16u * half;
       // jobs: one per K chunk of every tile (streaming) or of every distinct row tile (resident A)
       const int total = (resident ? (t1 - 1) / P.n_tiles - t0 / P.n_tiles + 1 : t1 - t0) * k_chunks;
       // issue stream state (runs PRAW - 1 jobs ahead of the conversion)
@@ -397,10 +415,10 @@ __global__ void __launch_bounds__(NTHREADS, 1) gemm_tf32x3_kernel(const __grid_c
           --i_left;
           const int k = i_kc * BK + col * 4;
           const bool kok = k < g.K;
-          float* dst = sRaw + (size_t)i_slot * L::RAW_STAGE + ct * 4;
+          float* dst = sRaw + (size_t)i_slot * L::RAW_STAGE + row0 * L::RAW_ROW + col * 4;
 #pragma unroll
           for (int i = 0; i < 4; ++i)
-            cp_async16(dst + i * (NCVT * 4), g.A + roff[i] + (kok ? k : 0), kok ? rbytes[i] : 0u);
+            cp_async16(dst + i * (32 * L::RAW_ROW), g.A + roff[i] + (kok ? k : 0), kok ? rbytes[i] : 0u);
           if (++i_kc == k_chunks) {
             i_kc = 0;
             const int m_old = i_t / P.n_tiles;
@@ -417,22 +435,27 @@ __global__ void __launch_bounds__(NTHREADS, 1) gemm_tf32x3_kernel(const __grid_c
       uint32_t par = 1;                          // parity to wait on a_empty: first pass through the ring is free
 #pragma unroll 1
       for (int j = 0; j < total; ++j) {
-        issue();
-        cp_async_wait<PRAW - 1>();               // this thread's copies of job j have landed
+        cp_async_wait<PRAW - 2>();               // this thread's copies of job j have landed ...
+        asm volatile("bar.sync 1, 256;" ::: "memory");   // ... and everyone's; everyone is done reading job j - 1
+        issue();                                 // job j + PRAW - 1 reuses the slot of job j - 1
         mbar_wait(&a_empty[st], par);
-        const float4* raw = reinterpret_cast<const float4*>(sRaw + (size_t)slot * L::RAW_STAGE) + ct;
-        float4* hi = reinterpret_cast<float4*>(sA + (size_t)st * L::A_STAGE) + col * BM + row0;
-        float4* lo = hi + BM * (BK / 4);
         if (!(P.dbg & 1)) {
+          tc_fence_after();
+          const float4* raw = reinterpret_cast<const float4*>(sRaw + (size_t)slot * L::RAW_STAGE + my_row * L::RAW_ROW + 16 * half);
+          float hi[16], lo[16];
 #pragma unroll
           for (int i = 0; i < 4; ++i) {
             float4 h, l;
-            split4(raw[i * NCVT], &h, &l);
-            hi[32 * i] = h;
-            lo[32 * i] = l;
+            split4(raw[i], &h, &l);
+            hi[4 * i] = h.x; hi[4 * i + 1] = h.y; hi[4 * i + 2] = h.z; hi[4 * i + 3] = h.w;
+            lo[4 * i] = l.x; lo[4 * i + 1] = l.y; lo[4 * i + 2] = l.z; lo[4 * i + 3] = l.w;
           }
+          const uint32_t ta = t_mine + (uint32_t)st * A_COLS;
+          tmem_st16(ta, hi);
+          tmem_st16(ta + BK, lo);
+          asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
         }
-        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy stores -> tensor-core reads
+        tc_fence_before();
         mbar_arrive(&a_full[st]);
         if (++st == SA) { st = 0; par ^= 1u; }
         if (++slot == PRAW) slot = 0;
@@ -459,9 +482,9 @@ __global__ void __launch_bounds__(NTHREADS, 1) gemm_tf32x3_kernel(const __grid_c
       // The whole warp walks the tiles (uniform control flow, so addresses and descriptors live in
       // uniform registers); one elected lane issues the MMAs of a chunk and the commits.
       const uint32_t idesc = umma_idesc(BN);
-      const uint32_t sA_u = smem_addr(sA), sB_u = smem_addr(sB);
-      // descriptor templates: LBO / SBO / version bits fixed, 14-bit start address added per use
-      const uint64_t tmplA = umma_desc(0, BM * 16, 128), tmplB = umma_desc(0, BN * 16, 128);
+      const uint32_t sB_u = smem_addr(sB);
+      // descriptor template: LBO / SBO / version bits fixed, 14-bit start address added per use
+      const uint64_t tmplB = umma_desc(0, BN * 16, 128);
       uint32_t a_it = 0, b_it = 0, acc_it = 0;
       for (int t = t0; t < t1; ++t) {
         const int n = t % P.n_tiles;
@@ -481,17 +504,16 @@ __global__ void __launch_bounds__(NTHREADS, 1) gemm_tf32x3_kernel(const __grid_c
             tc_fence_after();
             const bool seg_last = (kc % KSEG) == KSEG - 1 || kc == k_chunks - 1;
             if (elect_one()) {
-              const uint64_t dAh = tmplA | (uint64_t)(((sA_u + sa * (uint32_t)(L::A_STAGE * 4)) >> 4) & 0x3FFFu);
-              const uint64_t dAl = dAh + (uint64_t)((BM * BK * 4) >> 4);
+              const uint32_t tAh = tmem_a0 + sa * (uint32_t)A_COLS, tAl = tAh + BK;
               const uint64_t dBh = tmplB | (uint64_t)(((sB_u + sb * (uint32_t)(L::B_STAGE * 4)) >> 4) & 0x3FFFu);
               const uint64_t dBl = dBh + (uint64_t)((BN * BK * 4) >> 4);
               const uint32_t d = tmem_base + buf * BN;
 #pragma unroll
-              for (int j = 0; j < ((P.dbg & 2) ? 0 : BK / 8); ++j) {   // one MMA covers K = 8 tf32 = two 16-byte columns
-                const uint64_t oA = (uint64_t)((2 * j * BM * 16) >> 4), oB = (uint64_t)((2 * j * BN * 16) >> 4);
-                umma_tf32(d, dAl + oA, dBh + oB, idesc, (seg_first && j == 0) ? 0u : 1u);
-                umma_tf32(d, dAh + oA, dBl + oB, idesc, 1u);
-                umma_tf32(d, dAh + oA, dBh + oB, idesc, 1u);
+              for (int j = 0; j < ((P.dbg & 2) ? 0 : BK / 8); ++j) {   // one MMA covers K = 8 tf32: 8 TMEM columns of A,
+                const uint64_t oB = (uint64_t)((2 * j * BN * 16) >> 4); // two 16-byte columns of B
+                umma_tf32_ts(d, tAl + 8 * j, dBh + oB, idesc, (seg_first && j == 0) ? 0u : 1u);
+                umma_tf32_ts(d, tAh + 8 * j, dBl + oB, idesc, 1u);
+                umma_tf32_ts(d, tAh + 8 * j, dBh + oB, idesc, 1u);
               }
               umma_commit(&b_empty[sb]);
               if (!resident || last_m) umma_commit(&a_empty[sa]);
@@ -510,10 +532,10 @@ __global__ void __launch_bounds__(NTHREADS, 1) gemm_tf32x3_kernel(const __grid_c
       const bool dense = g.c_s3 == 1 && g.c_d == 1 && (g.c_s1 & 3) == 0 && (g.N & 3) == 0 &&
                          (reinterpret_cast<uintptr_t>(g.C) & 15) == 0 && (g.epilogue != 3 || (g.h_ld & 3) == 0);
       EpiCtx c{&P, acc_full, acc_empty, sEpi + warp * L::EPI_STAGE, tmem_base, t0, t1, k_chunks};
-      if (g.epilogue == 1) epilogue_role<BN, MULTI, 1, false>(c);
-      else if (g.epilogue == 0) { if (dense) epilogue_role<BN, MULTI, 0, true>(c); else epilogue_role<BN, MULTI, 0, false>(c); }
-      else if (g.epilogue == 2) { if (dense) epilogue_role<BN, MULTI, 2, true>(c); else epilogue_role<BN, MULTI, 2, false>(c); }
-      else { if (dense) epilogue_role<BN, MULTI, 3, true>(c); else epilogue_role<BN, MULTI, 3, false>(c); }
+      if (g.epilogue == 1) epilogue_role<BN, MULTI, NACC, 1, false>(c);
+      else if (g.epilogue == 0) { if (dense) epilogue_role<BN, MULTI, NACC, 0, true>(c); else epilogue_role<BN, MULTI, NACC, 0, false>(c); }
+      else if (g.epilogue == 2) { if (dense) epilogue_role<BN, MULTI, NACC, 2, true>(c); else epilogue_role<BN, MULTI, NACC, 2, false>(c); }
+      else { if (dense) epilogue_role<BN, MULTI, NACC, 3, true>(c); else epilogue_role<BN, MULTI, NACC, 3, false>(c); }
     }
   }
 
@@ -522,7 +544,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) gemm_tf32x3_kernel(const __grid_c
   if (warp == 13) {
     __syncwarp();
     tc_fence_after();
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)(NACC * BN)) : "memory");
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
   }
 }
 
@@ -564,17 +586,17 @@ __global__ void gemm_pack_kernel(const __grid_constant__ PackBatch pb) {
   }
 }
 
-template <int BN, bool MULTI, int SA, int PRAW, int SB>
+template <int BN, bool MULTI, int NACC, int SA, int PRAW, int SB>
 cudaError_t launch(const Batch& b, int ctas, cudaStream_t st) {
-  using L = Smem<BN, SA, PRAW, SB>;
+  using L = Smem<BN, PRAW, SB>;
   static bool attr_set = false;
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(gemm_tf32x3_kernel<BN, MULTI, SA, PRAW, SB>,
+    cudaError_t e = cudaFuncSetAttribute(gemm_tf32x3_kernel<BN, MULTI, NACC, SA, PRAW, SB>,
                                          cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L::BYTES);
     if (e != cudaSuccess) return e;
     attr_set = true;
   }
-  gemm_tf32x3_kernel<BN, MULTI, SA, PRAW, SB><<<ctas, NTHREADS, L::BYTES, st>>>(b);
+  gemm_tf32x3_kernel<BN, MULTI, NACC, SA, PRAW, SB><<<ctas, NTHREADS, L::BYTES, st>>>(b);
   return cudaGetLastError();
 }
 
@@ -684,9 +706,9 @@ extern "C" int e3b_gemm_run(const e3b_gemm_problem* problems, int32_t n, void* s
     ctas += want[i];
   }
   cudaError_t e;
-  if (multi) e = launch<64, true, 2, 7, 2>(b, ctas, (cudaStream_t)stream);
-  else if (bn == 64) e = launch<64, false, 3, 4, 2>(b, ctas, (cudaStream_t)stream);
-  else e = launch<128, false, 4, 1, 2>(b, ctas, (cudaStream_t)stream);
+  if (multi) e = launch<64, true, 4, 4, 6, 4>(b, ctas, (cudaStream_t)stream);
+  else if (bn == 64) e = launch<64, false, 4, 4, 6, 4>(b, ctas, (cudaStream_t)stream);
+  else e = launch<128, false, 2, 4, 3, 4>(b, ctas, (cudaStream_t)stream);
   if (e != cudaSuccess) return e3b_fail(E3B_ERR_CUDA, "gemm_run: %s", cudaGetErrorString(e));
   return E3B_OK;
 }
