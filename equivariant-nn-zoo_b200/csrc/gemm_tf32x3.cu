@@ -79,14 +79,19 @@ __device__ __forceinline__ void umma_tf32_ts(uint32_t tmem_d, uint32_t tmem_a, u
       ::"r"(tmem_d), "r"(tmem_a), "l"(db), "r"(idesc), "r"(accumulate)
       : "memory");
 }
-__device__ __forceinline__ void tmem_st16(uint32_t taddr, const float (&v)[16]) {
+__device__ __forceinline__ void tmem_st32(uint32_t taddr, const float (&v)[32]) {
   asm volatile(
-      "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};"
+      "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, "
+      "%17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32};"
       ::"r"(taddr), "r"(__float_as_uint(v[0])), "r"(__float_as_uint(v[1])), "r"(__float_as_uint(v[2])),
         "r"(__float_as_uint(v[3])), "r"(__float_as_uint(v[4])), "r"(__float_as_uint(v[5])), "r"(__float_as_uint(v[6])),
         "r"(__float_as_uint(v[7])), "r"(__float_as_uint(v[8])), "r"(__float_as_uint(v[9])), "r"(__float_as_uint(v[10])),
         "r"(__float_as_uint(v[11])), "r"(__float_as_uint(v[12])), "r"(__float_as_uint(v[13])), "r"(__float_as_uint(v[14])),
-        "r"(__float_as_uint(v[15]))
+        "r"(__float_as_uint(v[15])), "r"(__float_as_uint(v[16])), "r"(__float_as_uint(v[17])), "r"(__float_as_uint(v[18])),
+        "r"(__float_as_uint(v[19])), "r"(__float_as_uint(v[20])), "r"(__float_as_uint(v[21])), "r"(__float_as_uint(v[22])),
+        "r"(__float_as_uint(v[23])), "r"(__float_as_uint(v[24])), "r"(__float_as_uint(v[25])), "r"(__float_as_uint(v[26])),
+        "r"(__float_as_uint(v[27])), "r"(__float_as_uint(v[28])), "r"(__float_as_uint(v[29])), "r"(__float_as_uint(v[30])),
+        "r"(__float_as_uint(v[31]))
       : "memory");
 }
 __device__ __forceinline__ void umma_commit(uint64_t* bar) {
@@ -340,7 +345,7 @@ __device__ __forceinline__ void epilogue_role(const EpiCtx& c) {
 template <int BN, bool MULTI, int NACC, int SA, int PRAW, int SB>
 __global__ void __launch_bounds__(NTHREADS, 1) gemm_tf32x3_kernel(const __grid_constant__ Batch batch) {
   using L = Smem<BN, PRAW, SB>;
-  static_assert(NACC * BN + SA * A_COLS <= 512 && PRAW >= 2, "TMEM / ring configuration");
+  static_assert(NACC * BN + SA * A_COLS <= 512 && PRAW >= 4 && PRAW % 2 == 0, "TMEM / ring configuration");
   extern __shared__ unsigned char smem_dyn[];
   float* smem = reinterpret_cast<float*>((reinterpret_cast<uintptr_t>(smem_dyn) + 127) & ~(uintptr_t)127);
   float* sB = smem;                                   // [SB][hi|lo][c(8)][row(BN)][4]
@@ -369,7 +374,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) gemm_tf32x3_kernel(const __grid_c
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
   if (tid == 0) {
-    for (int s = 0; s < SA; ++s) { mbar_init(&a_full[s], NCVT); mbar_init(&a_empty[s], 1); }
+    for (int s = 0; s < SA; ++s) { mbar_init(&a_full[s], NCVT / 2); mbar_init(&a_empty[s], 1); }
     for (int s = 0; s < SB; ++s) { mbar_init(&b_full[s], 1); mbar_init(&b_empty[s], 1); }
     for (int s = 0; s < NACC; ++s) { mbar_init(&acc_full[s], 1); mbar_init(&acc_empty[s], 128); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -383,82 +388,94 @@ __global__ void __launch_bounds__(NTHREADS, 1) gemm_tf32x3_kernel(const __grid_c
   if (t1 > t0) {
     if (warp >= 4 && warp < 12) {
       // =============================== A converter ===============================
-      // load role : thread -> one 16-byte column `col` of the chunk and the 4 rows row0 + 32 i (a warp
+      // Two groups of 4 warps take alternate jobs (K chunks), so two chunks are in flight through the
+      // load -> split -> tcgen05.st chain at any time.  Within a group:
+      // load role : thread -> one 16-byte column `col` of the chunk and the 8 rows row0 + 16 i (a warp
       //             instruction reads 64 contiguous bytes of 8 rows: whole sectors);
-      // split role: thread -> ITS accumulator row (TMEM lane 32 * (warp % 4) + lane) and one half of the
-      //             chunk's 32 columns; the padded raw rows make the row-per-lane reads conflict-free.
+      // split role: thread -> ITS accumulator row (TMEM lane 32 * (warp % 4) + lane), all 32 columns;
+      //             the padded raw rows make the row-per-lane reads conflict-free.
+      constexpr int NG = 2;
       const int ct = tid - CVT0;                 // 0..255
-      const int cw = ct >> 5;
-      const int col = (cw & 1) * 4 + (lane >> 3);
-      const int row0 = 8 * (cw >> 1) + (lane & 7);
-      const int my_row = 32 * (cw & 3) + lane, half = cw >> 2;
-      const uint32_t t_mine = tmem_a0 + ((uint32_t)(32 * (cw & 3)) << 16) + 16u * half;
+      const int grp = ct >> 7, w = (ct >> 5) & 3;
+      const int col = (w & 1) * 4 + (lane >> 3);
+      const int row0 = 8 * (w >> 1) + (lane & 7);
+      const int my_row = 32 * w + lane;
+      const uint32_t t_mine = tmem_a0 + ((uint32_t)(32 * w) << 16);
+      float* raw_ring = sRaw + (size_t)grp * (PRAW / NG) * L::RAW_STAGE;
+      constexpr int PR = PRAW / NG;              // raw slots of one group
+      static_assert(PR >= 2, "raw ring");
       // jobs: one per K chunk of every tile (streaming) or of every distinct row tile (resident A)
       const int total = (resident ? (t1 - 1) / P.n_tiles - t0 / P.n_tiles + 1 : t1 - t0) * k_chunks;
-      // issue stream state (runs PRAW - 1 jobs ahead of the conversion)
-      int64_t roff[4];
-      uint32_t rbytes[4];
+      // issue stream state (runs PR - 1 of this group's jobs ahead of the conversion)
+      int64_t roff[8];
+      uint32_t rbytes[8];
       auto load_rows = [&](int m_tile) {
 #pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          const int r = m_tile * BM + row0 + 32 * i;
+        for (int i = 0; i < 8; ++i) {
+          const int r = m_tile * BM + row0 + 16 * i;
           const int q = (int)(((uint64_t)(uint32_t)r * P.a_mul) >> 40);
           roff[i] = (int64_t)q * g.a_s1 + (int64_t)(r - q * g.a_d) * g.a_s2;
           rbytes[i] = r < g.M ? 16u : 0u;
           if (r >= g.M) roff[i] = 0;
         }
       };
-      int i_t = t0, i_kc = 0, i_slot = 0, i_left = total;
-      load_rows(i_t / P.n_tiles);
+      int i_t = t0, i_kc = 0, i_slot = 0, i_job = 0;      // (i_t, i_kc) = coordinates of global job i_job
+      int m_loaded = -1;
+      auto advance = [&]() {                              // to the next global job
+        ++i_job;
+        if (++i_kc == k_chunks) {
+          i_kc = 0;
+          i_t = resident ? (i_t / P.n_tiles + 1) * P.n_tiles : i_t + 1;
+        }
+      };
+      for (int s = 0; s < grp; ++s) advance();            // first job of this group
       auto issue = [&]() {
-        if (i_left > 0 && !(P.dbg & 1)) {
-          --i_left;
+        if (i_job < total && !(P.dbg & 1)) {
+          const int m_tile = i_t / P.n_tiles;
+          if (m_tile != m_loaded) { load_rows(m_tile); m_loaded = m_tile; }
           const int k = i_kc * BK + col * 4;
           const bool kok = k < g.K;
-          float* dst = sRaw + (size_t)i_slot * L::RAW_STAGE + row0 * L::RAW_ROW + col * 4;
+          float* dst = raw_ring + (size_t)i_slot * L::RAW_STAGE + row0 * L::RAW_ROW + col * 4;
 #pragma unroll
-          for (int i = 0; i < 4; ++i)
-            cp_async16(dst + i * (32 * L::RAW_ROW), g.A + roff[i] + (kok ? k : 0), kok ? rbytes[i] : 0u);
-          if (++i_kc == k_chunks) {
-            i_kc = 0;
-            const int m_old = i_t / P.n_tiles;
-            i_t = resident ? (m_old + 1) * P.n_tiles : i_t + 1;
-            if (i_left > 0 && i_t / P.n_tiles != m_old) load_rows(i_t / P.n_tiles);
-          }
+          for (int i = 0; i < 8; ++i)
+            cp_async16(dst + i * (16 * L::RAW_ROW), g.A + roff[i] + (kok ? k : 0), kok ? rbytes[i] : 0u);
         }
-        if (++i_slot == PRAW) i_slot = 0;
+#pragma unroll 1
+        for (int s = 0; s < NG; ++s) advance();
+        if (++i_slot == PR) i_slot = 0;
         cp_async_commit();
       };
 #pragma unroll 1
-      for (int j = 0; j < PRAW - 1; ++j) issue();
-      int st = 0, slot = 0;
-      uint32_t par = 1;                          // parity to wait on a_empty: first pass through the ring is free
+      for (int j = 0; j < PR - 1; ++j) issue();
+      int slot = 0;
 #pragma unroll 1
-      for (int j = 0; j < total; ++j) {
-        cp_async_wait<PRAW - 2>();               // this thread's copies of job j have landed ...
-        asm volatile("bar.sync 1, 256;" ::: "memory");   // ... and everyone's; everyone is done reading job j - 1
-        issue();                                 // job j + PRAW - 1 reuses the slot of job j - 1
+      for (int j = grp; j < total; j += NG) {
+        const int st = j % SA;
+        const uint32_t par = (((uint32_t)j / SA) & 1u) ^ 1u;      // first pass through the ring is free
+        cp_async_wait<PR - 2>();                 // this thread's copies of job j have landed ...
+        if (grp == 0) asm volatile("bar.sync 1, 128;" ::: "memory");   // ... and the group's; the group is done
+        else asm volatile("bar.sync 2, 128;" ::: "memory");            // reading its previous job
+        issue();                                 // the group's job PR - 1 ahead reuses the slot just released
         mbar_wait(&a_empty[st], par);
         if (!(P.dbg & 1)) {
           tc_fence_after();
-          const float4* raw = reinterpret_cast<const float4*>(sRaw + (size_t)slot * L::RAW_STAGE + my_row * L::RAW_ROW + 16 * half);
-          float hi[16], lo[16];
+          const float4* raw = reinterpret_cast<const float4*>(raw_ring + (size_t)slot * L::RAW_STAGE + my_row * L::RAW_ROW);
+          float hi[32], lo[32];
 #pragma unroll
-          for (int i = 0; i < 4; ++i) {
+          for (int i = 0; i < 8; ++i) {
             float4 h, l;
             split4(raw[i], &h, &l);
             hi[4 * i] = h.x; hi[4 * i + 1] = h.y; hi[4 * i + 2] = h.z; hi[4 * i + 3] = h.w;
             lo[4 * i] = l.x; lo[4 * i + 1] = l.y; lo[4 * i + 2] = l.z; lo[4 * i + 3] = l.w;
           }
           const uint32_t ta = t_mine + (uint32_t)st * A_COLS;
-          tmem_st16(ta, hi);
-          tmem_st16(ta + BK, lo);
+          tmem_st32(ta, hi);
+          tmem_st32(ta + BK, lo);
           asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
         }
         tc_fence_before();
         mbar_arrive(&a_full[st]);
-        if (++st == SA) { st = 0; par ^= 1u; }
-        if (++slot == PRAW) slot = 0;
+        if (++slot == PR) slot = 0;
       }
       cp_async_wait<0>();
     } else if (warp == 12) {
@@ -708,7 +725,7 @@ extern "C" int e3b_gemm_run(const e3b_gemm_problem* problems, int32_t n, void* s
   cudaError_t e;
   if (multi) e = launch<64, true, 4, 4, 6, 4>(b, ctas, (cudaStream_t)stream);
   else if (bn == 64) e = launch<64, false, 4, 4, 6, 4>(b, ctas, (cudaStream_t)stream);
-  else e = launch<128, false, 2, 4, 3, 4>(b, ctas, (cudaStream_t)stream);
+  else e = launch<128, false, 2, 4, 4, 4>(b, ctas, (cudaStream_t)stream);
   if (e != cudaSuccess) return e3b_fail(E3B_ERR_CUDA, "gemm_run: %s", cudaGetErrorString(e));
   return E3B_OK;
 }
