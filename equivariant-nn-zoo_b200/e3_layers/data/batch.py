@@ -9,9 +9,18 @@ import torch
 from .data import Data, irreps_dim
 
 
-def _segments(counts):
+def _segments(counts, total=None):
+    """graph id of every node / edge.  With `total` (the number of rows, known from a per-node / per-edge
+    tensor) repeat_interleave does not have to read the counts back: no host synchronisation."""
     counts = counts.reshape(-1)
-    return torch.repeat_interleave(torch.arange(counts.numel(), device=counts.device), counts)
+    ids = torch.arange(counts.numel(), device=counts.device)
+    if total is None:
+        return torch.repeat_interleave(ids, counts)
+    return torch.repeat_interleave(ids, counts, output_size=total)
+
+
+def _tag(counts):
+    return (counts.data_ptr(), counts._version, counts.numel())
 
 
 class Batch(Data):
@@ -22,13 +31,32 @@ class Batch(Data):
         if "_n_edges" in self.data:
             self.edgeSegment()
 
+    def _rows(self, kind):
+        """number of nodes / edges if some tensor of that kind tells it, else None"""
+        if kind == "edge" and "edge_index" in self.data:
+            return int(self.data["edge_index"].shape[1])
+        for key, (per, _) in self.attrs.items():
+            if per == kind and key in self.data and not key.startswith("_"):
+                return int(self.data[key].shape[0])
+        return None
+
+    def _segment(self, kind, counts_key, seg_key):
+        counts = self.data[counts_key]
+        total = self._rows(kind)
+        old = self.data.get(seg_key)
+        # a Batch rebuilt from another Batch's tensors keeps the segment vector computed for the same counts
+        if old is not None and getattr(old, "_e3b_counts", None) == _tag(counts) and (total is None or old.shape[0] == total):
+            return old
+        seg = _segments(counts, total)
+        seg._e3b_counts = _tag(counts)
+        self.data[seg_key] = seg
+        return seg
+
     def nodeSegment(self):
-        self.data["_node_segment"] = _segments(self.data["_n_nodes"])
-        return self.data["_node_segment"]
+        return self._segment("node", "_n_nodes", "_node_segment")
 
     def edgeSegment(self):
-        self.data["_edge_segment"] = _segments(self.data["_n_edges"])
-        return self.data["_edge_segment"]
+        return self._segment("edge", "_n_edges", "_edge_segment")
 
     def computeCumsums(self):
         for what in ("node", "edge"):
