@@ -24,6 +24,11 @@ class GradientOutput(Module):
         self.func = build(func, **kwargs) if isinstance(func, (dict, ConfigDict)) else func
 
     def forward(self, data):
+        if self.training and torch.is_grad_enabled():
+            raise NotImplementedError(
+                "GradientOutput in training mode needs the graph of the gradient (create_graph=True, reference "
+                "nn/output.py:39-43) for force-matching losses; the second-order kernels are not built yet. "
+                "Call .eval() for energy+force / score evaluation, or train on energies only.")
         wrt = self.inputKeyMap(data)["x"]
         was = wrt.requires_grad
         wrt.requires_grad_(True)

@@ -1,0 +1,71 @@
+"""Host logic of the multi-GPU path on CPU: graph sharding and the flat gradient all-reduce
+(world_size 2, gloo; the GPU box runs the same code over NCCL)."""
+import os
+
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from e3b200 import parallel, synthetic
+
+
+def test_shard_graphs_balanced_and_complete():
+    n = torch.randint(3, 30, (257,), generator=torch.Generator().manual_seed(0))
+    cost = (n * (n - 1)).tolist()
+    for world in (1, 2, 4, 8):
+        bins = parallel.shard_graphs(cost, world)
+        assert sorted(i for b in bins for i in b) == list(range(257))
+        loads = [sum(cost[i] for i in b) for b in bins]
+        assert max(loads) - min(loads) <= max(cost)          # LPT bound
+    assert parallel.shard_graphs([], 2) == [[], []]
+
+
+def test_shard_batch_keeps_graphs_whole():
+    host = synthetic.qm9_like(19, seed=3)
+    parts = [parallel.shard_batch(host, r, 2) for r in range(2)]
+    assert sum(p["pos"].shape[0] for p in parts) == host["pos"].shape[0]
+    assert sum(p["_n_nodes"].numel() for p in parts) == 19
+    for p in parts:
+        assert int(p["_n_nodes"].sum()) == p["pos"].shape[0] == p["species"].shape[0]
+    # every molecule's coordinates arrive intact on exactly one rank
+    key = lambda t: sorted(round(float(x), 5) for x in t.reshape(-1))
+    all_rows = key(torch.cat([p["pos"] for p in parts]))
+    assert all_rows == key(host["pos"])
+
+
+def _worker(rank, world, port, q):
+    os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        torch.manual_seed(0)
+        lin = torch.nn.Linear(5, 3)
+        frozen = torch.nn.Parameter(torch.ones(2), requires_grad=False)
+        parallel.broadcast_parameters(lin)
+        x = torch.full((4, 5), float(rank + 1))
+        lin(x).sum().backward()
+        local = [p.grad.clone() for p in lin.parameters()]
+        flat = parallel.FlatGradients(list(lin.parameters()) + [frozen], n_scalars=2)
+        scal = flat.all_reduce([float(rank), 10.0])
+        q.put((rank, [g.tolist() for g in local], [p.grad.tolist() for p in lin.parameters()], scal.tolist()))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_flat_gradient_allreduce_world2():
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29611 + os.getpid() % 200
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = sorted(q.get(timeout=120) for _ in range(2))
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    (_, l0, g0, s0), (_, l1, g1, s1) = res
+    assert g0 == g1                                            # both ranks hold the same averaged gradient
+    for a, b, avg in zip(l0, l1, g0):
+        exp = ((torch.tensor(a) + torch.tensor(b)) / 2).tolist()
+        assert torch.allclose(torch.tensor(avg), torch.tensor(exp))
+    assert s0 == s1 == [0.5, 10.0]
