@@ -1,0 +1,149 @@
+#!/usr/bin/env python3
+"""Training entry point of the B200 drop-in (reference ``train.py``: same flag names for the in-scope
+options, ``--config <name>`` picks a registered config, one process per GPU, rank 0 logs and saves).
+
+In scope this round: regression on energies / dipoles (first-order parameter gradients through the
+fused interaction blocks), data-parallel over graphs with ONE flat gradient all-reduce per step.
+Force-matching and diffusion training need the second-order path and raise.
+Data: ``--data synthetic`` (seeded QM9-shaped molecules with a synthetic per-species target; there is no
+network for datasets) or an ``.npz`` with ``pos, species, _n_nodes`` and the target key.
+
+  python train.py --config config_energy --steps 20
+  python train.py --config config_energy --world_size 8        # spawns one process per GPU (reference launch_mp)
+"""
+import argparse
+import logging
+import os
+import sys
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, os.path.join(ROOT, "equivariant-nn-zoo_b200"))
+
+import numpy as np  # noqa: E402
+import torch  # noqa: E402
+import torch.distributed as dist  # noqa: E402
+import torch.multiprocessing as mp  # noqa: E402
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--config", required=True)
+    ap.add_argument("--config_spec", default="")
+    ap.add_argument("--name", default="default")
+    ap.add_argument("--workdir", default="results")
+    ap.add_argument("--seed", type=int, default=0)
+    ap.add_argument("--resume_from", default=None)
+    ap.add_argument("--log_period", type=int, default=10)
+    ap.add_argument("--save_period", type=int, default=2000)
+    ap.add_argument("--world_size", type=int, default=1)
+    ap.add_argument("--master_addr", default="127.0.0.1")
+    ap.add_argument("--master_port", default="10000")
+    ap.add_argument("--verbose", default="INFO")
+    ap.add_argument("--steps", type=int, default=100, help="optimiser steps (the reference runs until early stopping)")
+    ap.add_argument("--data", default="synthetic", help="'synthetic' or the path of an .npz dataset")
+    ap.add_argument("--n_graphs", type=int, default=4096, help="size of the synthetic dataset")
+    return ap.parse_args()
+
+
+def load_data(flags, config, target_key):
+    from e3b200 import synthetic
+
+    if flags.data != "synthetic":
+        z = np.load(flags.data)
+        return {k: torch.from_numpy(z[k]) for k in z.files}
+    data = synthetic.qm9_like(flags.n_graphs, seed=flags.seed)
+    n = data["_n_nodes"].reshape(-1)
+    seg = torch.repeat_interleave(torch.arange(n.numel()), n)
+    gen = torch.Generator().manual_seed(flags.seed + 1)
+    if target_key == "dipole":                                   # per-node 1x1o target
+        data[target_key] = 0.1 * torch.randn(data["pos"].shape[0], 3, generator=gen)
+    else:                                                        # per-graph scalar: composition energy + noise
+        per_species = -torch.arange(0, 120, dtype=torch.float32) * 0.37
+        e = torch.zeros(n.numel()).index_add_(0, seg, per_species[data["species"].reshape(-1)])
+        data[target_key] = (e + 0.01 * torch.randn(n.numel(), generator=gen)).view(-1, 1)
+    return data
+
+
+def main(rank, flags):
+    from e3_layers import configs
+    from e3_layers.data import Batch, computeEdgeIndex
+    from e3_layers.utils import build, setSeed
+    from e3b200 import parallel
+
+    world = flags.world_size
+    if "RANK" in os.environ:                                     # launched by torchrun
+        rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
+        local = int(os.environ.get("LOCAL_RANK", rank))
+    else:
+        local = rank
+        os.environ.setdefault("MASTER_ADDR", flags.master_addr)
+        os.environ.setdefault("MASTER_PORT", flags.master_port)
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
+    logging.basicConfig(level=getattr(logging, flags.verbose), format=f"[rank {rank}] %(message)s")
+
+    get = getattr(configs, flags.config, None)
+    assert get is not None, f"Config {flags.config} not found."
+    config = get(flags.config_spec) if flags.config_spec else get()
+    loss_coeffs = dict(config.loss_coeffs.items()) if hasattr(config.loss_coeffs, "items") else dict(config.loss_coeffs)
+    if any(k in ("forces", "score") for k in loss_coeffs):
+        raise NotImplementedError("force-matching / score-matching training needs the second-order kernels (not built yet)")
+    target_key = next(iter(loss_coeffs))
+    setSeed(flags.seed)                                          # identical initial weights on every rank
+    model = build(config.model_config).to(dev).train()
+    if flags.resume_from:
+        state = torch.load(flags.resume_from, map_location=dev)
+        model.load_state_dict({(k[7:] if k.startswith("module.") else k): v for k, v in state.items()})
+    parallel.broadcast_parameters(model)
+    opt = torch.optim.Adam(model.parameters(), lr=float(config.learning_rate))
+    flat = parallel.FlatGradients(model.parameters(), n_scalars=2)
+    r_max = float(config.model_config.r_max)
+
+    data = load_data(flags, config, target_key)
+    n_all = data["_n_nodes"].reshape(-1)
+    G = n_all.numel()
+    bs = int(config.batch_size) * world                          # global batch; every rank takes its shard
+    gen = torch.Generator().manual_seed(flags.seed)              # same permutation on every rank
+    starts = torch.cumsum(n_all, 0) - n_all
+    attrs = {"pos": ("node", "1x1o"), "species": ("node", "1x0e"), "_n_nodes": ("graph", "1x0e")}
+    out_dir = os.path.join(flags.workdir, flags.name)
+    t0 = time.time()
+    for step in range(flags.steps):
+        pick = torch.randperm(G, generator=gen)[:bs].sort().values
+        node_idx = torch.cat([torch.arange(int(starts[g]), int(starts[g] + n_all[g])) for g in pick])
+        host = {k: (v[node_idx] if v.shape[0] == int(n_all.sum()) else v[pick]) for k, v in data.items()}
+        mine = parallel.shard_batch(host, rank, world)
+        target = mine.pop(target_key).to(dev)
+        batch = Batch(dict(attrs), **{k: v.to(dev) for k, v in mine.items()})
+        d, a = computeEdgeIndex(batch.data, batch.attrs, r_max=r_max)
+        batch.update(d)
+        batch.attrs.update(a)
+        out = model(Batch(batch.attrs, **batch.data))
+        coeff, kind = loss_coeffs[target_key][0], loss_coeffs[target_key][1]
+        diff = out[target_key] - target
+        loss = coeff * (diff.abs().mean() if kind == "L1Loss" else (diff ** 2).mean())
+        opt.zero_grad(set_to_none=True)
+        loss.backward()
+        scal = flat.all_reduce([float(loss.detach()), float(diff.detach().abs().mean())])
+        opt.step()
+        if rank == 0 and (step % flags.log_period == 0 or step == flags.steps - 1):
+            logging.info("step %d loss %.6g mae %.6g (%.1f s)", step, float(scal[0]), float(scal[1]), time.time() - t0)
+        if rank == 0 and ((step + 1) % flags.save_period == 0 or step == flags.steps - 1):
+            os.makedirs(out_dir, exist_ok=True)
+            torch.save(model.state_dict(), os.path.join(out_dir, "model.pt"))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def launch_mp(flags):
+    if flags.world_size > 1 and "RANK" not in os.environ:
+        mp.spawn(main, args=(flags,), nprocs=flags.world_size, join=True)
+    else:
+        main(0, flags)
+
+
+if __name__ == "__main__":
+    launch_mp(parse())
