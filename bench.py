@@ -222,8 +222,15 @@ def run_ours(args):
         _, n_paths, mul, x_dim, y_dim, N, E = full[0][1]
         alg = tp_bytes(E, N, (n_paths * mul, x_dim, y_dim))
         ach = alg / (t_ms * 1e-3) / 1e9
-        roof = {"kernel": "tpf_S3<float> (fused gather + uvu CG tensor product + segmented sum, 30 paths, mul 64)",
-                "bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": None,
+        traffic = None     # dram bytes per launch of the same kernel from the committed ncu --set full capture
+        tpath = os.path.join(ROOT, "profiles", "r1_tpfp_S3_traffic.json")
+        if os.path.exists(tpath):
+            with open(tpath) as f:
+                tj = json.load(f)
+            if tj.get("n_edges") == E and tj.get("n_nodes") == N:
+                traffic = tj["traffic_bytes_per_launch"]
+        roof = {"kernel": "tpfp_S3<64> (fused gather + uvu CG tensor product + segmented sum, 30 paths, mul 64)",
+                "bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": traffic,
                 "peak_source": peak_src, "algorithmic_bytes_per_launch": alg, "avg_launch_ms": t_ms,
                 "launches_timed": len(full), "edges_per_s": E / (t_ms * 1e-3),
                 "bwd_avg_launch_ms": statistics.mean(x[0] for x in bwd) if bwd else None}

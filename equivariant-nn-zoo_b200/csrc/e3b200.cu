@@ -882,63 +882,65 @@ extern "C" int e3b_gate_bwd(const e3b_gate_desc* desc, int dtype, const void* in
   return check_launch("gate_bwd");
 }
 
-// the gate on the channel-fastest ("imu") layout: gated blocks are [m][u]; one thread per output element
+// the gate on the channel-fastest ("imu") layout: gated blocks are [m][u].  One block per node row,
+// threads stride over the output columns (coalesced, 32-bit index arithmetic only).
 template <typename T, bool BWD>
-__global__ void gate_imu_kernel(const __grid_constant__ GateLayout L, const T* __restrict__ in, const T* __restrict__ g_mi,
-                                const T* __restrict__ g_imu, int64_t n, T* __restrict__ out_mi, T* __restrict__ out_imu,
-                                T* __restrict__ gin) {
-  const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (idx >= n * L.out_dim) return;
-  const int64_t row = idx / L.out_dim;
-  int c = (int)(idx - row * L.out_dim);
-  const T* xin = in + row * L.in_dim;
-  const int64_t obase = row * L.out_dim;
-  if (c < L.n_scalars) {
-    int b = 0, o = c;
-    while (o >= L.d.scalar_mul[b]) { o -= L.d.scalar_mul[b]; ++b; }
-    T f, df;
-    act_eval<T>(L.d.scalar_act[b], xin[c], &f, &df);
-    const T cst = T(L.d.scalar_cst[b]);
-    if (BWD) {
-      const T go = (g_mi ? g_mi[obase + c] : T(0)) + (g_imu ? g_imu[obase + c] : T(0));
-      gin[row * L.in_dim + c] = go * cst * df;
-    } else {
-      if (out_mi) out_mi[obase + c] = cst * f;
-      if (out_imu) out_imu[obase + c] = cst * f;
-    }
-    return;
-  }
-  c -= L.n_scalars;
-  int b = 0, goff = 0, boff = 0;  // gated block b; goff = gate index offset; boff = offset of the block in the gated part
-  int dim = 2 * L.d.gated_l[0] + 1;
-  while (c >= boff + L.d.gated_mul[b] * dim) {
-    boff += L.d.gated_mul[b] * dim;
-    goff += L.d.gated_mul[b];
-    ++b;
-    dim = 2 * L.d.gated_l[b] + 1;
-  }
-  const int mul = L.d.gated_mul[b];
-  const int m = (c - boff) / mul, u = (c - boff) - m * mul;
-  const int in_col = L.n_scalars + L.n_gates + c;                       // imu position in the input row
-  const int64_t o_imu = obase + L.n_scalars + c;
-  const int64_t o_mi = obase + L.n_scalars + boff + u * dim + m;
-  T f, df;
-  act_eval<T>(L.d.gate_act[b], xin[L.n_scalars + goff + u], &f, &df);
-  const T cst = T(L.d.gate_cst[b]);
-  if (!BWD) {
-    const T v = xin[in_col] * (cst * f);
-    if (out_mi) out_mi[o_mi] = v;
-    if (out_imu) out_imu[o_imu] = v;
-  } else {
-    const T go = (g_mi ? g_mi[o_mi] : T(0)) + (g_imu ? g_imu[o_imu] : T(0));
-    gin[row * L.in_dim + in_col] = go * (cst * f);
-    if (m == 0) {   // d/d gate = sum_m go_m x_m cst f'
-      T s = T(0);
-      for (int mm = 0; mm < dim; ++mm) {
-        const T gm = (g_mi ? g_mi[o_mi + mm] : T(0)) + (g_imu ? g_imu[o_imu + (int64_t)mm * mul] : T(0));
-        s = fma_(gm, xin[in_col + mm * mul], s);
+__global__ void __launch_bounds__(256) gate_imu_kernel(const __grid_constant__ GateLayout L, const T* __restrict__ in,
+                                                       const T* __restrict__ g_mi, const T* __restrict__ g_imu, int64_t n,
+                                                       T* __restrict__ out_mi, T* __restrict__ out_imu, T* __restrict__ gin) {
+  for (int64_t row = blockIdx.x; row < n; row += gridDim.x) {
+    const T* xin = in + row * L.in_dim;
+    const int64_t obase = row * L.out_dim;
+    T* grow = BWD ? gin + row * L.in_dim : nullptr;
+    for (int c0 = threadIdx.x; c0 < L.out_dim; c0 += blockDim.x) {
+      if (c0 < L.n_scalars) {
+        int b = 0, o = c0;
+        while (o >= L.d.scalar_mul[b]) { o -= L.d.scalar_mul[b]; ++b; }
+        T f, df;
+        act_eval<T>(L.d.scalar_act[b], xin[c0], &f, &df);
+        const T cst = T(L.d.scalar_cst[b]);
+        if (BWD) {
+          const T go = (g_mi ? g_mi[obase + c0] : T(0)) + (g_imu ? g_imu[obase + c0] : T(0));
+          grow[c0] = go * cst * df;
+        } else {
+          if (out_mi) out_mi[obase + c0] = cst * f;
+          if (out_imu) out_imu[obase + c0] = cst * f;
+        }
+        continue;
       }
-      gin[row * L.in_dim + L.n_scalars + goff + u] = s * cst * df;
+      const int c = c0 - L.n_scalars;
+      int b = 0, goff = 0, boff = 0;  // gated block b; goff = gate index offset; boff = offset of the block in the gated part
+      int dim = 2 * L.d.gated_l[0] + 1;
+      while (c >= boff + L.d.gated_mul[b] * dim) {
+        boff += L.d.gated_mul[b] * dim;
+        goff += L.d.gated_mul[b];
+        ++b;
+        dim = 2 * L.d.gated_l[b] + 1;
+      }
+      const int mul = L.d.gated_mul[b];
+      const int m = (c - boff) / mul, u = (c - boff) - m * mul;
+      const int in_col = L.n_scalars + L.n_gates + c;                       // imu position in the input row
+      const int64_t o_imu = obase + L.n_scalars + c;
+      const int64_t o_mi = obase + L.n_scalars + boff + u * dim + m;
+      T f, df;
+      act_eval<T>(L.d.gate_act[b], xin[L.n_scalars + goff + u], &f, &df);
+      const T cst = T(L.d.gate_cst[b]);
+      if (!BWD) {
+        const T v = xin[in_col] * (cst * f);
+        if (out_mi) out_mi[o_mi] = v;
+        if (out_imu) out_imu[o_imu] = v;
+      } else {
+        const T go = (g_mi ? g_mi[o_mi] : T(0)) + (g_imu ? g_imu[o_imu] : T(0));
+        grow[in_col] = go * (cst * f);
+        if (m == 0) {   // d/d gate = sum_m go_m x_m cst f'
+          T s = T(0);
+          for (int mm = 0; mm < dim; ++mm) {
+            const T gm = (g_mi ? g_mi[o_mi + mm] : T(0)) + (g_imu ? g_imu[o_imu + (int64_t)mm * mul] : T(0));
+            s = fma_(gm, xin[in_col + mm * mul], s);
+          }
+          grow[L.n_scalars + goff + u] = s * cst * df;
+        }
+      }
     }
   }
 }
@@ -951,7 +953,7 @@ extern "C" int e3b_gate_imu_fwd(const e3b_gate_desc* desc, int dtype, const void
   if (!in || (!out_mul_ir && !out_imu)) return fail(E3B_ERR_INVALID, "gate_imu_fwd: null argument");
   const GateLayout L = gate_layout(desc);
   if (L.out_dim == 0) return E3B_OK;
-  DISPATCH_DTYPE(dtype, gate_imu_kernel<T, false><<<blocks_for(n * L.out_dim, 256), 256, 0, (cudaStream_t)stream>>>(
+  DISPATCH_DTYPE(dtype, gate_imu_kernel<T, false><<<(unsigned)(n < 148 * 64 ? n : 148 * 64), 256, 0, (cudaStream_t)stream>>>(
                             L, (const T*)in, nullptr, nullptr, n, (T*)out_mul_ir, (T*)out_imu, nullptr);)
   return check_launch("gate_imu_fwd");
 }
@@ -964,7 +966,7 @@ extern "C" int e3b_gate_imu_bwd(const e3b_gate_desc* desc, int dtype, const void
   if (!in || !gin || (!gout_mul_ir && !gout_imu)) return fail(E3B_ERR_INVALID, "gate_imu_bwd: null argument");
   const GateLayout L = gate_layout(desc);
   if (L.out_dim == 0) return E3B_OK;
-  DISPATCH_DTYPE(dtype, gate_imu_kernel<T, true><<<blocks_for(n * L.out_dim, 256), 256, 0, (cudaStream_t)stream>>>(
+  DISPATCH_DTYPE(dtype, gate_imu_kernel<T, true><<<(unsigned)(n < 148 * 64 ? n : 148 * 64), 256, 0, (cudaStream_t)stream>>>(
                             L, (const T*)in, (const T*)gout_mul_ir, (const T*)gout_imu, n, nullptr, nullptr, (T*)gin);)
   return check_launch("gate_imu_bwd");
 }
