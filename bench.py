@@ -31,9 +31,20 @@ for p in (ROOT, os.path.join(ROOT, "tests"), os.path.join(ROOT, "equivariant-nn-
 import torch  # noqa: E402
 
 GRAPHS_PER_GPU = 512
+W2_EDGES = 149452            # edges of the seed-0 W2 batch at r_max 5 (what the CUDA arm reports as edges_per_gpu)
 CPU_SAMPLE_GRAPHS = 32
 METRIC = "energy+force atoms/s"
 META = {"config": "config_energy_force", "seed": 0}
+
+
+WORKLOAD = ("W2: config_energy_force (n_dim 64, l_max 2, 5 interaction blocks, r_max 5.0) energy+force evaluation = "
+            "neighbour list + forward + position-gradient backward, 512 synthetic QM9-shaped molecules per GPU")
+
+
+def workload_config(world, n_atoms, n_edges):
+    return {"workload": WORKLOAD, "graphs_per_gpu": GRAPHS_PER_GPU, "atoms_per_gpu": n_atoms, "edges_per_gpu": n_edges,
+            "parallelism": f"graphs sharded over {world} rank(s), no data-path collective",
+            "l2": "no explicit flush: per-layer per-edge weights are E*W*4 B = %.2f GB >> 126 MB L2" % (n_edges * 1920 * 4 / 1e9)}
 
 
 def peaks():
@@ -103,11 +114,11 @@ def run_reference(args):
     value = n_atoms * args.steps / dt
     sample = (f"{CPU_SAMPLE_GRAPHS} of the {GRAPHS_PER_GPU} W2 molecules ({n_atoms} atoms, {n_edges} edges) per step, "
               f"neighbour list + forward + autograd forces, fp32")
+    full = synthetic.qm9_like(GRAPHS_PER_GPU, seed=0)            # the arm's workload (rank 0 batch), for the config block
     line = {"impl": "reference", "metric": METRIC, "value": value, "unit": "atoms/s", "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": "W2 config_energy_force energy+force, QM9-shaped molecules (bounded CPU sample)",
-                       "model": "config_energy_force n_dim=64 l_max=2 layers=5 r_max=5.0"},
+            "config": workload_config(args.gpus, full["pos"].shape[0], W2_EDGES),
             "cpu_baseline": {"value": value, "unit": "atoms/s", "cores": cores, "kind": "port", "sample": sample},
             "e2e": {"value": value, "unit": "atoms/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line), flush=True)
@@ -214,6 +225,17 @@ def run_ours(args):
 
     # ---- roofline of the dominant kernel: fused TP-conv forward of a full (30-path) layer ----------
     peak, peak_src = peaks()
+    if args.breakdown:
+        agg = {}
+        for tag, s, e in timing:
+            name = tag[1] if tag[0] == "stage" else ("f.tp_conv" if tag[0] == "fwd" else "b.tp_conv")
+            agg[name] = agg.get(name, 0.0) + s.elapsed_time(e)
+        tot = sum(agg.values())
+        print("# per-step device time of the interaction blocks by stage (CUDA events on the launch stream), ms",
+              file=sys.stderr)
+        for k, v in sorted(agg.items(), key=lambda kv: -kv[1]):
+            print(f"#   {k:22s} {v / args.steps:8.3f}  {100 * v / tot:5.1f}%", file=sys.stderr)
+        print(f"#   {'sum':22s} {tot / args.steps:8.3f}   (step {ms / args.steps:.3f} ms)", file=sys.stderr)
     full = [(s.elapsed_time(e), tag) for tag, s, e in timing if tag[0] == "fwd" and tag[1] == 30]
     bwd = [(s.elapsed_time(e), tag) for tag, s, e in timing if tag[0] == "bwd" and tag[1] == 30]
     roof = None
@@ -257,13 +279,7 @@ def run_ours(args):
     line = {"metric": METRIC, "value": value, "unit": "atoms/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": "W2: config_energy_force energy+force evaluation (neighbour list + forward + "
-                                   "position-gradient backward), 512 synthetic QM9-shaped molecules per GPU",
-                       "model": "config_energy_force n_dim=64 l_max=2 layers=5 r_max=5.0",
-                       "atoms_per_gpu": n_atoms, "edges_per_gpu": n_edges, "graphs_per_gpu": GRAPHS_PER_GPU,
-                       "parallelism": f"graphs sharded over {world} rank(s), no data-path collective",
-                       "l2": "no explicit flush: per-layer per-edge weights are E*W*4 B = %.2f GB >> 126 MB L2"
-                             % (n_edges * 1920 * 4 / 1e9)},
+            "config": workload_config(world, n_atoms, n_edges),
             "e2e": {"value": e2e_value, "unit": "atoms/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
             "gpu_launches": launches, "clocks": clocks, "roofline": roof, "cpu_baseline": cpu}
     print(json.dumps(line), flush=True)
@@ -278,6 +294,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", dest="no_cpu_baseline", action="store_true")
+    ap.add_argument("--breakdown", action="store_true", help="print the per-stage device time table to stderr")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

@@ -118,7 +118,8 @@ def ptr(t):
 
 
 def stream():
-    return torch.cuda.current_stream().cuda_stream
+    """raw cudaStream_t of torch's current stream (torch.cuda.current_stream() costs ~15 us per call)"""
+    return torch._C._cuda_getCurrentRawStream(torch.cuda.current_device())
 
 
 def dtype_code(t):

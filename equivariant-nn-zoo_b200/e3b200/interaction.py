@@ -159,16 +159,18 @@ class _Interaction(torch.autograd.Function):
             written.add(o)
         if len(written) < len(fi.feat_in):
             xl.zero_()
-        for wave in _waves(probs):
-            ops.gemm_run(wave)
+        with ops.stage("f.linear_1"):
+            for wave in _waves(probs):
+                ops.gemm_run(wave)
         # ---- radial MLP
         hs = fi.hs
         h = [er]
         for i in range(conv.fc.n_layers):
             last = i == conv.fc.n_layers - 1
             out = new(E, hs[i + 1])
-            ops.gemm_run([ops.gemm_problem(h[-1], P["fc"][i], out, E, a_rows=(h[-1].stride(0), 0, 1),
-                                           alpha=1.0 / math.sqrt(hs[i]), epilogue=0 if last else 2, act_cst=conv.fc.cst)])
+            with ops.stage("f.mlp_last" if last else "f.mlp_hidden"):
+                ops.gemm_run([ops.gemm_problem(h[-1], P["fc"][i], out, E, a_rows=(h[-1].stride(0), 0, 1),
+                                               alpha=1.0 / math.sqrt(hs[i]), epilogue=0 if last else 2, act_cst=conv.fc.cst)])
             h.append(out)
         w = h[-1]
         # ---- fused gather + CG tensor product + segmented sum
@@ -203,13 +205,16 @@ class _Interaction(torch.autograd.Function):
                           o, o in written))
         if len(written | {o for _, o, _ in probs}) < len(fi.conv_out):
             cv.zero_()
-        for wave in _waves(sc_probs):
-            ops.gemm_run(wave)
-        for wave in _waves(probs):
-            ops.gemm_run(wave)
+        with ops.stage("f.self_connection"):
+            for wave in _waves(sc_probs):
+                ops.gemm_run(wave)
+        with ops.stage("f.post_linear"):
+            for wave in _waves(probs):
+                ops.gemm_run(wave)
         # ---- gate, in both layouts
         out_mi, out_imu = new(N, fi.Dout), new(N, fi.Dout)
-        check(lib.e3b_gate_imu_fwd(ctypes.byref(fi.gate.desc), 0, ptr(cv), N, ptr(out_mi), ptr(out_imu), stream()))
+        with ops.stage("f.gate"):
+            check(lib.e3b_gate_imu_fwd(ctypes.byref(fi.gate.desc), 0, ptr(cv), N, ptr(out_mi), ptr(out_imu), stream()))
         count_launch()
         ctx.fi, ctx.csr, ctx.src_is_imu = fi, csr, src_is_imu
         # parameter gradients are produced in training mode only (module.train()): an energy+force
@@ -242,8 +247,9 @@ class _Interaction(torch.autograd.Function):
         P = fi.packs("bwd")
         # ---- gate
         g_cv = new(N, fi.Dconv)
-        check(lib.e3b_gate_imu_bwd(ctypes.byref(fi.gate.desc), 0, ptr(cv), ptr(g_mi.contiguous()) if g_mi is not None else None,
-                                   ptr(g_imu.contiguous()) if g_imu is not None else None, N, ptr(g_cv), stream()))
+        with ops.stage("b.gate"):
+            check(lib.e3b_gate_imu_bwd(ctypes.byref(fi.gate.desc), 0, ptr(cv), ptr(g_mi.contiguous()) if g_mi is not None else None,
+                                       ptr(g_imu.contiguous()) if g_imu is not None else None, N, ptr(g_cv), stream()))
         count_launch()
         # ---- post linear, transposed: g_mid[z, k, kk] = alpha sum_w W[kk, w] g_cv[z, k, w]
         post, sc, lin1 = conv.tp.linear, conv.sc, conv.linear_1
@@ -258,8 +264,9 @@ class _Interaction(torch.autograd.Function):
             written.add(i)
         if len(written) < len(fi.mid):
             g_mid.zero_()
-        for wave in _waves(probs):
-            ops.gemm_run(wave)
+        with ops.stage("b.post_linear"):
+            for wave in _waves(probs):
+                ops.gemm_run(wave)
         # ---- tensor-product convolution backward
         fast = plan.specialized
         alloc = torch.empty if fast else torch.zeros
@@ -276,7 +283,8 @@ class _Interaction(torch.autograd.Function):
             count_launch()
         g_Y = None
         if need_Y:
-            g_Y = gsh_part.sum(1) if n_part > 1 else gsh_part.view(E, plan.sh_dim)
+            with ops.stage("b.gsh_sum"):
+                g_Y = gsh_part.sum(1) if n_part > 1 else gsh_part.view(E, plan.sh_dim)
         # ---- radial MLP backward (data path): g_z_i = (g_z_{i+1} W_i^T) * act'(z_i), derivative from the stored h_i
         hs = fi.hs
         gz = [None] * (conv.fc.n_layers + 1)       # gz[i] = gradient wrt the INPUT of layer i (after its activation derivative)
@@ -286,15 +294,17 @@ class _Interaction(torch.autograd.Function):
             if not (need_er or need_params):
                 break
             out = new(E, hs[i])
-            ops.gemm_run([ops.gemm_problem(gz[i + 1], P["fc"][i], out, E, alpha=1.0 / math.sqrt(hs[i]),
-                                           epilogue=3 if i > 0 else 0, H=h[i] if i > 0 else None, act_cst=conv.fc.cst)])
+            with ops.stage("b.mlp_last" if i == conv.fc.n_layers - 1 else "b.mlp_hidden"):
+                ops.gemm_run([ops.gemm_problem(gz[i + 1], P["fc"][i], out, E, alpha=1.0 / math.sqrt(hs[i]),
+                                               epilogue=3 if i > 0 else 0, H=h[i] if i > 0 else None, act_cst=conv.fc.cst)])
             gz[i] = out
         g_er = gz[0] if need_er else None
         # ---- d/dx: linear_1 transposed on the reduced edge gradient + self-connection transposed
         g_x = g_xl = None
         if need_x:
             g_xl = new(N, fi.Din)
-            check(lib.e3b_segment_sum(0, ptr(gx_edge), plan.x_dim, ptr(csr.out_ptr), ptr(csr.out_eid), N, ptr(g_xl), stream()))
+            with ops.stage("b.segment_sum"):
+                check(lib.e3b_segment_sum(0, ptr(gx_edge), plan.x_dim, ptr(csr.out_ptr), ptr(csr.out_eid), N, ptr(g_xl), stream()))
             count_launch()
             g_x = new(N, fi.Din)
             probs, written = [], set()
@@ -314,11 +324,13 @@ class _Interaction(torch.autograd.Function):
                 sc_probs.append((g, i1, i1 in written))
             if len(written | {t for _, t, _ in sc_probs}) < len(fi.feat_in):
                 g_x.zero_()
-            for wave in _waves(probs):
-                ops.gemm_run(wave)
+            with ops.stage("b.linear_1"):
+                for wave in _waves(probs):
+                    ops.gemm_run(wave)
             # several self-connection paths may feed from one input block (0e -> scalars and gates)
-            for wave in _waves(sc_probs):
-                ops.gemm_run(wave)
+            with ops.stage("b.self_connection"):
+                for wave in _waves(sc_probs):
+                    ops.gemm_run(wave)
         # ---- parameter / attribute gradients (training only): library GEMMs on the saved activations
         g_params = [None] * len(ctx.needs_input_grad[7:])
         g_attrs = None

@@ -207,6 +207,23 @@ def radial_basis(r, bessel_w, r_max, r_min=0.0, one_over_r=True, cutoff_kind=0, 
 TIMING = None
 
 
+class stage:
+    """``with ops.stage("name"):`` brackets a group of launches with CUDA events when TIMING is a list
+    (bench.py --breakdown); free otherwise."""
+
+    def __init__(self, name):
+        self.name = name
+
+    def __enter__(self):
+        self.end = _timed(("stage", self.name))
+        return self
+
+    def __exit__(self, *exc):
+        if self.end is not None:
+            self.end.record()
+        return False
+
+
 def _timed(tag):
     if TIMING is None:
         return None
@@ -460,7 +477,7 @@ def gemm_run(problems):
     for g in problems:
         if g.M == 0 or g.N == 0:
             continue
-        classes.setdefault((g.K <= 64, lib.e3b_gemm_tile_n(g.N, g.K)), []).append(g)
+        classes.setdefault((g.K <= 64, g.N > 64), []).append(g)      # the launch classes of e3b_gemm_tile_n
     for group in classes.values():
         for lo in range(0, len(group), _lib.E3B_GEMM_MAX_GROUP):
             chunk = group[lo:lo + _lib.E3B_GEMM_MAX_GROUP]
