@@ -15,11 +15,11 @@
 // straight into TENSOR MEMORY (tcgen05.st); the MMAs take A from TMEM, so of the operands only B
 // crosses shared memory (the kernel was bound by shared-memory bandwidth with A staged there).
 //
-// One persistent CTA = 14 warps, warp-specialised:
-//   warps 0-3  epilogue   TMEM -> registers (tcgen05.ld) -> epilogue math -> global
-//   warps 4-11 converter  global -(cp.async)-> raw ring -> split hi/lo -> A ring in TMEM
-//   warp  12   producer   TMA bulk copies of packed B chunks into the B ring
-//   warp  13   MMA        one elected thread issues tcgen05.mma and commits to the mbarriers
+// One persistent CTA = 18 warps, warp-specialised:
+//   warps 0-7  epilogue   TMEM -> registers (tcgen05.ld) -> epilogue math -> global
+//   warps 8-15 converter  global -(cp.async)-> raw ring -> split hi/lo -> A ring in TMEM
+//   warp  16   producer   TMA bulk copies of packed B chunks into the B ring
+//   warp  17   MMA        one elected thread issues tcgen05.mma and commits to the mbarriers
 // Three pipelines (mbarrier full/empty pairs): A ring, B ring, two TMEM accumulators.  When the
 // whole K extent of a row tile fits the A ring it stays RESIDENT across the column tiles.
 // The tensor core accumulates with truncation, so an unbroken chain over a long K drifts
@@ -39,9 +39,10 @@ constexpr int BM = 128;     // UMMA M
 constexpr int BK = 32;      // floats per K chunk = 4 MMA K-steps of 8 = 8 sixteen-byte columns
 constexpr int KSEG = 2;     // chunks per accumulation chain (64 floats of K)
 constexpr int A_COLS = 2 * BK;   // TMEM columns of one A stage: 32 hi | 32 lo
-constexpr int NTHREADS = 448;
+constexpr int NTHREADS = 576;
 constexpr int NCVT = 256;    // converter threads (warps 4-11)
-constexpr int CVT0 = 128;   // first converter thread
+constexpr int CVT0 = 256;   // first converter thread
+constexpr int NEPI = 256;   // epilogue threads (warps 0-7)
 constexpr int MAXG = E3B_GEMM_MAX_GROUP;
 
 struct Problem {
@@ -167,11 +168,17 @@ __device__ __forceinline__ void split4(const float4 x, float4* hi, float4* lo) {
   lo->z = rna_tf32(x.z - hi->z); lo->w = rna_tf32(x.w - hi->w);
 }
 
-// ShiftedSoftPlus pieces (e3nn nn.FullyConnectedNet activation): ssp(z) = softplus(z) - ln 2
-__device__ __forceinline__ float ssp_f(float z) { return (z > 20.f ? z : log1pf(expf(z))) - 0.6931471805599453f; }
+// ShiftedSoftPlus pieces (e3nn nn.FullyConnectedNet activation): ssp(z) = softplus(z) - ln 2.
+// Only four epilogue warps per SM evaluate these, so they use the SFU approximations (ex2 / lg2):
+// absolute error <= ~2e-7 on values of order one, inside the 1e-5 budget of the block.
+__device__ __forceinline__ float ssp_f(float z) {
+  return (z > 15.f ? z : __logf(1.f + __expf(z))) - 0.6931471805599453f;
+}
 // d/dz [cst * ssp(z)] expressed through the stored output h = cst * ssp(z):
 // sigmoid(z) = 1 - exp(-softplus(z)) = 1 - 0.5 * exp(-h / cst)
-__device__ __forceinline__ float dssp_from_out(float h, float cst) { return cst * (1.f - 0.5f * expf(-h / cst)); }
+__device__ __forceinline__ float dssp_from_out(float h, float cst, float inv_cst) {
+  return cst * (1.f - 0.5f * __expf(-h * inv_cst));
+}
 
 template <int BN, int PRAW, int SB>
 struct Smem {
@@ -179,7 +186,7 @@ struct Smem {
   static constexpr int RAW_ROW = BK + 4;           // padded row (144 B): conflict-free row-per-lane reads
   static constexpr int RAW_STAGE = BM * RAW_ROW;
   static constexpr int EPI_STAGE = 32 * 36;        // per epilogue warp: 32 rows x (32 + 4 pad) floats
-  static constexpr size_t BYTES = (size_t)(SB * B_STAGE + PRAW * RAW_STAGE + 4 * EPI_STAGE) * 4 + 128 /*align slack*/;
+  static constexpr size_t BYTES = (size_t)(SB * B_STAGE + PRAW * RAW_STAGE + 8 * EPI_STAGE) * 4 + 128 /*align slack*/;
 };
 
 struct EpiCtx {
@@ -193,21 +200,24 @@ struct EpiCtx {
 
 template <int EPI> __device__ __forceinline__ float epi_apply(float o, float h, float cst) {
   if (EPI == 2) return cst * ssp_f(o);
-  if (EPI == 3) return o * dssp_from_out(h, cst);
+  if (EPI == 3) return o * dssp_from_out(h, cst, 1.f / cst);
   return o;
 }
 
-// Epilogue warps: thread = one accumulator row (TMEM lane).  DENSE outputs (unit column stride,
-// N % 4 == 0) are transposed through a warp-private staging tile so that every store instruction
-// writes whole 128-byte lines (4 rows x 128 B per warp instruction) instead of 32 partial sectors.
+// Epilogue warps (8): warp w drains TMEM lanes 32 (w % 4) .. +31 (thread = one accumulator row) of the column
+// half w / 4 of every tile.  DENSE outputs (unit column stride, N % 4 == 0) are transposed through a
+// warp-private staging tile so that every store instruction writes whole 128-byte lines (4 rows x 128 B per
+// warp instruction) instead of 32 partial sectors.
 template <int BN, bool MULTI, int NACC, int EPI, bool DENSE>
 __device__ __forceinline__ void epilogue_role(const EpiCtx& c) {
+  constexpr int HB = BN / 2;                     // columns of a tile handled by this warp
   const Problem& P = *c.P;
   const e3b_gemm_problem& g = P.p;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int q = warp & 3, cb0 = (warp >> 2) * HB;
   const int n_seg = (c.k_chunks + KSEG - 1) / KSEG;
   uint32_t acc_it = 0;
-  const uint32_t t_lane = c.tmem_base + ((uint32_t)(warp * 32) << 16);
+  const uint32_t t_lane = c.tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)cb0;
   const int t_row = lane >> 3, t_c4 = (lane & 7) * 4;     // transposed role: rows t_row + 4 i, columns t_c4..+3
   const float alpha = g.alpha, cst = g.act_cst;
   const bool accumulate = g.accumulate != 0;
@@ -220,120 +230,125 @@ __device__ __forceinline__ void epilogue_role(const EpiCtx& c) {
   for (int t = c.t0; t < c.t1; ++t) {
     const int m = t / P.n_tiles, n = t - m * P.n_tiles;
     if (m != m_cur) {
-    m_cur = m;
-    const int row = m * BM + tid;
-    row_ok = row < g.M;
-    if (row_ok && !DENSE) {
-      c_row = g.C + (int64_t)(row / g.c_d) * g.c_s1 + (int64_t)(row % g.c_d) * g.c_s2;
-      if (EPI == 3) h_row = g.H + (int64_t)row * g.h_ld;
-    }
-    if (EPI == 1) {
-#pragma unroll
-      for (int v = 0; v < (EPI == 1 ? 32 : 1); ++v)
-        aux[v] = (row_ok && v < (g.aux_cols > 0 ? g.aux_cols : g.V)) ? __ldg(g.aux + (int64_t)(row / g.aux_d) * g.aux_ld + v) : 0.f;
-    }
-    // DENSE: rows of this warp's quarter tile handled by this lane after the transposition
-    r_base = m * BM + warp * 32 + t_row;
-    }
-    {
-      const int n0 = n * BN;
-      float racc[MULTI ? BN : 1];
-      if (MULTI) {
-#pragma unroll
-        for (int i = 0; i < (MULTI ? BN : 1); ++i) racc[i] = 0.f;
+      m_cur = m;
+      const int row = m * BM + q * 32 + lane;
+      row_ok = row < g.M;
+      if (row_ok && !DENSE) {
+        c_row = g.C + (int64_t)(row / g.c_d) * g.c_s1 + (int64_t)(row % g.c_d) * g.c_s2;
+        if (EPI == 3) h_row = g.H + (int64_t)row * g.h_ld;
       }
-      float red[EPI == 1 ? BN / 16 : 1];   // epilogue 1: the reduced outputs of this column tile
-      for (int seg = 0; seg < (MULTI ? n_seg : 1); ++seg, ++acc_it) {
-        const uint32_t buf = acc_it % NACC;
-        mbar_wait(&c.acc_full[buf], (acc_it / NACC) & 1u);
-        tc_fence_after();
-        const bool last = !MULTI || seg == n_seg - 1;
+      if (EPI == 1) {
 #pragma unroll
-        for (int cb = 0; cb < BN; cb += 32) {
-          float v[32];
-          tmem_ld32(t_lane + buf * BN + (uint32_t)cb, v);
-          if (MULTI) {
+        for (int v = 0; v < (EPI == 1 ? 32 : 1); ++v)
+          aux[v] = (row_ok && v < (g.aux_cols > 0 ? g.aux_cols : g.V)) ? __ldg(g.aux + (int64_t)(row / g.aux_d) * g.aux_ld + v) : 0.f;
+      }
+      // DENSE: rows of this warp's quarter tile handled by this lane after the transposition
+      r_base = m * BM + q * 32 + t_row;
+    }
+    const int n0 = n * BN + cb0;                  // first column of this warp's half tile
+    float racc[MULTI ? HB : 1];
+    if (MULTI) {
 #pragma unroll
-            for (int i = 0; i < 32; ++i) { racc[(MULTI ? cb : 0) + (MULTI ? i : 0)] += v[i]; v[i] = racc[(MULTI ? cb : 0) + (MULTI ? i : 0)]; }
-          }
-          const int nb = n0 + cb;
-          if (!last || nb >= g.N || (P.dbg & 8)) continue;
-          if (DENSE) {
-            __syncwarp();
+      for (int i = 0; i < (MULTI ? HB : 1); ++i) racc[i] = 0.f;
+    }
+    float red[EPI == 1 ? HB / 16 : 1];            // epilogue 1: the reduced outputs of this half tile
+    for (int seg = 0; seg < (MULTI ? n_seg : 1); ++seg, ++acc_it) {
+      const uint32_t buf = acc_it % NACC;
+      mbar_wait(&c.acc_full[buf], (acc_it / NACC) & 1u);
+      tc_fence_after();
+      const bool last = !MULTI || seg == n_seg - 1;
 #pragma unroll
-            for (int i = 0; i < 8; ++i)
-              *reinterpret_cast<float4*>(c.stg + lane * 36 + 4 * i) =
-                  make_float4(alpha * v[4 * i], alpha * v[4 * i + 1], alpha * v[4 * i + 2], alpha * v[4 * i + 3]);
-            __syncwarp();
-            const int col = nb + t_c4;
-            if (col < g.N) {
-              float* dst = g.C + (int64_t)r_base * g.c_s1 + col;
-              const float* hp = EPI == 3 ? g.H + (int64_t)r_base * g.h_ld + col : nullptr;
+      for (int cb = 0; cb < HB; cb += 32) {
+        float v[32];
+        tmem_ld32(t_lane + buf * BN + (uint32_t)cb, v);
+        if (MULTI) {
 #pragma unroll
-              for (int i = 0; i < 8; ++i) {
-                if (r_base + 4 * i < g.M) {
-                  float4 o = *reinterpret_cast<const float4*>(c.stg + (t_row + 4 * i) * 36 + t_c4);
-                  float4 h = make_float4(0.f, 0.f, 0.f, 0.f);
-                  if (EPI == 3) h = __ldg(reinterpret_cast<const float4*>(hp + (int64_t)(4 * i) * g.h_ld));
-                  o.x = epi_apply<EPI>(o.x, h.x, cst); o.y = epi_apply<EPI>(o.y, h.y, cst);
-                  o.z = epi_apply<EPI>(o.z, h.z, cst); o.w = epi_apply<EPI>(o.w, h.w, cst);
-                  float4* d4 = reinterpret_cast<float4*>(dst + (int64_t)(4 * i) * g.c_s1);
-                  if (accumulate) { const float4 old = *d4; o.x += old.x; o.y += old.y; o.z += old.z; o.w += old.w; }
-                  *d4 = o;
-                }
-              }
-            }
-          } else if (EPI == 1) {
-            // weighted reduction over groups of V accumulator columns (self-connection)
-            if (g.V == 16) {
-              float s0 = 0.f, s1 = 0.f;
-#pragma unroll
-              for (int t = 0; t < 16; ++t) { s0 = fmaf(aux[EPI == 1 ? t : 0], v[t], s0); s1 = fmaf(aux[EPI == 1 ? t : 0], v[16 + t], s1); }
-              red[EPI == 1 ? cb / 16 : 0] = alpha * s0;
-              red[EPI == 1 ? cb / 16 + 1 : 0] = alpha * s1;
-            } else {
-              float s0 = 0.f;
-#pragma unroll
-              for (int t = 0; t < 32; ++t) s0 = fmaf(aux[EPI == 1 ? t : 0], v[t], s0);
-              red[EPI == 1 ? cb / 32 : 0] = alpha * s0;
-            }
-          } else {
-            // generic (strided) output: one scalar store per element
-            if (row_ok) {
-#pragma unroll
-              for (int i = 0; i < 32; ++i)
-                if (nb + i < g.N) {
-                  const float o = epi_apply<EPI>(alpha * v[i], EPI == 3 ? __ldg(h_row + nb + i) : 0.f, cst);
-                  float* cp = c_row + (int64_t)(nb + i) * g.c_s3;
-                  *cp = o + (accumulate ? *cp : 0.f);
-                }
-            }
-          }
+          for (int i = 0; i < 32; ++i) { racc[(MULTI ? cb : 0) + (MULTI ? i : 0)] += v[i]; v[i] = racc[(MULTI ? cb : 0) + (MULTI ? i : 0)]; }
         }
-        tc_fence_before();
-        mbar_arrive(&c.acc_empty[buf]);
-        if (EPI == 1 && last && row_ok) {
-          // outputs of this tile: columns n0 / V .. of the row; whole sectors when the row is contiguous
-          const int per = BN / g.V, oc0 = n0 / g.V, n_out = g.N / g.V;
-          float* c0 = c_row + (int64_t)oc0 * g.c_s3;
-          if (g.c_s3 == 1 && (per & 3) == 0 && oc0 + per <= n_out && (reinterpret_cast<uintptr_t>(c0) & 15) == 0) {
+        const int nb = n0 + cb;
+        if (!last || nb >= g.N || (P.dbg & 8)) continue;
+        if (DENSE) {
+          __syncwarp();
 #pragma unroll
-            for (int i = 0; i < (EPI == 1 ? BN / 16 : 1); i += 4) {
-              if (i < per) {
-                float4 o = make_float4(red[EPI == 1 ? i : 0], red[EPI == 1 ? i + 1 : 0], red[EPI == 1 ? i + 2 : 0], red[EPI == 1 ? i + 3 : 0]);
-                float4* d4 = reinterpret_cast<float4*>(c0 + i);
+          for (int i = 0; i < 8; ++i)
+            *reinterpret_cast<float4*>(c.stg + lane * 36 + 4 * i) =
+                make_float4(alpha * v[4 * i], alpha * v[4 * i + 1], alpha * v[4 * i + 2], alpha * v[4 * i + 3]);
+          __syncwarp();
+          const int col = nb + t_c4;
+          if (col < g.N) {
+            float* dst = g.C + (int64_t)r_base * g.c_s1 + col;
+            const float* hp = EPI == 3 ? g.H + (int64_t)r_base * g.h_ld + col : nullptr;
+            float4 hv[EPI == 3 ? 8 : 1];
+            if (EPI == 3) {                       // all eight loads in flight before the first use
+#pragma unroll
+              for (int i = 0; i < (EPI == 3 ? 8 : 1); ++i)
+                hv[i] = r_base + 4 * i < g.M ? __ldg(reinterpret_cast<const float4*>(hp + (int64_t)(4 * i) * g.h_ld))
+                                             : make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              if (r_base + 4 * i < g.M) {
+                float4 o = *reinterpret_cast<const float4*>(c.stg + (t_row + 4 * i) * 36 + t_c4);
+                const float4 h = hv[EPI == 3 ? i : 0];
+                o.x = epi_apply<EPI>(o.x, h.x, cst); o.y = epi_apply<EPI>(o.y, h.y, cst);
+                o.z = epi_apply<EPI>(o.z, h.z, cst); o.w = epi_apply<EPI>(o.w, h.w, cst);
+                float4* d4 = reinterpret_cast<float4*>(dst + (int64_t)(4 * i) * g.c_s1);
                 if (accumulate) { const float4 old = *d4; o.x += old.x; o.y += old.y; o.z += old.z; o.w += old.w; }
                 *d4 = o;
               }
             }
-          } else {
+          }
+        } else if (EPI == 1) {
+          // weighted reduction over groups of V accumulator columns (self-connection)
+          if (g.V == 16) {
+            float s0 = 0.f, s1 = 0.f;
 #pragma unroll
-            for (int i = 0; i < (EPI == 1 ? BN / 16 : 1); ++i)
-              if (i < per && oc0 + i < n_out) {
-                float* cp = c0 + (int64_t)i * g.c_s3;
-                *cp = red[EPI == 1 ? i : 0] + (accumulate ? *cp : 0.f);
+            for (int t2 = 0; t2 < 16; ++t2) { s0 = fmaf(aux[EPI == 1 ? t2 : 0], v[t2], s0); s1 = fmaf(aux[EPI == 1 ? t2 : 0], v[16 + t2], s1); }
+            red[EPI == 1 ? cb / 16 : 0] = alpha * s0;
+            red[EPI == 1 ? cb / 16 + 1 : 0] = alpha * s1;
+          } else {
+            float s0 = 0.f;
+#pragma unroll
+            for (int t2 = 0; t2 < 32; ++t2) s0 = fmaf(aux[EPI == 1 ? t2 : 0], v[t2], s0);
+            red[EPI == 1 ? cb / 32 : 0] = alpha * s0;
+          }
+        } else {
+          // generic (strided) output: one scalar store per element
+          if (row_ok) {
+#pragma unroll
+            for (int i = 0; i < 32; ++i)
+              if (nb + i < g.N) {
+                const float o = epi_apply<EPI>(alpha * v[i], EPI == 3 ? __ldg(h_row + nb + i) : 0.f, cst);
+                float* cp = c_row + (int64_t)(nb + i) * g.c_s3;
+                *cp = o + (accumulate ? *cp : 0.f);
               }
           }
+        }
+      }
+      tc_fence_before();
+      mbar_arrive(&c.acc_empty[buf]);
+      if (EPI == 1 && last && row_ok && n0 < g.N && !(P.dbg & 8)) {
+        // outputs of this half tile: columns n0 / V .. of the row; vector stores when the row is contiguous
+        const int per = HB / g.V, oc0 = n0 / g.V, n_out = g.N / g.V;
+        float* c0 = c_row + (int64_t)oc0 * g.c_s3;
+        const bool vec = g.c_s3 == 1 && oc0 + per <= n_out;
+        if (vec && per == 4 && (reinterpret_cast<uintptr_t>(c0) & 15) == 0) {
+          float4 o = make_float4(red[0], red[EPI == 1 && HB >= 32 ? 1 : 0], red[EPI == 1 && HB >= 64 ? 2 : 0], red[EPI == 1 && HB >= 64 ? 3 : 0]);
+          float4* d4 = reinterpret_cast<float4*>(c0);
+          if (accumulate) { const float4 old = *d4; o.x += old.x; o.y += old.y; o.z += old.z; o.w += old.w; }
+          *d4 = o;
+        } else if (vec && per == 2 && (reinterpret_cast<uintptr_t>(c0) & 7) == 0) {
+          float2 o = make_float2(red[0], red[EPI == 1 && HB >= 32 ? 1 : 0]);
+          float2* d2 = reinterpret_cast<float2*>(c0);
+          if (accumulate) { const float2 old = *d2; o.x += old.x; o.y += old.y; }
+          *d2 = o;
+        } else {
+#pragma unroll
+          for (int i = 0; i < (EPI == 1 ? HB / 16 : 1); ++i)
+            if (i < per && oc0 + i < n_out) {
+              float* cp = c0 + (int64_t)i * g.c_s3;
+              *cp = red[EPI == 1 ? i : 0] + (accumulate ? *cp : 0.f);
+            }
         }
       }
     }
@@ -350,7 +365,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) gemm_tf32x3_kernel(const __grid_c
   float* smem = reinterpret_cast<float*>((reinterpret_cast<uintptr_t>(smem_dyn) + 127) & ~(uintptr_t)127);
   float* sB = smem;                                   // [SB][hi|lo][c(8)][row(BN)][4]
   float* sRaw = sB + SB * L::B_STAGE;                 // [PRAW][row(128)][36]
-  float* sEpi = sRaw + PRAW * L::RAW_STAGE;           // [4 warps][32 rows][36]
+  float* sEpi = sRaw + PRAW * L::RAW_STAGE;           // [8 warps][32 rows][36]
   __shared__ uint64_t a_full[SA], a_empty[SA], b_full[SB], b_empty[SB], acc_full[NACC], acc_empty[NACC];
   __shared__ uint32_t tmem_base_smem;
 
@@ -369,14 +384,14 @@ __global__ void __launch_bounds__(NTHREADS, 1) gemm_tf32x3_kernel(const __grid_c
   const int k_chunks = P.k_chunks;
   const bool resident = k_chunks <= SA;
 
-  if (warp == 13) {  // TMEM allocation is warp-collective; the same warp frees it
+  if (warp == 17) {  // TMEM allocation is warp-collective; the same warp frees it
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_addr(&tmem_base_smem)), "r"(512u) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
   if (tid == 0) {
     for (int s = 0; s < SA; ++s) { mbar_init(&a_full[s], NCVT / 2); mbar_init(&a_empty[s], 1); }
     for (int s = 0; s < SB; ++s) { mbar_init(&b_full[s], 1); mbar_init(&b_empty[s], 1); }
-    for (int s = 0; s < NACC; ++s) { mbar_init(&acc_full[s], 1); mbar_init(&acc_empty[s], 128); }
+    for (int s = 0; s < NACC; ++s) { mbar_init(&acc_full[s], 1); mbar_init(&acc_empty[s], NEPI); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   tc_fence_before();
@@ -386,7 +401,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) gemm_tf32x3_kernel(const __grid_c
   const uint32_t tmem_a0 = tmem_base + NACC * BN;     // first A stage
 
   if (t1 > t0) {
-    if (warp >= 4 && warp < 12) {
+    if (warp >= 8 && warp < 16) {
       // =============================== A converter ===============================
       // Two groups of 4 warps take alternate jobs (K chunks), so two chunks are in flight through the
       // load -> split -> tcgen05.st chain at any time.  Within a group:
@@ -478,7 +493,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) gemm_tf32x3_kernel(const __grid_c
         if (++slot == PR) slot = 0;
       }
       cp_async_wait<0>();
-    } else if (warp == 12) {
+    } else if (warp == 16) {
       // =============================== B producer (TMA) ===============================
       if (lane == 0) {
         uint32_t it = 0;
@@ -494,7 +509,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) gemm_tf32x3_kernel(const __grid_c
             }
         }
       }
-    } else if (warp == 13) {
+    } else if (warp == 17) {
       // =============================== MMA issuer ===============================
       // The whole warp walks the tiles (uniform control flow, so addresses and descriptors live in
       // uniform registers); one elected lane issues the MMAs of a chunk and the commits.
@@ -544,7 +559,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) gemm_tf32x3_kernel(const __grid_c
         }
         if (resident && last_m) a_it += (uint32_t)k_chunks;
       }
-    } else if (warp < 4) {
+    } else if (warp < 8) {
       // =============================== epilogue ===============================
       const bool dense = g.c_s3 == 1 && g.c_d == 1 && (g.c_s1 & 3) == 0 && (g.N & 3) == 0 &&
                          (reinterpret_cast<uintptr_t>(g.C) & 15) == 0 && (g.epilogue != 3 || (g.h_ld & 3) == 0);
@@ -558,7 +573,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) gemm_tf32x3_kernel(const __grid_c
 
   tc_fence_before();
   __syncthreads();
-  if (warp == 13) {
+  if (warp == 17) {
     __syncwarp();
     tc_fence_after();
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
@@ -725,7 +740,7 @@ extern "C" int e3b_gemm_run(const e3b_gemm_problem* problems, int32_t n, void* s
   cudaError_t e;
   if (multi) e = launch<64, true, 4, 4, 6, 4>(b, ctas, (cudaStream_t)stream);
   else if (bn == 64) e = launch<64, false, 4, 4, 6, 4>(b, ctas, (cudaStream_t)stream);
-  else e = launch<128, false, 2, 4, 4, 4>(b, ctas, (cudaStream_t)stream);
+  else e = launch<128, false, 2, 4, 4, 3>(b, ctas, (cudaStream_t)stream);
   if (e != cudaSuccess) return e3b_fail(E3B_ERR_CUDA, "gemm_run: %s", cudaGetErrorString(e));
   return E3B_OK;
 }
