@@ -15,11 +15,12 @@
 // straight into TENSOR MEMORY (tcgen05.st); the MMAs take A from TMEM, so of the operands only B
 // crosses shared memory (the kernel was bound by shared-memory bandwidth with A staged there).
 //
-// One persistent CTA = 18 warps, warp-specialised:
+// One persistent CTA = 19 warps, warp-specialised:
 //   warps 0-7  epilogue   TMEM -> registers (tcgen05.ld) -> epilogue math -> global
 //   warps 8-15 converter  global -(cp.async)-> raw ring -> split hi/lo -> A ring in TMEM
 //   warp  16   producer   TMA bulk copies of packed B chunks into the B ring
-//   warp  17   MMA        one elected thread issues tcgen05.mma and commits to the mbarriers
+//   warps 17-18 MMA       one elected thread each issues tcgen05.mma and commits to the mbarriers (long K: the two
+//                         alternate accumulation chains, halving the per-chunk issue overhead; else warp 17 alone)
 // Three pipelines (mbarrier full/empty pairs): A ring, B ring, two TMEM accumulators.  When the
 // whole K extent of a row tile fits the A ring it stays RESIDENT across the column tiles.
 // The tensor core accumulates with truncation, so an unbroken chain over a long K drifts
@@ -39,7 +40,7 @@ constexpr int BM = 128;     // UMMA M
 constexpr int BK = 32;      // floats per K chunk = 4 MMA K-steps of 8 = 8 sixteen-byte columns
 constexpr int KSEG = 2;     // chunks per accumulation chain (64 floats of K)
 constexpr int A_COLS = 2 * BK;   // TMEM columns of one A stage: 32 hi | 32 lo
-constexpr int NTHREADS = 576;
+constexpr int NTHREADS = 608;
 constexpr int NCVT = 256;    // converter threads (warps 4-11)
 constexpr int CVT0 = 256;   // first converter thread
 constexpr int NEPI = 256;   // epilogue threads (warps 0-7)
@@ -335,7 +336,8 @@ __device__ __forceinline__ void epilogue_role(const EpiCtx& c) {
         }
       }
       tc_fence_before();
-      mbar_arrive(&c.acc_empty[buf]);
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&c.acc_empty[buf]);
       if (EPI == 1 && last && row_ok && n0 < g.N && !(P.dbg & 8)) {
         // outputs of this half tile: columns n0 / V .. of the row; vector stores when the row is contiguous
         const int per = HB / g.V, oc0 = n0 / g.V, n_out = g.N / g.V;
@@ -397,10 +399,10 @@ __global__ void __launch_bounds__(NTHREADS, 1) gemm_tf32x3_kernel(const __grid_c
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_addr(&tmem_base_smem)), "r"(512u) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
-  if (tid == 0) {
-    for (int s = 0; s < SA; ++s) { mbar_init(&a_full[s], NCVT / 2); mbar_init(&a_empty[s], 1); }
+  if (tid == 0) {   // arrival counts: one per converter warp of the filling group / per epilogue warp
+    for (int s = 0; s < SA; ++s) { mbar_init(&a_full[s], NCVT / 2 / 32); mbar_init(&a_empty[s], 1); }
     for (int s = 0; s < SB; ++s) { mbar_init(&b_full[s], 1); mbar_init(&b_empty[s], 1); }
-    for (int s = 0; s < NACC; ++s) { mbar_init(&acc_full[s], 1); mbar_init(&acc_empty[s], NEPI); }
+    for (int s = 0; s < NACC; ++s) { mbar_init(&acc_full[s], 1); mbar_init(&acc_empty[s], NEPI / 32); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   tc_fence_before();
@@ -498,7 +500,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) gemm_tf32x3_kernel(const __grid_c
           asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
         }
         tc_fence_before();
-        mbar_arrive(&a_full[st]);
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&a_full[st]);  // 128 arrivals per stage cost more than the conversion itself
         if (++slot == PR) slot = 0;
       }
       cp_async_wait<0>();
@@ -518,8 +521,11 @@ __global__ void __launch_bounds__(NTHREADS, 1) gemm_tf32x3_kernel(const __grid_c
             }
         }
       }
-    } else if (warp == 17) {
+    } else if (warp == 17 || warp == 18) {
       // =============================== MMA issuer ===============================
+      const bool dual = MULTI && !resident;       // every stage is consumed by exactly one chain -> chains can alternate
+      const uint32_t mi = warp - 17;
+      if (mi == 0 || dual) {
       // The whole warp walks the tiles (uniform control flow, so addresses and descriptors live in
       // uniform registers); one elected lane issues the MMAs of a chunk and the commits.
       const uint32_t idesc = umma_idesc(BN);
@@ -534,6 +540,13 @@ __global__ void __launch_bounds__(NTHREADS, 1) gemm_tf32x3_kernel(const __grid_c
           uint32_t buf = 0;
           for (int kc = 0; kc < k_chunks; ++kc) {
             const bool seg_first = (kc % KSEG) == 0;
+            const bool seg_last = (kc % KSEG) == KSEG - 1 || kc == k_chunks - 1;
+            if (dual && (acc_it & 1u) != mi) {      // the other issuer's chain
+              if (seg_last) ++acc_it;
+              ++b_it;
+              ++a_it;
+              continue;
+            }
             if (seg_first) {
               buf = acc_it % NACC;
               mbar_wait(&acc_empty[buf], ((acc_it / NACC) & 1u) ^ 1u);
@@ -543,7 +556,6 @@ __global__ void __launch_bounds__(NTHREADS, 1) gemm_tf32x3_kernel(const __grid_c
             if (!resident || first_m) mbar_wait(&a_full[sa], (a_idx / SA) & 1u);
             mbar_wait(&b_full[sb], (b_it / SB) & 1u);
             tc_fence_after();
-            const bool seg_last = (kc % KSEG) == KSEG - 1 || kc == k_chunks - 1;
             if (elect_one()) {
               const uint32_t tAh = tmem_a0 + sa * (uint32_t)A_COLS, tAl = tAh + BK;
               const uint64_t dBh = tmplB | (uint64_t)(((sB_u + sb * (uint32_t)(L::B_STAGE * 4)) >> 4) & 0x3FFFu);
@@ -567,6 +579,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) gemm_tf32x3_kernel(const __grid_c
           }
         }
         if (resident && last_m) a_it += (uint32_t)k_chunks;
+      }
       }
     } else if (warp < 8) {
       // =============================== epilogue ===============================
