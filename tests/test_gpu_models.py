@@ -104,3 +104,28 @@ def test_full_size_invariants_w2():
     out_r = product_harness.run_product(model, inp, torch.float32, DEV, pre_edge={"r_max": 5.0})
     assert harness.rel_err(out_r["energy"], out["energy"]) < 1e-5
     assert harness.rel_err(out_r["forces"].cpu(), out["forces"].cpu() @ R.T) < 1e-4
+
+
+def test_graphed_evaluator_matches_eager():
+    """CUDA-graph replay of the model step (e3b200.graphed) against the eager path: same shapes hit the cache,
+    new inputs are honoured (different species, rigidly moved positions -> same edge count)."""
+    from e3b200.graphed import GraphedEvaluator
+
+    meta = {"config": "config_energy_force", "seed": 8}
+    model = product_harness.build_product(meta, torch.float32, DEV)
+    ev = GraphedEvaluator(model, r_max=5.0)
+    base = synthetic.qm9_like(16, seed=6)
+    variants = [base, dict(base), dict(base)]
+    variants[1]["species"] = base["species"].flip(0).contiguous()
+    variants[2]["pos"] = base["pos"] + torch.tensor([0.3, -0.2, 0.1])        # translation: same neighbour list
+    for v in variants:
+        eager = product_harness.run_product(model, v, torch.float32, DEV, pre_edge={"r_max": 5.0})
+        got = ev({k: t.to(DEV) for k, t in v.items()})
+        assert harness.rel_err(got["energy"], eager["energy"]) < 1e-6
+        assert harness.rel_err(got["forces"], eager["forces"]) < 1e-5
+    assert ev.misses == 1 and ev.hits == 2
+    # a different shape misses and is captured separately
+    other = synthetic.qm9_like(5, seed=1)
+    got = ev({k: t.to(DEV) for k, t in other.items()})
+    eager = product_harness.run_product(model, other, torch.float32, DEV, pre_edge={"r_max": 5.0})
+    assert harness.rel_err(got["forces"], eager["forces"]) < 1e-5 and ev.misses == 2
