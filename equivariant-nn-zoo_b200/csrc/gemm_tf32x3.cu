@@ -53,6 +53,7 @@ struct Problem {
                          // in row-major order (tile t = row tile t / n_tiles, column tile t % n_tiles)
   int32_t cta_begin;     // first CTA (blockIdx.x) of this problem
   uint64_t a_mul;        // ceil(2^40 / a_d): r / a_d == (r * a_mul) >> 40 for r < 2^31, a_d < 512
+  uint64_t c_mul;        // the same for c_d
   int32_t dbg;           // E3B_GEMM_DEBUG bisection bits: 1 skip A load+convert, 2 skip MMA, 4 skip B loads, 8 skip stores
 };
 struct Batch {
@@ -286,7 +287,6 @@ __device__ __forceinline__ void epilogue_role(const EpiCtx& c) {
           __syncwarp();
           const int col = nb + t_c4;
           if (col < g.N) {
-            float* dst = g.C + (int64_t)r_base * g.c_s1 + col;
             const float* hp = EPI == 3 ? g.H + (int64_t)r_base * g.h_ld + col : nullptr;
             float4 hv[EPI == 3 ? 8 : 1];
             if (EPI == 3) {                       // all eight loads in flight before the first use
@@ -302,7 +302,9 @@ __device__ __forceinline__ void epilogue_role(const EpiCtx& c) {
                 const float4 h = hv[EPI == 3 ? i : 0];
                 o.x = epi_apply<EPI>(o.x, h.x, cst); o.y = epi_apply<EPI>(o.y, h.y, cst);
                 o.z = epi_apply<EPI>(o.z, h.z, cst); o.w = epi_apply<EPI>(o.w, h.w, cst);
-                float4* d4 = reinterpret_cast<float4*>(dst + (int64_t)(4 * i) * g.c_s1);
+                const int r = r_base + 4 * i;            // affine row addressing (irreps blocks written in place)
+                const int rq = (int)(((uint64_t)(uint32_t)r * P.c_mul) >> 40);
+                float4* d4 = reinterpret_cast<float4*>(g.C + (int64_t)rq * g.c_s1 + (int64_t)(r - rq * g.c_d) * g.c_s2 + col);
                 if (accumulate) { const float4 old = *d4; o.x += old.x; o.y += old.y; o.z += old.z; o.w += old.w; }
                 *d4 = o;
               }
@@ -583,7 +585,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) gemm_tf32x3_kernel(const __grid_c
       }
     } else if (warp < 8) {
       // =============================== epilogue ===============================
-      const bool dense = g.c_s3 == 1 && g.c_d == 1 && (g.c_s1 & 3) == 0 && (g.N & 3) == 0 &&
+      const bool dense = g.c_s3 == 1 && (g.c_s1 & 3) == 0 && (g.c_s2 & 3) == 0 && (g.N & 3) == 0 &&
                          (reinterpret_cast<uintptr_t>(g.C) & 15) == 0 && (g.epilogue != 3 || (g.h_ld & 3) == 0);
       EpiCtx c{&P, acc_full, acc_empty, sEpi + warp * L::EPI_STAGE, tmem_base, t0, t1, k_chunks};
       if (g.epilogue == 1) epilogue_role<BN, MULTI, NACC, 1, false>(c);
@@ -721,6 +723,8 @@ extern "C" int e3b_gemm_run(const e3b_gemm_problem* problems, int32_t n, void* s
     if (p.a_d >= 512) return e3b_fail(E3B_ERR_UNSUPPORTED, "gemm_run: a_d must be < 512");
     { static const int dbg = [] { const char* v = getenv("E3B_GEMM_DEBUG"); return v ? atoi(v) : 0; }(); P.dbg = dbg; }
     P.a_mul = ((1ull << 40) + (uint64_t)p.a_d - 1) / (uint64_t)p.a_d;
+    if (p.c_d >= 512) return e3b_fail(E3B_ERR_UNSUPPORTED, "gemm_run: c_d must be < 512");
+    P.c_mul = ((1ull << 40) + (uint64_t)p.c_d - 1) / (uint64_t)p.c_d;
     work[b.n] = (double)P.m_tiles * P.n_tiles * (P.k_chunks + 2);
     total_work += work[b.n];
     ++b.n;
