@@ -748,14 +748,19 @@ extern "C" int e3b_segment_sum(int dtype, const void* src, int64_t width, const 
 
 // ------------------------------------------------------------------------------------------
 // Gate (e3nn nn.Gate as wired at nn/message_passing.py:191-207)
+// fp32: SFU approximations (ex2 / lg2 based, relative error ~1e-6 on the values the gate sees: the gate is
+// evaluated once per feature element and would otherwise spend most of its time in libm range reduction)
 template <typename T> __device__ __forceinline__ T exp_(T v);
-template <> __device__ __forceinline__ float exp_<float>(float v) { return expf(v); }
+template <> __device__ __forceinline__ float exp_<float>(float v) { return __expf(v); }
 template <> __device__ __forceinline__ double exp_<double>(double v) { return exp(v); }
 template <typename T> __device__ __forceinline__ T tanh_(T v);
-template <> __device__ __forceinline__ float tanh_<float>(float v) { return tanhf(v); }
+template <> __device__ __forceinline__ float tanh_<float>(float v) {
+  const float a = fminf(fabsf(v), 15.f), e = __expf(2.f * a);          // tanh|v| = 1 - 2 / (e^{2|v|} + 1)
+  return copysignf(1.f - __fdividef(2.f, e + 1.f), v);
+}
 template <> __device__ __forceinline__ double tanh_<double>(double v) { return tanh(v); }
 template <typename T> __device__ __forceinline__ T log1p_(T v);
-template <> __device__ __forceinline__ float log1p_<float>(float v) { return log1pf(v); }
+template <> __device__ __forceinline__ float log1p_<float>(float v) { return __logf(1.f + v); }
 template <> __device__ __forceinline__ double log1p_<double>(double v) { return log1p(v); }
 
 template <typename T>
@@ -882,64 +887,62 @@ extern "C" int e3b_gate_bwd(const e3b_gate_desc* desc, int dtype, const void* in
   return check_launch("gate_bwd");
 }
 
-// the gate on the channel-fastest ("imu") layout: gated blocks are [m][u].  One block per node row,
-// threads stride over the output columns (coalesced, 32-bit index arithmetic only).
+// the gate on the channel-fastest ("imu") layout: gated blocks are [m][u].  One block per node row; a
+// thread takes one scalar, or one (gated block, channel u) pair and walks its 2l+1 components, so the gate
+// activation and the block lookup are evaluated once per channel; all accesses are coalesced over u.
 template <typename T, bool BWD>
 __global__ void __launch_bounds__(256) gate_imu_kernel(const __grid_constant__ GateLayout L, const T* __restrict__ in,
                                                        const T* __restrict__ g_mi, const T* __restrict__ g_imu, int64_t n,
                                                        T* __restrict__ out_mi, T* __restrict__ out_imu, T* __restrict__ gin) {
+  const int n_items = L.n_scalars + L.n_gates;
   for (int64_t row = blockIdx.x; row < n; row += gridDim.x) {
     const T* xin = in + row * L.in_dim;
     const int64_t obase = row * L.out_dim;
     T* grow = BWD ? gin + row * L.in_dim : nullptr;
-    for (int c0 = threadIdx.x; c0 < L.out_dim; c0 += blockDim.x) {
-      if (c0 < L.n_scalars) {
-        int b = 0, o = c0;
+    for (int it = threadIdx.x; it < n_items; it += blockDim.x) {
+      if (it < L.n_scalars) {
+        int b = 0, o = it;
         while (o >= L.d.scalar_mul[b]) { o -= L.d.scalar_mul[b]; ++b; }
         T f, df;
-        act_eval<T>(L.d.scalar_act[b], xin[c0], &f, &df);
+        act_eval<T>(L.d.scalar_act[b], xin[it], &f, &df);
         const T cst = T(L.d.scalar_cst[b]);
         if (BWD) {
-          const T go = (g_mi ? g_mi[obase + c0] : T(0)) + (g_imu ? g_imu[obase + c0] : T(0));
-          grow[c0] = go * cst * df;
+          const T go = (g_mi ? g_mi[obase + it] : T(0)) + (g_imu ? g_imu[obase + it] : T(0));
+          grow[it] = go * cst * df;
         } else {
-          if (out_mi) out_mi[obase + c0] = cst * f;
-          if (out_imu) out_imu[obase + c0] = cst * f;
+          if (out_mi) out_mi[obase + it] = cst * f;
+          if (out_imu) out_imu[obase + it] = cst * f;
         }
         continue;
       }
-      const int c = c0 - L.n_scalars;
-      int b = 0, goff = 0, boff = 0;  // gated block b; goff = gate index offset; boff = offset of the block in the gated part
-      int dim = 2 * L.d.gated_l[0] + 1;
-      while (c >= boff + L.d.gated_mul[b] * dim) {
-        boff += L.d.gated_mul[b] * dim;
+      const int gi = it - L.n_scalars;               // index of the gate scalar
+      int b = 0, goff = 0, boff = 0;                 // gated block b; its first gate; its offset in the gated part
+      while (gi >= goff + L.d.gated_mul[b]) {
         goff += L.d.gated_mul[b];
+        boff += L.d.gated_mul[b] * (2 * L.d.gated_l[b] + 1);
         ++b;
-        dim = 2 * L.d.gated_l[b] + 1;
       }
-      const int mul = L.d.gated_mul[b];
-      const int m = (c - boff) / mul, u = (c - boff) - m * mul;
-      const int in_col = L.n_scalars + L.n_gates + c;                       // imu position in the input row
-      const int64_t o_imu = obase + L.n_scalars + c;
-      const int64_t o_mi = obase + L.n_scalars + boff + u * dim + m;
+      const int mul = L.d.gated_mul[b], dim = 2 * L.d.gated_l[b] + 1, u = gi - goff;
       T f, df;
-      act_eval<T>(L.d.gate_act[b], xin[L.n_scalars + goff + u], &f, &df);
+      act_eval<T>(L.d.gate_act[b], xin[L.n_scalars + gi], &f, &df);
       const T cst = T(L.d.gate_cst[b]);
+      const int in0 = L.n_scalars + L.n_gates + boff + u;                 // component m at + m * mul
+      const int64_t o_imu = obase + L.n_scalars + boff + u;               // component m at + m * mul
+      const int64_t o_mi = obase + L.n_scalars + boff + (int64_t)u * dim; // component m at + m
       if (!BWD) {
-        const T v = xin[in_col] * (cst * f);
-        if (out_mi) out_mi[o_mi] = v;
-        if (out_imu) out_imu[o_imu] = v;
-      } else {
-        const T go = (g_mi ? g_mi[o_mi] : T(0)) + (g_imu ? g_imu[o_imu] : T(0));
-        grow[in_col] = go * (cst * f);
-        if (m == 0) {   // d/d gate = sum_m go_m x_m cst f'
-          T s = T(0);
-          for (int mm = 0; mm < dim; ++mm) {
-            const T gm = (g_mi ? g_mi[o_mi + mm] : T(0)) + (g_imu ? g_imu[o_imu + (int64_t)mm * mul] : T(0));
-            s = fma_(gm, xin[in_col + mm * mul], s);
-          }
-          grow[L.n_scalars + goff + u] = s * cst * df;
+        for (int m = 0; m < dim; ++m) {
+          const T v = xin[in0 + m * mul] * (cst * f);
+          if (out_mi) out_mi[o_mi + m] = v;
+          if (out_imu) out_imu[o_imu + (int64_t)m * mul] = v;
         }
+      } else {
+        T s = T(0);
+        for (int m = 0; m < dim; ++m) {
+          const T go = (g_mi ? g_mi[o_mi + m] : T(0)) + (g_imu ? g_imu[o_imu + (int64_t)m * mul] : T(0));
+          grow[in0 + m * mul] = go * (cst * f);
+          s = fma_(go, xin[in0 + m * mul], s);
+        }
+        grow[L.n_scalars + gi] = s * cst * df;       // d/d gate = sum_m go_m x_m cst f'
       }
     }
   }
