@@ -887,6 +887,96 @@ extern "C" int e3b_gate_bwd(const e3b_gate_desc* desc, int dtype, const void* in
   return check_launch("gate_bwd");
 }
 
+// second derivative of the activations (force-matching training differentiates the gate backward again)
+template <typename T>
+__device__ __forceinline__ void act_eval2(int code, T x, T* f, T* df, T* d2f) {
+  act_eval<T>(code, x, f, df);
+  switch (code) {
+    case 1: {  // silu: s (1 - s) (2 + x (1 - 2 s))
+      const T s = T(1) / (T(1) + exp_<T>(-x));
+      *d2f = s * (T(1) - s) * (T(2) + x * (T(1) - T(2) * s));
+    } break;
+    case 2: {  // tanh
+      const T t = *f;
+      *d2f = T(-2) * t * (T(1) - t * t);
+    } break;
+    case 3: {  // shifted softplus
+      const T s = *df;
+      *d2f = s * (T(1) - s);
+    } break;
+    case 4: {  // tanh(x) |x|
+      const T t = tanh_<T>(x), ax = x < T(0) ? -x : x, sg = x > T(0) ? T(1) : (x < T(0) ? T(-1) : T(0));
+      *d2f = (T(1) - t * t) * (T(2) * sg - T(2) * t * ax);
+    } break;
+    default: *d2f = T(0);
+  }
+}
+
+// Adjoint of the gate backward: with gin = B(in, gout) and a cotangent ggin of gin, writes
+//   g_in = d<ggin, B>/d in   [n, in_dim]      g_gout = d<ggin, B>/d gout   [n, out_dim]
+// one thread per output element, same indexing as gate_kernel
+template <typename T>
+__global__ void gate_bwd2_kernel(const __grid_constant__ GateLayout L, const T* __restrict__ in,
+                                 const T* __restrict__ gout, const T* __restrict__ ggin, int64_t n,
+                                 T* __restrict__ g_in, T* __restrict__ g_gout) {
+  const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= n * L.out_dim) return;
+  const int64_t row = idx / L.out_dim;
+  int c = (int)(idx - row * L.out_dim);
+  const T* xin = in + row * L.in_dim;
+  const T* hin = ggin + row * L.in_dim;
+  T* oin = g_in + row * L.in_dim;
+  if (c < L.n_scalars) {
+    int b = 0, o = c;
+    while (o >= L.d.scalar_mul[b]) { o -= L.d.scalar_mul[b]; ++b; }
+    T f, df, d2f;
+    act_eval2<T>(L.d.scalar_act[b], xin[c], &f, &df, &d2f);
+    const T cst = T(L.d.scalar_cst[b]);
+    oin[c] = hin[c] * cst * d2f * gout[idx];
+    g_gout[idx] = hin[c] * cst * df;
+    return;
+  }
+  c -= L.n_scalars;
+  int b = 0, goff = 0;
+  int dim = 2 * L.d.gated_l[0] + 1;
+  while (c >= L.d.gated_mul[b] * dim) {
+    c -= L.d.gated_mul[b] * dim;
+    goff += L.d.gated_mul[b];
+    ++b;
+    dim = 2 * L.d.gated_l[b] + 1;
+  }
+  const int u = c / dim;
+  const int in_col = (int)(L.n_scalars + L.n_gates + (idx - row * L.out_dim - L.n_scalars));
+  const int gate_col = L.n_scalars + goff + u;
+  T f, df, d2f;
+  act_eval2<T>(L.d.gate_act[b], xin[gate_col], &f, &df, &d2f);
+  const T cst = T(L.d.gate_cst[b]);
+  const T hg = hin[gate_col];
+  g_gout[idx] = hin[in_col] * (cst * f) + hg * (cst * df) * xin[in_col];
+  oin[in_col] = hg * (cst * df) * gout[idx];
+  if (c - u * dim == 0) {
+    T s1 = T(0), s2 = T(0);
+    for (int m = 0; m < dim; ++m) {
+      s1 = fma_(hin[in_col + m], gout[idx + m], s1);
+      s2 = fma_(xin[in_col + m], gout[idx + m], s2);
+    }
+    oin[gate_col] = cst * (df * s1 + hg * d2f * s2);
+  }
+}
+
+extern "C" int e3b_gate_bwd2(const e3b_gate_desc* desc, int dtype, const void* in, const void* gout, const void* ggin,
+                             int64_t n, void* g_in, void* g_gout, void* stream) {
+  int rc = gate_check(desc);
+  if (rc) return rc;
+  if (n == 0) return E3B_OK;
+  if (!in || !gout || !ggin || !g_in || !g_gout) return fail(E3B_ERR_INVALID, "gate_bwd2: null argument");
+  const GateLayout L = gate_layout(desc);
+  if (L.out_dim == 0) return E3B_OK;
+  DISPATCH_DTYPE(dtype, gate_bwd2_kernel<T><<<blocks_for(n * L.out_dim, 256), 256, 0, (cudaStream_t)stream>>>(
+                            L, (const T*)in, (const T*)gout, (const T*)ggin, n, (T*)g_in, (T*)g_gout);)
+  return check_launch("gate_bwd2");
+}
+
 // the gate on the channel-fastest ("imu") layout: gated blocks are [m][u].  One block per node row; a
 // thread takes one scalar, or one (gated block, channel u) pair and walks its 2l+1 components, so the gate
 // activation and the block lookup are evaluated once per channel; all accesses are coalesced over u.

@@ -132,14 +132,16 @@ class MessagePassing(Module):
 
     def forward(self, data, attrs):
         skip = data["input_features"]
-        if skip.dtype == torch.float32 and skip.is_cuda and self.fused.reason is None and FUSED_BLOCKS:
+        if (skip.dtype == torch.float32 and skip.is_cuda and self.fused.reason is None and FUSED_BLOCKS
+                and not ops.second_order_active()):
             edge_index = data["edge_index"]
             csr = ops.graph_of(edge_index, skip.shape[0])
             out, out_imu = interaction.interaction(self.fused, skip, data["node_attrs"], data["edge_radial"],
                                                    data["edge_spherical"], csr)
             out._e3b_imu = out_imu       # the next block gathers from the channel-fastest twin
         else:
-            # fp64 correctness mode / irregular irreps: the same kernels composed op by op
+            # fp64 correctness mode / irregular irreps / second-order mode (graph of the gradient): the same
+            # kernels composed op by op
             out = self.conv(data, attrs)[0]["output_features"]
             out = self.equivariant_nonlin(out)
         if self.resnet:

@@ -10,10 +10,11 @@ from .sequential import Module
 
 
 class GradientOutput(Module):
-    """gradients = sign * d(sum y)/dx through the wrapped network.  The backward pass runs the
-    hand-written backward kernels (first order).  In training mode the reference builds the
-    graph of the gradient as well (force-matching losses); that second-order path is not part of
-    this round and raises loudly instead of silently training on energies only."""
+    """gradients = sign * d(sum y)/dx through the wrapped network (hand-written backward kernels).
+    In training mode the reference builds the graph of the gradient as well (``create_graph=
+    self.training``, nn/output.py:39-43) so that force-matching losses can be differentiated with
+    respect to the parameters: the network then runs in second-order mode (``ops.second_order``),
+    where every backward kernel is itself a differentiable node."""
 
     def __init__(self, func, x, y, gradients, sign: float = 1.0, **kwargs):
         super().__init__()
@@ -24,18 +25,18 @@ class GradientOutput(Module):
         self.func = build(func, **kwargs) if isinstance(func, (dict, ConfigDict)) else func
 
     def forward(self, data):
-        if self.training and torch.is_grad_enabled():
-            raise NotImplementedError(
-                "GradientOutput in training mode needs the graph of the gradient (create_graph=True, reference "
-                "nn/output.py:39-43) for force-matching losses; the second-order kernels are not built yet. "
-                "Call .eval() for energy+force / score evaluation, or train on energies only.")
+        create_graph = bool(self.training and torch.is_grad_enabled())
         wrt = self.inputKeyMap(data)["x"]
         was = wrt.requires_grad
         wrt.requires_grad_(True)
         with torch.enable_grad():
-            out = self.func(data)
+            if create_graph:
+                with ops.second_order():
+                    out = self.func(data)
+            else:
+                out = self.func(data)
             y = self.inputKeyMap(out)["y"]
-            (grad,) = torch.autograd.grad(y.sum(), wrt, create_graph=False)
+            (grad,) = torch.autograd.grad(y.sum(), wrt, create_graph=create_graph)
         wrt.requires_grad_(was)
         is_per = self.inputKeyMap(data.attrs)["x"][0]
         out.attrs.update(self.outputKeyMap({"gradients": (is_per, self.irreps_out["gradients"])}))

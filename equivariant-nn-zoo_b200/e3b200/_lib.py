@@ -70,6 +70,7 @@ SIGNATURES = {
     "e3b_segment_sum": (c_int, [c_int, c_vp, c_i64, c_vp, c_vp, c_i64, c_vp, c_vp]),
     "e3b_gate_fwd": (c_int, [ctypes.POINTER(GateDesc), c_int, c_vp, c_i64, c_vp, c_vp]),
     "e3b_gate_bwd": (c_int, [ctypes.POINTER(GateDesc), c_int, c_vp, c_vp, c_i64, c_vp, c_vp]),
+    "e3b_gate_bwd2": (c_int, [ctypes.POINTER(GateDesc), c_int, c_vp, c_vp, c_vp, c_i64, c_vp, c_vp, c_vp]),
     "e3b_gate_imu_fwd": (c_int, [ctypes.POINTER(GateDesc), c_int, c_vp, c_i64, c_vp, c_vp, c_vp]),
     "e3b_gate_imu_bwd": (c_int, [ctypes.POINTER(GateDesc), c_int, c_vp, c_vp, c_vp, c_i64, c_vp, c_vp]),
     "e3b_gemm_tile_n": (c_int, [c_i32, c_i32]),

@@ -11,6 +11,29 @@ from ._lib import check, count_launch, dtype_code, ptr, require_cuda, stream
 
 
 # ------------------------------------------------------------------------------------------
+# Second-order mode: set by GradientOutput while it runs its network in training mode, where the
+# graph of the position gradient is needed (force-matching losses).  The interaction blocks then
+# compose op by op from the Functions below, whose backward passes are differentiable again;
+# the single-node fused block (e3b200.interaction) is first order only.
+_SECOND_ORDER = 0
+
+
+class second_order:
+    def __enter__(self):
+        global _SECOND_ORDER
+        _SECOND_ORDER += 1
+
+    def __exit__(self, *exc):
+        global _SECOND_ORDER
+        _SECOND_ORDER -= 1
+        return False
+
+
+def second_order_active():
+    return _SECOND_ORDER > 0
+
+
+# ------------------------------------------------------------------------------------------
 # graph structure
 class GraphCSR:
     """Both groupings of an edge list edge_index [2, E] over N nodes (reference convention:
@@ -97,109 +120,245 @@ def radius_graph(pos, n_nodes_per_graph, r_max):
 
 
 # ------------------------------------------------------------------------------------------
+# Kernel launchers (no autograd).  The autograd Functions below are written on top of these, and
+# their backward passes are themselves Functions, so that the graph of a gradient can be built
+# (reference nn/output.py:39-43: create_graph=self.training, force-matching losses).  When the
+# backward runs without create_graph, autograd executes it in no-grad mode and the inner
+# Functions record nothing.
+def k_edge_fwd(pos, edge_index, want_len=True):
+    lib = _lib.load()
+    require_cuda(pos, edge_index)
+    pos = pos.contiguous()
+    E = edge_index.shape[1]
+    vec = torch.empty(E, 3, dtype=pos.dtype, device=pos.device)
+    length = torch.empty(E, dtype=pos.dtype, device=pos.device) if want_len else None
+    check(lib.e3b_edge_vectors_fwd(dtype_code(pos), ptr(pos), ptr(edge_index), E, ptr(vec), ptr(length), stream()))
+    count_launch()
+    return vec, length
+
+
+def k_edge_scatter(gvec, glen, vec, length, n, csr):
+    """gpos[a] = sum over edges into a of (gvec + glen vec/len) - the same over edges out of a"""
+    lib = _lib.load()
+    gpos = torch.empty(n, 3, dtype=vec.dtype, device=vec.device)
+    gvec = gvec.contiguous() if gvec is not None else None
+    glen = glen.contiguous() if glen is not None else None
+    check(lib.e3b_edge_vectors_bwd(dtype_code(vec), ptr(gvec), ptr(glen), ptr(vec), ptr(length), n,
+                                   ptr(csr.in_ptr), ptr(csr.in_eid), ptr(csr.out_ptr), ptr(csr.out_eid), ptr(gpos), stream()))
+    count_launch()
+    return gpos
+
+
+def k_sh_fwd(vec, lmax, normalize):
+    lib = _lib.load()
+    require_cuda(vec)
+    n = vec.shape[0]
+    sh = torch.empty(n, (lmax + 1) ** 2, dtype=vec.dtype, device=vec.device)
+    check(lib.e3b_sh_fwd(dtype_code(vec), ptr(vec), n, lmax, int(normalize), ptr(sh), stream()))
+    count_launch()
+    return sh
+
+
+def k_sh_bwd(vec, gsh, lmax, normalize):
+    lib = _lib.load()
+    gvec = torch.empty_like(vec)
+    check(lib.e3b_sh_bwd(dtype_code(vec), ptr(vec), ptr(gsh.contiguous()), vec.shape[0], lmax, int(normalize),
+                         ptr(gvec), stream()))
+    count_launch()
+    return gvec
+
+
+def k_radial_fwd(r, bw, params):
+    lib = _lib.load()
+    require_cuda(r, bw)
+    r_max, r_min, one_over_r, cutoff_kind, p = params
+    n, nb = r.shape[0], bw.shape[0]
+    out = torch.empty(n, nb, dtype=r.dtype, device=r.device)
+    check(lib.e3b_radial_fwd(dtype_code(r), ptr(r), n, ptr(bw), nb, r_max, r_min, one_over_r, cutoff_kind, p,
+                             ptr(out), stream()))
+    count_launch()
+    return out
+
+
+def k_radial_bwd(r, gout, bw, params, need_w):
+    """-> (d/dr [n], d/d bessel_w [n_basis] or None)"""
+    lib = _lib.load()
+    r_max, r_min, one_over_r, cutoff_kind, p = params
+    n, nb = r.shape[0], bw.shape[0]
+    gr = torch.empty_like(r)
+    nblk = lib.e3b_radial_bwd_blocks(n)
+    part = torch.empty(nblk, nb, dtype=r.dtype, device=r.device)
+    check(lib.e3b_radial_bwd(dtype_code(r), ptr(r), ptr(gout.contiguous()), n, ptr(bw), nb, r_max, r_min, one_over_r,
+                             cutoff_kind, p, ptr(gr), ptr(part), stream()))
+    count_launch()
+    return gr, (part.sum(0) if need_w else None)
+
+
+# closed forms of the two per-edge embeddings, used ONLY to differentiate their backward kernels
+# once more (Hessian-vector products of a [E,3] -> [E,9] and a [E] -> [E,n_basis] map); values and
+# first derivatives always come from the kernels above
+def _sh_closed_form(vec, lmax, normalize):
+    x, y, z = vec.unbind(-1)
+    if normalize:
+        r = (x * x + y * y + z * z).sqrt().clamp_min(1e-12)
+        x, y, z = x / r, y / r, z / r
+    s3, s5 = 1.7320508075688772, 2.23606797749979
+    cols = [torch.ones_like(x)]
+    if lmax >= 1:
+        cols += [s3 * x, s3 * y, s3 * z]
+    if lmax >= 2:
+        cols += [s5 * s3 * x * z, s5 * s3 * x * y, s5 * (y * y - 0.5 * (x * x + z * z)), s5 * s3 * y * z,
+                 s5 * (s3 / 2) * (z * z - x * x)]
+    return torch.stack(cols, dim=-1)
+
+
+def _radial_closed_form(r, bw, params):
+    r_max, r_min, one_over_r, cutoff_kind, p = params
+    span = r_max - r_min
+    b = (2.0 / span) * torch.sin(bw * r.unsqueeze(-1) / span)
+    if one_over_r:
+        b = b / r.unsqueeze(-1)
+    x = r / r_max
+    if cutoff_kind == 1:
+        c = (x - 1) ** 2 * (x + 1) ** 2 * (x.abs() < 1.0).to(r.dtype)
+    else:
+        c = (1.0 - ((p + 1.0) * (p + 2.0) / 2.0) * torch.pow(x, p) + p * (p + 2.0) * torch.pow(x, p + 1.0)
+             - (p * (p + 1.0) / 2) * torch.pow(x, p + 2.0)) * (x < 1.0).to(r.dtype)
+    return b * c.unsqueeze(-1)
+
+
+def _vjp_of_vjp(closed_form, inputs, cotangent, hhs):
+    """inputs: tensors (detached here); B_i = d<cotangent, closed_form(*inputs)>/d inputs[i];
+    returns the gradients of sum_i <hhs[i], B_i> (None entries skipped) with respect to every
+    input and to the cotangent."""
+    with torch.enable_grad():
+        leaves = [t.detach().requires_grad_(True) for t in inputs]
+        cot = cotangent.detach().requires_grad_(True)
+        out = closed_form(*leaves)
+        idx = [i for i, h in enumerate(hhs) if h is not None]
+        Bs = torch.autograd.grad(out, [leaves[i] for i in idx], cot, create_graph=True)
+        grads = torch.autograd.grad(Bs, leaves + [cot], [hhs[i] for i in idx], allow_unused=True)
+    return grads
+
+
+# ------------------------------------------------------------------------------------------
 class _EdgeVectors(torch.autograd.Function):
     @staticmethod
     def forward(ctx, pos, edge_index, csr):
-        lib = _lib.load()
-        require_cuda(pos, edge_index)
-        pos = pos.contiguous()
-        E = edge_index.shape[1]
-        vec = torch.empty(E, 3, dtype=pos.dtype, device=pos.device)
-        length = torch.empty(E, dtype=pos.dtype, device=pos.device)
-        check(lib.e3b_edge_vectors_fwd(dtype_code(pos), ptr(pos), ptr(edge_index), E, ptr(vec), ptr(length), stream()))
-        count_launch()
-        ctx.csr = csr
-        ctx.save_for_backward(vec, length)
-        ctx.n = pos.shape[0]
+        vec, length = k_edge_fwd(pos, edge_index)
+        ctx.csr, ctx.n = csr, pos.shape[0]
+        ctx.save_for_backward(vec, length, edge_index)
+        ctx.set_materialize_grads(False)
         return vec, length
 
     @staticmethod
-    @once_differentiable
     def backward(ctx, gvec, glen):
-        lib = _lib.load()
-        vec, length = ctx.saved_tensors
-        g = ctx.csr
-        gpos = torch.empty(ctx.n, 3, dtype=vec.dtype, device=vec.device)
-        gvec = gvec.contiguous() if gvec is not None else None
-        glen = glen.contiguous() if glen is not None else None
-        check(lib.e3b_edge_vectors_bwd(dtype_code(vec), ptr(gvec), ptr(glen), ptr(vec), ptr(length), ctx.n,
-                                       ptr(g.in_ptr), ptr(g.in_eid), ptr(g.out_ptr), ptr(g.out_eid), ptr(gpos), stream()))
-        count_launch()
-        return gpos, None, None
+        vec, length, edge_index = ctx.saved_tensors
+        if gvec is None and glen is None:
+            return None, None, None
+        return _EdgeVectorsBwd.apply(gvec, glen, vec, length, edge_index, ctx.csr, ctx.n), None, None
+
+
+class _EdgeVectorsBwd(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, gvec, glen, vec, length, edge_index, csr, n):
+        ctx.save_for_backward(glen, vec, length, edge_index)
+        return k_edge_scatter(gvec, glen, vec, length, n, csr)
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, hpos):
+        # gpos = S(gvec + glen vec / len), S = adjoint of D: pos -> pos[dst] - pos[src]
+        glen, vec, length, edge_index = ctx.saved_tensors
+        d, _ = k_edge_fwd(hpos.contiguous(), edge_index, want_len=False)           # D hpos  [E,3]
+        g_gvec = d if ctx.needs_input_grad[0] else None
+        g_glen = g_vec = g_len = None
+        if glen is not None:
+            inv = torch.where(length > 0, 1.0 / length, torch.zeros_like(length))
+            dv = (d * vec).sum(-1)
+            g_glen = dv * inv
+            g_vec = d * (glen * inv).unsqueeze(-1)
+            g_len = -glen * dv * inv * inv
+        return g_gvec, g_glen, g_vec, g_len, None, None, None
 
 
 def edge_vectors(pos, edge_index, csr):
-    return _EdgeVectors.apply(pos, edge_index.contiguous(), csr)
+    return _EdgeVectors.apply(pos.contiguous(), edge_index.contiguous(), csr)
 
 
 class _SphericalHarmonics(torch.autograd.Function):
     @staticmethod
     def forward(ctx, vec, lmax, normalize):
-        lib = _lib.load()
-        require_cuda(vec)
-        vec = vec.contiguous()
-        n = vec.shape[0]
-        sh = torch.empty(n, (lmax + 1) ** 2, dtype=vec.dtype, device=vec.device)
-        check(lib.e3b_sh_fwd(dtype_code(vec), ptr(vec), n, lmax, int(normalize), ptr(sh), stream()))
-        count_launch()
         ctx.save_for_backward(vec)
         ctx.lmax, ctx.normalize = lmax, int(normalize)
-        return sh
+        return k_sh_fwd(vec, lmax, normalize)
+
+    @staticmethod
+    def backward(ctx, gsh):
+        (vec,) = ctx.saved_tensors
+        return _SphericalHarmonicsBwd.apply(vec, gsh, ctx.lmax, ctx.normalize), None, None
+
+
+class _SphericalHarmonicsBwd(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, vec, gsh, lmax, normalize):
+        ctx.save_for_backward(vec, gsh)
+        ctx.lmax, ctx.normalize = lmax, normalize
+        return k_sh_bwd(vec, gsh, lmax, normalize)
 
     @staticmethod
     @once_differentiable
-    def backward(ctx, gsh):
-        lib = _lib.load()
-        (vec,) = ctx.saved_tensors
-        gvec = torch.empty_like(vec)
-        check(lib.e3b_sh_bwd(dtype_code(vec), ptr(vec), ptr(gsh.contiguous()), vec.shape[0], ctx.lmax, ctx.normalize,
-                             ptr(gvec), stream()))
-        count_launch()
-        return gvec, None, None
+    def backward(ctx, hvec):
+        vec, gsh = ctx.saved_tensors
+        g_vec, g_gsh = _vjp_of_vjp(lambda v: _sh_closed_form(v, ctx.lmax, ctx.normalize), [vec], gsh, [hvec])
+        return g_vec, g_gsh, None, None
 
 
 def spherical_harmonics(vec, lmax, normalize=True):
     """[n,3] -> [n,(lmax+1)^2], e3nn 'component' normalisation, l <= 2"""
-    return _SphericalHarmonics.apply(vec, lmax, normalize)
+    return _SphericalHarmonics.apply(vec.contiguous(), lmax, normalize)
 
 
 class _Radial(torch.autograd.Function):
     @staticmethod
     def forward(ctx, r, bessel_w, r_max, r_min, one_over_r, cutoff_kind, p):
-        lib = _lib.load()
-        require_cuda(r, bessel_w)
-        r = r.contiguous().reshape(-1)
         bw = bessel_w.to(r.dtype).contiguous()
-        n, nb = r.shape[0], bw.shape[0]
-        out = torch.empty(n, nb, dtype=r.dtype, device=r.device)
-        check(lib.e3b_radial_fwd(dtype_code(r), ptr(r), n, ptr(bw), nb, r_max, r_min, int(one_over_r), cutoff_kind,
-                                 float(p), ptr(out), stream()))
-        count_launch()
-        ctx.save_for_backward(r, bw)
         ctx.params = (r_max, r_min, int(one_over_r), cutoff_kind, float(p))
-        ctx.w_dtype = bessel_w.dtype
-        return out
+        ctx.save_for_backward(r, bessel_w)
+        return k_radial_fwd(r, bw, ctx.params)
+
+    @staticmethod
+    def backward(ctx, gout):
+        r, bessel_w = ctx.saved_tensors
+        gr, gw = _RadialBwd.apply(r, gout, bessel_w, ctx.params, ctx.needs_input_grad[1])
+        return gr, gw, None, None, None, None, None
+
+
+class _RadialBwd(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, r, gout, bessel_w, params, need_w):
+        bw = bessel_w.to(r.dtype).contiguous()
+        ctx.save_for_backward(r, gout, bessel_w)
+        ctx.params, ctx.need_w = params, need_w
+        ctx.set_materialize_grads(False)
+        gr, gw = k_radial_bwd(r, gout, bw, params, need_w)
+        return gr, (gw.to(bessel_w.dtype) if gw is not None else None)
 
     @staticmethod
     @once_differentiable
-    def backward(ctx, gout):
-        lib = _lib.load()
-        r, bw = ctx.saved_tensors
-        r_max, r_min, one_over_r, cutoff_kind, p = ctx.params
-        n, nb = r.shape[0], bw.shape[0]
-        gr = torch.empty_like(r)
-        nblk = lib.e3b_radial_bwd_blocks(n)
-        part = torch.empty(nblk, nb, dtype=r.dtype, device=r.device)
-        check(lib.e3b_radial_bwd(dtype_code(r), ptr(r), ptr(gout.contiguous()), n, ptr(bw), nb, r_max, r_min, one_over_r,
-                                 cutoff_kind, p, ptr(gr), ptr(part), stream()))
-        count_launch()
-        gw = part.sum(0).to(ctx.w_dtype) if ctx.needs_input_grad[1] else None
-        return gr, gw, None, None, None, None, None
+    def backward(ctx, hr, hw):
+        r, gout, bessel_w = ctx.saved_tensors
+        if hr is None and hw is None:
+            return None, None, None, None, None
+        bw = bessel_w.to(r.dtype)
+        g_r, g_bw, g_gout = _vjp_of_vjp(lambda rr, ww: _radial_closed_form(rr, ww, ctx.params), [r, bw], gout,
+                                        [hr, hw.to(r.dtype) if hw is not None else None])
+        return g_r, g_gout, (g_bw.to(bessel_w.dtype) if g_bw is not None else None), None, None
 
 
 def radial_basis(r, bessel_w, r_max, r_min=0.0, one_over_r=True, cutoff_kind=0, p=6.0):
     """Bessel x cutoff embedding of distances r [n] -> [n, n_basis]"""
-    return _Radial.apply(r, bessel_w, float(r_max), float(r_min), one_over_r, int(cutoff_kind), p)
+    return _Radial.apply(r.contiguous().reshape(-1), bessel_w, float(r_max), float(r_min), one_over_r, int(cutoff_kind), p)
 
 
 # When a list, every fused TP-conv launch appends (tag, start_event, end_event) recorded on the
@@ -273,85 +432,156 @@ class TPPlan:
             pass
 
 
-class _TPConv(torch.autograd.Function):
-    @staticmethod
-    def forward(ctx, x, sh, w, plan, csr):
-        lib = _lib.load()
-        require_cuda(x, sh, w)
-        x, sh, w = x.contiguous(), sh.contiguous(), w.contiguous()
-        N, E = x.shape[0], sh.shape[0]
-        assert x.shape[1] == plan.x_dim and sh.shape[1] == plan.sh_dim and w.shape == (E, plan.w_dim), \
-            (x.shape, sh.shape, w.shape, plan.x_dim, plan.sh_dim, plan.w_dim)
-        assert csr.n_nodes == N and csr.n_edges == E
-        y = torch.empty(N, plan.y_dim, dtype=x.dtype, device=x.device)
-        tag = ("fwd", len(plan.structure.paths), plan.structure.uniform_mul, plan.x_dim, plan.y_dim, N, E)
-        end = _timed(tag)
-        check(lib.e3b_tpconv_fwd(plan.handle, dtype_code(x), N, E, ptr(x), ptr(sh), ptr(w), ptr(csr.in_ptr),
-                                 ptr(csr.in_nbr), ptr(csr.in_eid), ptr(y), stream()))
+def k_tp_fwd(plan, csr, x, sh, w):
+    lib = _lib.load()
+    require_cuda(x, sh, w)
+    N, E = x.shape[0], sh.shape[0]
+    assert x.shape[1] == plan.x_dim and sh.shape[1] == plan.sh_dim and w.shape == (E, plan.w_dim), \
+        (x.shape, sh.shape, w.shape, plan.x_dim, plan.sh_dim, plan.w_dim)
+    assert csr.n_nodes == N and csr.n_edges == E
+    y = torch.empty(N, plan.y_dim, dtype=x.dtype, device=x.device)
+    end = _timed(("fwd", len(plan.structure.paths), plan.structure.uniform_mul, plan.x_dim, plan.y_dim, N, E))
+    check(lib.e3b_tpconv_fwd(plan.handle, dtype_code(x), N, E, ptr(x), ptr(sh), ptr(w), ptr(csr.in_ptr),
+                             ptr(csr.in_nbr), ptr(csr.in_eid), ptr(y), stream()))
+    if end is not None:
+        end.record()
+    count_launch()
+    return y
+
+
+def k_tp_bwd(plan, csr, x, sh, w, gy, need_x, need_sh):
+    """-> (d/dx [N, x_dim] or None, d/dsh [E, sh_dim] or None, d/dw [E, w_dim])"""
+    lib = _lib.load()
+    N, E = x.shape[0], sh.shape[0]
+    fast = plan.specialized and x.dtype == torch.float32
+    alloc = torch.empty if fast else torch.zeros
+    n_part = plan.n_part_f32 if fast else 1
+    gx_edge = alloc(E, plan.x_dim, dtype=x.dtype, device=x.device) if need_x else None
+    gsh_part = alloc(E, n_part, plan.sh_dim, dtype=x.dtype, device=x.device) if need_sh else None
+    gw = torch.empty_like(w)
+    if E:
+        gy = gy.contiguous()
+        end = _timed(("bwd", len(plan.structure.paths), plan.structure.uniform_mul, plan.x_dim, plan.y_dim, N, E))
+        check(lib.e3b_tpconv_bwd(plan.handle, dtype_code(x), N, E, ptr(x), ptr(sh), ptr(w), ptr(gy),
+                                 ptr(csr.in_ptr), ptr(csr.in_nbr), ptr(csr.in_eid), ptr(gx_edge), ptr(gsh_part),
+                                 ptr(gw), stream()))
         if end is not None:
             end.record()
         count_launch()
+    gx = None
+    if need_x:
+        gx = k_segment_sum(gx_edge, csr.out_ptr, csr.out_eid, N)
+    gsh = None
+    if need_sh:
+        gsh = gsh_part.sum(1) if n_part > 1 else gsh_part.view(E, plan.sh_dim)
+    return gx, gsh, gw
+
+
+def k_segment_sum(src2, seg_ptr, ids, n_out):
+    """out[s] = sum of the rows ids[k] (k itself when ids is None), k in [seg_ptr[s], seg_ptr[s+1])"""
+    lib = _lib.load()
+    require_cuda(src2)
+    out = torch.empty(n_out, src2.shape[1], dtype=src2.dtype, device=src2.device)
+    check(lib.e3b_segment_sum(dtype_code(src2), ptr(src2), src2.shape[1], ptr(seg_ptr), ptr(ids), n_out, ptr(out), stream()))
+    count_launch()
+    return out
+
+
+def _add(a, b):
+    return b if a is None else (a if b is None else a + b)
+
+
+class _TPConv(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, sh, w, plan, csr):
         ctx.plan, ctx.csr = plan, csr
         ctx.save_for_backward(x, sh, w)
-        return y
+        return k_tp_fwd(plan, csr, x, sh, w)
 
     @staticmethod
-    @once_differentiable
     def backward(ctx, gy):
-        lib = _lib.load()
         x, sh, w = ctx.saved_tensors
-        plan, csr = ctx.plan, ctx.csr
-        N, E = x.shape[0], sh.shape[0]
-        fast = plan.specialized and x.dtype == torch.float32
-        alloc = torch.empty if fast else torch.zeros
-        n_part = plan.n_part_f32 if fast else 1
-        need_x, need_sh = ctx.needs_input_grad[0], ctx.needs_input_grad[1]
-        gx_edge = alloc(E, plan.x_dim, dtype=x.dtype, device=x.device) if need_x else None
-        gsh_part = alloc(E, n_part, plan.sh_dim, dtype=x.dtype, device=x.device) if need_sh else None
-        gw = torch.empty_like(w)
-        if E:
-            gy = gy.contiguous()
-            end = _timed(("bwd", len(plan.structure.paths), plan.structure.uniform_mul, plan.x_dim, plan.y_dim, N, E))
-            check(lib.e3b_tpconv_bwd(plan.handle, dtype_code(x), N, E, ptr(x), ptr(sh), ptr(w), ptr(gy),
-                                     ptr(csr.in_ptr), ptr(csr.in_nbr), ptr(csr.in_eid), ptr(gx_edge), ptr(gsh_part),
-                                     ptr(gw), stream()))
-            if end is not None:
-                end.record()
-            count_launch()
-        gx = None
-        if need_x:
-            gx = torch.empty_like(x)
-            check(lib.e3b_segment_sum(dtype_code(x), ptr(gx_edge), plan.x_dim, ptr(csr.out_ptr), ptr(csr.out_eid), N,
-                                      ptr(gx), stream()))
-            count_launch()
-        gsh = None
-        if need_sh:
-            gsh = gsh_part.sum(1) if n_part > 1 else gsh_part.view(E, plan.sh_dim)
+        gx, gsh, gw = _TPConvBwd.apply(x, sh, w, gy, ctx.plan, ctx.csr, ctx.needs_input_grad[0], ctx.needs_input_grad[1])
         return gx, gsh, gw, None, None
+
+
+class _TPConvBwd(torch.autograd.Function):
+    """(x, sh, w, gy) -> (d/dx, d/dsh, d/dw) of <gy, T(x, sh, w)>.  T is trilinear, so the
+    adjoint of this map is made of T and of this map with one argument replaced by a cotangent:
+    with F(x, sh, w, g) = <g, T(x, sh, w)> and cotangents (hx, hsh, hw) of the three outputs,
+    the pulled-back scalar is F(hx, sh, w, gy) + F(x, hsh, w, gy) + F(x, sh, hw, gy)."""
+
+    @staticmethod
+    def forward(ctx, x, sh, w, gy, plan, csr, need_x, need_sh):
+        ctx.plan, ctx.csr = plan, csr
+        ctx.save_for_backward(x, sh, w, gy)
+        ctx.set_materialize_grads(False)
+        return k_tp_bwd(plan, csr, x, sh, w, gy, need_x, need_sh)
+
+    @staticmethod
+    def backward(ctx, hx, hsh, hw):
+        x, sh, w, gy = ctx.saved_tensors
+        plan, csr = ctx.plan, ctx.csr
+        nx, nsh, nw, ngy = ctx.needs_input_grad[:4]
+        g_x = g_sh = g_w = g_gy = None
+        if hx is not None:                                   # F(hx, sh, w, gy)
+            hx = hx.contiguous()
+            if ngy:
+                g_gy = _add(g_gy, _TPConv.apply(hx, sh, w, plan, csr))
+            if nsh or nw:
+                _, a, b = _TPConvBwd.apply(hx, sh, w, gy, plan, csr, False, nsh)
+                g_sh, g_w = _add(g_sh, a), _add(g_w, b if nw else None)
+        if hsh is not None:                                  # F(x, hsh, w, gy)
+            hsh = hsh.contiguous()
+            if ngy:
+                g_gy = _add(g_gy, _TPConv.apply(x, hsh, w, plan, csr))
+            if nx or nw:
+                a, _, b = _TPConvBwd.apply(x, hsh, w, gy, plan, csr, nx, False)
+                g_x, g_w = _add(g_x, a), _add(g_w, b if nw else None)
+        if hw is not None:                                   # F(x, sh, hw, gy)
+            hw = hw.contiguous()
+            if ngy:
+                g_gy = _add(g_gy, _TPConv.apply(x, sh, hw, plan, csr))
+            if nx or nsh:
+                a, b, _ = _TPConvBwd.apply(x, sh, hw, gy, plan, csr, nx, nsh)
+                g_x, g_sh = _add(g_x, a), _add(g_sh, b)
+        return g_x, g_sh, g_w, g_gy, None, None, None, None
 
 
 def tp_conv(x_imu, sh, w, plan, csr):
     """y[n] = sum over incoming edges of the weighted uvu tensor product (imu layouts)."""
-    return _TPConv.apply(x_imu, sh, w, plan, csr)
+    return _TPConv.apply(x_imu.contiguous(), sh.contiguous(), w.contiguous(), plan, csr)
 
 
 # ------------------------------------------------------------------------------------------
 class _SegmentSum(torch.autograd.Function):
     @staticmethod
     def forward(ctx, src, seg_ptr, seg_index, n_out):
-        lib = _lib.load()
-        require_cuda(src)
         src2 = src.contiguous().reshape(src.shape[0], -1)
-        out = torch.empty(n_out, src2.shape[1], dtype=src.dtype, device=src.device)
-        check(lib.e3b_segment_sum(dtype_code(src2), ptr(src2), src2.shape[1], ptr(seg_ptr), None, n_out, ptr(out), stream()))
-        count_launch()
-        ctx.save_for_backward(seg_index)
+        out = k_segment_sum(src2, seg_ptr, None, n_out)
+        ctx.save_for_backward(seg_ptr, seg_index)
+        ctx.n_out = n_out
         return out.reshape(n_out, *src.shape[1:])
 
     @staticmethod
     def backward(ctx, g):
-        (seg_index,) = ctx.saved_tensors
-        return g[seg_index], None, None, None
+        seg_ptr, seg_index = ctx.saved_tensors
+        return _SegmentBroadcast.apply(g, seg_ptr, seg_index, ctx.n_out), None, None, None
+
+
+class _SegmentBroadcast(torch.autograd.Function):
+    """rows of a segment all receive the segment's value (adjoint of the segmented sum)"""
+
+    @staticmethod
+    def forward(ctx, g, seg_ptr, seg_index, n_out):
+        ctx.save_for_backward(seg_ptr, seg_index)
+        ctx.n_out = n_out
+        return g[seg_index]
+
+    @staticmethod
+    def backward(ctx, h):
+        seg_ptr, seg_index = ctx.saved_tensors
+        return _SegmentSum.apply(h, seg_ptr, seg_index, ctx.n_out), None, None, None
 
 
 def segment_sum(src, seg_ptr, seg_index, n_out):
@@ -364,33 +594,63 @@ def segment_sum(src, seg_ptr, seg_index, n_out):
 ACT_CODES = {None: 0, "silu": 1, "tanh": 2, "ssp": 3, "tanhlu": 4, "abs": 5}
 
 
+def k_gate_fwd(desc, x, out_dim):
+    lib = _lib.load()
+    require_cuda(x)
+    out = torch.empty(x.shape[0], out_dim, dtype=x.dtype, device=x.device)
+    check(lib.e3b_gate_fwd(ctypes.byref(desc), dtype_code(x), ptr(x), x.shape[0], ptr(out), stream()))
+    count_launch()
+    return out
+
+
+def k_gate_bwd(desc, x, gout):
+    lib = _lib.load()
+    gin = torch.empty_like(x)
+    check(lib.e3b_gate_bwd(ctypes.byref(desc), dtype_code(x), ptr(x), ptr(gout.contiguous()), x.shape[0], ptr(gin), stream()))
+    count_launch()
+    return gin
+
+
+def k_gate_bwd2(desc, x, gout, ggin):
+    """adjoint of k_gate_bwd: -> (d<ggin, gin>/dx, d<ggin, gin>/dgout)"""
+    lib = _lib.load()
+    g_x, g_gout = torch.empty_like(x), torch.empty_like(gout)
+    check(lib.e3b_gate_bwd2(ctypes.byref(desc), dtype_code(x), ptr(x), ptr(gout.contiguous()), ptr(ggin.contiguous()),
+                            x.shape[0], ptr(g_x), ptr(g_gout), stream()))
+    count_launch()
+    return g_x, g_gout
+
+
 class _Gate(torch.autograd.Function):
     @staticmethod
     def forward(ctx, x, desc, out_dim):
-        lib = _lib.load()
-        require_cuda(x)
-        x = x.contiguous()
-        out = torch.empty(x.shape[0], out_dim, dtype=x.dtype, device=x.device)
-        check(lib.e3b_gate_fwd(ctypes.byref(desc), dtype_code(x), ptr(x), x.shape[0], ptr(out), stream()))
-        count_launch()
         ctx.desc = desc
         ctx.save_for_backward(x)
-        return out
+        return k_gate_fwd(desc, x, out_dim)
+
+    @staticmethod
+    def backward(ctx, gout):
+        (x,) = ctx.saved_tensors
+        return _GateBwd.apply(x, gout.contiguous(), ctx.desc), None, None
+
+
+class _GateBwd(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, gout, desc):
+        ctx.desc = desc
+        ctx.save_for_backward(x, gout)
+        return k_gate_bwd(desc, x, gout)
 
     @staticmethod
     @once_differentiable
-    def backward(ctx, gout):
-        lib = _lib.load()
-        (x,) = ctx.saved_tensors
-        gin = torch.empty_like(x)
-        check(lib.e3b_gate_bwd(ctypes.byref(ctx.desc), dtype_code(x), ptr(x), ptr(gout.contiguous()), x.shape[0],
-                               ptr(gin), stream()))
-        count_launch()
-        return gin, None, None
+    def backward(ctx, ggin):
+        x, gout = ctx.saved_tensors
+        g_x, g_gout = k_gate_bwd2(ctx.desc, x, gout, ggin)
+        return g_x, g_gout, None
 
 
 def gate(x, desc, out_dim):
-    return _Gate.apply(x, desc, out_dim)
+    return _Gate.apply(x.contiguous(), desc, out_dim)
 
 
 def layout_convert(x, irreps, to_imu):

@@ -197,6 +197,13 @@ E3B_API int e3b_gate_fwd(const e3b_gate_desc* desc, int dtype, const void* in, i
 E3B_API int e3b_gate_bwd(const e3b_gate_desc* desc, int dtype, const void* in, const void* gout, int64_t n, void* gin,
                  void* stream);
 
+/* Adjoint of e3b_gate_bwd (second order, needed when the reference differentiates its position
+ * gradient again: nn/output.py:39-43, create_graph=self.training).  With gin = gate_bwd(in, gout)
+ * and a cotangent ggin [n, in_dim] of gin:  g_in = d<ggin, gin>/d in  [n, in_dim],
+ * g_gout = d<ggin, gin>/d gout  [n, out_dim].                                                   */
+E3B_API int e3b_gate_bwd2(const e3b_gate_desc* desc, int dtype, const void* in, const void* gout, const void* ggin,
+                          int64_t n, void* g_in, void* g_gout, void* stream);
+
 /* The same gate on the library's channel-fastest layout: `in` is [scalars | gates | gated] with the
  * gated blocks stored [m][u]; the result is written in the imu layout (out_imu) and / or e3nn's
  * mul_ir layout (out_mul_ir); either may be NULL.  The backward accepts the gradient in either or

@@ -63,11 +63,3 @@ def test_energy_training_step_reduces_loss():
         opt.step()
         losses.append(float(loss))
     assert losses[-1] < losses[0]
-
-
-def test_force_training_raises_loudly():
-    meta = {"config": "config_energy_force", "seed": 5}
-    inputs = synthetic.qm9_like(3, seed=4, n_min=3, n_max=6)
-    model = product_harness.build_product(meta, torch.float32, DEV).train()
-    with pytest.raises(NotImplementedError):
-        product_harness.run_product(model, inputs, torch.float32, DEV, pre_edge={"r_max": 5.0})

@@ -120,10 +120,10 @@ _NAMES = ["graph_of", "radius_graph", "edge_vectors", "spherical_harmonics", "ra
           "segment_sum", "gate"]
 
 
-def patch(monkeypatch):
+def patch(monkeypatch, names=None):
     import e3_layers.data.compute_edge as ce
 
-    for n in _NAMES:
+    for n in (names or _NAMES):
         monkeypatch.setattr(ops, n, globals()[n])
     # the product's computeEdgeIndex refuses CPU tensors; lift that guard for the emulation only
     orig = ce.computeEdgeIndex
@@ -137,3 +137,104 @@ def patch(monkeypatch):
 
     monkeypatch.setattr(ce, "computeEdgeIndex", compute_edge_index_cpu)
     return orig
+
+
+# ---------------------------------------------------------------------------------------------
+# Kernel-level stand-ins: replace only the launchers ``ops.k_*`` so that the product's OWN autograd
+# Functions (including the differentiable backward nodes of the second-order mode) run on a CPU.
+def _grad_of(fn, inputs, cotangent, wanted):
+    """values of d<cotangent, fn(*inputs)>/d inputs[i] for i in wanted (None elsewhere)"""
+    with torch.enable_grad():
+        leaves = [t.detach().requires_grad_(True) for t in inputs]
+        out = fn(*leaves)
+        gs = torch.autograd.grad(out, [leaves[i] for i in wanted], cotangent.detach(), allow_unused=True)
+    res = [None] * len(inputs)
+    for i, g in zip(wanted, gs):
+        res[i] = g if g is not None else torch.zeros_like(inputs[i])
+    return res
+
+
+def k_edge_fwd(pos, edge_index, want_len=True):
+    vec = pos[edge_index[1]] - pos[edge_index[0]]
+    return vec, (torch.linalg.norm(vec, dim=-1) if want_len else None)
+
+
+def _edge_endpoints(csr):
+    """(src, dst) per edge id from the two groupings of a GraphCSR"""
+    E, N = csr.n_edges, csr.n_nodes
+    dst = torch.empty(E, dtype=torch.long)
+    src = torch.empty(E, dtype=torch.long)
+    in_eid = csr.in_eid.long() if csr.in_eid is not None else torch.arange(E)
+    out_eid = csr.out_eid.long() if csr.out_eid is not None else torch.arange(E)
+    dst[in_eid] = torch.repeat_interleave(torch.arange(N), csr.in_ptr[1:] - csr.in_ptr[:-1])
+    src[out_eid] = torch.repeat_interleave(torch.arange(N), csr.out_ptr[1:] - csr.out_ptr[:-1])
+    return src, dst
+
+
+def k_edge_scatter(gvec, glen, vec, length, n, csr):
+    src, dst = _edge_endpoints(csr)
+    tot = torch.zeros_like(vec)
+    if gvec is not None:
+        tot = tot + gvec
+    if glen is not None:
+        tot = tot + (glen / length).unsqueeze(-1) * vec
+    return torch.zeros(n, 3, dtype=vec.dtype).index_add_(0, dst, tot).index_add_(0, src, -tot)
+
+
+def k_sh_fwd(vec, lmax, normalize):
+    return spherical_harmonics(vec, lmax, bool(normalize))
+
+
+def k_sh_bwd(vec, gsh, lmax, normalize):
+    return _grad_of(lambda v: spherical_harmonics(v, lmax, bool(normalize)), [vec], gsh, [0])[0]
+
+
+def k_radial_fwd(r, bw, params):
+    return radial_basis(r, bw, *params)
+
+
+def k_radial_bwd(r, gout, bw, params, need_w):
+    gr, gw = _grad_of(lambda rr, ww: radial_basis(rr, ww, *params), [r, bw], gout, [0, 1])
+    return gr, (gw if need_w else None)
+
+
+def k_tp_fwd(plan, csr, x, sh, w):
+    return tp_conv(x, sh, w, plan, csr)
+
+
+def k_tp_bwd(plan, csr, x, sh, w, gy, need_x, need_sh):
+    wanted = ([0] if need_x else []) + ([1] if need_sh else []) + [2]
+    gx, gsh, gw = _grad_of(lambda a, b, c: tp_conv(a, b, c, plan, csr), [x, sh, w], gy, wanted)
+    return gx, gsh, gw
+
+
+def k_segment_sum(src2, seg_ptr, ids, n_out):
+    seg = torch.repeat_interleave(torch.arange(n_out), seg_ptr[1:] - seg_ptr[:-1])
+    rows = src2[ids.long()] if ids is not None else src2[:len(seg)]
+    return torch.zeros(n_out, src2.shape[1], dtype=src2.dtype).index_add_(0, seg, rows)
+
+
+def k_gate_fwd(desc, x, out_dim):
+    return gate(x, desc, out_dim)
+
+
+def k_gate_bwd(desc, x, gout):
+    return _grad_of(lambda a: gate(a, desc, None), [x], gout, [0])[0]
+
+
+def k_gate_bwd2(desc, x, gout, ggin):
+    with torch.enable_grad():
+        a = x.detach().requires_grad_(True)
+        g = gout.detach().requires_grad_(True)
+        (gin,) = torch.autograd.grad(gate(a, desc, None), a, g, create_graph=True)
+        gx, gg = torch.autograd.grad(gin, [a, g], ggin.detach(), allow_unused=True)
+    return (gx if gx is not None else torch.zeros_like(x)), (gg if gg is not None else torch.zeros_like(gout))
+
+
+_KERNELS = ["k_edge_fwd", "k_edge_scatter", "k_sh_fwd", "k_sh_bwd", "k_radial_fwd", "k_radial_bwd", "k_tp_fwd", "k_tp_bwd",
+            "k_segment_sum", "k_gate_fwd", "k_gate_bwd", "k_gate_bwd2"]
+
+
+def patch_kernels(monkeypatch):
+    """like patch(), but BELOW the product's autograd Functions: only the launchers and the graph helpers"""
+    return patch(monkeypatch, names=["graph_of", "radius_graph", "TPPlan"] + _KERNELS)
