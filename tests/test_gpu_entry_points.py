@@ -26,3 +26,14 @@ def test_train_then_inference(tmp_path):
     assert r.returncode == 0, r.stderr[-2000:]
     z = np.load(out)
     assert z["total_energy"].shape == (40, 1) and np.isfinite(z["total_energy"]).all()
+
+
+def test_train_energy_force(tmp_path):
+    """force matching through the second-order mode (reference config_energy_force.py:30 loss)"""
+    wd = str(tmp_path)
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "train.py"), "--config", "config_energy_force", "--steps", "3",
+                        "--n_graphs", "64", "--workdir", wd, "--name", "f", "--log_period", "1"],
+                       capture_output=True, text=True, timeout=900)
+    assert r.returncode == 0, r.stderr[-2000:]
+    assert os.path.exists(os.path.join(wd, "f", "model.pt"))
+    assert "step 2 loss" in r.stderr

@@ -13,12 +13,17 @@ import product_harness
 from e3_layers.data import Batch, computeEdgeIndex
 from e3b200 import synthetic
 
-G = int(sys.argv[1]) if len(sys.argv) > 1 else 512
+TRAIN = "--train" in sys.argv          # force-matching training step (second-order mode) instead of the evaluation
+args = [a for a in sys.argv[1:] if not a.startswith("--")]
+G = int(args[0]) if args else 512
 dev = torch.device("cuda")
 model = product_harness.build_product({"config": "config_energy_force", "seed": 0}, torch.float32, dev)
 host = synthetic.qm9_like(G, seed=0)
 attrs = {"pos": ("node", "1x1o"), "species": ("node", "1x0e"), "_n_nodes": ("graph", "1x0e")}
 res = {k: v.to(dev) for k, v in host.items()}
+if TRAIN:
+    model.train()
+    opt = torch.optim.Adam(model.parameters(), lr=1e-3)
 
 
 def step():
@@ -26,7 +31,13 @@ def step():
     d, a = computeEdgeIndex(batch.data, batch.attrs, r_max=5.0)
     batch.update(d)
     batch.attrs.update(a)
-    return model(Batch(batch.attrs, **batch.data))
+    out = model(Batch(batch.attrs, **batch.data))
+    if TRAIN:
+        loss = 1e3 * (out["energy"] ** 2).mean() + 3e4 * ((out["forces"] - 0.1) ** 2).mean()
+        opt.zero_grad(set_to_none=True)
+        loss.backward()
+        opt.step()
+    return out
 
 
 for _ in range(3):

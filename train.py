@@ -2,9 +2,11 @@
 """Training entry point of the B200 drop-in (reference ``train.py``: same flag names for the in-scope
 options, ``--config <name>`` picks a registered config, one process per GPU, rank 0 logs and saves).
 
-In scope this round: regression on energies / dipoles (first-order parameter gradients through the
-fused interaction blocks), data-parallel over graphs with ONE flat gradient all-reduce per step.
-Force-matching and diffusion training need the second-order path and raise.
+In scope: regression on energies / dipoles (first-order parameter gradients through the fused
+interaction blocks) and energy+force matching (``config_energy_force``: the graph of the position
+gradient is built by the second-order mode of ``GradientOutput``), data-parallel over graphs with ONE
+flat gradient all-reduce per step.  Score-matching (diffusion) training needs the SDE machinery of
+``run/sde_utils.py`` and raises.
 Data: ``--data synthetic`` (seeded QM9-shaped molecules with a synthetic per-species target; there is no
 network for datasets) or an ``.npz`` with ``pos, species, _n_nodes`` and the target key.
 
@@ -46,7 +48,7 @@ def parse():
     return ap.parse_args()
 
 
-def load_data(flags, config, target_key):
+def load_data(flags, config, target_keys):
     from e3b200 import synthetic
 
     if flags.data != "synthetic":
@@ -56,12 +58,29 @@ def load_data(flags, config, target_key):
     n = data["_n_nodes"].reshape(-1)
     seg = torch.repeat_interleave(torch.arange(n.numel()), n)
     gen = torch.Generator().manual_seed(flags.seed + 1)
-    if target_key == "dipole":                                   # per-node 1x1o target
-        data[target_key] = 0.1 * torch.randn(data["pos"].shape[0], 3, generator=gen)
-    else:                                                        # per-graph scalar: composition energy + noise
+    if "dipole" in target_keys:                                  # per-node 1x1o target
+        data["dipole"] = 0.1 * torch.randn(data["pos"].shape[0], 3, generator=gen)
+    energy_key = next((k for k in target_keys if k in ("energy", "total_energy")), None)
+    if energy_key is not None:
+        # per-graph scalar: composition energy + a smooth pair potential, so that energies and forces are consistent
         per_species = -torch.arange(0, 120, dtype=torch.float32) * 0.37
-        e = torch.zeros(n.numel()).index_add_(0, seg, per_species[data["species"].reshape(-1)])
-        data[target_key] = (e + 0.01 * torch.randn(n.numel(), generator=gen)).view(-1, 1)
+        pos = data["pos"].double().requires_grad_(True)
+        starts = torch.cumsum(n, 0) - n
+        ii, jj = [], []
+        for g in range(n.numel()):
+            a = torch.arange(int(starts[g]), int(starts[g] + n[g]))
+            i, j = torch.meshgrid(a, a, indexing="ij")
+            keep = i < j
+            ii.append(i[keep])
+            jj.append(j[keep])
+        ii, jj = torch.cat(ii), torch.cat(jj)
+        r = (pos[ii] - pos[jj]).norm(dim=-1)
+        pair = torch.zeros(n.numel(), dtype=torch.float64).index_add_(0, seg[ii], 0.5 * torch.exp(-r))
+        e = torch.zeros(n.numel(), dtype=torch.float64).index_add_(0, seg, per_species[data["species"].reshape(-1)].double()) + pair
+        if "forces" in target_keys:
+            (g_pos,) = torch.autograd.grad(e.sum(), pos)
+            data["forces"] = (-g_pos).float()
+        data[energy_key] = (e.detach().float() + 0.01 * torch.randn(n.numel(), generator=gen)).view(-1, 1)
     return data
 
 
@@ -89,9 +108,9 @@ def main(rank, flags):
     assert get is not None, f"Config {flags.config} not found."
     config = get(flags.config_spec) if flags.config_spec else get()
     loss_coeffs = dict(config.loss_coeffs.items()) if hasattr(config.loss_coeffs, "items") else dict(config.loss_coeffs)
-    if any(k in ("forces", "score") for k in loss_coeffs):
-        raise NotImplementedError("force-matching / score-matching training needs the second-order kernels (not built yet)")
-    target_key = next(iter(loss_coeffs))
+    if any(k.startswith("score") for k in loss_coeffs):
+        raise NotImplementedError("score-matching training needs the SDE loss of run/sde_utils.py (not on this path yet)")
+    target_keys = list(loss_coeffs)
     setSeed(flags.seed)                                          # identical initial weights on every rank
     model = build(config.model_config).to(dev).train()
     if flags.resume_from:
@@ -102,7 +121,7 @@ def main(rank, flags):
     flat = parallel.FlatGradients(model.parameters(), n_scalars=2)
     r_max = float(config.model_config.r_max)
 
-    data = load_data(flags, config, target_key)
+    data = load_data(flags, config, target_keys)
     n_all = data["_n_nodes"].reshape(-1)
     G = n_all.numel()
     bs = int(config.batch_size) * world                          # global batch; every rank takes its shard
@@ -116,18 +135,21 @@ def main(rank, flags):
         node_idx = torch.cat([torch.arange(int(starts[g]), int(starts[g] + n_all[g])) for g in pick])
         host = {k: (v[node_idx] if v.shape[0] == int(n_all.sum()) else v[pick]) for k, v in data.items()}
         mine = parallel.shard_batch(host, rank, world)
-        target = mine.pop(target_key).to(dev)
+        targets = {k: mine.pop(k).to(dev) for k in target_keys}
         batch = Batch(dict(attrs), **{k: v.to(dev) for k, v in mine.items()})
         d, a = computeEdgeIndex(batch.data, batch.attrs, r_max=r_max)
         batch.update(d)
         batch.attrs.update(a)
         out = model(Batch(batch.attrs, **batch.data))
-        coeff, kind = loss_coeffs[target_key][0], loss_coeffs[target_key][1]
-        diff = out[target_key] - target
-        loss = coeff * (diff.abs().mean() if kind == "L1Loss" else (diff ** 2).mean())
+        loss, mae = 0.0, 0.0                                     # reference run/loss.py:274-287: sum of coeff * mean loss
+        for k in target_keys:
+            coeff, kind = loss_coeffs[k][0], loss_coeffs[k][1]
+            diff = out[k] - targets[k]
+            loss = loss + coeff * (diff.abs().mean() if kind == "L1Loss" else (diff ** 2).mean())
+            mae = mae + diff.detach().abs().mean()
         opt.zero_grad(set_to_none=True)
         loss.backward()
-        scal = flat.all_reduce([float(loss.detach()), float(diff.detach().abs().mean())])
+        scal = flat.all_reduce([float(loss.detach()), float(mae)])
         opt.step()
         if rank == 0 and (step % flags.log_period == 0 or step == flags.steps - 1):
             logging.info("step %d loss %.6g mae %.6g (%.1f s)", step, float(scal[0]), float(scal[1]), time.time() - t0)
