@@ -74,7 +74,7 @@ class ClockSampler(threading.Thread):
                     self.rows.append(parts)
             except Exception:
                 pass
-            self._halt.wait(0.2)
+            self._halt.wait(0.02)
 
     def stop(self):
         self._halt.set()
@@ -128,6 +128,55 @@ def run_reference(args):
 def tp_bytes(E, N, st_mul_dims):
     W, D_in, D_mid = st_mul_dims
     return E * (4 * W + 4) + (N + 1) * 8 + N * (12 + 4 * D_in + 4 * D_mid)
+
+
+def training_step_time(model, resident, attrs, Batch, computeEdgeIndex, n_atoms, world, dev, dist, steps=4, warmup=2):
+    """One optimiser step of config_energy_force on the same batch: neighbour list, forward, position gradient WITH
+    its graph (second-order mode of GradientOutput), the reference's loss 1e3 MSE(E) + 3e4 MSE(F)
+    (config_energy_force.py:30), backward to the parameters, flat-gradient all-reduce (N > 1), Adam."""
+    from e3b200 import parallel
+
+    model.train()
+    opt = torch.optim.Adam(model.parameters(), lr=1e-4)
+    flat = parallel.FlatGradients(model.parameters())
+    state = {k: v.detach().clone() for k, v in model.state_dict().items()}
+    g = torch.Generator().manual_seed(1)
+    e_t = torch.randn(resident["_n_nodes"].shape[0], 1, generator=g).to(dev)
+    f_t = (0.1 * torch.randn(n_atoms, 3, generator=g)).to(dev)
+
+    def step():
+        batch = Batch(dict(attrs), **{k: v.clone() for k, v in resident.items()})
+        d, a = computeEdgeIndex(batch.data, batch.attrs, r_max=5.0)
+        batch.update(d)
+        batch.attrs.update(a)
+        out = model(Batch(batch.attrs, **batch.data))
+        loss = 1e3 * ((out["energy"] - e_t) ** 2).mean() + 3e4 * ((out["forces"] - f_t) ** 2).mean()
+        opt.zero_grad(set_to_none=True)
+        loss.backward()
+        flat.all_reduce()
+        opt.step()
+
+    for _ in range(warmup):
+        step()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        step()
+    e1.record()
+    torch.cuda.synchronize()
+    t = torch.tensor([e0.elapsed_time(e1) / steps], device=dev)
+    atoms = torch.tensor([float(n_atoms)], device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dist.all_reduce(atoms)
+    model.load_state_dict(state)          # the optimiser steps above must not leak into anything measured later
+    model.zero_grad(set_to_none=True)
+    return {"what": "force-matching training step of the same workload: energy+force forward, graph of the position gradient "
+                    "(second-order mode), loss 1e3 MSE(E) + 3e4 MSE(F), backward, gradient all-reduce, Adam",
+            "ms_per_step": float(t), "atoms_per_s": float(atoms) / (float(t) * 1e-3), "steps": steps, "warmup": warmup}
 
 
 def run_ours(args):
@@ -193,7 +242,6 @@ def run_ours(args):
     ms = ev0.elapsed_time(ev1)
     launches = _lib.launch_count - launches0
     timing, ops.TIMING = ops.TIMING, None
-    clocks = sampler.stop()
     timing_how = "CUDA events around every launch of the kernel inside the timed region (launch stream)"
     if evaluator is not None:
         # a replayed CUDA graph cannot be bracketed kernel by kernel: time the SAME kernels on the SAME inputs in
@@ -234,8 +282,15 @@ def run_ours(args):
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     e2e_value = float(atoms_all.item()) * args.steps / float(t.item())
+    clocks = sampler.stop()      # sampled over the device-timed region, the eager kernel-timing pass and the e2e region
     h2d = sum(v.numel() * v.element_size() for v in pinned.values())
     d2h = e_host.numel() * e_host.element_size() + f_host.numel() * f_host.element_size()
+
+    # ---- the force-matching TRAINING step of the same workload (configs[1]), reported beside the headline ----------
+    training = None
+    if not args.no_training:
+        training = training_step_time(model, resident, attrs, Batch, computeEdgeIndex, n_atoms, world, dev, dist)
+        model.eval()
 
     if rank != 0:
         if world > 1:
@@ -302,7 +357,7 @@ def run_ours(args):
             "e2e": {"value": e2e_value, "unit": "atoms/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
             "gpu_launches": launches, "execution": "eager" if args.eager else "CUDA graph of the model step per (atoms, "
             "edges, graphs) signature, neighbour list eager (e3b200.graphed.GraphedEvaluator)",
-            "clocks": clocks, "roofline": roof, "cpu_baseline": cpu}
+            "clocks": clocks, "roofline": roof, "cpu_baseline": cpu, "training": training}
     print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
@@ -315,6 +370,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", dest="no_cpu_baseline", action="store_true")
+    ap.add_argument("--no-training", dest="no_training", action="store_true",
+                    help="skip the extra measurement of the force-matching training step")
     ap.add_argument("--breakdown", action="store_true", help="print the per-stage device time table to stderr (implies --eager)")
     ap.add_argument("--eager", action="store_true", help="run the step op by op instead of replaying its CUDA graph")
     args = ap.parse_args()

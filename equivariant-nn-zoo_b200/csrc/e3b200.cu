@@ -1103,3 +1103,102 @@ extern "C" int e3b_layout_convert(int dtype, const void* in, int64_t n, int32_t 
                             L, (const T*)in, n, to_imu, (T*)out);)
   return check_launch("layout_convert");
 }
+
+// ------------------------------------------------------------------------------------------
+// LayerNormalization (nn/pointwise.py:32-51): per node and irreps block b (all mul (2l+1) entries)
+//   y = x * rinv * std_b,   rinv = (sum x^2 / mul_b + eps)^-1/2
+// One warp per (node, block); 4 warps per CTA walk the blocks of a node round-robin.
+template <typename T> __device__ __forceinline__ T rsqrt_(T v);
+template <> __device__ __forceinline__ float rsqrt_<float>(float v) { return 1.0f / sqrtf(v); }
+template <> __device__ __forceinline__ double rsqrt_<double>(double v) { return 1.0 / sqrt(v); }
+
+#define LN_ROWS 8   // nodes per CTA in the backward (their std partials are reduced in shared memory)
+
+template <typename T>
+__global__ void __launch_bounds__(128) layernorm_fwd_kernel(const __grid_constant__ LayoutDesc L, const T* __restrict__ x,
+                                                            const T* __restrict__ stdw, T eps, int64_t n,
+                                                            T* __restrict__ y, T* __restrict__ rinv) {
+  const int64_t row = blockIdx.x;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const T* xr = x + row * L.dim;
+  T* yr = y + row * L.dim;
+  for (int b = warp; b < L.n_blocks; b += 4) {
+    const int len = L.mul[b] * (2 * L.l[b] + 1);
+    T s = 0;
+    for (int i = lane; i < len; i += 32) { const T v = xr[L.off[b] + i]; s = fma_(v, v, s); }
+    s = warp_sum(s);
+    s = __shfl_sync(0xffffffffu, s, 0);
+    const T r = rsqrt_<T>(s / T(L.mul[b]) + eps);
+    const T f = r * stdw[b];
+    for (int i = lane; i < len; i += 32) yr[L.off[b] + i] = xr[L.off[b] + i] * f;
+    if (lane == 0) rinv[row * L.n_blocks + b] = r;
+  }
+}
+
+// g_x = std (gy r - x r^3 / mul <gy, x>);  g_std partial per CTA = sum over its rows of r <gy, x>
+template <typename T>
+__global__ void __launch_bounds__(128) layernorm_bwd_kernel(const __grid_constant__ LayoutDesc L, const T* __restrict__ x,
+                                                            const T* __restrict__ gy, const T* __restrict__ rinv,
+                                                            const T* __restrict__ stdw, int64_t n, T* __restrict__ gx,
+                                                            T* __restrict__ gstd_partial) {
+  __shared__ double part[E3B_MAX_BLOCKS];
+  if (threadIdx.x < E3B_MAX_BLOCKS) part[threadIdx.x] = 0.0;
+  __syncthreads();
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  for (int k = 0; k < LN_ROWS; ++k) {
+    const int64_t row = (int64_t)blockIdx.x * LN_ROWS + k;
+    if (row >= n) break;
+    const T* xr = x + row * L.dim;
+    const T* gr = gy + row * L.dim;
+    T* or_ = gx + row * L.dim;
+    for (int b = warp; b < L.n_blocks; b += 4) {
+      const int len = L.mul[b] * (2 * L.l[b] + 1);
+      T dot = 0;
+      for (int i = lane; i < len; i += 32) dot = fma_(gr[L.off[b] + i], xr[L.off[b] + i], dot);
+      dot = warp_sum(dot);
+      dot = __shfl_sync(0xffffffffu, dot, 0);
+      const T r = rinv[row * L.n_blocks + b], sd = stdw[b];
+      const T c1 = sd * r, c2 = sd * r * r * r / T(L.mul[b]) * dot;
+      for (int i = lane; i < len; i += 32) or_[L.off[b] + i] = gr[L.off[b] + i] * c1 - xr[L.off[b] + i] * c2;
+      if (lane == 0) atomicAdd(&part[b], (double)(r * dot));   // shared-memory atomic, <= 8 rows x few blocks
+    }
+  }
+  __syncthreads();
+  if (gstd_partial && threadIdx.x < L.n_blocks) gstd_partial[(int64_t)blockIdx.x * L.n_blocks + threadIdx.x] = (T)part[threadIdx.x];
+}
+
+static int layernorm_desc(int32_t n_blocks, const int32_t* h_mul, const int32_t* h_l, LayoutDesc* L) {
+  if (n_blocks <= 0 || n_blocks > E3B_MAX_BLOCKS || !h_mul || !h_l) return fail(E3B_ERR_INVALID, "layernorm: bad blocks");
+  L->n_blocks = n_blocks;
+  int off = 0;
+  for (int b = 0; b < n_blocks; ++b) { L->mul[b] = h_mul[b]; L->l[b] = h_l[b]; L->off[b] = off; off += h_mul[b] * (2 * h_l[b] + 1); }
+  L->dim = off;
+  return E3B_OK;
+}
+
+extern "C" int64_t e3b_layernorm_bwd_blocks(int64_t n) { return (n + LN_ROWS - 1) / LN_ROWS; }
+
+extern "C" int e3b_layernorm_fwd(int dtype, const void* x, int64_t n, int32_t n_blocks, const int32_t* h_mul,
+                                 const int32_t* h_l, const void* std_w, double eps, void* y, void* rinv, void* stream) {
+  LayoutDesc L;
+  int rc = layernorm_desc(n_blocks, h_mul, h_l, &L);
+  if (rc) return rc;
+  if (n == 0 || L.dim == 0) return E3B_OK;
+  if (!x || !std_w || !y || !rinv) return fail(E3B_ERR_INVALID, "layernorm_fwd: null argument");
+  DISPATCH_DTYPE(dtype, layernorm_fwd_kernel<T><<<(unsigned)n, 128, 0, (cudaStream_t)stream>>>(
+                            L, (const T*)x, (const T*)std_w, (T)eps, n, (T*)y, (T*)rinv);)
+  return check_launch("layernorm_fwd");
+}
+
+extern "C" int e3b_layernorm_bwd(int dtype, const void* x, const void* gy, const void* rinv, int64_t n, int32_t n_blocks,
+                                 const int32_t* h_mul, const int32_t* h_l, const void* std_w, void* gx,
+                                 void* gstd_partial, void* stream) {
+  LayoutDesc L;
+  int rc = layernorm_desc(n_blocks, h_mul, h_l, &L);
+  if (rc) return rc;
+  if (n == 0 || L.dim == 0) return E3B_OK;
+  if (!x || !gy || !rinv || !std_w || !gx) return fail(E3B_ERR_INVALID, "layernorm_bwd: null argument");
+  DISPATCH_DTYPE(dtype, layernorm_bwd_kernel<T><<<(unsigned)e3b_layernorm_bwd_blocks(n), 128, 0, (cudaStream_t)stream>>>(
+                            L, (const T*)x, (const T*)gy, (const T*)rinv, (const T*)std_w, n, (T*)gx, (T*)gstd_partial);)
+  return check_launch("layernorm_bwd");
+}

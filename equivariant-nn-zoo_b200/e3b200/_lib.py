@@ -77,6 +77,9 @@ SIGNATURES = {
     "e3b_gemm_packed_floats": (c_i64, [c_i32, c_i32]),
     "e3b_gemm_pack": (c_int, [ctypes.POINTER(GemmPackDesc), c_i32, c_vp]),
     "e3b_gemm_run": (c_int, [ctypes.POINTER(GemmProblem), c_i32, c_vp]),
+    "e3b_layernorm_fwd": (c_int, [c_int, c_vp, c_i64, c_i32, c_vp, c_vp, c_vp, c_f64, c_vp, c_vp, c_vp]),
+    "e3b_layernorm_bwd_blocks": (c_i64, [c_i64]),
+    "e3b_layernorm_bwd": (c_int, [c_int, c_vp, c_vp, c_vp, c_i64, c_i32, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp]),
     "e3b_layout_convert": (c_int, [c_int, c_vp, c_i64, c_i32, c_vp, c_vp, c_int, c_vp, c_vp]),
 }
 

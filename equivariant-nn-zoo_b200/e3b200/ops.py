@@ -653,6 +653,44 @@ def gate(x, desc, out_dim):
     return _Gate.apply(x.contiguous(), desc, out_dim)
 
 
+class _LayerNorm(torch.autograd.Function):
+    """per (node, irreps block): x / sqrt(sum x^2 / mul + eps) * std_block (first order; the second-order
+    mode uses the closed form in e3_layers.nn.pointwise.LayerNormalization)"""
+
+    @staticmethod
+    def forward(ctx, x, std, muls, ls, eps):
+        lib = _lib.load()
+        require_cuda(x, std)
+        nb = len(muls)
+        c_mul, c_l = (ctypes.c_int32 * nb)(*muls), (ctypes.c_int32 * nb)(*ls)
+        sw = std.to(x.dtype).contiguous()
+        y = torch.empty_like(x)
+        rinv = torch.empty(x.shape[0], nb, dtype=x.dtype, device=x.device)
+        check(lib.e3b_layernorm_fwd(dtype_code(x), ptr(x), x.shape[0], nb, c_mul, c_l, ptr(sw), float(eps), ptr(y), ptr(rinv), stream()))
+        count_launch()
+        ctx.save_for_backward(x, rinv, sw)
+        ctx.blocks, ctx.std_dtype = (c_mul, c_l, nb), std.dtype
+        return y
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, gy):
+        lib = _lib.load()
+        x, rinv, sw = ctx.saved_tensors
+        c_mul, c_l, nb = ctx.blocks
+        gx = torch.empty_like(x)
+        part = torch.empty(lib.e3b_layernorm_bwd_blocks(x.shape[0]), nb, dtype=x.dtype, device=x.device) \
+            if ctx.needs_input_grad[1] else None
+        check(lib.e3b_layernorm_bwd(dtype_code(x), ptr(x), ptr(gy.contiguous()), ptr(rinv), x.shape[0], nb, c_mul, c_l,
+                                    ptr(sw), ptr(gx), ptr(part), stream()))
+        count_launch()
+        return gx, (part.sum(0).to(ctx.std_dtype) if part is not None else None), None, None, None
+
+
+def layer_norm(x, std, muls, ls, eps=1e-6):
+    return _LayerNorm.apply(x.contiguous(), std, tuple(muls), tuple(ls), eps)
+
+
 def layout_convert(x, irreps, to_imu):
     """kernel-side mul_ir <-> imu conversion (no autograd; used for buffers/tests)"""
     lib = _lib.load()

@@ -274,6 +274,20 @@ E3B_API int64_t e3b_gemm_packed_floats(int32_t N, int32_t K);
 E3B_API int e3b_gemm_pack(const e3b_gemm_pack_desc* descs, int32_t n, void* stream);
 E3B_API int e3b_gemm_run(const e3b_gemm_problem* problems, int32_t n, void* stream);
 
+/* ---------------------------------------------------------------------------------------
+ * LayerNormalization.  Replaces nn/pointwise.py:32-51 (used when normalize=True,
+ * nn/message_passing.py:238-240,255-257; config_diffusion_CA.py:126): per node and irreps
+ * block b (all mul_b (2 l_b + 1) entries, mul_ir layout)
+ *   y = x * rinv * std[b],  rinv = (sum x^2 / mul_b + eps)^-1/2     (rinv [n, n_blocks] is kept for the backward)
+ * Backward: g_x, and per-CTA partial sums of d/d std ([e3b_layernorm_bwd_blocks(n), n_blocks],
+ * summed by the caller; may be NULL).                                                            */
+E3B_API int e3b_layernorm_fwd(int dtype, const void* x, int64_t n, int32_t n_blocks, const int32_t* h_mul,
+                              const int32_t* h_l, const void* std_w, double eps, void* y, void* rinv, void* stream);
+E3B_API int64_t e3b_layernorm_bwd_blocks(int64_t n);
+E3B_API int e3b_layernorm_bwd(int dtype, const void* x, const void* gy, const void* rinv, int64_t n, int32_t n_blocks,
+                              const int32_t* h_mul, const int32_t* h_l, const void* std_w, void* g_x,
+                              void* g_std_partial, void* stream);
+
 /* mul_ir <-> imu layout conversion of feature rows (blocks: mul, l). to_imu = 1: [u][m]->[m][u] */
 E3B_API int e3b_layout_convert(int dtype, const void* in, int64_t n, int32_t n_blocks, const int32_t* mul,
                        const int32_t* l, int to_imu, void* out, void* stream);

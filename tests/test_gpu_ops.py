@@ -184,3 +184,37 @@ def test_gate_and_segment_sum_and_layout(dtype):
     t = torch.randn(11, irr.dim, generator=g, dtype=torch.float64).to(dtype)
     assert torch.equal(ops.layout_convert(t.to(DEV), irr, True).cpu(), layout.to_imu(t, irr))
     assert torch.equal(ops.layout_convert(layout.to_imu(t, irr).contiguous().to(DEV), irr, False).cpu(), t)
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.float64])
+def test_layer_normalization_kernel(dtype):
+    """kernel (first order) against the oracle's LayerNormalization, values and both gradients"""
+    from e3_layers.nn.pointwise import LayerNormalization
+
+    irr = "64x0e+64x0o+64x1e+64x1o+64x2e+64x2o"
+    g = torch.Generator().manual_seed(3)
+    x = torch.randn(37, 1152, generator=g, dtype=torch.float64).to(dtype)
+    x[5] = 0                                                    # an all-zero row exercises the eps
+    std = (1.0 + 0.1 * torch.randn(6, generator=g, dtype=torch.float64)).to(dtype)
+    go = torch.randn(37, 1152, generator=g, dtype=torch.float64).to(dtype)
+    torch.set_default_dtype(dtype)
+    try:
+        ref_mod = ref_layers.LayerNormalization(irr, irr)
+        mod = LayerNormalization(irr, irr).to(DEV)
+    finally:
+        torch.set_default_dtype(torch.float32)
+    with torch.no_grad():
+        ref_mod.std.copy_(std)
+        mod.std.copy_(std.to(DEV))
+    xr = x.clone().requires_grad_(True)
+    yr = ref_mod({"input": xr}, {})[0]["output"]
+    gxr, gsr = torch.autograd.grad(yr, (xr, ref_mod.std), go)
+    xd = x.clone().to(DEV).requires_grad_(True)
+    n0 = ops._lib.launch_count
+    yd = mod({"input": xd}, {})[0]["output"]
+    gxd, gsd = torch.autograd.grad(yd, (xd, mod.std), go.to(DEV))
+    assert ops._lib.launch_count - n0 == 2                      # one kernel forward, one backward
+    assert rel(yd, yr) < TOL[dtype] and rel(gxd, gxr) < TOL[dtype] * 5 and rel(gsd, gsr) < TOL[dtype] * 5
+    with ops.second_order():                                    # the closed form used in second-order mode agrees
+        y2 = mod({"input": xd}, {})[0]["output"]
+    assert rel(y2, yr) < TOL[dtype]
