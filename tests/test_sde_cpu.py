@@ -1,0 +1,65 @@
+"""VP-SDE / PC sampler host logic (e3_layers.run) against the oracle restatement (oracle/ref_sde.py) with
+identical recorded noise, on the CPU: the model underneath runs on the TEST-ONLY kernel stand-ins.
+Closed-form checks pin the oracle's SDE pieces themselves (the reference ships no tests)."""
+import math
+
+import pytest
+import torch
+
+import product_harness
+import torch_emulation
+from e3_layers.run import VPSDE, LangevinCorrector, EulerMaruyamaPredictor, get_pc_sampler, get_sde_loss_fn
+from e3b200 import synthetic
+from sde_harness import Noise, oracle_data, oracle_model_fn, product_batch, ref_sde
+
+
+def test_vpsde_closed_forms():
+    sde = ref_sde.VPSDE({"pos": 3})
+    data = {"t": torch.tensor([[0.3], [1.0]], dtype=torch.float64), "_node_segment": torch.tensor([0, 0, 1])}
+    std = sde.std(data)
+    for row, t in zip((0, 2), (0.3, 1.0)):
+        integral = 0.1 * t + 0.5 * (20 - 0.1) * t * t            # int_0^t beta(s) ds
+        assert abs(float(std[row]) - math.sqrt(1 - math.exp(-integral))) < 1e-12
+    assert abs(float(sde.alphas[0]) - (1 - 0.1 / 1000)) < 1e-7 and abs(float(sde.alphas[-1]) - (1 - 20 / 1000)) < 1e-7
+    # one forward Euler-Maruyama step with zero noise is the pure drift
+    x0 = torch.ones(3, 3, dtype=torch.float64)
+    d = {"pos": x0.clone(), **data}
+    sde.sde_step(d, 1e-3, iter([torch.zeros(3, 3, dtype=torch.float64)]))
+    beta = 0.1 + torch.tensor([0.3, 0.3, 1.0], dtype=torch.float64).view(-1, 1) * 19.9
+    assert torch.allclose(d["pos"], x0 - 0.5 * beta * x0 * 1e-3, atol=1e-15)
+
+
+def test_pc_sampler_and_loss_match_oracle_fp64(monkeypatch):
+    torch_emulation.patch(monkeypatch)
+    meta = {"config": "config_diffusion", "seed": 2}
+    inputs = synthetic.diffusion_like(3, seed=1, n_min=3, n_max=6)
+    N = inputs["pos"].shape[0]
+    iters = 2
+    # --- oracle
+    osde = ref_sde.VPSDE({"pos": 3}, N=50)
+    ref, nfe = ref_sde.pc_sampler(osde, oracle_model_fn(meta, inputs), oracle_data(inputs), snr=0.16, n_steps=1,
+                                  noise=Noise((N, 3), 1 + 2 * iters, seed=7), max_iterations=iters)
+    # --- product (CPU tensors, emulated kernels, eager)
+    model = product_harness.build_product(meta, torch.float64, "cpu")
+    sde = VPSDE({"pos": 3}, N=50)
+    sde.randn_like = Noise((N, 3), 1 + 2 * iters, seed=7).randn_like
+    sampler = get_pc_sampler(sde, EulerMaruyamaPredictor, LangevinCorrector, lambda b: b, snr=0.16, n_steps=1,
+                             max_iterations=iters, graph=False)
+    torch.set_default_dtype(torch.float64)
+    try:
+        out, nfe2 = sampler(model, product_batch(inputs, torch.float64, "cpu"))
+    finally:
+        torch.set_default_dtype(torch.float32)
+    assert nfe == nfe2 == 2 * iters
+    assert float((out["pos"] - ref["pos"]).abs().max()) < 1e-9 * float(ref["pos"].abs().max())
+    # --- score-matching loss with recorded t and z
+    t = torch.tensor([0.2, 0.5, 0.9], dtype=torch.float64)
+    ref_loss = ref_sde.sde_loss(osde, oracle_model_fn(meta, inputs), oracle_data(inputs), t, Noise((N, 3), 1, seed=9))
+    sde.randn_like = Noise((N, 3), 1, seed=9).randn_like
+    monkeypatch.setattr(torch, "rand", lambda *a, **k: ((t - 1e-5) / (1 - 1e-5)).to(k.get("device", "cpu")))
+    torch.set_default_dtype(torch.float64)
+    try:
+        loss, _ = get_sde_loss_fn(sde, train=False)(model, product_batch(inputs, torch.float64, "cpu"))
+    finally:
+        torch.set_default_dtype(torch.float32)
+    assert abs(float(loss) - float(ref_loss)) < 1e-9 * abs(float(ref_loss))
