@@ -45,13 +45,6 @@ class GemmPackDesc(ctypes.Structure):
 
 
 E3B_GEMM_MAX_GROUP = 8
-E3B_MLP_MAX_HIDDEN = 4
-
-
-class MlpHiddenDesc(ctypes.Structure):
-    _fields_ = [("W", c_vp * E3B_MLP_MAX_HIDDEN), ("alpha", c_f32 * E3B_MLP_MAX_HIDDEN), ("k_in", c_i32), ("width", c_i32),
-                ("n_layers", c_i32), ("act_cst", c_f32)]
-
 
 # name -> (restype, argtypes); must list EVERY symbol include/e3b200.h declares
 SIGNATURES = {
@@ -84,10 +77,6 @@ SIGNATURES = {
     "e3b_gemm_packed_floats": (c_i64, [c_i32, c_i32]),
     "e3b_gemm_pack": (c_int, [ctypes.POINTER(GemmPackDesc), c_i32, c_vp]),
     "e3b_gemm_run": (c_int, [ctypes.POINTER(GemmProblem), c_i32, c_vp]),
-    "e3b_mlp_hidden_supported": (c_int, [c_i32, c_i32, c_i32]),
-    "e3b_mlp_hidden_fwd": (c_int, [ctypes.POINTER(MlpHiddenDesc), c_vp, c_i64, c_i64, ctypes.POINTER(c_vp), c_vp]),
-    "e3b_mlp_hidden_bwd": (c_int, [ctypes.POINTER(MlpHiddenDesc), c_vp, ctypes.POINTER(c_vp), c_i64, ctypes.POINTER(c_vp),
-                                   c_vp, c_vp]),
     "e3b_layernorm_fwd": (c_int, [c_int, c_vp, c_i64, c_i32, c_vp, c_vp, c_vp, c_f64, c_vp, c_vp, c_vp]),
     "e3b_layernorm_bwd_blocks": (c_i64, [c_i64]),
     "e3b_layernorm_bwd": (c_int, [c_int, c_vp, c_vp, c_vp, c_i64, c_i32, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp]),
@@ -112,7 +101,7 @@ def load():
             fn.argtypes = args
         if lib.e3b_abi_version() != 1:
             raise RuntimeError("libe3b200.so ABI version mismatch")
-        for which, st in enumerate((TpDesc, GateDesc, GemmProblem, GemmPackDesc, MlpHiddenDesc)):
+        for which, st in enumerate((TpDesc, GateDesc, GemmProblem, GemmPackDesc)):
             if lib.e3b_struct_size(which) != ctypes.sizeof(st):
                 raise RuntimeError(f"libe3b200.so struct layout mismatch for {st.__name__}")
         _lib = lib

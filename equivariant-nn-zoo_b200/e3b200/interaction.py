@@ -58,20 +58,6 @@ class FusedInteraction:
         self.Vg = 16 if self.V <= 16 else 32           # epilogue group width (attributes zero-extended)
         self._cache = {}
         self.reason = self._unsupported()
-        # hidden layers of the radial MLP as ONE kernel per direction (csrc/mlp_hidden.cu) when a kernel exists
-        n_hidden = conv.fc.n_layers - 1
-        self.mlp_fused = bool(n_hidden >= 1 and len(set(self.hs[1:-1])) == 1 and
-                              _lib.load().e3b_mlp_hidden_supported(self.hs[0], self.hs[1], n_hidden))
-
-    def mlp_desc(self):
-        d = _lib.MlpHiddenDesc()
-        n_hidden = self.fc.n_layers - 1
-        for i in range(n_hidden):
-            W = getattr(self.fc, f"layer{i}").weight
-            assert W.is_contiguous() and W.dtype == torch.float32
-            d.W[i], d.alpha[i] = W.data_ptr(), 1.0 / math.sqrt(self.hs[i])
-        d.k_in, d.width, d.n_layers, d.act_cst = self.hs[0], self.hs[1], n_hidden, self.fc.cst
-        return d
 
     # -- which layers take the fused path -------------------------------------------------------
     def _unsupported(self):
@@ -179,18 +165,8 @@ class _Interaction(torch.autograd.Function):
         # ---- radial MLP
         hs = fi.hs
         h = [er]
-        n_fc = conv.fc.n_layers
-        first = 0
-        if fi.mlp_fused:
-            outs = [new(E, hs[1]) for _ in range(n_fc - 1)]
-            arr = (ctypes.c_void_p * _lib.E3B_MLP_MAX_HIDDEN)(*[o.data_ptr() for o in outs])
-            with ops.stage("f.mlp_hidden"):
-                check(lib.e3b_mlp_hidden_fwd(ctypes.byref(fi.mlp_desc()), ptr(er), er.stride(0), E, arr, stream()))
-            count_launch()
-            h += outs
-            first = n_fc - 1
-        for i in range(first, n_fc):
-            last = i == n_fc - 1
+        for i in range(conv.fc.n_layers):
+            last = i == conv.fc.n_layers - 1
             out = new(E, hs[i + 1])
             with ops.stage("f.mlp_last" if last else "f.mlp_hidden"):
                 ops.gemm_run([ops.gemm_problem(h[-1], P["fc"][i], out, E, a_rows=(h[-1].stride(0), 0, 1),
@@ -314,28 +290,11 @@ class _Interaction(torch.autograd.Function):
         gz = [None] * (conv.fc.n_layers + 1)       # gz[i] = gradient wrt the INPUT of layer i (after its activation derivative)
         gz[conv.fc.n_layers] = gw
         lo = 0 if need_er else 1
-        n_fc = conv.fc.n_layers
-        for i in range(n_fc - 1, lo - 1, -1):
+        for i in range(conv.fc.n_layers - 1, lo - 1, -1):
             if not (need_er or need_params):
                 break
-            if fi.mlp_fused and i < n_fc - 1:
-                # the hidden layers in one kernel: from d/dz of the last hidden layer down to d/d(edge_radial)
-                c_vp = ctypes.c_void_p * _lib.E3B_MLP_MAX_HIDDEN
-                saved = c_vp(*[h[l].data_ptr() if 1 <= l < n_fc - 1 else None for l in range(_lib.E3B_MLP_MAX_HIDDEN)])
-                outs = c_vp()
-                if need_params:
-                    for l in range(1, n_fc - 1):
-                        gz[l] = new(E, hs[l])
-                        outs[l] = gz[l].data_ptr()
-                if need_er:
-                    gz[0] = new(E, hs[0])
-                with ops.stage("b.mlp_hidden"):
-                    check(lib.e3b_mlp_hidden_bwd(ctypes.byref(fi.mlp_desc()), ptr(gz[n_fc - 1]), saved, E, outs,
-                                                 ptr(gz[0]) if need_er else None, stream()))
-                count_launch()
-                break
             out = new(E, hs[i])
-            with ops.stage("b.mlp_last" if i == n_fc - 1 else "b.mlp_hidden"):
+            with ops.stage("b.mlp_last" if i == conv.fc.n_layers - 1 else "b.mlp_hidden"):
                 ops.gemm_run([ops.gemm_problem(gz[i + 1], P["fc"][i], out, E, alpha=1.0 / math.sqrt(hs[i]),
                                                epilogue=3 if i > 0 else 0, H=h[i] if i > 0 else None, act_cst=conv.fc.cst)])
             gz[i] = out

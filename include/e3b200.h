@@ -48,7 +48,7 @@ typedef enum {
 E3B_API int e3b_abi_version(void);
 E3B_API const char* e3b_last_error(void);
 /* sizeof of the ABI structs as compiled (0 e3b_tp_desc, 1 e3b_gate_desc, 2 e3b_gemm_problem,
- * 3 e3b_gemm_pack_desc, 4 e3b_mlp_hidden_desc) so that a binding can verify its own struct layout; -1 otherwise */
+ * 3 e3b_gemm_pack_desc) so that a binding can verify its own struct layout; -1 otherwise */
 E3B_API int64_t e3b_struct_size(int which);
 
 /* ---------------------------------------------------------------------------------------
@@ -273,30 +273,6 @@ E3B_API int e3b_gemm_tile_n(int32_t N, int32_t K);
 E3B_API int64_t e3b_gemm_packed_floats(int32_t N, int32_t K);
 E3B_API int e3b_gemm_pack(const e3b_gemm_pack_desc* descs, int32_t n, void* stream);
 E3B_API int e3b_gemm_run(const e3b_gemm_problem* problems, int32_t n, void* stream);
-
-/* ---------------------------------------------------------------------------------------
- * Hidden layers of the radial MLP, fused.  Replaces the first `invariant_layers` layers of the e3nn
- * nn.FullyConnectedNet built at nn/message_passing.py:74-79 and applied at :93:
- *   h_0 = x [n, k_in];  h_{i+1} = act_cst * ssp(alpha[i] * h_i W[i]),  W[0] [k_in, width], W[i>0] [width, width]
- * (row-major fp32 parameter tensors, used in place).  fp32 only.  Forward stores h_1 .. h_L through the HOST
- * array h_h_out of L device pointers (entries may be NULL).  Backward starts from g_top = d/dz_L [n, width]
- * (gradient with respect to the pre-activation of h_L, as produced by e3b_gemm_run epilogue 3 of the last
- * layer), reads the saved h_i (host array, index i = 1 .. L-1), optionally stores d/dz_i (host array
- * h_gz_out, index i = 1 .. L-1, may be NULL) and d/dx [n, k_in] (may be NULL).
- * Kernels exist for (k_in, width) in {(8,64), (8,32), (32,64)}: ask e3b_mlp_hidden_supported first.   */
-#define E3B_MLP_MAX_HIDDEN 4
-typedef struct {
-  const void* W[E3B_MLP_MAX_HIDDEN];
-  float alpha[E3B_MLP_MAX_HIDDEN];
-  int32_t k_in, width, n_layers;
-  float act_cst;
-} e3b_mlp_hidden_desc;
-
-E3B_API int e3b_mlp_hidden_supported(int32_t k_in, int32_t width, int32_t n_layers);
-E3B_API int e3b_mlp_hidden_fwd(const e3b_mlp_hidden_desc* desc, const void* x, int64_t ldx, int64_t n,
-                               void* const* h_h_out, void* stream);
-E3B_API int e3b_mlp_hidden_bwd(const e3b_mlp_hidden_desc* desc, const void* g_top, const void* const* h_h_saved,
-                               int64_t n, void* const* h_gz_out, void* g_x, void* stream);
 
 /* ---------------------------------------------------------------------------------------
  * LayerNormalization.  Replaces nn/pointwise.py:32-51 (used when normalize=True,

@@ -3,7 +3,6 @@ interaction-block budget; the kernel itself is held to 2e-6 relative to the row 
 import pytest
 import torch
 
-import harness
 from e3b200 import ops
 
 pytestmark = pytest.mark.gpu
@@ -124,58 +123,3 @@ def test_gemm_many_row_tiles_long_k():
     C = torch.empty(M, N, device=DEV)
     ops.gemm_tf32x3(A.to(DEV), B.to(DEV), C, M, N, K)
     assert _rel(C, A.double() @ B.double().T) < 2e-6
-
-
-@pytest.mark.parametrize("k_in,width,n_hidden", [(8, 64, 3), (8, 32, 3), (32, 64, 3), (8, 64, 1), (8, 64, 4)])
-def test_fused_hidden_mlp_kernels(k_in, width, n_hidden):
-    """csrc/mlp_hidden.cu (hidden layers of the radial MLP in one kernel per direction) against fp64 torch autograd"""
-    import ctypes
-    import math
-
-    from e3b200 import _lib
-    from e3b200.dense import ACT_CST
-
-    lib = _lib.load()
-    assert lib.e3b_mlp_hidden_supported(k_in, width, n_hidden)
-    assert not lib.e3b_mlp_hidden_supported(12, 64, 3)
-    g = torch.Generator().manual_seed(k_in + width + n_hidden)
-    E = 1000 + 37                                                   # not a multiple of the 128-row tile
-    x = torch.randn(E, k_in, generator=g)
-    Ws = [torch.randn(k_in if i == 0 else width, width, generator=g) for i in range(n_hidden)]
-    g_top = torch.randn(E, width, generator=g)
-    cst = ACT_CST["ssp"]
-    # fp64 reference: h_{i+1} = cst ssp(h_i W_i / sqrt(fan_in)); loss = <g_top, z_L> with z_L the last pre-activation
-    xr = x.double().requires_grad_(True)
-    h, hs, zs = xr, [], []
-    for W in Ws:
-        z = h @ W.double() / math.sqrt(W.shape[0])
-        zs.append(z)
-        h = cst * (torch.nn.functional.softplus(z) - math.log(2.0))
-        hs.append(h)
-    grads = torch.autograd.grad(zs[-1], [xr] + zs[:-1], g_top.double())
-    d = _lib.MlpHiddenDesc()
-    Wd = [W.to(DEV).contiguous() for W in Ws]
-    for i, W in enumerate(Wd):
-        d.W[i], d.alpha[i] = W.data_ptr(), 1.0 / math.sqrt(W.shape[0])
-    d.k_in, d.width, d.n_layers, d.act_cst = k_in, width, n_hidden, cst
-    xd = x.to(DEV)
-    outs = [torch.empty(E, width, device=DEV) for _ in range(n_hidden)]
-    arr = (ctypes.c_void_p * _lib.E3B_MLP_MAX_HIDDEN)(*[o.data_ptr() for o in outs])
-    _lib.check(lib.e3b_mlp_hidden_fwd(ctypes.byref(d), xd.data_ptr(), k_in, E, arr, _lib.stream()))
-    for got, ref in zip(outs, hs):
-        assert harness.rel_err(got, ref) < 2e-6
-    # backward from d/dz_L
-    saved = (ctypes.c_void_p * _lib.E3B_MLP_MAX_HIDDEN)(*[outs[l - 1].data_ptr() if 1 <= l < n_hidden else None
-                                                           for l in range(_lib.E3B_MLP_MAX_HIDDEN)])
-    gz = [None] + [torch.empty(E, width, device=DEV) for _ in range(1, n_hidden)]
-    gz_arr = (ctypes.c_void_p * _lib.E3B_MLP_MAX_HIDDEN)(*[t.data_ptr() if t is not None else None for t in gz])
-    gx = torch.empty(E, k_in, device=DEV)
-    gt = g_top.to(DEV)
-    _lib.check(lib.e3b_mlp_hidden_bwd(ctypes.byref(d), gt.data_ptr(), saved, E, gz_arr, gx.data_ptr(), _lib.stream()))
-    assert harness.rel_err(gx, grads[0]) < 5e-6
-    for l in range(1, n_hidden):
-        assert harness.rel_err(gz[l], grads[l]) < 5e-6
-    # the optional outputs really are optional
-    gx2 = torch.empty(E, k_in, device=DEV)
-    _lib.check(lib.e3b_mlp_hidden_bwd(ctypes.byref(d), gt.data_ptr(), saved, E, None, gx2.data_ptr(), _lib.stream()))
-    assert torch.equal(gx2, gx)
