@@ -13,6 +13,7 @@ import math
 import torch
 from torch import nn
 
+from . import ops
 from .irreps import Irreps
 
 # normalize2mom constants (e3nn estimates E[act(z)^2]^-1/2 by Monte-Carlo with 1e6 float64
@@ -26,6 +27,14 @@ ACT_CST = {
 }
 # parity of each activation as a function: +1 even, -1 odd, 0 neither
 ACT_PARITY = {"ssp": 0, "silu": 0, "tanh": -1, "tanhlu": -1, "abs": 1}
+
+
+def _mm(x, W, alpha):
+    """alpha * x @ W.  In second-order mode the product is a tcgen05 node whose backward is differentiable again
+    (ops.dense); otherwise a library GEMM."""
+    if ops.second_order_active() and ops.dense_supported(x, W):
+        return ops.dense(x, W, alpha)
+    return torch.matmul(x, W * alpha)
 
 
 def _mask(irreps, touched):
@@ -77,7 +86,7 @@ class Linear(nn.Module):
         for i, o, off, alpha in self.paths:
             mi, mo = self.irreps_in[i].mul, self.irreps_out[o].mul
             W = self.weight[off:off + mi * mo].reshape(mi, mo)
-            y = torch.matmul(self._block_in(x, i), W * alpha)        # [z, d, mo]
+            y = _mm(self._block_in(x, i), W, alpha)        # [z, d, mo]
             acc[o] = y if acc[o] is None else acc[o] + y
         boff = 0
         for o in self.bias_blocks:
@@ -122,7 +131,7 @@ class RadialMLP(nn.Module):
     def forward(self, h):
         for i in range(self.n_layers):
             W = getattr(self, f"layer{i}").weight
-            h = torch.matmul(h, W * (1.0 / math.sqrt(W.shape[0])))
+            h = _mm(h, W, 1.0 / math.sqrt(W.shape[0]))
             if i < self.n_layers - 1:
                 h = ssp(h) * self.cst
         return h
@@ -167,7 +176,7 @@ class ScalarAttrTensorProduct(nn.Module):
             ab = attrs[:, self._s2[i2]]
             # outer product over (u, v) -> K = m1*m2, then one GEMM per instruction
             xa = (xb.unsqueeze(2) * ab.reshape(z, 1, m2, 1)).reshape(z, m1 * m2, d).transpose(1, 2)  # [z, d, K]
-            y = torch.matmul(xa, W * alpha)  # [z, d, mo]
+            y = _mm(xa, W, alpha)  # [z, d, mo]
             acc[o] = y if acc[o] is None else acc[o] + y
         cols = []
         for o, blk in enumerate(self.irreps_out):

@@ -33,6 +33,27 @@ def second_order_active():
     return _SECOND_ORDER > 0
 
 
+# Set by GradientOutput around its autograd.grad call: that backward pass differentiates with respect to the
+# positions alone, so dense Functions skip their weight gradients (reductions over all edges / nodes that the
+# engine would throw away; built-in torch ops prune them by themselves).
+_POSITIONS_ONLY = 0
+
+
+class positions_only:
+    def __enter__(self):
+        global _POSITIONS_ONLY
+        _POSITIONS_ONLY += 1
+
+    def __exit__(self, *exc):
+        global _POSITIONS_ONLY
+        _POSITIONS_ONLY -= 1
+        return False
+
+
+def positions_only_active():
+    return _POSITIONS_ONLY > 0
+
+
 # ------------------------------------------------------------------------------------------
 # graph structure
 class GraphCSR:
@@ -798,3 +819,58 @@ def gemm_tf32x3(A, B, C, M, N, K, a_rows=None, c_rows=None, c_col_stride=1, alph
     gemm_run([gemm_problem(A, Bp, C, M, a_rows=a_rows, c_rows=c_rows, c_col_stride=c_col_stride, alpha=alpha,
                            epilogue=epilogue, aux=reduce_aux, aux_d=aux_d, H=H, act_cst=act_cst, accumulate=accumulate)])
     return C
+
+
+# ------------------------------------------------------------------------------------------
+# Dense map with a small weight matrix as a differentiable node on the tensor cores (second-order mode):
+# products of the form [many rows, K] x [K, N] run on the tcgen05 3xTF32 kernel, whichever argument the
+# weight is; the weight gradient (a reduction over the rows) is a library GEMM.  The backward is made of the
+# same node with the weight transposed, so the graph of a gradient can be differentiated again.
+FORCE_DENSE_FUNCTION = False       # tests: take this path on CPU tensors too (with the launcher replaced)
+
+
+def k_dense(x, W, alpha, trans):
+    """alpha * x @ (W^T if trans else W); x [M, K] contiguous fp32, W a 2-D fp32 view (any strides)"""
+    require_cuda(x, W)
+    M, K = x.shape
+    N = W.shape[0] if trans else W.shape[1]
+    s_n, s_k = (W.stride(0), W.stride(1)) if trans else (W.stride(1), W.stride(0))
+    (Bp,) = gemm_pack([(W, 0, s_n, 0, s_k, 1, 0, N, K)])
+    out = torch.empty(M, N, dtype=torch.float32, device=x.device)
+    gemm_run([gemm_problem(x, Bp, out, M, alpha=alpha)])
+    return out
+
+
+def dense_supported(x, W):
+    K = x.shape[-1]
+    ok = FORCE_DENSE_FUNCTION or (x.is_cuda and x.dtype == torch.float32 and W.dtype == torch.float32)
+    return (ok and x.dtype == W.dtype and K % 4 == 0
+            and x.numel() > 0 and W.numel() > 0 and x.numel() // K < 2 ** 31)
+
+
+class _Dense(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, W, alpha, trans):
+        ctx.alpha, ctx.trans = alpha, trans
+        ctx.save_for_backward(x, W)
+        return k_dense(x, W, alpha, trans)
+
+    @staticmethod
+    def backward(ctx, gy):
+        x, W = ctx.saved_tensors
+        gx = gW = None
+        gy = gy.contiguous()
+        if ctx.needs_input_grad[0]:
+            N = gy.shape[1]
+            gx = _Dense.apply(gy, W, ctx.alpha, not ctx.trans) if N % 4 == 0 else \
+                ctx.alpha * (gy @ (W if ctx.trans else W.t()))
+        if ctx.needs_input_grad[1] and not positions_only_active():
+            gW = ctx.alpha * (gy.t() @ x if ctx.trans else x.t() @ gy)
+        return gx, gW, None, None
+
+
+def dense(x, W, alpha):
+    """alpha * x @ W for x [..., K] and W [K, N] (a view of a parameter)"""
+    K, N = W.shape
+    x2 = x.reshape(-1, K).contiguous()
+    return _Dense.apply(x2, W, float(alpha), False).reshape(*x.shape[:-1], N)

@@ -111,6 +111,25 @@ def test_gate_and_pooling_second_order(dtype):
         assert rel(a, b) < TOL[dtype], name
 
 
+@pytest.mark.parametrize("M,K,N", [(1500, 64, 1920), (700, 1920, 64), (333, 8, 64), (900, 1024, 256)])
+def test_dense_node_second_order(M, K, N):
+    """ops.dense (tcgen05 3xTF32 node, backward made of the same node) against fp64 torch.matmul, twice differentiated"""
+    g = torch.Generator().manual_seed(M + K + N)
+    x = torch.randn(M, K, generator=g)
+    Wflat = torch.randn(K * N + 7, generator=g)
+
+    def ref_fn(a, wf):
+        return 0.3 * torch.tanh(a @ wf[7:].reshape(K, N))         # a view of a flat parameter, as dense.Linear uses
+
+    def our_fn(a, wf):
+        return torch.tanh(ops.dense(a, wf[7:].reshape(K, N), 0.3))
+
+    ref = _second_order(lambda a, wf: torch.tanh(0.3 * (a @ wf[7:].reshape(K, N))), [x.double(), Wflat.double()], "cpu", 3)
+    out = _second_order(our_fn, [x, Wflat], DEV, 3)
+    for name, a, b in zip(["y", "gx", "gW", "ddx", "ddW", "ddgy"], out, ref):
+        assert rel(a, b) < 2e-5, name
+
+
 def _loss(energy, forces):
     we = torch.linspace(0.5, 1.5, energy.numel(), dtype=energy.dtype, device=energy.device).view_as(energy)
     wf = torch.linspace(-1.0, 2.0, forces.numel(), dtype=forces.dtype, device=forces.device).view_as(forces)

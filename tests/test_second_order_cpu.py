@@ -37,8 +37,21 @@ def _oracle_grads(meta, inputs, pre_edge):
     return float(loss), {n: p.grad.clone() for n, p in model.named_parameters() if p.grad is not None}
 
 
-def test_force_loss_parameter_gradients_fp64(monkeypatch):
+@pytest.mark.parametrize("dense_function", [False, True])
+def test_force_loss_parameter_gradients_fp64(monkeypatch, dense_function):
+    """dense_function: the dense maps as ops._Dense nodes (the tcgen05 path of the second-order mode) instead of
+    plain torch.matmul"""
     torch_emulation.patch_kernels(monkeypatch)
+    from e3b200 import ops
+    monkeypatch.setattr(ops, "FORCE_DENSE_FUNCTION", dense_function)
+    calls = {"n": 0}
+    if dense_function:
+        orig = ops.k_dense
+
+        def counted(*a, **k):
+            calls["n"] += 1
+            return orig(*a, **k)
+        monkeypatch.setattr(ops, "k_dense", counted)
     import e3_layers.data.compute_edge as ce
 
     meta = {"config": "config_energy_force", "seed": 3}
@@ -57,3 +70,4 @@ def test_force_loss_parameter_gradients_fp64(monkeypatch):
     for n in ref:
         err = harness.rel_err(got[n], ref[n])
         assert err < 1e-9, (n, err)
+    assert (calls["n"] > 100) == dense_function

@@ -231,7 +231,11 @@ def k_gate_bwd2(desc, x, gout, ggin):
     return (gx if gx is not None else torch.zeros_like(x)), (gg if gg is not None else torch.zeros_like(gout))
 
 
-_KERNELS = ["k_edge_fwd", "k_edge_scatter", "k_sh_fwd", "k_sh_bwd", "k_radial_fwd", "k_radial_bwd", "k_tp_fwd", "k_tp_bwd",
+def k_dense(x, W, alpha, trans):
+    return alpha * (x @ (W.t() if trans else W))
+
+
+_KERNELS = ["k_dense", "k_edge_fwd", "k_edge_scatter", "k_sh_fwd", "k_sh_bwd", "k_radial_fwd", "k_radial_bwd", "k_tp_fwd", "k_tp_bwd",
             "k_segment_sum", "k_gate_fwd", "k_gate_bwd", "k_gate_bwd2"]
 
 
