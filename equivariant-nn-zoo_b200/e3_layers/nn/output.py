@@ -36,7 +36,7 @@ class GradientOutput(Module):
             else:
                 out = self.func(data)
             y = self.inputKeyMap(out)["y"]
-            with ops.positions_only():                       # this backward pass needs no parameter gradients
+            with ops.positions_only(wrt):                    # this backward pass needs no parameter gradients
                 (grad,) = torch.autograd.grad(y.sum(), wrt, create_graph=create_graph)
         wrt.requires_grad_(was)
         is_per = self.inputKeyMap(data.attrs)["x"][0]

@@ -163,10 +163,19 @@ class ScalarAttrTensorProduct(nn.Module):
         self.weight = nn.Parameter(torch.randn(off))
         self.register_buffer("output_mask", _mask(self.irreps_out, {o for _, _, o, _, _ in self.paths}))
         self._s1, self._s2 = self.irreps_in1.slices(), self.irreps_in2.slices()
+        self._spec = None
+        if len(self.irreps_in2) == 1:
+            self._spec = ops.SCSpec(self.irreps_in1, self.irreps_out, self.irreps_in2.dim,
+                                    [(i1, o, off, alpha) for i1, _, o, off, alpha in self.paths])
 
     def forward(self, x, attrs):
         """x mul_ir [z, in1.dim], attrs [z, in2.dim] -> mul_ir [z, out.dim]"""
         z = x.shape[0]
+        if (ops.second_order_active() and self._spec is not None and self._spec.ok and z > 0
+                and ((x.is_cuda and x.dtype == torch.float32) or ops.FORCE_DENSE_FUNCTION)):
+            # second-order mode: trilinear tcgen05 nodes on the channel-fastest layout, no (u, v) outer product
+            y = ops.self_connection(ops.layout(x, self.irreps_in1, True), attrs, self.weight, self._spec)
+            return ops.layout(y, self.irreps_out, False)
         acc = [None] * len(self.irreps_out)
         for i1, i2, o, off, alpha in self.paths:
             m1, m2, mo = self.irreps_in1[i1].mul, self.irreps_in2[i2].mul, self.irreps_out[o].mul

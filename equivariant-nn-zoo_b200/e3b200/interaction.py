@@ -118,19 +118,7 @@ class FusedInteraction:
         return out
 
 
-def _waves(problems_with_target):
-    """[(problem, target block id)] -> launches such that accumulating problems run after the first
-    writer of their block; sets .accumulate accordingly.  `written` blocks are tracked by the caller."""
-    waves = []
-    depth = {}
-    for g, tgt, pre_written in problems_with_target:
-        d = depth.get(tgt, 1 if pre_written else 0)
-        g.accumulate = 1 if d > 0 else 0
-        while len(waves) <= d:
-            waves.append([])
-        waves[d].append(g)
-        depth[tgt] = d + 1
-    return [w for w in waves if w]
+_waves = ops.gemm_waves
 
 
 class _Interaction(torch.autograd.Function):

@@ -34,24 +34,46 @@ def second_order_active():
 
 
 # Set by GradientOutput around its autograd.grad call: that backward pass differentiates with respect to the
-# positions alone, so dense Functions skip their weight gradients (reductions over all edges / nodes that the
-# engine would throw away; built-in torch ops prune them by themselves).
-_POSITIONS_ONLY = 0
+# positions alone, so dense Functions skip the gradients of arguments that do not depend on them (weight
+# gradients are reductions over all edges / nodes that the engine would throw away; built-in torch ops prune
+# such outputs by themselves, Python Functions have to ask).
+_POSITIONS_ONLY = []      # stack of (wrt tensor, memo of graph nodes known not to reach it)
 
 
 class positions_only:
+    def __init__(self, wrt):
+        self.wrt = wrt
+
     def __enter__(self):
-        global _POSITIONS_ONLY
-        _POSITIONS_ONLY += 1
+        _POSITIONS_ONLY.append((self.wrt, set()))
 
     def __exit__(self, *exc):
-        global _POSITIONS_ONLY
-        _POSITIONS_ONLY -= 1
+        _POSITIONS_ONLY.pop()
         return False
 
 
-def positions_only_active():
-    return _POSITIONS_ONLY > 0
+def needs_grad_now(t):
+    """False when the running backward pass differentiates with respect to one tensor only (GradientOutput's
+    position gradient) and `t` does not depend on it; True otherwise.  Walks t's autograd graph (memoised)."""
+    if not _POSITIONS_ONLY:
+        return True
+    wrt, dead = _POSITIONS_ONLY[-1]
+    if t is wrt:
+        return True
+    root = t.grad_fn
+    if root is None:
+        return False
+    stack, seen = [root], []
+    while stack:
+        fn = stack.pop()
+        if fn is None or fn in dead:
+            continue
+        if getattr(fn, "variable", None) is wrt:
+            return True
+        dead.add(fn)             # provisional; a positive answer returns before anyone relies on it
+        seen.append(fn)
+        stack.extend(nf for nf, _ in fn.next_functions)
+    return False
 
 
 # ------------------------------------------------------------------------------------------
@@ -864,7 +886,7 @@ class _Dense(torch.autograd.Function):
             N = gy.shape[1]
             gx = _Dense.apply(gy, W, ctx.alpha, not ctx.trans) if N % 4 == 0 else \
                 ctx.alpha * (gy @ (W if ctx.trans else W.t()))
-        if ctx.needs_input_grad[1] and not positions_only_active():
+        if ctx.needs_input_grad[1] and needs_grad_now(W):
             gW = ctx.alpha * (gy.t() @ x if ctx.trans else x.t() @ gy)
         return gx, gW, None, None
 
@@ -874,3 +896,152 @@ def dense(x, W, alpha):
     K, N = W.shape
     x2 = x.reshape(-1, K).contiguous()
     return _Dense.apply(x2, W, float(alpha), False).reshape(*x.shape[:-1], N)
+
+
+# ------------------------------------------------------------------------------------------
+def gemm_waves(problems_with_target):
+    """[(problem, target block id, block already written)] -> list of launches such that a problem accumulating into
+    a block runs after the first writer of that block; sets .accumulate accordingly."""
+    waves, depth = [], {}
+    for g, tgt, pre_written in problems_with_target:
+        d = depth.get(tgt, 1 if pre_written else 0)
+        g.accumulate = 1 if d > 0 else 0
+        while len(waves) <= d:
+            waves.append([])
+        waves[d].append(g)
+        depth[tgt] = d + 1
+    return [w for w in waves if w]
+
+
+class SCSpec:
+    """Static description of a self-connection (e3nn FullyConnectedTensorProduct with one block of scalar
+    attributes, nn/message_passing.py:81-87) for the trilinear nodes below; rows in the imu layout."""
+
+    def __init__(self, irreps_in, irreps_out, V, paths):
+        self.irreps_in, self.irreps_out, self.V = irreps_in, irreps_out, V
+        self.Vg = 16 if V <= 16 else 32
+        self.paths = paths                      # (i_in, i_out, weight offset, alpha)
+        self.x_off, self.Din = self._offsets(irreps_in)
+        self.c_off, self.Dout = self._offsets(irreps_out)
+        self.ok = (V <= 32 and all(b.mul % 4 == 0 for b in irreps_in) and all(b.mul % 4 == 0 for b in irreps_out))
+
+    @staticmethod
+    def _offsets(irreps):
+        out, o = [], 0
+        for b in irreps:
+            out.append(o)
+            o += b.dim
+        return out, o
+
+
+def k_sc(spec, src, attrs, W, to_out):
+    """to_out: y[z,d,w] = alpha sum_{u,v} W[u,v,w] src[z,d,u] a[z,v]   (src = features, rows of irreps_in)
+    else:     gx[z,d,u] = alpha sum_{v,w} W[u,v,w] src[z,d,w] a[z,v]  (src = output gradient, rows of irreps_out)
+    tcgen05 GEMMs with the attribute contraction in the epilogue; imu layouts."""
+    require_cuda(src, attrs, W)
+    N, V, Vg = src.shape[0], spec.V, spec.Vg
+    views = []
+    for i, o, off, alpha in spec.paths:
+        m1, mo = spec.irreps_in[i].mul, spec.irreps_out[o].mul
+        views.append((W, off, 1, mo, V * mo, Vg, V, mo * Vg, m1) if to_out else (W, off, V * mo, mo, 1, Vg, V, m1 * Vg, mo))
+    packs = gemm_pack(views)
+    D_src, D_dst = (spec.Din, spec.Dout) if to_out else (spec.Dout, spec.Din)
+    dst = torch.empty(N, D_dst, dtype=torch.float32, device=src.device)
+    probs, written = [], set()
+    for q, (i, o, off, alpha) in enumerate(spec.paths):
+        bi, bo = spec.irreps_in[i], spec.irreps_out[o]
+        d = bi.ir.dim
+        if to_out:
+            g = gemm_problem(src, packs[q], dst, N * d, a_off=spec.x_off[i], a_rows=(D_src, bi.mul, d), c_off=spec.c_off[o],
+                             c_rows=(D_dst, bo.mul, d), alpha=alpha, epilogue=1, aux=attrs, aux_d=d, aux_group=Vg)
+            tgt = o
+        else:
+            g = gemm_problem(src, packs[q], dst, N * d, a_off=spec.c_off[o], a_rows=(D_src, bo.mul, d), c_off=spec.x_off[i],
+                             c_rows=(D_dst, bi.mul, d), alpha=alpha, epilogue=1, aux=attrs, aux_d=d, aux_group=Vg)
+            tgt = i
+        probs.append((g, tgt, False))
+        written.add(tgt)
+    if len(written) < len(spec.irreps_out if to_out else spec.irreps_in):
+        dst.zero_()
+    for wave in gemm_waves(probs):
+        gemm_run(wave)
+    return dst
+
+
+def _sc_reductions(spec, x, a, W, g, want_a, want_W):
+    """d/da and d/dW of <g, S(x, a, W)> as plain torch contractions (differentiable again by torch):
+    t[z,u,w] = sum_d x[z,d,u] g[z,d,w] first (4x fewer flops than going through the (u,v) outer product)."""
+    N, V = x.shape[0], spec.V
+    ga = torch.zeros_like(a) if want_a else None
+    gW = [] if want_W else None
+    for i, o, off, alpha in spec.paths:
+        bi, bo = spec.irreps_in[i], spec.irreps_out[o]
+        xb = x[:, spec.x_off[i]:spec.x_off[i] + bi.dim].reshape(N, bi.ir.dim, bi.mul)
+        gb = g[:, spec.c_off[o]:spec.c_off[o] + bo.dim].reshape(N, bi.ir.dim, bo.mul)
+        t = torch.bmm(xb.transpose(1, 2), gb)                                  # [z, u, w]
+        if want_W:
+            gW.append((off, alpha * (a.t() @ t.reshape(N, -1)).reshape(V, bi.mul, bo.mul).transpose(0, 1).reshape(-1)))
+        if want_a:
+            Wp = W[off:off + bi.mul * V * bo.mul].reshape(bi.mul, V, bo.mul)
+            ga = ga + alpha * (t.reshape(N, -1) @ Wp.transpose(0, 1).reshape(V, -1).t())
+    if want_W:
+        flat = torch.zeros_like(W)
+        pieces = sorted(gW, key=lambda p: p[0])
+        # paths tile the flat weight without gaps (e3nn layout): one concatenation instead of slice assignments
+        if sum(p[1].numel() for p in pieces) == W.numel():
+            flat = torch.cat([p[1] for p in pieces])
+        else:
+            for off, piece in pieces:
+                flat = flat + torch.nn.functional.pad(piece, (off, W.numel() - off - piece.numel()))
+        gW = flat
+    return ga, gW
+
+
+class _SC(torch.autograd.Function):
+    """y = S(x, a, W) (to_out) or gx = Sx(g, a, W) (not to_out): the two row-parallel partial derivatives of the
+    quadrilinear form F(x, a, W, g) = <g, S(x, a, W)>; each one's backward is the other plus two reductions."""
+
+    @staticmethod
+    def forward(ctx, src, a, W, spec, to_out):
+        ctx.spec, ctx.to_out = spec, to_out
+        ctx.save_for_backward(src, a, W)
+        return k_sc(spec, src, a, W, to_out)
+
+    @staticmethod
+    def backward(ctx, h):
+        src, a, W = ctx.saved_tensors
+        spec = ctx.spec
+        h = h.contiguous()
+        g_src = _SC.apply(h, a, W, spec, not ctx.to_out) if ctx.needs_input_grad[0] else None
+        want_a = ctx.needs_input_grad[1] and needs_grad_now(a)
+        want_W = ctx.needs_input_grad[2] and needs_grad_now(W)
+        ga = gW = None
+        if want_a or want_W:
+            x, g = (src, h) if ctx.to_out else (h, src)
+            ga, gW = _sc_reductions(spec, x, a, W, g, want_a, want_W)
+        return g_src, ga, gW, None, None
+
+
+def self_connection(x_imu, attrs, W, spec):
+    return _SC.apply(x_imu.contiguous(), attrs.contiguous(), W.contiguous(), spec, True)
+
+
+class _Layout(torch.autograd.Function):
+    """mul_ir <-> imu conversion of feature rows as a node (a permutation: the adjoint is the inverse)"""
+
+    @staticmethod
+    def forward(ctx, x, irreps, to_imu):
+        ctx.irreps, ctx.to_imu = irreps, to_imu
+        return k_layout(x, irreps, to_imu)
+
+    @staticmethod
+    def backward(ctx, g):
+        return _Layout.apply(g.contiguous(), ctx.irreps, not ctx.to_imu), None, None
+
+
+def k_layout(x, irreps, to_imu):
+    return layout_convert(x, irreps, to_imu)
+
+
+def layout(x, irreps, to_imu):
+    return _Layout.apply(x.contiguous(), irreps, to_imu)

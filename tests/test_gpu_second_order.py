@@ -130,6 +130,41 @@ def test_dense_node_second_order(M, K, N):
         assert rel(a, b) < 2e-5, name
 
 
+def test_self_connection_nodes_second_order():
+    """ScalarAttrTensorProduct through the trilinear tcgen05 nodes (second-order mode) against its plain torch
+    formulation in fp64, differentiated twice with respect to features, attributes and weights"""
+    from e3b200 import dense
+    from e3b200.irreps import Irreps
+
+    irr_in, irr_out = Irreps("32x0e+32x0o+32x1e+32x1o+32x2e"), Irreps("32x0e+32x0o+96x0e+32x1e+32x1o+32x2e")
+    torch.manual_seed(0)
+    mod = dense.ScalarAttrTensorProduct(irr_in, Irreps("16x0e"), irr_out)
+    g = torch.Generator().manual_seed(1)
+    x = torch.randn(41, irr_in.dim, generator=g)
+    a = torch.randn(41, 16, generator=g)
+    W = mod.weight.detach().clone()
+
+    def run(xx, aa, ww, second):
+        saved = mod.weight
+        del mod._parameters["weight"]
+        mod.weight = ww                               # a plain tensor in the graph of the test's leaves
+        try:
+            if second:
+                with ops.second_order():
+                    return mod(xx, aa)
+            return mod(xx, aa)
+        finally:
+            del mod.weight
+            mod._parameters["weight"] = saved
+
+    ref = _second_order(lambda xx, aa, ww: run(xx, aa, ww, False), [x.double(), a.double(), W.double()], "cpu", 2)
+    mod.to(DEV)
+    out = _second_order(lambda xx, aa, ww: run(xx, aa, ww, True), [x, a, W], DEV, 2)
+    names = ["y", "gx", "ga", "gW", "ddx", "dda", "ddW", "ddgy"]
+    for name, p, q in zip(names, out, ref):
+        assert rel(p, q) < 2e-5, name
+
+
 def _loss(energy, forces):
     we = torch.linspace(0.5, 1.5, energy.numel(), dtype=energy.dtype, device=energy.device).view_as(energy)
     wf = torch.linspace(-1.0, 2.0, forces.numel(), dtype=forces.dtype, device=forces.device).view_as(forces)

@@ -52,6 +52,12 @@ def test_force_loss_parameter_gradients_fp64(monkeypatch, dense_function):
             calls["n"] += 1
             return orig(*a, **k)
         monkeypatch.setattr(ops, "k_dense", counted)
+        orig_sc = ops.k_sc
+
+        def counted_sc(*a, **k):
+            calls["sc"] = calls.get("sc", 0) + 1
+            return orig_sc(*a, **k)
+        monkeypatch.setattr(ops, "k_sc", counted_sc)
     import e3_layers.data.compute_edge as ce
 
     meta = {"config": "config_energy_force", "seed": 3}
@@ -71,3 +77,5 @@ def test_force_loss_parameter_gradients_fp64(monkeypatch, dense_function):
         err = harness.rel_err(got[n], ref[n])
         assert err < 1e-9, (n, err)
     assert (calls["n"] > 100) == dense_function
+    # self-connection: per block one forward node, one in the position gradient, two in the second backward
+    assert calls.get("sc", 0) == (4 * 5 - 2 if dense_function else 0), calls

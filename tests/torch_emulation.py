@@ -235,7 +235,28 @@ def k_dense(x, W, alpha, trans):
     return alpha * (x @ (W.t() if trans else W))
 
 
-_KERNELS = ["k_dense", "k_edge_fwd", "k_edge_scatter", "k_sh_fwd", "k_sh_bwd", "k_radial_fwd", "k_radial_bwd", "k_tp_fwd", "k_tp_bwd",
+def k_sc(spec, src, attrs, W, to_out):
+    N, V = src.shape[0], spec.V
+    dst = src.new_zeros(N, spec.Dout if to_out else spec.Din)
+    for i, o, off, alpha in spec.paths:
+        bi, bo = spec.irreps_in[i], spec.irreps_out[o]
+        d = bi.ir.dim
+        Wp = W[off:off + bi.mul * V * bo.mul].reshape(bi.mul, V, bo.mul)
+        if to_out:
+            xb = src[:, spec.x_off[i]:spec.x_off[i] + bi.dim].reshape(N, d, bi.mul)
+            dst[:, spec.c_off[o]:spec.c_off[o] + bo.dim] += alpha * torch.einsum("uvw,zdu,zv->zdw", Wp, xb, attrs).reshape(N, -1)
+        else:
+            gb = src[:, spec.c_off[o]:spec.c_off[o] + bo.dim].reshape(N, d, bo.mul)
+            dst[:, spec.x_off[i]:spec.x_off[i] + bi.dim] += alpha * torch.einsum("uvw,zdw,zv->zdu", Wp, gb, attrs).reshape(N, -1)
+    return dst
+
+
+def k_layout(x, irreps, to_imu):
+    from e3b200 import layout
+    return (layout.to_imu if to_imu else layout.from_imu)(x, irreps).contiguous()
+
+
+_KERNELS = ["k_sc", "k_layout", "k_dense", "k_edge_fwd", "k_edge_scatter", "k_sh_fwd", "k_sh_bwd", "k_radial_fwd", "k_radial_bwd", "k_tp_fwd", "k_tp_bwd",
             "k_segment_sum", "k_gate_fwd", "k_gate_bwd", "k_gate_bwd2"]
 
 
