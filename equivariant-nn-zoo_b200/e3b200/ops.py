@@ -969,31 +969,38 @@ def k_sc(spec, src, attrs, W, to_out):
 
 
 def _sc_reductions(spec, x, a, W, g, want_a, want_W):
-    """d/da and d/dW of <g, S(x, a, W)> as plain torch contractions (differentiable again by torch):
-    t[z,u,w] = sum_d x[z,d,u] g[z,d,w] first (4x fewer flops than going through the (u,v) outer product)."""
+    """d/da and d/dW of <g, S(x, a, W)>:  t[z,u,w] = sum_d x[z,d,u] g[z,d,w] per path first (4x fewer flops than
+    going through the (u,v) outer product), then ONE skinny GEMM over all paths for each of the two results
+    (a^T T and T Wcat): they are bound by reading T once instead of once per path.  Plain torch contractions,
+    so the graph of these gradients can be differentiated again by torch."""
     N, V = x.shape[0], spec.V
-    ga = torch.zeros_like(a) if want_a else None
-    gW = [] if want_W else None
+    ts, wcols, metas = [], [], []
     for i, o, off, alpha in spec.paths:
         bi, bo = spec.irreps_in[i], spec.irreps_out[o]
         xb = x[:, spec.x_off[i]:spec.x_off[i] + bi.dim].reshape(N, bi.ir.dim, bi.mul)
         gb = g[:, spec.c_off[o]:spec.c_off[o] + bo.dim].reshape(N, bi.ir.dim, bo.mul)
-        t = torch.bmm(xb.transpose(1, 2), gb)                                  # [z, u, w]
-        if want_W:
-            gW.append((off, alpha * (a.t() @ t.reshape(N, -1)).reshape(V, bi.mul, bo.mul).transpose(0, 1).reshape(-1)))
+        ts.append(torch.bmm(xb.transpose(1, 2), gb).reshape(N, bi.mul * bo.mul))     # [z, (u, w)]
+        metas.append((off, alpha, bi.mul, bo.mul))
         if want_a:
             Wp = W[off:off + bi.mul * V * bo.mul].reshape(bi.mul, V, bo.mul)
-            ga = ga + alpha * (t.reshape(N, -1) @ Wp.transpose(0, 1).reshape(V, -1).t())
+            wcols.append(alpha * Wp.transpose(0, 1).reshape(V, -1))                  # [v, (u, w)]
+    T = torch.cat(ts, dim=1)                                                          # [z, sum_p m1 mo]
+    ga = T @ torch.cat(wcols, dim=1).t() if want_a else None
+    gW = None
     if want_W:
-        flat = torch.zeros_like(W)
-        pieces = sorted(gW, key=lambda p: p[0])
-        # paths tile the flat weight without gaps (e3nn layout): one concatenation instead of slice assignments
-        if sum(p[1].numel() for p in pieces) == W.numel():
-            flat = torch.cat([p[1] for p in pieces])
+        full = a.t() @ T                                                              # [v, sum_p m1 mo]
+        pieces, c0 = [], 0
+        for off, alpha, m1, mo in metas:
+            blk = full[:, c0:c0 + m1 * mo].reshape(V, m1, mo).transpose(0, 1).reshape(-1)   # -> [u, v, w]
+            pieces.append((off, alpha * blk))
+            c0 += m1 * mo
+        pieces.sort(key=lambda p: p[0])
+        if sum(p[1].numel() for p in pieces) == W.numel():       # e3nn layout: the paths tile the flat weight
+            gW = torch.cat([p[1] for p in pieces])
         else:
+            gW = torch.zeros_like(W)
             for off, piece in pieces:
-                flat = flat + torch.nn.functional.pad(piece, (off, W.numel() - off - piece.numel()))
-        gW = flat
+                gW = gW + torch.nn.functional.pad(piece, (off, W.numel() - off - piece.numel()))
     return ga, gW
 
 
