@@ -129,3 +129,27 @@ def test_graphed_evaluator_matches_eager():
     got = ev({k: t.to(DEV) for k, t in other.items()})
     eager = product_harness.run_product(model, other, torch.float32, DEV, pre_edge={"r_max": 5.0})
     assert harness.rel_err(got["forces"], eager["forces"]) < 1e-5 and ev.misses == 2
+
+
+def test_ragged_batch_with_isolated_atoms():
+    """single-atom molecules (no edges at all) and a far-apart pair inside an ordinary batch: empty CSR segments
+    through every kernel, fp32 product vs fp64 oracle, forces of isolated atoms exactly zero"""
+    meta = {"config": "config_energy_force", "seed": 6}
+    inputs = synthetic.qm9_like(7, seed=8, n_min=1, n_max=9)
+    n = inputs["_n_nodes"].reshape(-1).clone()
+    n[0], n[3] = 1, 1                                     # force two single-atom graphs (re-partition the same atoms)
+    n[-1] = inputs["pos"].shape[0] - int(n[:-1].sum())
+    assert int(n[-1]) >= 1
+    inputs["_n_nodes"] = n.view(-1, 1)
+    inputs["pos"][int(n[0])] += 40.0                      # an atom of graph 1 far away from everything: no edges either
+    oracle = harness.build_oracle(meta, torch.float64)
+    ref = harness.run_oracle(oracle, inputs, torch.float64, pre_edge={"r_max": 5.0})
+    model = product_harness.build_product(meta, torch.float32, DEV)
+    out = product_harness.run_product(model, inputs, torch.float32, DEV, pre_edge={"r_max": 5.0})
+    assert torch.equal(out["edge_index"].cpu(), ref["edge_index"])
+    assert harness.rel_err(out["energy"], ref["energy"]) < 1e-5
+    assert harness.rel_err(out["forces"], ref["forces"]) < 1e-5
+    assert float(out["forces"][0].abs().max()) == 0.0 and float(out["forces"][int(n[0])].abs().max()) == 0.0
+    # the same batch through the second-order (training) mode
+    tr = product_harness.run_product(model.train(), inputs, torch.float32, DEV, pre_edge={"r_max": 5.0})
+    assert harness.rel_err(tr["forces"], ref["forces"]) < 1e-5

@@ -76,3 +76,32 @@ def test_csr_of_arbitrary_edge_list():
     for n in range(N):
         seg = in_eid[in_ptr[n]:in_ptr[n + 1]]
         assert torch.equal(seg, seg.sort().values)
+
+
+def test_criteria_edges_bit_exact_vs_oracle():
+    """computeEdgeIndex(criteria=...) (compute_edge.py:73-75; config_diffusion_CA.py:58-64 without its random part):
+    radius edges OR same-chain |i - j| < 5 OR a seeded mask, self loops removed, reference order, _n_edges"""
+    from e3_layers.data import computeEdgeIndex
+
+    p = synthetic.protein_like(700, seed=3)
+    two = {k: torch.cat([p[k], p[k]]) for k in ("CA", "chain_id")}            # two graphs in one batch
+    two["chain_id"][700:] += 10
+    n_nodes = torch.tensor([[700], [700]])
+    mask_seed = torch.Generator().manual_seed(5)
+    extra = torch.rand(2 * 700 * 700, generator=mask_seed) < 0.01                  # one entry per candidate pair
+
+    def criteria(data, edge_index):
+        src, dst = edge_index[0], edge_index[1]
+        chain = data["chain_id"].view(-1)
+        keep = (chain[src] == chain[dst]) & ((src - dst).abs() < 5)
+        return keep | extra.to(src.device)
+
+    ref_data = {"CA": two["CA"], "chain_id": two["chain_id"], "_n_nodes": n_nodes}
+    d, _ = ref_layers.computeEdgeIndex(ref_data, {}, r_max=8.0 / 25.83, key="CA", criteria=criteria)
+    data = {"CA": two["CA"].to(DEV), "chain_id": two["chain_id"].to(DEV), "_n_nodes": n_nodes.to(DEV)}
+    out, attrs = computeEdgeIndex(data, {}, r_max=8.0 / 25.83, key="CA", criteria=criteria)
+    assert torch.equal(out["edge_index"].cpu(), d["edge_index"])                   # same set, same order
+    assert torch.equal(data["_n_edges"].cpu(), ref_data["_n_edges"])
+    assert attrs["_n_edges"] == ("graph", "1x0e")
+    csr = ops.graph_of(out["edge_index"], 1400)
+    _check_csr(out["edge_index"], csr, 1400)
