@@ -69,8 +69,9 @@ def needs_grad_now(t):
         if fn is None or fn in dead:
             continue
         if getattr(fn, "variable", None) is wrt:
+            dead.difference_update(seen)      # nodes visited on the way may well reach it: forget them again
             return True
-        dead.add(fn)             # provisional; a positive answer returns before anyone relies on it
+        dead.add(fn)
         seen.append(fn)
         stack.extend(nf for nf, _ in fn.next_functions)
     return False

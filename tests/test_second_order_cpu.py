@@ -79,3 +79,23 @@ def test_force_loss_parameter_gradients_fp64(monkeypatch, dense_function):
     assert (calls["n"] > 100) == dense_function
     # self-connection: per block one forward node, one in the position gradient, two in the second backward
     assert calls.get("sc", 0) == (4 * 5 - 2 if dense_function else 0), calls
+
+
+def test_needs_grad_now_memo_is_sound():
+    """ops.needs_grad_now: the memo of 'does not reach the positions' nodes must not swallow nodes seen on the way
+    to a positive answer"""
+    from e3b200 import ops
+
+    pos = torch.randn(4, 3, requires_grad=True)
+    w = torch.randn(3, requires_grad=True)
+    shared = pos * 2.0                      # reaches pos
+    other = w * 3.0                         # does not
+    mixed = other.sum() + shared            # DFS may visit `other`'s branch first or last
+    assert ops.needs_grad_now(other)        # outside the context everything is needed
+    with ops.positions_only(pos):
+        assert not ops.needs_grad_now(other)
+        assert ops.needs_grad_now(mixed)
+        assert ops.needs_grad_now(shared)   # was visited during the positive walk above: must still be positive
+        assert ops.needs_grad_now(mixed * 1.0)
+        assert not ops.needs_grad_now(w) and ops.needs_grad_now(pos)
+        assert not ops.needs_grad_now(torch.zeros(2))
