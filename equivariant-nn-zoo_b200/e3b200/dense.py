@@ -71,6 +71,7 @@ class Linear(nn.Module):
             self.register_buffer("bias", torch.zeros(0))
         self.register_buffer("output_mask", _mask(self.irreps_out, {o for _, o, _, _ in self.paths} | set(self.bias_blocks)))
         self._in_slices, self._out_slices = self.irreps_in.slices(), self.irreps_out.slices()
+        self._spec = ops.SCSpec(self.irreps_in, self.irreps_out, 0, list(self.paths))
 
     def _block_in(self, x, i):
         """-> [z, d, mul] view/copy of input block i (contraction index last)"""
@@ -80,8 +81,26 @@ class Linear(nn.Module):
             return blk.reshape(-1, b.ir.dim, b.mul)
         return blk.reshape(-1, b.mul, b.ir.dim).transpose(1, 2)
 
+    def _forward_node(self, x):
+        """second-order mode: the whole map as ONE bilinear tcgen05 node (grouped launch over the irreps blocks)"""
+        xi = x if self.in_layout == "imu" else ops.layout(x, self.irreps_in, True)
+        y = ops.block_linear(xi, self.weight, self._spec)
+        if self.bias_blocks:
+            cols, boff = [], 0
+            for o, blk in enumerate(self.irreps_out):
+                if o in self.bias_blocks:
+                    cols.append(self.bias[boff:boff + blk.mul])
+                    boff += blk.mul
+                else:
+                    cols.append(y.new_zeros(blk.dim))
+            y = y + torch.cat(cols)                      # scalar blocks: imu and mul_ir coincide
+        return y if self.out_layout == "imu" else ops.layout(y, self.irreps_out, False)
+
     def forward(self, x):
         z = x.shape[0]
+        if (ops.second_order_active() and self.paths and self._spec.ok and z > 0
+                and ((x.is_cuda and x.dtype == torch.float32) or ops.FORCE_DENSE_FUNCTION)):
+            return self._forward_node(x)
         acc = [None] * len(self.irreps_out)
         for i, o, off, alpha in self.paths:
             mi, mo = self.irreps_in[i].mul, self.irreps_out[o].mul

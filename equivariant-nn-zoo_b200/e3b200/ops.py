@@ -915,12 +915,14 @@ def gemm_waves(problems_with_target):
 
 
 class SCSpec:
-    """Static description of a self-connection (e3nn FullyConnectedTensorProduct with one block of scalar
-    attributes, nn/message_passing.py:81-87) for the trilinear nodes below; rows in the imu layout."""
+    """Static description of a block-wise dense map between irreps for the multilinear nodes below; rows in the
+    imu layout.  V > 0: self-connection (e3nn FullyConnectedTensorProduct with one block of V scalar attributes,
+    nn/message_passing.py:81-87), weight blocks [u, v, w].  V == 0: per-irrep linear map (e3nn o3.Linear,
+    nn/message_passing.py:58-63, nn/pointwise.py:87-92), weight blocks [u, w], no attributes."""
 
     def __init__(self, irreps_in, irreps_out, V, paths):
         self.irreps_in, self.irreps_out, self.V = irreps_in, irreps_out, V
-        self.Vg = 16 if V <= 16 else 32
+        self.Vg = 0 if V == 0 else (16 if V <= 16 else 32)
         self.paths = paths                      # (i_in, i_out, weight offset, alpha)
         self.x_off, self.Din = self._offsets(irreps_in)
         self.c_off, self.Dout = self._offsets(irreps_out)
@@ -938,27 +940,34 @@ class SCSpec:
 def k_sc(spec, src, attrs, W, to_out):
     """to_out: y[z,d,w] = alpha sum_{u,v} W[u,v,w] src[z,d,u] a[z,v]   (src = features, rows of irreps_in)
     else:     gx[z,d,u] = alpha sum_{v,w} W[u,v,w] src[z,d,w] a[z,v]  (src = output gradient, rows of irreps_out)
-    tcgen05 GEMMs with the attribute contraction in the epilogue; imu layouts."""
+    (without the v index and `a` when spec.V == 0).  Grouped tcgen05 GEMMs, one problem per irreps block pair,
+    the attribute contraction in the epilogue; imu layouts."""
     require_cuda(src, attrs, W)
     N, V, Vg = src.shape[0], spec.V, spec.Vg
     views = []
     for i, o, off, alpha in spec.paths:
         m1, mo = spec.irreps_in[i].mul, spec.irreps_out[o].mul
-        views.append((W, off, 1, mo, V * mo, Vg, V, mo * Vg, m1) if to_out else (W, off, V * mo, mo, 1, Vg, V, m1 * Vg, mo))
+        if V:
+            views.append((W, off, 1, mo, V * mo, Vg, V, mo * Vg, m1) if to_out else (W, off, V * mo, mo, 1, Vg, V, m1 * Vg, mo))
+        else:
+            views.append((W, off, 1, 0, mo, 1, 0, mo, m1) if to_out else (W, off, mo, 0, 1, 1, 0, m1, mo))
     packs = gemm_pack(views)
     D_src, D_dst = (spec.Din, spec.Dout) if to_out else (spec.Dout, spec.Din)
     dst = torch.empty(N, D_dst, dtype=torch.float32, device=src.device)
+    extra = dict(epilogue=1, aux=attrs, aux_group=Vg) if V else {}
     probs, written = [], set()
     for q, (i, o, off, alpha) in enumerate(spec.paths):
         bi, bo = spec.irreps_in[i], spec.irreps_out[o]
         d = bi.ir.dim
+        if V:
+            extra["aux_d"] = d
         if to_out:
             g = gemm_problem(src, packs[q], dst, N * d, a_off=spec.x_off[i], a_rows=(D_src, bi.mul, d), c_off=spec.c_off[o],
-                             c_rows=(D_dst, bo.mul, d), alpha=alpha, epilogue=1, aux=attrs, aux_d=d, aux_group=Vg)
+                             c_rows=(D_dst, bo.mul, d), alpha=alpha, **extra)
             tgt = o
         else:
             g = gemm_problem(src, packs[q], dst, N * d, a_off=spec.c_off[o], a_rows=(D_src, bo.mul, d), c_off=spec.x_off[i],
-                             c_rows=(D_dst, bi.mul, d), alpha=alpha, epilogue=1, aux=attrs, aux_d=d, aux_group=Vg)
+                             c_rows=(D_dst, bi.mul, d), alpha=alpha, **extra)
             tgt = i
         probs.append((g, tgt, False))
         written.add(tgt)
@@ -975,6 +984,20 @@ def _sc_reductions(spec, x, a, W, g, want_a, want_W):
     (a^T T and T Wcat): they are bound by reading T once instead of once per path.  Plain torch contractions,
     so the graph of these gradients can be differentiated again by torch."""
     N, V = x.shape[0], spec.V
+    if V == 0:                      # plain linear map: dW[u, w] = alpha sum_{z,d} x[z,d,u] g[z,d,w] per block pair
+        pieces = []
+        for i, o, off, alpha in spec.paths:
+            bi, bo = spec.irreps_in[i], spec.irreps_out[o]
+            xb = x[:, spec.x_off[i]:spec.x_off[i] + bi.dim].reshape(-1, bi.mul)
+            gb = g[:, spec.c_off[o]:spec.c_off[o] + bo.dim].reshape(-1, bo.mul)
+            pieces.append((off, (alpha * (xb.t() @ gb)).reshape(-1)))
+        pieces.sort(key=lambda p: p[0])
+        if sum(p[1].numel() for p in pieces) == W.numel():
+            return None, torch.cat([p[1] for p in pieces])
+        gW = torch.zeros_like(W)
+        for off, piece in pieces:
+            gW = gW + torch.nn.functional.pad(piece, (off, W.numel() - off - piece.numel()))
+        return None, gW
     ts, wcols, metas = [], [], []
     for i, o, off, alpha in spec.paths:
         bi, bo = spec.irreps_in[i], spec.irreps_out[o]
@@ -1021,7 +1044,7 @@ class _SC(torch.autograd.Function):
         spec = ctx.spec
         h = h.contiguous()
         g_src = _SC.apply(h, a, W, spec, not ctx.to_out) if ctx.needs_input_grad[0] else None
-        want_a = ctx.needs_input_grad[1] and needs_grad_now(a)
+        want_a = a is not None and ctx.needs_input_grad[1] and needs_grad_now(a)
         want_W = ctx.needs_input_grad[2] and needs_grad_now(W)
         ga = gW = None
         if want_a or want_W:
@@ -1032,6 +1055,11 @@ class _SC(torch.autograd.Function):
 
 def self_connection(x_imu, attrs, W, spec):
     return _SC.apply(x_imu.contiguous(), attrs.contiguous(), W.contiguous(), spec, True)
+
+
+def block_linear(x_imu, W, spec):
+    """per-irrep linear map (spec.V == 0) as one bilinear node: imu rows in, imu rows out"""
+    return _SC.apply(x_imu.contiguous(), None, W.contiguous(), spec, True)
 
 
 class _Layout(torch.autograd.Function):

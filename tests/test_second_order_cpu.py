@@ -76,9 +76,9 @@ def test_force_loss_parameter_gradients_fp64(monkeypatch, dense_function):
     for n in ref:
         err = harness.rel_err(got[n], ref[n])
         assert err < 1e-9, (n, err)
-    assert (calls["n"] > 100) == dense_function
-    # self-connection: per block one forward node, one in the position gradient, two in the second backward
-    assert calls.get("sc", 0) == (4 * 5 - 2 if dense_function else 0), calls
+    # the dense maps really went through the nodes: radial MLP / heads via k_dense, self-connection and the per-irrep
+    # linear maps via k_sc (forward, position gradient and second backward of each)
+    assert (calls["n"] > 50) == dense_function and (calls.get("sc", 0) > 50) == dense_function, calls
 
 
 def test_needs_grad_now_memo_is_sound():

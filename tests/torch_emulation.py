@@ -241,13 +241,17 @@ def k_sc(spec, src, attrs, W, to_out):
     for i, o, off, alpha in spec.paths:
         bi, bo = spec.irreps_in[i], spec.irreps_out[o]
         d = bi.ir.dim
-        Wp = W[off:off + bi.mul * V * bo.mul].reshape(bi.mul, V, bo.mul)
+        if V:
+            Wp = W[off:off + bi.mul * V * bo.mul].reshape(bi.mul, V, bo.mul)
+            Weff = torch.einsum("uvw,zv->zuw", Wp, attrs)
+        else:
+            Weff = W[off:off + bi.mul * bo.mul].reshape(1, bi.mul, bo.mul).expand(N, -1, -1)
         if to_out:
             xb = src[:, spec.x_off[i]:spec.x_off[i] + bi.dim].reshape(N, d, bi.mul)
-            dst[:, spec.c_off[o]:spec.c_off[o] + bo.dim] += alpha * torch.einsum("uvw,zdu,zv->zdw", Wp, xb, attrs).reshape(N, -1)
+            dst[:, spec.c_off[o]:spec.c_off[o] + bo.dim] += alpha * torch.einsum("zuw,zdu->zdw", Weff, xb).reshape(N, -1)
         else:
             gb = src[:, spec.c_off[o]:spec.c_off[o] + bo.dim].reshape(N, d, bo.mul)
-            dst[:, spec.x_off[i]:spec.x_off[i] + bi.dim] += alpha * torch.einsum("uvw,zdw,zv->zdu", Wp, gb, attrs).reshape(N, -1)
+            dst[:, spec.x_off[i]:spec.x_off[i] + bi.dim] += alpha * torch.einsum("zuw,zdw->zdu", Weff, gb).reshape(N, -1)
     return dst
 
 
