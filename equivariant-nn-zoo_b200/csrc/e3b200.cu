@@ -1202,60 +1202,3 @@ extern "C" int e3b_layernorm_bwd(int dtype, const void* x, const void* gy, const
                             L, (const T*)x, (const T*)gy, (const T*)rinv, (const T*)std_w, n, (T*)gx, (T*)gstd_partial);)
   return check_launch("layernorm_bwd");
 }
-
-// ------------------------------------------------------------------------------------------
-// Skinny reduction over rows: out[s][v][c] = sum_{z in split s} a[z][v] * t[z][c]   (a [n, V], V <= 32; t [n, C])
-// The weight gradient of the self-connection (nn/message_passing.py:81-87) is a^T T with T the [n, sum m1*mo]
-// per-node contraction of features and output gradients: a GEMM with a 16-row output and K = all nodes, which the
-// library GEMMs run at a few TFLOP/s.  It is bound by reading T once: a thread owns one column c (coalesced
-// loads across the warp), keeps its V partial sums in registers and reads the attribute row as a broadcast.
-// The row range is split over blockIdx.y; the caller sums the `splits` partial results.
-template <typename T, int V>
-__global__ void __launch_bounds__(128) skinny_atb_kernel(const T* __restrict__ a, const T* __restrict__ t, int64_t n,
-                                                         int64_t C, int v_actual, T* __restrict__ out) {
-  const int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  const int64_t per = (n + gridDim.y - 1) / gridDim.y;
-  const int64_t z0 = (int64_t)blockIdx.y * per, z1 = z0 + per < n ? z0 + per : n;
-  if (c >= C) return;
-  T acc[V];
-#pragma unroll
-  for (int v = 0; v < V; ++v) acc[v] = T(0);
-  int64_t z = z0;
-  for (; z + 4 <= z1; z += 4) {            // four independent loads in flight per thread
-    T tv[4];
-#pragma unroll
-    for (int j = 0; j < 4; ++j) tv[j] = t[(z + j) * C + c];
-#pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      const T* __restrict__ ar = a + (z + j) * v_actual;
-#pragma unroll
-      for (int v = 0; v < V; ++v)
-        if (v < v_actual) acc[v] = fma_(ldg(ar + v), tv[j], acc[v]);
-    }
-  }
-  for (; z < z1; ++z) {
-    const T tv = t[z * C + c];
-    const T* __restrict__ ar = a + z * v_actual;
-#pragma unroll
-    for (int v = 0; v < V; ++v)
-      if (v < v_actual) acc[v] = fma_(ldg(ar + v), tv, acc[v]);
-  }
-  T* __restrict__ o = out + (int64_t)blockIdx.y * v_actual * C + c;
-#pragma unroll
-  for (int v = 0; v < V; ++v)
-    if (v < v_actual) o[(int64_t)v * C] = acc[v];
-}
-
-extern "C" int e3b_skinny_atb(int dtype, const void* a, const void* t, int64_t n, int32_t V, int64_t C, int32_t splits,
-                              void* out, void* stream) {
-  if (V <= 0 || V > 32 || splits <= 0 || splits > 65535) return fail(E3B_ERR_INVALID, "skinny_atb: V in 1..32, splits in 1..65535");
-  if (C == 0) return E3B_OK;
-  if (!a || !t || !out) return fail(E3B_ERR_INVALID, "skinny_atb: null argument");
-  const dim3 grid(blocks_for(C, 128), (unsigned)splits);
-  if (V <= 16) {
-    DISPATCH_DTYPE(dtype, skinny_atb_kernel<T, 16><<<grid, 128, 0, (cudaStream_t)stream>>>((const T*)a, (const T*)t, n, C, V, (T*)out);)
-  } else {
-    DISPATCH_DTYPE(dtype, skinny_atb_kernel<T, 32><<<grid, 128, 0, (cudaStream_t)stream>>>((const T*)a, (const T*)t, n, C, V, (T*)out);)
-  }
-  return check_launch("skinny_atb");
-}

@@ -288,13 +288,6 @@ E3B_API int e3b_layernorm_bwd(int dtype, const void* x, const void* gy, const vo
                               const int32_t* h_mul, const int32_t* h_l, const void* std_w, void* g_x,
                               void* g_std_partial, void* stream);
 
-/* Skinny reduction over rows: out[s][v][c] = sum over the rows z of split s of a[z][v] * t[z][c]
- * (a [n, V] with V <= 32, t [n, C], out [splits, V, C]; the caller sums the splits).  Replaces the weight
- * gradient GEMM of the self-connection (autograd of e3nn FullyConnectedTensorProduct,
- * nn/message_passing.py:81-87,116-117): 16 output rows, K = all nodes.                                     */
-E3B_API int e3b_skinny_atb(int dtype, const void* a, const void* t, int64_t n, int32_t V, int64_t C, int32_t splits,
-                           void* out, void* stream);
-
 /* mul_ir <-> imu layout conversion of feature rows (blocks: mul, l). to_imu = 1: [u][m]->[m][u] */
 E3B_API int e3b_layout_convert(int dtype, const void* in, int64_t n, int32_t n_blocks, const int32_t* mul,
                        const int32_t* l, int to_imu, void* out, void* stream);

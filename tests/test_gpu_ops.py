@@ -218,13 +218,3 @@ def test_layer_normalization_kernel(dtype):
     with ops.second_order():                                    # the closed form used in second-order mode agrees
         y2 = mod({"input": xd}, {})[0]["output"]
     assert rel(y2, yr) < TOL[dtype]
-
-
-@pytest.mark.parametrize("dtype", [torch.float32, torch.float64])
-@pytest.mark.parametrize("n,V,C", [(8337, 16, 4100), (70, 16, 130), (1000, 32, 257), (5, 3, 8)])
-def test_skinny_reduction_kernel(dtype, n, V, C):
-    g = torch.Generator().manual_seed(n + V + C)
-    a = torch.randn(n, V, generator=g, dtype=torch.float64).to(dtype)
-    t = torch.randn(n, C, generator=g, dtype=torch.float64).to(dtype)
-    got = ops.k_skinny_atb(a.to(DEV), t.to(DEV))
-    assert rel(got, a.double().t() @ t.double()) < TOL[dtype] * 5

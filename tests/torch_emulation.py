@@ -260,11 +260,7 @@ def k_layout(x, irreps, to_imu):
     return (layout.to_imu if to_imu else layout.from_imu)(x, irreps).contiguous()
 
 
-def k_skinny_atb(a, t):
-    return a.t() @ t
-
-
-_KERNELS = ["k_skinny_atb", "k_sc", "k_layout", "k_dense", "k_edge_fwd", "k_edge_scatter", "k_sh_fwd", "k_sh_bwd", "k_radial_fwd", "k_radial_bwd", "k_tp_fwd", "k_tp_bwd",
+_KERNELS = ["k_sc", "k_layout", "k_dense", "k_edge_fwd", "k_edge_scatter", "k_sh_fwd", "k_sh_bwd", "k_radial_fwd", "k_radial_bwd", "k_tp_fwd", "k_tp_bwd",
             "k_segment_sum", "k_gate_fwd", "k_gate_bwd", "k_gate_bwd2"]
 
 
