@@ -158,8 +158,9 @@ class ExponentialMovingAverage:
 
 
 def get_step_fn(sde, train, optimizer=None, reduce_mean=False, continuous=True, likelihood_weighting=False,
-                grad_clid_norm=None, grad_acc=1):
-    """one training / evaluation step over ``state = {model, optimizer, ema, step}`` (sde_utils.py:204-257)"""
+                grad_clid_norm=None, grad_acc=1, grad_sync=None):
+    """one training / evaluation step over ``state = {model, optimizer, ema, step}`` (sde_utils.py:204-257).
+    ``grad_sync``: called after the backward pass (the flat gradient all-reduce that stands in for the reference's DDP)"""
     loss_fn = get_sde_loss_fn(sde, train, reduce_mean=reduce_mean, continuous=True, likelihood_weighting=likelihood_weighting)
 
     def step_fn(state, batch):
@@ -168,6 +169,8 @@ def get_step_fn(sde, train, optimizer=None, reduce_mean=False, continuous=True, 
             opt = state["optimizer"]
             loss, losses = loss_fn(model, batch)
             loss.backward()
+            if grad_sync is not None:
+                grad_sync()
             if grad_clid_norm is not None:
                 torch.nn.utils.clip_grad_norm_(model.parameters(), max_norm=grad_clid_norm)
             if state["step"] != 0 and state["step"] % grad_acc == 0:

@@ -37,3 +37,17 @@ def test_train_energy_force(tmp_path):
     assert r.returncode == 0, r.stderr[-2000:]
     assert os.path.exists(os.path.join(wd, "f", "model.pt"))
     assert "step 2 loss" in r.stderr
+
+
+def test_train_diffusion_score_matching(tmp_path):
+    """reference train.py:70-215 (train_diffusion) on synthetic W4 molecules: VP-SDE loss, EMA, checkpoint"""
+    wd = str(tmp_path)
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "train.py"), "--config", "config_diffusion", "--steps", "4",
+                        "--workdir", wd, "--name", "d", "--log_period", "1"], capture_output=True, text=True, timeout=900)
+    assert r.returncode == 0, r.stderr[-2000:]
+    assert os.path.exists(os.path.join(wd, "d", "model.pt")) and "step 3 training_loss" in r.stderr
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "train.py"), "--config", "config_diffusion_CA", "--steps", "3",
+                        "--n_res", "150", "--workdir", wd, "--name", "p", "--log_period", "1"],
+                       capture_output=True, text=True, timeout=900)
+    assert r.returncode == 0, r.stderr[-2000:]
+    assert "step 2 training_loss" in r.stderr

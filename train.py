@@ -5,8 +5,8 @@ options, ``--config <name>`` picks a registered config, one process per GPU, ran
 In scope: regression on energies / dipoles (first-order parameter gradients through the fused
 interaction blocks) and energy+force matching (``config_energy_force``: the graph of the position
 gradient is built by the second-order mode of ``GradientOutput``), data-parallel over graphs with ONE
-flat gradient all-reduce per step.  Score-matching (diffusion) training needs the SDE machinery of
-``run/sde_utils.py`` and raises.
+flat gradient all-reduce per step, and score matching for the diffusion configs (``train_diffusion``: VP-SDE
+loss of ``e3_layers.run``, EMA, gradient clipping / accumulation).
 Data: ``--data synthetic`` (seeded QM9-shaped molecules with a synthetic per-species target; there is no
 network for datasets) or an ``.npz`` with ``pos, species, _n_nodes`` and the target key.
 
@@ -45,6 +45,15 @@ def parse():
     ap.add_argument("--steps", type=int, default=100, help="optimiser steps (the reference runs until early stopping)")
     ap.add_argument("--data", default="synthetic", help="'synthetic' or the path of an .npz dataset")
     ap.add_argument("--n_graphs", type=int, default=4096, help="size of the synthetic dataset")
+    # score-based configs: the reference reads these from a score_sde_pytorch config file (--sde_config, an external
+    # repository); the defaults below are that repository's configs/vp/cifar10_ncsnpp_continuous.py, which the
+    # reference's README uses
+    ap.add_argument("--sde_config", default=None, help="accepted for compatibility; the VP-SDE settings come from the flags below")
+    ap.add_argument("--beta_min", type=float, default=0.1)
+    ap.add_argument("--beta_max", type=float, default=20.0)
+    ap.add_argument("--num_scales", type=int, default=1000)
+    ap.add_argument("--ema_rate", type=float, default=0.9999)
+    ap.add_argument("--n_res", type=int, default=400, help="residues of the synthetic protein graphs (config_diffusion_CA)")
     return ap.parse_args()
 
 
@@ -107,9 +116,9 @@ def main(rank, flags):
     get = getattr(configs, flags.config, None)
     assert get is not None, f"Config {flags.config} not found."
     config = get(flags.config_spec) if flags.config_spec else get()
+    if "diffusion" in flags.config:
+        return train_diffusion(config, flags, rank, world, dev)
     loss_coeffs = dict(config.loss_coeffs.items()) if hasattr(config.loss_coeffs, "items") else dict(config.loss_coeffs)
-    if any(k.startswith("score") for k in loss_coeffs):
-        raise NotImplementedError("score-matching training needs the SDE loss of run/sde_utils.py (not on this path yet)")
     target_keys = list(loss_coeffs)
     setSeed(flags.seed)                                          # identical initial weights on every rank
     model = build(config.model_config).to(dev).train()
@@ -153,6 +162,59 @@ def main(rank, flags):
         opt.step()
         if rank == 0 and (step % flags.log_period == 0 or step == flags.steps - 1):
             logging.info("step %d loss %.6g mae %.6g (%.1f s)", step, float(scal[0]), float(scal[1]), time.time() - t0)
+        if rank == 0 and ((step + 1) % flags.save_period == 0 or step == flags.steps - 1):
+            os.makedirs(out_dir, exist_ok=True)
+            torch.save(model.state_dict(), os.path.join(out_dir, "model.pt"))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def train_diffusion(config, flags, rank, world, dev):
+    """Score-matching training (reference train.py:70-215 ``train_diffusion``): VP-SDE perturbation of the diffused
+    keys, continuous-time loss, gradient clipping / accumulation from the e3 config, EMA of the parameters, one flat
+    gradient all-reduce per step.  Synthetic data: W4 molecules (config_diffusion) or W5 C-alpha graphs."""
+    from e3_layers.data import Batch
+    from e3_layers.run import VPSDE, ExponentialMovingAverage, get_step_fn
+    from e3_layers.utils import build, setSeed
+    from e3b200 import parallel, synthetic
+
+    setSeed(flags.seed)
+    model = build(config.model_config).to(dev).train()
+    if flags.resume_from:
+        state = torch.load(flags.resume_from, map_location=dev)
+        model.load_state_dict({(k[7:] if k.startswith("module.") else k): v for k, v in state.items()})
+    parallel.broadcast_parameters(model)
+    keys = getattr(config, "diffusion_keys", None)
+    keys = dict(keys.items()) if keys is not None and hasattr(keys, "items") else {"pos": 3}
+    sde = VPSDE(keys, beta_min=flags.beta_min, beta_max=flags.beta_max, N=flags.num_scales)
+    opt = torch.optim.Adam(model.parameters(), lr=float(config.learning_rate))
+    flat = parallel.FlatGradients(model.parameters())
+    state = {"model": model, "optimizer": opt, "ema": ExponentialMovingAverage(model.parameters(), decay=flags.ema_rate), "step": 0}
+    clip = getattr(config, "grad_clid_norm", None)
+    step_fn = get_step_fn(sde, train=True, optimizer=opt, reduce_mean=True, grad_clid_norm=clip,
+                          grad_acc=int(getattr(config, "grad_acc", 1)), grad_sync=flat.all_reduce if world > 1 else None)
+    protein = "CA" in keys
+    attrs_of = {"pos": ("node", "1x1o"), "CA": ("node", "1x1o"), "species": ("node", "1x0e"), "chain_id": ("node", "1x0e"),
+                "id": ("node", "1x0e"), "t": ("graph", "1x0e"), "bond_type": ("edge", "1x0e"), "_n_nodes": ("graph", "1x0e"),
+                "_n_edges": ("graph", "1x0e")}
+    pool = []
+    for i in range(4):                                           # a small pool of synthetic batches, one shard per rank
+        seed = flags.seed + 100 * i + rank
+        b = synthetic.protein_like(flags.n_res, seed=seed) if protein else synthetic.diffusion_like(int(config.batch_size), seed=seed)
+        if protein:                                              # the model's first layer builds the neighbour list itself
+            b.pop("edge_index"), b.pop("_n_edges")
+        b.pop("t")
+        pool.append({k: v.to(dev) for k, v in b.items()})
+    out_dir = os.path.join(flags.workdir, flags.name)
+    t0, window = time.time(), []
+    for step in range(flags.steps):
+        b = pool[step % len(pool)]
+        batch = Batch({k: attrs_of[k] for k in b}, **{k: v.clone() for k, v in b.items()})
+        loss, losses = step_fn(state, batch)
+        window.append(loss)
+        if rank == 0 and (step % flags.log_period == 0 or step == flags.steps - 1):
+            logging.info("step %d training_loss %.5e (%.1f s)", step, sum(window) / len(window), time.time() - t0)
+            window = []
         if rank == 0 and ((step + 1) % flags.save_period == 0 or step == flags.steps - 1):
             os.makedirs(out_dir, exist_ok=True)
             torch.save(model.state_dict(), os.path.join(out_dir, "model.pt"))
