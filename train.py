@@ -209,7 +209,7 @@ def train_diffusion(config, flags, rank, world, dev):
     t0, window = time.time(), []
     for step in range(flags.steps):
         b = pool[step % len(pool)]
-        batch = Batch({k: attrs_of[k] for k in b}, **{k: v.clone() for k, v in b.items()})
+        batch = Batch({k: attrs_of[k] for k in b if k in attrs_of}, **{k: v.clone() for k, v in b.items()})
         loss, losses = step_fn(state, batch)
         window.append(loss)
         if rank == 0 and (step % flags.log_period == 0 or step == flags.steps - 1):
