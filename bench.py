@@ -134,12 +134,11 @@ def training_step_time(model, resident, attrs, Batch, computeEdgeIndex, n_atoms,
     """One optimiser step of config_energy_force on the same batch: neighbour list, forward, position gradient WITH
     its graph (second-order mode of GradientOutput), the reference's loss 1e3 MSE(E) + 3e4 MSE(F)
     (config_energy_force.py:30), backward to the parameters, flat-gradient all-reduce (N > 1), Adam."""
-    from e3b200 import parallel
+    from e3b200 import optim
 
     model.train()
-    opt = torch.optim.Adam(model.parameters(), lr=1e-4)
-    flat = parallel.FlatGradients(model.parameters())
     state = {k: v.detach().clone() for k, v in model.state_dict().items()}
+    opt = optim.FlatAdam(model, lr=1e-4)          # flat parameter / gradient buffers, fused Adam kernel
     g = torch.Generator().manual_seed(1)
     e_t = torch.randn(resident["_n_nodes"].shape[0], 1, generator=g).to(dev)
     f_t = (0.1 * torch.randn(n_atoms, 3, generator=g)).to(dev)
@@ -151,9 +150,9 @@ def training_step_time(model, resident, attrs, Batch, computeEdgeIndex, n_atoms,
         batch.attrs.update(a)
         out = model(Batch(batch.attrs, **batch.data))
         loss = 1e3 * ((out["energy"] - e_t) ** 2).mean() + 3e4 * ((out["forces"] - f_t) ** 2).mean()
-        opt.zero_grad(set_to_none=True)
+        opt.zero_grad()
         loss.backward()
-        flat.all_reduce()
+        opt.all_reduce()
         opt.step()
 
     for _ in range(warmup):

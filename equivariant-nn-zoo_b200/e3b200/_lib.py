@@ -80,6 +80,8 @@ SIGNATURES = {
     "e3b_layernorm_fwd": (c_int, [c_int, c_vp, c_i64, c_i32, c_vp, c_vp, c_vp, c_f64, c_vp, c_vp, c_vp]),
     "e3b_layernorm_bwd_blocks": (c_i64, [c_i64]),
     "e3b_layernorm_bwd": (c_int, [c_int, c_vp, c_vp, c_vp, c_i64, c_i32, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp]),
+    "e3b_adam_ema_step": (c_int, [c_vp, c_vp, c_vp, c_vp, c_vp, c_i64, c_f32, c_f32, c_f32, c_f32, c_f32, c_i64, c_f32, c_vp,
+                                  c_vp, c_vp]),
     "e3b_layout_convert": (c_int, [c_int, c_vp, c_i64, c_i32, c_vp, c_vp, c_int, c_vp, c_vp]),
 }
 

@@ -24,6 +24,10 @@ class GraphedEvaluator:
         self.cache, self.max_entries = {}, max_entries
         self.hits = self.misses = 0
 
+    def _weights_tag(self):
+        """a captured graph has the packed weights of its capture baked in: new parameter values -> new capture"""
+        return (ops.WEIGHTS_EPOCH, sum(p._version for p in self.model.parameters()))
+
     def _run(self, tensors, edge_index, n_edges):
         from e3_layers.data import Batch
 
@@ -38,7 +42,7 @@ class GraphedEvaluator:
         -> dict of output tensors (owned by the evaluator until the next call with the same shapes)"""
         pos = tensors["pos"]
         edge_index, n_edges, csr = ops.radius_graph(pos, tensors["_n_nodes"].reshape(-1), self.r_max)
-        key = (pos.shape[0], edge_index.shape[1], tensors["_n_nodes"].numel()) + tuple(sorted(tensors))
+        key = (pos.shape[0], edge_index.shape[1], tensors["_n_nodes"].numel(), self._weights_tag()) + tuple(sorted(tensors))
         e = self.cache.get(key)
         if e is None:
             self.misses += 1

@@ -80,7 +80,7 @@ class FusedInteraction:
 
     def packs(self, role):
         """role 'fwd' | 'bwd' -> dict of PackedWeight lists, repacked only when a parameter changed"""
-        key = tuple((p.data_ptr(), p._version) for p in self._params())
+        key = (ops.WEIGHTS_EPOCH,) + tuple((p.data_ptr(), p._version) for p in self._params())
         hit = self._cache.get(role)
         if hit is not None and hit[0] == key:
             return hit[1]

@@ -17,6 +17,10 @@ from ._lib import check, count_launch, dtype_code, ptr, require_cuda, stream
 # the single-node fused block (e3b200.interaction) is first order only.
 _SECOND_ORDER = 0
 
+# bumped whenever parameter memory is rewritten behind torch's version counters (e3b200.optim.FlatAdam): part of
+# the key of every cache of packed tensor-core weights
+WEIGHTS_EPOCH = 0
+
 
 class second_order:
     def __enter__(self):

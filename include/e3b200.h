@@ -288,6 +288,17 @@ E3B_API int e3b_layernorm_bwd(int dtype, const void* x, const void* gy, const vo
                               const int32_t* h_mul, const int32_t* h_l, const void* std_w, void* g_x,
                               void* g_std_partial, void* stream);
 
+/* ---------------------------------------------------------------------------------------
+ * Optimiser step on a flat fp32 parameter buffer: Adam (torch.optim.Adam semantics: the reference's optimiser,
+ * run/trainer.py:370-386, train.py:103-107) fused with the exponential moving average of the parameters
+ * (torch_ema as used in run/trainer.py and run/sde_utils.py:232-248; `ema` may be NULL).  `step` >= 1 is the
+ * number of this update (bias corrections).  grad_scale: optional DEVICE float multiplying the gradient
+ * (clipping coefficient); skip: optional DEVICE int, non-zero = leave everything untouched (non-finite
+ * gradients, run/sde_utils.py:240-246).                                                                     */
+E3B_API int e3b_adam_ema_step(void* param, const void* grad, void* exp_avg, void* exp_avg_sq, void* ema, int64_t n,
+                              float lr, float beta1, float beta2, float eps, float weight_decay, int64_t step,
+                              float ema_decay, const void* grad_scale, const void* skip, void* stream);
+
 /* mul_ir <-> imu layout conversion of feature rows (blocks: mul, l). to_imu = 1: [u][m]->[m][u] */
 E3B_API int e3b_layout_convert(int dtype, const void* in, int64_t n, int32_t n_blocks, const int32_t* mul,
                        const int32_t* l, int to_imu, void* out, void* stream);

@@ -69,3 +69,46 @@ def test_flat_gradient_allreduce_world2():
         exp = ((torch.tensor(a) + torch.tensor(b)) / 2).tolist()
         assert torch.allclose(torch.tensor(avg), torch.tensor(exp))
     assert s0 == s1 == [0.5, 10.0]
+
+
+def _worker_flat_adam(rank, world, port, q):
+    from e3b200 import optim
+
+    os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        torch.manual_seed(0)
+        lin = torch.nn.Linear(5, 3)
+        parallel.broadcast_parameters(lin)
+        opt = optim.FlatAdam(lin, lr=1e-2)                       # parameters and gradients become views of flat buffers
+        x = torch.full((4, 5), float(rank + 1))
+        opt.zero_grad()
+        lin(x).sum().backward()
+        aliased = all(p.grad.data_ptr() >= opt.grad.data_ptr() for p in lin.parameters())
+        local = opt.grad.clone()
+        opt.all_reduce()                                         # ONE collective on the buffer, no gather / scatter copies
+        loud = False
+        try:
+            opt.step()                                           # the fused kernel needs a CUDA device: no CPU fallback
+        except RuntimeError:
+            loud = True
+        q.put((rank, local.tolist(), opt.grad.tolist(), [p.grad.reshape(-1).tolist() for p in lin.parameters()], aliased, loud))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_flat_adam_buffers_allreduce_world2():
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29411 + os.getpid() % 200
+    procs = [ctx.Process(target=_worker_flat_adam, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = sorted(q.get(timeout=120) for _ in range(2))
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    (_, l0, g0, v0, a0, loud0), (_, l1, g1, v1, a1, loud1) = res
+    assert a0 and a1 and loud0 and loud1
+    assert g0 == g1 and torch.allclose(torch.tensor(g0), (torch.tensor(l0) + torch.tensor(l1)) / 2)
+    assert sum(v0, []) == g0                                     # the parameters' .grad ARE the buffer

@@ -27,7 +27,7 @@ def main():
     a = ap.parse_args()
     import product_harness
     from e3_layers.data import Batch, computeEdgeIndex
-    from e3b200 import _lib, parallel, synthetic
+    from e3b200 import _lib, optim, parallel, synthetic
 
     world, rank, local = (int(os.environ.get(k, d)) for k, d in (("WORLD_SIZE", 1), ("RANK", 0), ("LOCAL_RANK", 0)))
     torch.cuda.set_device(local)
@@ -36,8 +36,7 @@ def main():
         dist.init_process_group("nccl", device_id=dev)
     model = product_harness.build_product({"config": "config_energy_force", "seed": 0}, torch.float32, dev).train()
     parallel.broadcast_parameters(model)
-    opt = torch.optim.Adam(model.parameters(), lr=1e-3)
-    flat = parallel.FlatGradients(model.parameters(), n_scalars=1)
+    opt = optim.FlatAdam(model, lr=1e-3)
     host = synthetic.qm9_like(a.graphs, seed=rank)
     attrs = {"pos": ("node", "1x1o"), "species": ("node", "1x0e"), "_n_nodes": ("graph", "1x0e")}
     res = {k: v.to(dev) for k, v in host.items()}
@@ -53,9 +52,9 @@ def main():
         batch.attrs.update(at)
         out = model(Batch(batch.attrs, **batch.data))
         loss = 1e3 * ((out["energy"] - e_t) ** 2).mean() + 3e4 * ((out["forces"] - f_t) ** 2).mean()
-        opt.zero_grad(set_to_none=True)
+        opt.zero_grad()
         loss.backward()
-        flat.all_reduce([0.0])
+        opt.all_reduce()
         opt.step()
         return loss
 

@@ -97,7 +97,7 @@ def main(rank, flags):
     from e3_layers import configs
     from e3_layers.data import Batch, computeEdgeIndex
     from e3_layers.utils import build, setSeed
-    from e3b200 import parallel
+    from e3b200 import optim, parallel
 
     world = flags.world_size
     if "RANK" in os.environ:                                     # launched by torchrun
@@ -126,8 +126,10 @@ def main(rank, flags):
         state = torch.load(flags.resume_from, map_location=dev)
         model.load_state_dict({(k[7:] if k.startswith("module.") else k): v for k, v in state.items()})
     parallel.broadcast_parameters(model)
-    opt = torch.optim.Adam(model.parameters(), lr=float(config.learning_rate))
-    flat = parallel.FlatGradients(model.parameters(), n_scalars=2)
+    # flat parameter / gradient buffers: one all-reduce, one fused Adam + EMA kernel per step (e3b200.optim)
+    opt = optim.FlatAdam(model, lr=float(config.learning_rate),
+                         ema_decay=float(config.ema_decay) if getattr(config, "use_ema", False) else None,
+                         ema_use_num_updates=bool(getattr(config, "ema_use_num_updates", True)))
     r_max = float(config.model_config.r_max)
 
     data = load_data(flags, config, target_keys)
@@ -156,12 +158,17 @@ def main(rank, flags):
             diff = out[k] - targets[k]
             loss = loss + coeff * (diff.abs().mean() if kind == "L1Loss" else (diff ** 2).mean())
             mae = mae + diff.detach().abs().mean()
-        opt.zero_grad(set_to_none=True)
+        opt.zero_grad()
         loss.backward()
-        scal = flat.all_reduce([float(loss.detach()), float(mae)])
+        opt.all_reduce()
         opt.step()
-        if rank == 0 and (step % flags.log_period == 0 or step == flags.steps - 1):
-            logging.info("step %d loss %.6g mae %.6g (%.1f s)", step, float(scal[0]), float(scal[1]), time.time() - t0)
+        if step % flags.log_period == 0 or step == flags.steps - 1:
+            scal = torch.stack([loss.detach(), torch.as_tensor(mae, device=dev)])
+            if world > 1:                                        # logging scalars: averaged over the ranks on log steps only
+                dist.all_reduce(scal)
+                scal /= world
+            if rank == 0:
+                logging.info("step %d loss %.6g mae %.6g (%.1f s)", step, float(scal[0]), float(scal[1]), time.time() - t0)
         if rank == 0 and ((step + 1) % flags.save_period == 0 or step == flags.steps - 1):
             os.makedirs(out_dir, exist_ok=True)
             torch.save(model.state_dict(), os.path.join(out_dir, "model.pt"))
