@@ -193,9 +193,9 @@ def run_ours(args):
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
-        # keep stdout to the ONE JSON line: NCCL prints its version banner there at the VERSION debug level
-        if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
-            os.environ["NCCL_DEBUG"] = "WARN"
+        # keep stdout to the ONE JSON line: whatever NCCL_DEBUG level the box sets (its version banner goes to stdout),
+        # NCCL's own logging is sent to stderr
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         dist.init_process_group("nccl", device_id=dev)
 
     _lib.load()
