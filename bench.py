@@ -195,6 +195,9 @@ def run_ours(args):
     if world > 1:
         # keep stdout to the ONE JSON line: whatever NCCL_DEBUG level the box sets (its version banner goes to stdout),
         # NCCL's own logging is sent to stderr
+        # (NCCL honours NCCL_DEBUG_FILE only above the VERSION level, so VERSION / unset is raised to WARN)
+        if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
+            os.environ["NCCL_DEBUG"] = "WARN"
         os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         dist.init_process_group("nccl", device_id=dev)
 
