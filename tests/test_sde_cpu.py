@@ -63,3 +63,38 @@ def test_pc_sampler_and_loss_match_oracle_fp64(monkeypatch):
     finally:
         torch.set_default_dtype(torch.float32)
     assert abs(float(loss) - float(ref_loss)) < 1e-9 * abs(float(ref_loss))
+
+
+def test_step_fn_follows_the_reference_quirks(monkeypatch):
+    """get_step_fn (reference sde_utils.py:204-257): no optimiser step at step 0, gradient accumulation over
+    grad_acc steps, EMA updated every call, evaluation runs on the EMA weights and restores the live ones,
+    the grad_sync hook (flat gradient all-reduce) runs after every backward."""
+    from e3_layers.run import ExponentialMovingAverage, get_step_fn
+
+    torch_emulation.patch(monkeypatch)
+    meta = {"config": "config_diffusion", "seed": 2}
+    inputs = synthetic.diffusion_like(2, seed=1, n_min=3, n_max=5)
+    model = product_harness.build_product(meta, torch.float64, "cpu").train()
+    sde = VPSDE({"pos": 3}, N=50)
+    opt = torch.optim.Adam(model.parameters(), lr=1e-3)
+    state = {"model": model, "optimizer": opt, "ema": ExponentialMovingAverage(model.parameters(), decay=0.5), "step": 0}
+    synced = []
+    step = get_step_fn(sde, train=True, optimizer=opt, grad_clid_norm=1.0, grad_acc=2, grad_sync=lambda: synced.append(1))
+    flat = lambda: torch.cat([p.detach().reshape(-1).clone() for p in model.parameters()])
+    torch.set_default_dtype(torch.float64)
+    try:
+        p0 = flat()
+        batch = lambda: product_batch({k: v for k, v in inputs.items() if k != "t"}, torch.float64, "cpu")
+        loss0, parts = step(state, batch())                       # step 0: backward only
+        assert torch.equal(flat(), p0) and state["step"] == 1 and loss0 == loss0 and "pos" in parts and "total" in parts
+        step(state, batch())                                      # step 1: 1 % 2 != 0 -> still accumulating
+        assert torch.equal(flat(), p0)
+        step(state, batch())                                      # step 2: optimiser step with the accumulated gradient
+        p2 = flat()
+        assert not torch.equal(p2, p0) and len(synced) == 3
+        ema = torch.cat([s.reshape(-1) for s in state["ema"].shadow])
+        assert not torch.equal(ema, p2) and not torch.equal(ema, p0)      # lags behind the live weights
+        val, _ = get_step_fn(sde, train=False)(state, batch())
+        assert val == val and torch.equal(flat(), p2)             # evaluation on the EMA weights leaves the live ones alone
+    finally:
+        torch.set_default_dtype(torch.float32)
