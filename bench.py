@@ -293,9 +293,16 @@ def run_ours(args):
     d2h = e_host.numel() * e_host.element_size() + f_host.numel() * f_host.element_size()
 
     # ---- the force-matching TRAINING step of the same workload (configs[1]), reported beside the headline ----------
+    # (by default only at N = 1, like the CPU baseline: the headline line of a multi-rank run must not depend on an
+    #  extra with its own collectives; --training forces it, profiles/r1_bench_v6_2gpu.json was taken that way)
     training = None
-    if not args.no_training:
-        training = training_step_time(model, resident, attrs, Batch, computeEdgeIndex, n_atoms, world, dev, dist)
+    if not args.no_training and (world == 1 or args.training):
+        try:
+            training = training_step_time(model, resident, attrs, Batch, computeEdgeIndex, n_atoms, world, dev, dist)
+        except Exception as exc:                     # noqa: BLE001 -- reported in the line, never hides the headline
+            if world > 1:
+                raise
+            training = {"error": f"{type(exc).__name__}: {exc}"[:300]}
         model.eval()
 
     if rank != 0:
@@ -378,6 +385,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", dest="no_cpu_baseline", action="store_true")
     ap.add_argument("--no-training", dest="no_training", action="store_true",
                     help="skip the extra measurement of the force-matching training step")
+    ap.add_argument("--training", action="store_true", help="measure the training step at N > 1 too")
     ap.add_argument("--breakdown", action="store_true", help="print the per-stage device time table to stderr (implies --eager)")
     ap.add_argument("--eager", action="store_true", help="run the step op by op instead of replaying its CUDA graph")
     args = ap.parse_args()
