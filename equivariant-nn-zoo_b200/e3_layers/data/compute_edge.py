@@ -4,7 +4,8 @@
 with edges in lexicographic (source, destination) order, writes ``_n_edges`` into the incoming
 ``data`` dict -- but runs the all-pairs-within-a-graph radius search as a CUDA kernel
 (``e3b_radius_graph_*``) with the reference's exact fp32 predicate.  ``criteria`` edges are OR-ed
-in from the callable's mask, evaluated only on the candidate pairs it can add."""
+in from the callable's mask; a pre-existing ``edge_index`` is merged in and the per-edge tensors are carried over to
+the new numbering (zero-padded), as the reference does for the bond lists of its datasets."""
 import torch
 
 from e3b200 import ops
@@ -42,19 +43,36 @@ def computeEdgeIndex(data, attrs, r_max=None, key="pos", criteria=None):
     if not pos.is_cuda:
         raise RuntimeError("computeEdgeIndex (B200 path) needs CUDA tensors; there is no CPU fallback")
     n_nodes = data["_n_nodes"].reshape(-1)
-    if "edge_index" in data:
-        raise NotImplementedError("merging a pre-existing edge_index (compute_edge.py:77-100) is out of scope; "
-                                  "drop 'edge_index' before recomputing, as sde_sampling.py:237-242 does")
+    N = pos.shape[0]
     edge_index, n_edges, csr = ops.radius_graph(pos, n_nodes, r_max)
+    merged = False
     if criteria is not None:
         pairs = _all_pairs(n_nodes, pos.device)
         extra = criteria(data, pairs) & (pairs[0] != pairs[1])
-        N = pos.shape[0]
         keys = torch.cat([edge_index[0] * N + edge_index[1], (pairs[0] * N + pairs[1])[extra]])
-        keys = torch.unique(keys)                                # sorted -> reference order
+        merged = True
+    if "edge_index" in data:
+        # a pre-existing edge list (compute_edge.py:77-100; e.g. the bonds of qm9_edge.hdf5 under the complete graph of
+        # config_diffusion.py:50): its edges are kept -- even self loops, the reference re-adds them after its self-loop
+        # filter -- and every per-edge tensor is carried over to the new numbering, zero-padded for the new edges.
+        # The reference finds the old edges by a Python double loop over sorted lists; here: sorted keys + searchsorted.
+        old = data["edge_index"].to(pos.device)
+        old_keys = old[0] * N + old[1]
+        keys = torch.cat([keys if merged else edge_index[0] * N + edge_index[1], old_keys])
+        merged = True
+    if merged:
+        keys = torch.unique(keys)                                # sorted -> reference order (source, then destination)
         edge_index = torch.stack([keys // N, keys % N])
         seg = torch.repeat_interleave(torch.arange(n_nodes.numel(), device=pos.device), n_nodes.to(pos.device))
         n_edges = torch.bincount(seg[edge_index[0]], minlength=n_nodes.numel()).view(-1, 1)
+    if "edge_index" in data:
+        edge_map = torch.searchsorted(keys, old_keys)
+        for k in list(attrs):
+            if attrs[k][0] == "edge" and k in data and k != "edge_index":
+                tmp = data[k]
+                new = torch.zeros(edge_index.shape[1], tmp.shape[1], dtype=tmp.dtype, device=pos.device)
+                new[edge_map] = tmp.to(pos.device)
+                data[k] = new
     attrs["_n_edges"] = ("graph", "1x0e")
     data["_n_edges"] = n_edges
     return {"edge_index": edge_index}, attrs

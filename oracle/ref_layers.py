@@ -109,10 +109,20 @@ def computeEdgeVector(data, attrs, key="pos", with_lengths=True):
     return data, attrs
 
 
+def _compute_edge_map(a, b):
+    """computeEdgeMap, data/compute_edge.py:77-84: position in b of every column of a (both sorted alike)"""
+    j, lst = 0, []
+    for i in range(a.shape[1]):
+        while not bool((b[:, j] == a[:, i]).all()):
+            j += 1
+        lst.append(j)
+    return torch.tensor(lst, dtype=torch.long)
+
+
 def computeEdgeIndex(data, attrs, r_max=None, key="pos", criteria=None):
-    """data/compute_edge.py:38-113 without the pre-existing-edge remap branch (:77-100):
-    per graph all ordered pairs (a slow, b fast), keep ||pos[a]-pos[b]|| < r_max (fp32 norm,
-    strict) OR criteria, AND a != b.  Returns only the new keys like the reference (:110-113)."""
+    """data/compute_edge.py:38-113: per graph all ordered pairs (a slow, b fast), keep ||pos[a]-pos[b]|| < r_max
+    (fp32 norm, strict) OR criteria, AND a != b; then (:86-100) a pre-existing edge list is re-added and the per-edge
+    tensors are mapped to the new numbering, zero-padded for the new edges.  Returns only the new keys (:110-113)."""
     pos = torch.as_tensor(data[key], dtype=torch.get_default_dtype())
     n_nodes = data["_n_nodes"].reshape(-1).tolist()
     chunks, cnt = [], 0
@@ -128,7 +138,16 @@ def computeEdgeIndex(data, attrs, r_max=None, key="pos", criteria=None):
     if criteria is not None:
         mask = torch.logical_or(mask, criteria(data, ei))
     mask = torch.logical_and(mask, ei[0] != ei[1])
+    if "edge_index" in data:                                       # :86-88
+        mask[_compute_edge_map(data["edge_index"], ei)] = True
     ei = ei[:, mask]
+    if "edge_index" in data:                                       # :93-100
+        edge_map = _compute_edge_map(data["edge_index"], ei)
+        for k in attrs:
+            if attrs[k][0] == "edge":
+                tmp = data[k]
+                data[k] = torch.zeros(ei.shape[1], tmp.shape[1], dtype=tmp.dtype)
+                data[k][edge_map] = tmp
     seg = torch.repeat_interleave(torch.arange(len(n_nodes)), torch.tensor(n_nodes, dtype=torch.long))
     n_edges = torch.bincount(seg[ei[0]], minlength=len(n_nodes)).view(-1, 1)
     attrs["_n_edges"] = ("graph", "1x0e")

@@ -105,3 +105,43 @@ def test_criteria_edges_bit_exact_vs_oracle():
     assert attrs["_n_edges"] == ("graph", "1x0e")
     csr = ops.graph_of(out["edge_index"], 1400)
     _check_csr(out["edge_index"], csr, 1400)
+
+
+def test_pre_existing_edges_are_merged_and_attributes_remapped():
+    """compute_edge.py:86-100 (the bonds of the dataset under the recomputed graph, config_diffusion.py:50 / :73-83):
+    edge list and remapped, zero-padded per-edge tensors bit-exact against the oracle's restatement of the reference's
+    double loop"""
+    from e3_layers.data import computeEdgeIndex
+
+    b = synthetic.qm9_like(9, seed=4, n_min=3, n_max=12)
+    n = b["_n_nodes"].reshape(-1)
+    g = torch.Generator().manual_seed(2)
+    # a sparse symmetric "bond" list inside every molecule, in the reference's (source, destination) order
+    src, dst, off = [], [], 0
+    for k in n.tolist():
+        a = torch.arange(off, off + k)
+        i, j = torch.meshgrid(a, a, indexing="ij")
+        keep = (torch.rand(k, k, generator=g) < 0.25)
+        keep = (keep | keep.T) & (i != j)
+        src.append(i[keep])
+        dst.append(j[keep])
+        off += k
+    bonds = torch.stack([torch.cat(src), torch.cat(dst)])
+    order = torch.argsort(bonds[0] * off + bonds[1])
+    bonds = bonds[:, order]
+    bond_type = torch.randint(1, 4, (bonds.shape[1], 1), generator=g)
+    extra = torch.randn(bonds.shape[1], 3, generator=g)                     # a float per-edge tensor too
+    attrs = {"pos": ("node", "1x1o"), "bond_type": ("edge", "1x0e"), "bond_vec": ("edge", "1x1o")}
+    for r_max in (1.7, 9999.0):                                             # sparse radius graph / complete graph
+        ref_data = {"pos": b["pos"], "_n_nodes": b["_n_nodes"], "edge_index": bonds.clone(), "bond_type": bond_type.clone(),
+                    "bond_vec": extra.clone()}
+        d, _ = ref_layers.computeEdgeIndex(ref_data, dict(attrs), r_max=r_max)
+        data = {"pos": b["pos"].to(DEV), "_n_nodes": b["_n_nodes"].to(DEV), "edge_index": bonds.to(DEV),
+                "bond_type": bond_type.to(DEV), "bond_vec": extra.to(DEV)}
+        out, _ = computeEdgeIndex(data, dict(attrs), r_max=r_max)
+        assert torch.equal(out["edge_index"].cpu(), d["edge_index"]), r_max
+        assert torch.equal(data["bond_type"].cpu(), ref_data["bond_type"]) and data["bond_type"].dtype == torch.int64
+        assert torch.equal(data["bond_vec"].cpu(), ref_data["bond_vec"])
+        assert torch.equal(data["_n_edges"].cpu(), ref_data["_n_edges"])
+        if r_max < 100:
+            assert out["edge_index"].shape[1] > bonds.shape[1]              # the radius part really added edges

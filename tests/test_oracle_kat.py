@@ -107,3 +107,16 @@ def test_oracle_forces_vs_finite_difference():
             e.append(o["energy"].sum())
         fd = -(e[0] - e[1]) / (2 * h)
         assert abs(float(fd - out["forces"][i, c])) < 1e-6 * max(1.0, float(out["forces"].abs().max()))
+
+
+def test_edge_merge_kat():
+    """computeEdgeIndex with a pre-existing edge list (compute_edge.py:86-100), by hand: 3 atoms on a line at
+    x = 0, 1, 3 with r_max 1.5 -> radius edges (0,1), (1,0); the old list holds the bond (1,2), (2,1) with types 7, 9"""
+    from oracle import ref_layers
+
+    data = {"pos": torch.tensor([[0.0, 0, 0], [1.0, 0, 0], [3.0, 0, 0]]), "_n_nodes": torch.tensor([[3]]),
+            "edge_index": torch.tensor([[1, 2], [2, 1]]), "bond_type": torch.tensor([[7], [9]])}
+    attrs = {"pos": ("node", "1x1o"), "bond_type": ("edge", "1x0e")}
+    d, attrs = ref_layers.computeEdgeIndex(data, attrs, r_max=1.5)
+    assert d["edge_index"].tolist() == [[0, 1, 1, 2], [1, 0, 2, 1]]
+    assert data["bond_type"].reshape(-1).tolist() == [0, 0, 7, 9] and data["_n_edges"].tolist() == [[4]]
