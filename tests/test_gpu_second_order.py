@@ -245,3 +245,32 @@ def test_force_matching_training_reduces_loss():
         opt.step()
         losses.append(float(loss.detach()))
     assert losses[-1] < losses[0], losses
+
+
+def test_force_loss_gradients_are_rotation_invariant():
+    """size-independent property of the second-order path: a loss built from energies and |forces|^2 is invariant
+    under a rigid rotation + inversion of the inputs, so its parameter gradients must not change (fp64 mode)"""
+    from oracle import wigner
+
+    meta = {"config": "config_energy_force", "seed": 12}
+    inputs = synthetic.qm9_like(5, seed=9, n_min=3, n_max=10)
+    R = -wigner.rand_rotation(torch.Generator().manual_seed(4))            # improper: rotation x inversion
+
+    def grads(inp):
+        model = product_harness.build_product(meta, torch.float64, DEV).train()
+        data = dict(inp)
+        data["pos"] = inp["pos"].double()
+        out = product_harness.run_product(model, data, torch.float64, DEV, pre_edge={"r_max": 5.0})
+        loss = (out["energy"] ** 2).sum() + (out["forces"] ** 2).sum()
+        loss.backward()
+        return float(loss.detach()), {n: p.grad.detach().cpu() for n, p in model.named_parameters() if p.grad is not None}
+
+    # rotate in fp64 from the same fp32-representable coordinates so that both runs see exactly related inputs
+    base = dict(inputs)
+    l0, g0 = grads(base)
+    rot = dict(inputs)
+    rot["pos"] = inputs["pos"].double() @ R.T
+    l1, g1 = grads(rot)
+    assert abs(l0 - l1) < 1e-9 * abs(l0)
+    for n in g0:
+        assert rel(g1[n], g0[n]) < 1e-7, (n, rel(g1[n], g0[n]))
