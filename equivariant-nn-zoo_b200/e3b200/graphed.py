@@ -41,23 +41,24 @@ class GraphedEvaluator:
         """tensors: dict(pos [N,3] f32, species [N,1] i64, _n_nodes [G,1] i64, ...) on the GPU.
         -> dict of output tensors (owned by the evaluator until the next call with the same shapes)"""
         pos = tensors["pos"]
-        edge_index, n_edges, csr = ops.radius_graph(pos, tensors["_n_nodes"].reshape(-1), self.r_max)
-        key = (pos.shape[0], edge_index.shape[1], tensors["_n_nodes"].numel(), self._weights_tag()) + tuple(sorted(tensors))
+        st = ops.radius_graph_count(pos, tensors["_n_nodes"].reshape(-1), self.r_max)      # the step's one host sync
+        key = (pos.shape[0], st.E, tensors["_n_nodes"].numel(), self._weights_tag()) + tuple(sorted(tensors))
         e = self.cache.get(key)
         if e is None:
             self.misses += 1
+            edge_index, n_edges, csr = ops.radius_graph_finish(st)
             if len(self.cache) >= self.max_entries or self.model.training:
                 return self._run(tensors, edge_index, n_edges)
             return self._capture(key, tensors, edge_index, n_edges, csr)
         self.hits += 1
+        # hit: the GPU is idle from the synchronisation above until the replay below is enqueued, so as little as
+        # possible is launched in between -- the edges are written straight into the graph's static buffers
+        ops.radius_graph_fill(st, edge_index=e.edge_index, rev=e.csr.in_eid)
+        e.csr.in_ptr.copy_(st.row_ptr, non_blocking=True)                 # out_ptr is the same tensor
+        e.csr.in_nbr.copy_(e.edge_index[1], non_blocking=True)            # int64 -> int32
+        e.n_edges.copy_(ops.edges_per_graph(st), non_blocking=True)
         for k, v in tensors.items():
             e.static_in[k].copy_(v, non_blocking=True)
-        e.edge_index.copy_(edge_index, non_blocking=True)
-        e.n_edges.copy_(n_edges, non_blocking=True)
-        for name in ("in_ptr", "in_nbr", "in_eid", "out_ptr", "out_eid"):
-            dst, src = getattr(e.csr, name), getattr(csr, name)
-            if dst is not None and src is not None and dst.data_ptr() != src.data_ptr():
-                dst.copy_(src, non_blocking=True)
         e.graph.replay()
         _lib.count_launch(e.launches)
         return e.out

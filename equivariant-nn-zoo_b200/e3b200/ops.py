@@ -137,34 +137,66 @@ def graph_of(edge_index, n_nodes):
     return g
 
 
-def radius_graph(pos, n_nodes_per_graph, r_max):
-    """Neighbour list in the reference's order plus its CSR views.
-    pos [N,3] float32 (cuda), n_nodes_per_graph int64 [G].  -> edge_index int64 [2,E], n_edges [G], GraphCSR"""
+class _NeighbourCount:
+    """state between the two phases of the neighbour list (the caller sizes / chooses the edge arrays in between)"""
+    __slots__ = ("pos", "node_ptr", "G", "N", "r_max", "row_ptr", "E")
+
+
+def radius_graph_count(pos, n_nodes_per_graph, r_max):
+    """phase 1: per-atom degrees -> row_ptr, and the edge count E (the ONE host synchronisation of the step)"""
     lib = _lib.load()
     require_cuda(pos)
     if pos.dtype != torch.float32:
         pos = pos.float()  # the reference predicate is evaluated in the default dtype (fp32)
-    pos = pos.contiguous()
-    N = pos.shape[0]
+    st = _NeighbourCount()
+    st.pos = pos.contiguous()
+    st.N, st.r_max = pos.shape[0], float(r_max)
     counts = n_nodes_per_graph.reshape(-1).to(device=pos.device, dtype=torch.int64)
-    G = counts.numel()
-    node_ptr = _exclusive_scan(counts, G)
-    deg = torch.zeros(max(N, 1), dtype=torch.int32, device=pos.device)
-    check(lib.e3b_radius_graph_count(ptr(pos), 3, ptr(node_ptr), G, N, float(r_max), ptr(deg), stream()))
-    row_ptr = _exclusive_scan(deg[:N].long(), N)
-    E = int(row_ptr[-1].item()) if N else 0   # the one host sync: the caller must size edge_index
-    edge_index = torch.empty(2, E, dtype=torch.int64, device=pos.device)
-    rev = torch.empty(E, dtype=torch.int32, device=pos.device)
-    check(lib.e3b_radius_graph_fill(ptr(pos), 3, ptr(node_ptr), G, N, float(r_max), ptr(row_ptr), E,
+    st.G = counts.numel()
+    st.node_ptr = _exclusive_scan(counts, st.G)
+    deg = torch.zeros(max(st.N, 1), dtype=torch.int32, device=pos.device)
+    check(lib.e3b_radius_graph_count(ptr(st.pos), 3, ptr(st.node_ptr), st.G, st.N, st.r_max, ptr(deg), stream()))
+    st.row_ptr = _exclusive_scan(deg[:st.N].long(), st.N)
+    st.E = int(st.row_ptr[-1].item()) if st.N else 0   # the one host sync: the caller must size edge_index
+    count_launch(2)
+    return st
+
+
+def radius_graph_fill(st, edge_index=None, rev=None):
+    """phase 2: the edges in the reference's order into `edge_index` [2,E] int64 and, per slot, the id of the
+    reversed edge into `rev` [E] int32 (allocated here unless the caller passes its own buffers)"""
+    lib = _lib.load()
+    dev = st.pos.device
+    if edge_index is None:
+        edge_index = torch.empty(2, st.E, dtype=torch.int64, device=dev)
+    if rev is None:
+        rev = torch.empty(st.E, dtype=torch.int32, device=dev)
+    assert edge_index.shape == (2, st.E) and rev.shape == (st.E,) and edge_index.is_contiguous() and rev.is_contiguous()
+    check(lib.e3b_radius_graph_fill(ptr(st.pos), 3, ptr(st.node_ptr), st.G, st.N, st.r_max, ptr(st.row_ptr), st.E,
                                     ptr(edge_index), ptr(rev), stream()))
-    count_launch(3)
+    count_launch()
+    return edge_index, rev
+
+
+def edges_per_graph(st):
+    g = st.row_ptr[st.node_ptr]
+    return (g[1:] - g[:-1]).view(-1, 1)
+
+
+def radius_graph(pos, n_nodes_per_graph, r_max):
+    """Neighbour list in the reference's order plus its CSR views.
+    pos [N,3] float32 (cuda), n_nodes_per_graph int64 [G].  -> edge_index int64 [2,E], n_edges [G], GraphCSR"""
+    st = radius_graph_count(pos, n_nodes_per_graph, r_max)
+    return radius_graph_finish(st)
+
+
+def radius_graph_finish(st):
+    edge_index, rev = radius_graph_fill(st)
     # symmetric graph: in-edges of n are the reversed out-edges; slot k of node n holds the
     # edge (nbr -> n) whose id is rev[k]; out-grouping is the identity (edges sorted by source)
-    csr = GraphCSR(N, E, row_ptr, edge_index[1].to(torch.int32), rev, row_ptr, None)
+    csr = GraphCSR(st.N, st.E, st.row_ptr, edge_index[1].to(torch.int32), rev, st.row_ptr, None)
     edge_index._e3b_csr = csr
-    graph_ptr_edges = row_ptr[node_ptr]
-    n_edges = (graph_ptr_edges[1:] - graph_ptr_edges[:-1]).view(-1, 1)
-    return edge_index, n_edges, csr
+    return edge_index, edges_per_graph(st), csr
 
 
 # ------------------------------------------------------------------------------------------
