@@ -155,6 +155,324 @@ extern "C" int e3b_radius_graph_fill(const float* pos, int64_t pos_stride, const
   return rc;
 }
 
+// ------------------------------------------------------------------------------------------
+// Neighbour list with pair predicates evaluated inside the sweep (the `criteria` callable of
+// config_diffusion_CA.py:58-64: same chain and |a - b| < 5, OR a Bernoulli(p) draw per ordered pair) and, for
+// large radius-only graphs, a cell list.  Same warp-per-atom sweep, same exact predicate, same output order.
+__device__ __forceinline__ float pair_uniform(unsigned long long seed, int64_t a, int64_t b) {
+  // counter-based: splitmix64 finaliser of (seed, a, b) -> 24 random bits -> [0, 1)
+  unsigned long long x = seed ^ ((unsigned long long)a * 0x9E3779B97F4A7C15ull + (unsigned long long)b * 0xC2B2AE3D27D4EB4Full +
+                                 0x165667B19E3779F9ull);
+  x ^= x >> 30; x *= 0xBF58476D1CE4E5B9ull;
+  x ^= x >> 27; x *= 0x94D049BB133111EBull;
+  x ^= x >> 31;
+  return (float)(x >> 40) * (1.0f / 16777216.0f);
+}
+
+struct PairCrit {
+  const int64_t* seg;        // per-node segment id (chain), or NULL
+  long long max_sep;         // |a - b| < max_sep within a segment
+  float p;                   // Bernoulli probability per ordered pair, 0 = off
+  const float* uniforms;     // explicit uniforms indexed like the reference's all-pairs list, or NULL (hash RNG)
+  const int64_t* pair_ptr;   // [G+1] exclusive scan of n_g^2 (with uniforms)
+  unsigned long long seed;
+};
+
+__device__ __forceinline__ bool pair_extra(const PairCrit& c, int64_t a, int64_t b, int g, int64_t b0, int64_t n_g) {
+  bool hit = false;
+  if (c.seg) {
+    const long long d = a > b ? a - b : b - a;
+    hit = c.seg[a] == c.seg[b] && d < c.max_sep;
+  }
+  if (!hit && c.p > 0.f) {
+    const float u = c.uniforms ? c.uniforms[c.pair_ptr[g] + (a - b0) * n_g + (b - b0)] : pair_uniform(c.seed, a, b);
+    hit = u < c.p;
+  }
+  return hit;
+}
+
+template <bool FILL>
+__global__ void __launch_bounds__(256) pair_graph_kernel(const float* __restrict__ pos, int64_t stride,
+                                                         const int64_t* __restrict__ node_ptr, int n_graphs,
+                                                         int64_t n_nodes, float r_max, PairCrit crit, int32_t* __restrict__ deg,
+                                                         const int64_t* __restrict__ row_ptr, int64_t n_edges,
+                                                         int64_t* __restrict__ edge_index) {
+  const int lane = threadIdx.x & 31;
+  const int64_t a = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (a >= n_nodes) return;
+  const int g = find_graph(node_ptr, n_graphs, a);
+  const int64_t b0 = node_ptr[g], b1 = node_ptr[g + 1];
+  const float ax = pos[a * stride], ay = pos[a * stride + 1], az = pos[a * stride + 2];
+  int64_t cursor = FILL ? row_ptr[a] : 0;
+  int count = 0;
+  for (int64_t base = b0; base < b1; base += 32) {
+    const int64_t b = base + lane;
+    bool hit = false;
+    if (b < b1 && b != a) hit = within(pos, stride, ax, ay, az, b, r_max) || pair_extra(crit, a, b, g, b0, b1 - b0);
+    const unsigned m = __ballot_sync(0xffffffffu, hit);
+    if (FILL) {
+      if (hit) {
+        const int64_t p = cursor + __popc(m & ((1u << lane) - 1u));
+        edge_index[p] = a;
+        edge_index[n_edges + p] = b;
+      }
+      cursor += __popc(m);
+    } else {
+      count += __popc(m);
+    }
+  }
+  if (!FILL && lane == 0) deg[a] = count;
+}
+
+static PairCrit to_crit(const e3b_pair_criteria* c) {
+  PairCrit k;
+  k.seg = c->segment; k.max_sep = c->max_separation; k.p = c->p_random; k.uniforms = c->uniforms;
+  k.pair_ptr = c->pair_ptr; k.seed = c->seed;
+  return k;
+}
+
+extern "C" int e3b_pair_graph_count(const float* pos, int64_t pos_stride, const int64_t* node_ptr, int32_t n_graphs,
+                                    int64_t n_nodes, float r_max, const e3b_pair_criteria* crit, int32_t* deg, void* stream) {
+  if (n_nodes == 0) return E3B_OK;
+  if (!pos || !node_ptr || !deg || !crit || n_graphs <= 0) return fail(E3B_ERR_INVALID, "pair_graph_count: null/empty argument");
+  if (crit->uniforms && !crit->pair_ptr) return fail(E3B_ERR_INVALID, "pair_graph_count: uniforms need pair_ptr");
+  pair_graph_kernel<false><<<blocks_for(n_nodes, 8), 256, 0, (cudaStream_t)stream>>>(
+      pos, pos_stride, node_ptr, n_graphs, n_nodes, r_max, to_crit(crit), deg, nullptr, 0, nullptr);
+  return check_launch("pair_graph_count");
+}
+
+extern "C" int e3b_pair_graph_fill(const float* pos, int64_t pos_stride, const int64_t* node_ptr, int32_t n_graphs,
+                                   int64_t n_nodes, float r_max, const e3b_pair_criteria* crit, const int64_t* row_ptr,
+                                   int64_t n_edges, int64_t* edge_index, void* stream) {
+  if (n_nodes == 0 || n_edges == 0) return E3B_OK;
+  if (!pos || !node_ptr || !row_ptr || !edge_index || !crit) return fail(E3B_ERR_INVALID, "pair_graph_fill: null argument");
+  pair_graph_kernel<true><<<blocks_for(n_nodes, 8), 256, 0, (cudaStream_t)stream>>>(
+      pos, pos_stride, node_ptr, n_graphs, n_nodes, r_max, to_crit(crit), nullptr, row_ptr, n_edges, edge_index);
+  return check_launch("pair_graph_fill");
+}
+
+// ---- cell list.  Per graph with >= min_nodes atoms: bounding box -> uniform grid with cells of >= 1.001 r_max
+// (so atoms closer than r_max sit in adjacent cells whatever the fp32 rounding of the cell coordinate), at most
+// cell_ptr[g+1] - cell_ptr[g] cells (the caller reserves ~2 cells per atom; the cells grow if the box is sparse).
+// Atoms are binned with integer atomics (the order inside a cell is arbitrary); the sweep collects the hits of the
+// 27 surrounding cells in shared memory and writes them in ascending b by rank, so the output is bit-identical to
+// the all-pairs sweep.  Smaller graphs of the same batch take the all-pairs loop inside the same kernel.
+struct CellGrid {
+  float ox, oy, oz, ix, iy, iz;   // origin, cells per unit length
+  int nx, ny, nz;                 // nx == 0: graph not binned
+  int pad;
+  long long base;                 // first cell of this graph
+};
+static_assert(sizeof(CellGrid) == E3B_CELL_GRID_BYTES, "e3b200.h: E3B_CELL_GRID_BYTES");
+
+__global__ void __launch_bounds__(256) cell_grid_kernel(const float* __restrict__ pos, int64_t stride,
+                                                        const int64_t* __restrict__ node_ptr, int n_graphs, float r_max,
+                                                        int64_t min_nodes, const int64_t* __restrict__ cell_ptr,
+                                                        CellGrid* __restrict__ grids) {
+  const int lane = threadIdx.x & 31;
+  const int g = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (g >= n_graphs) return;
+  const int64_t b0 = node_ptr[g], b1 = node_ptr[g + 1];
+  CellGrid cg;
+  cg.ox = cg.oy = cg.oz = cg.ix = cg.iy = cg.iz = 0.f;
+  cg.nx = cg.ny = cg.nz = 0; cg.pad = 0; cg.base = cell_ptr[g];
+  const int64_t cap = cell_ptr[g + 1] - cell_ptr[g];
+  if (b1 - b0 >= min_nodes && cap >= 1) {
+    float lo[3] = {3.4e38f, 3.4e38f, 3.4e38f}, hi[3] = {-3.4e38f, -3.4e38f, -3.4e38f};
+    for (int64_t b = b0 + lane; b < b1; b += 32)
+      for (int d = 0; d < 3; ++d) { const float v = pos[b * stride + d]; lo[d] = fminf(lo[d], v); hi[d] = fmaxf(hi[d], v); }
+    for (int o = 16; o; o >>= 1)
+      for (int d = 0; d < 3; ++d) {
+        lo[d] = fminf(lo[d], __shfl_xor_sync(0xffffffffu, lo[d], o));
+        hi[d] = fmaxf(hi[d], __shfl_xor_sync(0xffffffffu, hi[d], o));
+      }
+    int dcap = 1;
+    while ((int64_t)(dcap + 1) * (dcap + 1) * (dcap + 1) <= cap && dcap < 1024) ++dcap;
+    int n[3];
+    float inv[3];
+    const float cell = r_max * 1.001f;
+    for (int d = 0; d < 3; ++d) {
+      const float ext = hi[d] - lo[d];
+      int k = ext > 0.f && cell > 0.f ? (int)fminf(floorf(ext / cell), (float)dcap) : 1;
+      if (k < 1) k = 1;
+      n[d] = k;
+      inv[d] = ext > 0.f ? (float)k / ext : 0.f;
+      // (x - lo) * inv <= k (1 + 2^-22); the coordinate is clamped to k - 1 in cell_coord
+    }
+    cg.ox = lo[0]; cg.oy = lo[1]; cg.oz = lo[2];
+    cg.ix = inv[0]; cg.iy = inv[1]; cg.iz = inv[2];
+    cg.nx = n[0]; cg.ny = n[1]; cg.nz = n[2];
+  }
+  if (lane == 0) grids[g] = cg;
+}
+
+__device__ __forceinline__ void cell_coord(const CellGrid& cg, float x, float y, float z, int& cx, int& cy, int& cz) {
+  cx = min(cg.nx - 1, max(0, (int)((x - cg.ox) * cg.ix)));
+  cy = min(cg.ny - 1, max(0, (int)((y - cg.oy) * cg.iy)));
+  cz = min(cg.nz - 1, max(0, (int)((z - cg.oz) * cg.iz)));
+}
+
+__global__ void cell_assign_kernel(const float* __restrict__ pos, int64_t stride, const int64_t* __restrict__ node_ptr,
+                                   int n_graphs, int64_t n_nodes, const CellGrid* __restrict__ grids,
+                                   int32_t* __restrict__ cell_of, int32_t* __restrict__ cell_count) {
+  const int64_t a = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (a >= n_nodes) return;
+  const int g = find_graph(node_ptr, n_graphs, a);
+  const CellGrid cg = grids[g];
+  if (cg.nx == 0) { cell_of[a] = -1; return; }
+  int cx, cy, cz;
+  cell_coord(cg, pos[a * stride], pos[a * stride + 1], pos[a * stride + 2], cx, cy, cz);
+  const int32_t c = (int32_t)(cg.base + ((long long)cx * cg.ny + cy) * cg.nz + cz);
+  cell_of[a] = c;
+  atomicAdd(&cell_count[c], 1);
+}
+
+__global__ void cell_scatter_kernel(const int32_t* __restrict__ cell_of, int64_t n_nodes, const int64_t* __restrict__ cell_start,
+                                    int32_t* __restrict__ cursor, int32_t* __restrict__ sorted) {
+  const int64_t a = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (a >= n_nodes) return;
+  const int32_t c = cell_of[a];
+  if (c < 0) return;
+  sorted[cell_start[c] + atomicAdd(&cursor[c], 1)] = (int32_t)a;
+}
+
+constexpr int CELL_BUF = 512;   // hits buffered per warp in the fill pass (beyond: all-pairs loop for that atom)
+
+template <bool FILL>
+__global__ void __launch_bounds__(256) cell_graph_kernel(const float* __restrict__ pos, int64_t stride,
+                                                         const int64_t* __restrict__ node_ptr, int n_graphs,
+                                                         int64_t n_nodes, float r_max, const CellGrid* __restrict__ grids,
+                                                         const int64_t* __restrict__ cell_start,
+                                                         const int32_t* __restrict__ sorted, int32_t* __restrict__ deg,
+                                                         const int64_t* __restrict__ row_ptr, int64_t n_edges,
+                                                         int64_t* __restrict__ edge_index) {
+  __shared__ int32_t buf_all[FILL ? 8 * CELL_BUF : 1];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int64_t a = (int64_t)blockIdx.x * (blockDim.x >> 5) + warp;
+  if (a >= n_nodes) return;
+  const int g = find_graph(node_ptr, n_graphs, a);
+  const int64_t b0 = node_ptr[g], b1 = node_ptr[g + 1];
+  const CellGrid cg = grids[g];
+  const float ax = pos[a * stride], ay = pos[a * stride + 1], az = pos[a * stride + 2];
+  const int64_t first = FILL ? row_ptr[a] : 0;
+  const int64_t want = FILL ? row_ptr[a + 1] - first : 0;
+  if (cg.nx == 0 || (FILL && want > CELL_BUF)) {      // all-pairs sweep (small graph, or more hits than the buffer holds)
+    int64_t cursor = first;
+    int count = 0;
+    for (int64_t base = b0; base < b1; base += 32) {
+      const int64_t b = base + lane;
+      bool hit = false;
+      if (b < b1 && b != a) hit = within(pos, stride, ax, ay, az, b, r_max);
+      const unsigned m = __ballot_sync(0xffffffffu, hit);
+      if (FILL) {
+        if (hit) {
+          const int64_t p = cursor + __popc(m & ((1u << lane) - 1u));
+          edge_index[p] = a;
+          edge_index[n_edges + p] = b;
+        }
+        cursor += __popc(m);
+      } else {
+        count += __popc(m);
+      }
+    }
+    if (!FILL && lane == 0) deg[a] = count;
+    return;
+  }
+  int32_t* buf = buf_all + (FILL ? warp * CELL_BUF : 0);
+  int cx, cy, cz;
+  cell_coord(cg, ax, ay, az, cx, cy, cz);
+  int count = 0;
+  for (int dx = -1; dx <= 1; ++dx) {
+    const int x = cx + dx;
+    if (x < 0 || x >= cg.nx) continue;
+    for (int dy = -1; dy <= 1; ++dy) {
+      const int y = cy + dy;
+      if (y < 0 || y >= cg.ny) continue;
+      // the three cells z-1, z, z+1 are consecutive in memory: one contiguous range of `sorted`
+      const int z0 = max(cz - 1, 0), z1 = min(cz + 1, cg.nz - 1);
+      const long long c0 = cg.base + ((long long)x * cg.ny + y) * cg.nz;
+      const int64_t i0 = cell_start[c0 + z0], i1 = cell_start[c0 + z1 + 1];
+      for (int64_t base = i0; base < i1; base += 32) {
+        const int64_t i = base + lane;
+        int64_t b = -1;
+        bool hit = false;
+        if (i < i1) {
+          b = sorted[i];
+          if (b != a) hit = within(pos, stride, ax, ay, az, b, r_max);
+        }
+        const unsigned m = __ballot_sync(0xffffffffu, hit);
+        if (FILL && hit) buf[count + __popc(m & ((1u << lane) - 1u))] = (int32_t)b;
+        count += __popc(m);
+      }
+    }
+  }
+  if (!FILL) {
+    if (lane == 0) deg[a] = count;
+    return;
+  }
+  __syncwarp();
+  // rank = number of smaller hits (they are distinct): ascending b, the reference's order
+  for (int i = lane; i < count; i += 32) {
+    const int32_t v = buf[i];
+    int r = 0;
+    for (int j = 0; j < count; ++j) r += buf[j] < v;
+    edge_index[first + r] = a;
+    edge_index[n_edges + first + r] = v;
+  }
+}
+
+extern "C" int e3b_cell_graph_bin(const float* pos, int64_t pos_stride, const int64_t* node_ptr, int32_t n_graphs,
+                                  int64_t n_nodes, float r_max, int64_t min_nodes, const int64_t* cell_ptr, void* grids,
+                                  int32_t* cell_of, int32_t* cell_count, void* stream) {
+  if (n_nodes == 0) return E3B_OK;
+  if (!pos || !node_ptr || !cell_ptr || !grids || !cell_of || !cell_count || n_graphs <= 0)
+    return fail(E3B_ERR_INVALID, "cell_graph_bin: null/empty argument");
+  cell_grid_kernel<<<blocks_for(n_graphs, 8), 256, 0, (cudaStream_t)stream>>>(pos, pos_stride, node_ptr, n_graphs, r_max,
+                                                                             min_nodes, cell_ptr, (CellGrid*)grids);
+  int rc = check_launch("cell_grid");
+  if (rc) return rc;
+  cell_assign_kernel<<<blocks_for(n_nodes, 256), 256, 0, (cudaStream_t)stream>>>(pos, pos_stride, node_ptr, n_graphs, n_nodes,
+                                                                                 (const CellGrid*)grids, cell_of, cell_count);
+  return check_launch("cell_assign");
+}
+
+extern "C" int e3b_cell_graph_sort(const int32_t* cell_of, int64_t n_nodes, const int64_t* cell_start, int32_t* cursor,
+                                   int32_t* sorted, void* stream) {
+  if (n_nodes == 0) return E3B_OK;
+  if (!cell_of || !cell_start || !cursor || !sorted) return fail(E3B_ERR_INVALID, "cell_graph_sort: null argument");
+  cell_scatter_kernel<<<blocks_for(n_nodes, 256), 256, 0, (cudaStream_t)stream>>>(cell_of, n_nodes, cell_start, cursor, sorted);
+  return check_launch("cell_scatter");
+}
+
+extern "C" int e3b_cell_graph_count(const float* pos, int64_t pos_stride, const int64_t* node_ptr, int32_t n_graphs,
+                                    int64_t n_nodes, float r_max, const void* grids, const int64_t* cell_start,
+                                    const int32_t* sorted, int32_t* deg, void* stream) {
+  if (n_nodes == 0) return E3B_OK;
+  if (!pos || !node_ptr || !grids || !cell_start || !sorted || !deg) return fail(E3B_ERR_INVALID, "cell_graph_count: null argument");
+  cell_graph_kernel<false><<<blocks_for(n_nodes, 8), 256, 0, (cudaStream_t)stream>>>(
+      pos, pos_stride, node_ptr, n_graphs, n_nodes, r_max, (const CellGrid*)grids, cell_start, sorted, deg, nullptr, 0, nullptr);
+  return check_launch("cell_graph_count");
+}
+
+extern "C" int e3b_cell_graph_fill(const float* pos, int64_t pos_stride, const int64_t* node_ptr, int32_t n_graphs,
+                                   int64_t n_nodes, float r_max, const void* grids, const int64_t* cell_start,
+                                   const int32_t* sorted, const int64_t* row_ptr, int64_t n_edges, int64_t* edge_index,
+                                   int32_t* rev, void* stream) {
+  if (n_nodes == 0 || n_edges == 0) return E3B_OK;
+  if (!pos || !node_ptr || !grids || !cell_start || !sorted || !row_ptr || !edge_index)
+    return fail(E3B_ERR_INVALID, "cell_graph_fill: null argument");
+  cell_graph_kernel<true><<<blocks_for(n_nodes, 8), 256, 0, (cudaStream_t)stream>>>(
+      pos, pos_stride, node_ptr, n_graphs, n_nodes, r_max, (const CellGrid*)grids, cell_start, sorted, nullptr, row_ptr,
+      n_edges, edge_index);
+  int rc = check_launch("cell_graph_fill");
+  if (rc) return rc;
+  if (rev) {
+    reverse_edge_kernel<<<blocks_for(n_edges, 256), 256, 0, (cudaStream_t)stream>>>(edge_index, row_ptr, n_edges, rev);
+    rc = check_launch("radius_graph_reverse");
+  }
+  return rc;
+}
+
 // Grouped CSR of an arbitrary edge list: node n's segment lists, in ascending edge id, the
 // edges whose `which_row` endpoint is n.  One warp per node sweeps... no: the edge list is
 // unsorted, so: pass 1 scatter with an atomic cursor, pass 2 per-segment sort (ascending id).
@@ -1212,41 +1530,66 @@ extern "C" int e3b_layernorm_bwd(int dtype, const void* x, const void* gy, const
 // when the gradients hold Inf/NaN -> the step is skipped (sde_utils.py:240-246) without a host round trip.
 struct AdamArgs {
   float lr, beta1, beta2, eps, weight_decay, bias1, bias2_sqrt, ema_decay;
+  double beta1d, beta2d;
 };
 
+// step_in / step_out (device int64, may be NULL): number of updates APPLIED so far.  torch.optim.Adam does not
+// advance its step when the caller skips an update, so with a device-side skip flag the count lives on the device
+// too: the bias corrections use *step_in + 1 and thread 0 writes *step_out = *step_in + (skipped ? 0 : 1) (two
+// distinct locations, swapped by the caller, so no thread reads a value written by this launch).  A skipped step
+// still moves the moving average (torch_ema's update follows every step of the reference loop, skipped or not).
 __global__ void __launch_bounds__(256) adam_ema_kernel(float* __restrict__ p, const float* __restrict__ g,
                                                        float* __restrict__ m, float* __restrict__ v,
                                                        float* __restrict__ ema, int64_t n, AdamArgs a,
-                                                       const float* __restrict__ grad_scale, const int* __restrict__ skip) {
-  if (skip && *skip) return;
-  const float gs = grad_scale ? *grad_scale : 1.f;
+                                                       const float* __restrict__ grad_scale, const int* __restrict__ skip,
+                                                       const long long* __restrict__ step_in, long long* __restrict__ step_out) {
+  const bool skipped = skip && *skip;
+  float bias1 = a.bias1, bias2_sqrt = a.bias2_sqrt;
+  if (step_in) {
+    const long long t = *step_in + 1;
+    bias1 = (float)(1.0 - pow(a.beta1d, (double)t));
+    bias2_sqrt = (float)sqrt(1.0 - pow(a.beta2d, (double)t));
+    if (blockIdx.x == 0 && threadIdx.x == 0) *step_out = *step_in + (skipped ? 0 : 1);
+  }
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  if (skipped) {
+    if (ema)
+      for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride)
+        ema[i] = fmaf(a.ema_decay, ema[i] - p[i], p[i]);
+    return;
+  }
+  const float gs = grad_scale ? *grad_scale : 1.f;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
     const float w = p[i];
     float gi = g[i] * gs;
     if (a.weight_decay != 0.f) gi = fmaf(a.weight_decay, w, gi);
     const float mi = fmaf(a.beta1, m[i], (1.f - a.beta1) * gi);
     const float vi = fmaf(a.beta2, v[i], (1.f - a.beta2) * gi * gi);
-    const float denom = sqrtf(vi) / a.bias2_sqrt + a.eps;
-    const float wn = w - (a.lr / a.bias1) * (mi / denom);
+    const float denom = sqrtf(vi) / bias2_sqrt + a.eps;
+    const float wn = w - (a.lr / bias1) * (mi / denom);
     m[i] = mi; v[i] = vi; p[i] = wn;
     if (ema) ema[i] = fmaf(a.ema_decay, ema[i] - wn, wn);      // decay * ema + (1 - decay) * w
   }
 }
 
 extern "C" int e3b_adam_ema_step(void* param, const void* grad, void* exp_avg, void* exp_avg_sq, void* ema, int64_t n,
-                                 float lr, float beta1, float beta2, float eps, float weight_decay, int64_t step,
-                                 float ema_decay, const void* grad_scale, const void* skip, void* stream) {
+                                 float lr, double beta1, double beta2, float eps, float weight_decay, int64_t step,
+                                 float ema_decay, const void* grad_scale, const void* skip, const void* step_in,
+                                 void* step_out, void* stream) {
   if (n == 0) return E3B_OK;
-  if (!param || !grad || !exp_avg || !exp_avg_sq || step < 1) return fail(E3B_ERR_INVALID, "adam_ema_step: bad argument");
+  if (!param || !grad || !exp_avg || !exp_avg_sq) return fail(E3B_ERR_INVALID, "adam_ema_step: bad argument");
+  if ((step_in == nullptr) != (step_out == nullptr) || (step_in && step_in == step_out))
+    return fail(E3B_ERR_INVALID, "adam_ema_step: step_in / step_out must be two distinct device scalars (or both NULL)");
+  if (!step_in && step < 1) return fail(E3B_ERR_INVALID, "adam_ema_step: step >= 1 needed without a device step counter");
   AdamArgs a;
-  a.lr = lr; a.beta1 = beta1; a.beta2 = beta2; a.eps = eps; a.weight_decay = weight_decay; a.ema_decay = ema_decay;
-  a.bias1 = (float)(1.0 - pow((double)beta1, (double)step));
-  a.bias2_sqrt = (float)sqrt(1.0 - pow((double)beta2, (double)step));
+  a.lr = lr; a.beta1 = (float)beta1; a.beta2 = (float)beta2; a.eps = eps; a.weight_decay = weight_decay; a.ema_decay = ema_decay;
+  a.beta1d = beta1; a.beta2d = beta2;
+  a.bias1 = (float)(1.0 - pow(beta1, (double)(step < 1 ? 1 : step)));
+  a.bias2_sqrt = (float)sqrt(1.0 - pow(beta2, (double)(step < 1 ? 1 : step)));
   const int64_t want = (n + 255) / 256;
   const unsigned grid = (unsigned)(want < 148 * 8 ? want : 148 * 8);
   adam_ema_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>((float*)param, (const float*)grad, (float*)exp_avg,
                                                           (float*)exp_avg_sq, (float*)ema, n, a, (const float*)grad_scale,
-                                                          (const int*)skip);
+                                                          (const int*)skip, (const long long*)step_in, (long long*)step_out);
   return check_launch("adam_ema_step");
 }

@@ -4,7 +4,7 @@ LayerNormalization, 32 radial functions + relative sequence-position embedding, 
 the first model layer (radius 8 A on scaled coordinates OR same-chain |i-j| < 5 OR 2 % random)."""
 from functools import partial
 
-import torch
+from e3b200 import ops
 
 from ..data import computeEdgeIndex, computeEdgeVector
 from ..nn import Concat, PointwiseLinear, RadialBasisEncoding, RelativePositionEncoding, symmetricCutoff
@@ -14,11 +14,9 @@ from .config_diffusion import time_conditioning
 from .layer_configs import featureModel
 
 
-def criteria(data, edge_index, p_random=0.02):
-    src, dst = edge_index[0], edge_index[1]
-    chain = data["chain_id"].view(-1)
-    keep = (chain[src] == chain[dst]) & ((src - dst).abs() < 5)
-    return keep | (torch.rand(src.shape[0], device=src.device) < p_random)
+# same chain and |i - j| < 5, or 2 % of all ordered pairs (reference config_diffusion_CA.py:58-64); a PairCriteria is
+# evaluated inside the neighbour-list sweep and is also a callable with the reference's criteria(data, edge_index) protocol
+criteria = ops.PairCriteria(segment_key="chain_id", max_separation=5, p_random=0.02)
 
 
 def get_config(spec=""):

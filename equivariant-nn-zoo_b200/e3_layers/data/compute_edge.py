@@ -3,8 +3,9 @@
 ``computeEdgeIndex`` keeps the reference contract -- returns ``({"edge_index": [2,E] int64}, attrs)``
 with edges in lexicographic (source, destination) order, writes ``_n_edges`` into the incoming
 ``data`` dict -- but runs the all-pairs-within-a-graph radius search as a CUDA kernel
-(``e3b_radius_graph_*``) with the reference's exact fp32 predicate.  ``criteria`` edges are OR-ed
-in from the callable's mask; a pre-existing ``edge_index`` is merged in and the per-edge tensors are carried over to
+(``e3b_radius_graph_*``, a cell list for large graphs) with the reference's exact fp32 predicate.  A
+``PairCriteria`` (chain / sequence separation / random pairs: the criteria of ``config_diffusion_CA``) is evaluated
+inside the same sweep (``e3b_pair_graph_*``); any other ``criteria`` callable is OR-ed in from its mask over all pairs; a pre-existing ``edge_index`` is merged in and the per-edge tensors are carried over to
 the new numbering (zero-padded), as the reference does for the bond lists of its datasets."""
 import torch
 
@@ -44,9 +45,11 @@ def computeEdgeIndex(data, attrs, r_max=None, key="pos", criteria=None):
         raise RuntimeError("computeEdgeIndex (B200 path) needs CUDA tensors; there is no CPU fallback")
     n_nodes = data["_n_nodes"].reshape(-1)
     N = pos.shape[0]
-    edge_index, n_edges, csr = ops.radius_graph(pos, n_nodes, r_max)
+    fast = isinstance(criteria, ops.PairCriteria)          # predicates evaluated inside the neighbour-list sweep
+    edge_index, n_edges, csr = ops.radius_graph(pos, n_nodes, r_max, criteria if fast else None, data)
     merged = False
-    if criteria is not None:
+    if criteria is not None and not fast:
+        # a foreign callable (reference protocol criteria(data, edge_index) -> mask): evaluated on every ordered pair
         pairs = _all_pairs(n_nodes, pos.device)
         extra = criteria(data, pairs) & (pairs[0] != pairs[1])
         keys = torch.cat([edge_index[0] * N + edge_index[1], (pairs[0] * N + pairs[1])[extra]])

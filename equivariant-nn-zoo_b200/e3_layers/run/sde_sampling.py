@@ -165,10 +165,12 @@ def get_pc_sampler(sde, predictor, corrector, inverse_scaler, snr, n_steps=1, co
         timesteps = torch.linspace(sde.T, eps, sde.N, device=dev, dtype=dtype)
         n_iter = sde.N if max_iterations is None else min(sde.N, max_iterations)
         rebuild = _model_rebuilds_edges(model)
-        inputs = set(batch.keys())
         use_graph = bool(graph and dev.type == "cuda" and not rebuild and "edge_index" in batch)
         with torch.no_grad():
+            # the sampler owns 't' (sde_sampling.py:231-236 sets it every iteration): dataset batches do not carry it,
+            # so it is assigned BEFORE the set of graph inputs is recorded
             batch["t"] = timesteps[0].expand(len(batch)).reshape(-1, 1).clone()
+            inputs = set(batch.keys())
             if use_graph:
                 static_t = batch["t"]
                 side = torch.cuda.Stream()

@@ -131,30 +131,51 @@ def get_sde_loss_fn(sde, train, reduce_mean=True, continuous=True, likelihood_we
 
 
 class ExponentialMovingAverage:
-    """the part of torch_ema the reference's step function uses (update / store / copy_to / restore)"""
+    """The moving average the reference's diffusion loop builds (``train.py:103`` ->
+    score_sde_pytorch ``models/ema.py``): only parameters with ``requires_grad`` are tracked, and with
+    ``use_num_updates`` (the default there) the decay warms up as ``min(decay, (1 + n) / (10 + n))`` so that the
+    average leaves the random initial weights within a few hundred steps even at ``ema_rate = 0.9999``."""
 
-    def __init__(self, parameters, decay=0.999):
+    def __init__(self, parameters, decay=0.999, use_num_updates=True):
+        if not 0.0 <= decay <= 1.0:
+            raise ValueError("decay must be between 0 and 1")
         self.decay = decay
-        self.shadow = [p.detach().clone() for p in parameters]
+        self.num_updates = 0 if use_num_updates else None
+        self.shadow = [p.detach().clone() for p in parameters if p.requires_grad]
         self.backup = None
+
+    def current_decay(self):
+        if self.num_updates is None:
+            return self.decay
+        return min(self.decay, (1.0 + self.num_updates) / (10.0 + self.num_updates))
 
     @torch.no_grad()
     def update(self, parameters):
-        ps = [p.detach() for p in parameters]
-        torch._foreach_lerp_(self.shadow, ps, 1.0 - self.decay)       # one multi-tensor kernel
+        if self.num_updates is not None:
+            self.num_updates += 1
+        ps = [p.detach() for p in parameters if p.requires_grad]
+        torch._foreach_lerp_(self.shadow, ps, 1.0 - self.current_decay())       # one multi-tensor kernel
 
     def store(self, parameters):
-        self.backup = [p.detach().clone() for p in parameters]
+        self.backup = [p.detach().clone() for p in parameters if p.requires_grad]
 
     @torch.no_grad()
     def copy_to(self, parameters):
-        for s, p in zip(self.shadow, parameters):
+        for s, p in zip(self.shadow, [p for p in parameters if p.requires_grad]):
             p.copy_(s)
 
     @torch.no_grad()
     def restore(self, parameters):
-        for b, p in zip(self.backup, parameters):
+        for b, p in zip(self.backup, [p for p in parameters if p.requires_grad]):
             p.copy_(b)
+
+    def state_dict(self):
+        return {"decay": self.decay, "num_updates": self.num_updates, "shadow_params": [s.clone() for s in self.shadow]}
+
+    def load_state_dict(self, state):
+        self.decay, self.num_updates = state["decay"], state["num_updates"]
+        for s, v in zip(self.shadow, state["shadow_params"]):
+            s.copy_(v.to(s.device))
 
 
 def get_step_fn(sde, train, optimizer=None, reduce_mean=False, continuous=True, likelihood_weighting=False,

@@ -44,7 +44,13 @@ class GemmPackDesc(ctypes.Structure):
                 ("K", c_i32), ("dst", c_vp)]
 
 
+class PairCriteriaStruct(ctypes.Structure):
+    _fields_ = [("segment", c_vp), ("max_separation", c_i64), ("p_random", c_f32), ("uniforms", c_vp), ("pair_ptr", c_vp),
+                ("seed", ctypes.c_uint64)]
+
+
 E3B_GEMM_MAX_GROUP = 8
+CELL_GRID_BYTES = 48
 
 # name -> (restype, argtypes); must list EVERY symbol include/e3b200.h declares
 SIGNATURES = {
@@ -53,6 +59,13 @@ SIGNATURES = {
     "e3b_struct_size": (c_i64, [c_int]),
     "e3b_radius_graph_count": (c_int, [c_vp, c_i64, c_vp, c_i32, c_i64, c_f32, c_vp, c_vp]),
     "e3b_radius_graph_fill": (c_int, [c_vp, c_i64, c_vp, c_i32, c_i64, c_f32, c_vp, c_i64, c_vp, c_vp, c_vp]),
+    "e3b_pair_graph_count": (c_int, [c_vp, c_i64, c_vp, c_i32, c_i64, c_f32, ctypes.POINTER(PairCriteriaStruct), c_vp, c_vp]),
+    "e3b_pair_graph_fill": (c_int, [c_vp, c_i64, c_vp, c_i32, c_i64, c_f32, ctypes.POINTER(PairCriteriaStruct), c_vp, c_i64, c_vp,
+                                    c_vp]),
+    "e3b_cell_graph_bin": (c_int, [c_vp, c_i64, c_vp, c_i32, c_i64, c_f32, c_i64, c_vp, c_vp, c_vp, c_vp, c_vp]),
+    "e3b_cell_graph_sort": (c_int, [c_vp, c_i64, c_vp, c_vp, c_vp, c_vp]),
+    "e3b_cell_graph_count": (c_int, [c_vp, c_i64, c_vp, c_i32, c_i64, c_f32, c_vp, c_vp, c_vp, c_vp, c_vp]),
+    "e3b_cell_graph_fill": (c_int, [c_vp, c_i64, c_vp, c_i32, c_i64, c_f32, c_vp, c_vp, c_vp, c_vp, c_i64, c_vp, c_vp, c_vp]),
     "e3b_csr_fill": (c_int, [c_vp, c_i64, c_i64, c_int, c_vp, c_vp, c_vp, c_vp]),
     "e3b_edge_vectors_fwd": (c_int, [c_int, c_vp, c_vp, c_i64, c_vp, c_vp, c_vp]),
     "e3b_edge_vectors_bwd": (c_int, [c_int, c_vp, c_vp, c_vp, c_vp, c_i64, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp]),
@@ -80,8 +93,8 @@ SIGNATURES = {
     "e3b_layernorm_fwd": (c_int, [c_int, c_vp, c_i64, c_i32, c_vp, c_vp, c_vp, c_f64, c_vp, c_vp, c_vp]),
     "e3b_layernorm_bwd_blocks": (c_i64, [c_i64]),
     "e3b_layernorm_bwd": (c_int, [c_int, c_vp, c_vp, c_vp, c_i64, c_i32, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp]),
-    "e3b_adam_ema_step": (c_int, [c_vp, c_vp, c_vp, c_vp, c_vp, c_i64, c_f32, c_f32, c_f32, c_f32, c_f32, c_i64, c_f32, c_vp,
-                                  c_vp, c_vp]),
+    "e3b_adam_ema_step": (c_int, [c_vp, c_vp, c_vp, c_vp, c_vp, c_i64, c_f32, c_f64, c_f64, c_f32, c_f32, c_i64, c_f32, c_vp,
+                                  c_vp, c_vp, c_vp, c_vp]),
     "e3b_layout_convert": (c_int, [c_int, c_vp, c_i64, c_i32, c_vp, c_vp, c_int, c_vp, c_vp]),
 }
 

@@ -14,7 +14,8 @@ Forward, per layer (every step is a libe3b200 kernel; feature rows stay in the c
 
 Backward (first order) runs the transposed GEMMs from the same parameter tensors (packed per
 role), the backward tensor-product kernel and the activation-derivative epilogues.  Parameter
-gradients, needed only when training, are plain library GEMMs on the saved activations."""
+gradients (skipped in the position-gradient pass of an energy+force evaluation) are library GEMMs on the saved
+activations."""
 import ctypes
 import math
 
@@ -205,9 +206,10 @@ class _Interaction(torch.autograd.Function):
             check(lib.e3b_gate_imu_fwd(ctypes.byref(fi.gate.desc), 0, ptr(cv), N, ptr(out_mi), ptr(out_imu), stream()))
         count_launch()
         ctx.fi, ctx.csr, ctx.src_is_imu = fi, csr, src_is_imu
-        # parameter gradients are produced in training mode only (module.train()): an energy+force
-        # evaluation differentiates with respect to positions alone and must not pay for them
-        ctx.want_params = bool(fi.mp.training and any(p.requires_grad for p in params))
+        # parameter gradients are produced whenever a parameter requires them, in training AND in evaluation mode
+        # (fine-tuning under model.eval(), gradient diagnostics); the one pass that must not pay for them -- the
+        # position gradient of an energy+force evaluation -- is marked by GradientOutput with ops.positions_only
+        ctx.want_params = bool(any(p.requires_grad for p in params))
         ctx.save_for_backward(x_imu, attrs, Y, xl, cv, *h, mid if ctx.want_params else None)
         ctx.n_h = len(h)
         return out_mi, out_imu
@@ -228,8 +230,9 @@ class _Interaction(torch.autograd.Function):
         new = lambda *s: torch.empty(*s, dtype=torch.float32, device=dev)
         need_x = ctx.needs_input_grad[0] or ctx.needs_input_grad[1]
         need_attrs, need_er, need_Y = ctx.needs_input_grad[2], ctx.needs_input_grad[3], ctx.needs_input_grad[4]
-        need_params = ctx.want_params and any(ctx.needs_input_grad[7:])
-        need_attrs = need_attrs and ctx.want_params
+        pos_only = ops.positions_only_active()          # parameters never depend on the positions
+        need_params = ctx.want_params and any(ctx.needs_input_grad[7:]) and not pos_only
+        need_attrs = need_attrs and ops.needs_grad_now(attrs)
         if g_mi is None and g_imu is None:
             return (None,) * (7 + len(ctx.needs_input_grad[7:]))
         P = fi.packs("bwd")

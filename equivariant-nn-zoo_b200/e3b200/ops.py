@@ -56,6 +56,10 @@ class positions_only:
         return False
 
 
+def positions_only_active():
+    return bool(_POSITIONS_ONLY)
+
+
 def needs_grad_now(t):
     """False when the running backward pass differentiates with respect to one tensor only (GradientOutput's
     position gradient) and `t` does not depend on it; True otherwise.  Walks t's autograd graph (memoised)."""
@@ -137,13 +141,73 @@ def graph_of(edge_index, n_nodes):
     return g
 
 
+class PairCriteria:
+    """The `criteria` of the protein config (reference ``configs/config_diffusion_CA.py:58-64``) in a form the
+    neighbour-list kernel evaluates inside its sweep: same segment (chain) and |a - b| < max_separation, OR a
+    Bernoulli(p_random) draw per ordered pair.  Also a plain callable ``criteria(data, edge_index) -> mask`` with
+    the reference's protocol, so generic callers keep working.
+
+    Randomness: the reference draws ``torch.rand(n_pairs)`` over its all-pairs list.  If ``data`` carries
+    ``_pair_uniforms`` (that vector: one float32 per ordered pair, graphs concatenated, a slow / b fast) the kernel
+    reads it -- a seeded run is then reproduced edge for edge.  Otherwise a counter-based hash of (seed, a, b) is
+    used, with a fresh seed drawn from torch's CPU generator per call (``torch.manual_seed`` makes it repeatable)."""
+
+    def __init__(self, segment_key=None, max_separation=0, p_random=0.0):
+        self.segment_key, self.max_separation, self.p_random = segment_key, int(max_separation), float(p_random)
+
+    def __call__(self, data, edge_index):
+        src, dst = edge_index[0], edge_index[1]
+        keep = torch.zeros(src.shape[0], dtype=torch.bool, device=src.device)
+        if self.segment_key is not None:
+            seg = data[self.segment_key].view(-1)
+            keep = (seg[src] == seg[dst]) & ((src - dst).abs() < self.max_separation)
+        if self.p_random > 0:
+            u = data.get("_pair_uniforms") if hasattr(data, "get") else None
+            if u is None:
+                u = torch.rand(src.shape[0]).to(src.device)            # CPU generator, as the reference
+            keep = keep | (u.to(src.device) < self.p_random)
+        return keep
+
+
 class _NeighbourCount:
     """state between the two phases of the neighbour list (the caller sizes / chooses the edge arrays in between)"""
-    __slots__ = ("pos", "node_ptr", "G", "N", "r_max", "row_ptr", "E")
+    __slots__ = ("pos", "node_ptr", "G", "N", "r_max", "row_ptr", "E", "crit", "crit_keep", "cells")
 
 
-def radius_graph_count(pos, n_nodes_per_graph, r_max):
-    """phase 1: per-atom degrees -> row_ptr, and the edge count E (the ONE host synchronisation of the step)"""
+CELL_MIN_NODES = int(__import__("os").environ.get("E3B_CELL_MIN", "1024"))   # graphs this large are binned (cell list)
+
+
+def _use_cells(N, G):
+    """the graph sizes live on the device; the dispatch uses the mean size, which the host knows from the shapes
+    (graphs below CELL_MIN_NODES take the all-pairs loop inside the cell-list kernel anyway)"""
+    return G > 0 and N // G >= CELL_MIN_NODES
+
+
+def _crit_struct(st, criteria, data, counts):
+    """e3b_pair_criteria for the kernel + the tensors it points to (kept alive on `st`)"""
+    dev = st.pos.device
+    c = _lib.PairCriteriaStruct()
+    keep = []
+    if criteria.segment_key is not None:
+        seg = data[criteria.segment_key].reshape(-1).to(device=dev, dtype=torch.int64).contiguous()
+        keep.append(seg)
+        c.segment, c.max_separation = ptr(seg), criteria.max_separation
+    c.p_random = criteria.p_random
+    if criteria.p_random > 0:
+        u = data.get("_pair_uniforms")
+        if u is not None:
+            u = u.reshape(-1).to(device=dev, dtype=torch.float32).contiguous()
+            pair_ptr = _exclusive_scan(counts * counts, st.G)
+            keep += [u, pair_ptr]
+            c.uniforms, c.pair_ptr = ptr(u), ptr(pair_ptr)
+        else:
+            c.seed = int(torch.randint(0, 2 ** 62, (1,)).item())      # CPU generator: no device synchronisation
+    return c, keep
+
+
+def radius_graph_count(pos, n_nodes_per_graph, r_max, criteria=None, data=None):
+    """phase 1: per-atom degrees -> row_ptr, and the edge count E (the ONE host synchronisation of the step).
+    criteria: None | PairCriteria (evaluated in the sweep); large radius-only graphs are binned into a cell list."""
     lib = _lib.load()
     require_cuda(pos)
     if pos.dtype != torch.float32:
@@ -154,26 +218,63 @@ def radius_graph_count(pos, n_nodes_per_graph, r_max):
     counts = n_nodes_per_graph.reshape(-1).to(device=pos.device, dtype=torch.int64)
     st.G = counts.numel()
     st.node_ptr = _exclusive_scan(counts, st.G)
-    deg = torch.zeros(max(st.N, 1), dtype=torch.int32, device=pos.device)
-    check(lib.e3b_radius_graph_count(ptr(st.pos), 3, ptr(st.node_ptr), st.G, st.N, st.r_max, ptr(deg), stream()))
+    st.crit = st.crit_keep = st.cells = None
+    dev = pos.device
+    deg = torch.zeros(max(st.N, 1), dtype=torch.int32, device=dev)
+    if criteria is not None:
+        st.crit, st.crit_keep = _crit_struct(st, criteria, data if data is not None else {}, counts)
+        check(lib.e3b_pair_graph_count(ptr(st.pos), 3, ptr(st.node_ptr), st.G, st.N, st.r_max, ctypes.byref(st.crit), ptr(deg),
+                                       stream()))
+        count_launch()
+    elif _use_cells(st.N, st.G):
+        C = 2 * st.N + st.G                                            # about two cells per atom, known without a sync
+        cell_ptr = _exclusive_scan(2 * counts + 1, st.G)
+        grids = torch.empty(st.G * _lib.CELL_GRID_BYTES, dtype=torch.uint8, device=dev)
+        cell_of = torch.empty(st.N, dtype=torch.int32, device=dev)
+        cell_count = torch.zeros(C, dtype=torch.int32, device=dev)
+        check(lib.e3b_cell_graph_bin(ptr(st.pos), 3, ptr(st.node_ptr), st.G, st.N, st.r_max, CELL_MIN_NODES, ptr(cell_ptr),
+                                     ptr(grids), ptr(cell_of), ptr(cell_count), stream()))
+        cell_start = _exclusive_scan(cell_count.long(), C)
+        cursor = torch.zeros(C, dtype=torch.int32, device=dev)
+        order = torch.empty(st.N, dtype=torch.int32, device=dev)
+        check(lib.e3b_cell_graph_sort(ptr(cell_of), st.N, ptr(cell_start), ptr(cursor), ptr(order), stream()))
+        check(lib.e3b_cell_graph_count(ptr(st.pos), 3, ptr(st.node_ptr), st.G, st.N, st.r_max, ptr(grids), ptr(cell_start),
+                                       ptr(order), ptr(deg), stream()))
+        st.cells = (grids, cell_start, order)
+        count_launch(4)
+    else:
+        check(lib.e3b_radius_graph_count(ptr(st.pos), 3, ptr(st.node_ptr), st.G, st.N, st.r_max, ptr(deg), stream()))
+        count_launch()
     st.row_ptr = _exclusive_scan(deg[:st.N].long(), st.N)
     st.E = int(st.row_ptr[-1].item()) if st.N else 0   # the one host sync: the caller must size edge_index
-    count_launch(2)
+    count_launch()
     return st
 
 
 def radius_graph_fill(st, edge_index=None, rev=None):
     """phase 2: the edges in the reference's order into `edge_index` [2,E] int64 and, per slot, the id of the
-    reversed edge into `rev` [E] int32 (allocated here unless the caller passes its own buffers)"""
+    reversed edge into `rev` [E] int32 (allocated here unless the caller passes its own buffers; no `rev` with
+    criteria edges, which are not symmetric)"""
     lib = _lib.load()
     dev = st.pos.device
     if edge_index is None:
         edge_index = torch.empty(2, st.E, dtype=torch.int64, device=dev)
+    assert edge_index.shape == (2, st.E) and edge_index.is_contiguous()
+    if st.crit is not None:
+        check(lib.e3b_pair_graph_fill(ptr(st.pos), 3, ptr(st.node_ptr), st.G, st.N, st.r_max, ctypes.byref(st.crit),
+                                      ptr(st.row_ptr), st.E, ptr(edge_index), stream()))
+        count_launch()
+        return edge_index, None
     if rev is None:
         rev = torch.empty(st.E, dtype=torch.int32, device=dev)
-    assert edge_index.shape == (2, st.E) and rev.shape == (st.E,) and edge_index.is_contiguous() and rev.is_contiguous()
-    check(lib.e3b_radius_graph_fill(ptr(st.pos), 3, ptr(st.node_ptr), st.G, st.N, st.r_max, ptr(st.row_ptr), st.E,
-                                    ptr(edge_index), ptr(rev), stream()))
+    assert rev.shape == (st.E,) and rev.is_contiguous()
+    if st.cells is not None:
+        grids, cell_start, order = st.cells
+        check(lib.e3b_cell_graph_fill(ptr(st.pos), 3, ptr(st.node_ptr), st.G, st.N, st.r_max, ptr(grids), ptr(cell_start),
+                                      ptr(order), ptr(st.row_ptr), st.E, ptr(edge_index), ptr(rev), stream()))
+    else:
+        check(lib.e3b_radius_graph_fill(ptr(st.pos), 3, ptr(st.node_ptr), st.G, st.N, st.r_max, ptr(st.row_ptr), st.E,
+                                        ptr(edge_index), ptr(rev), stream()))
     count_launch()
     return edge_index, rev
 
@@ -183,18 +284,21 @@ def edges_per_graph(st):
     return (g[1:] - g[:-1]).view(-1, 1)
 
 
-def radius_graph(pos, n_nodes_per_graph, r_max):
+def radius_graph(pos, n_nodes_per_graph, r_max, criteria=None, data=None):
     """Neighbour list in the reference's order plus its CSR views.
     pos [N,3] float32 (cuda), n_nodes_per_graph int64 [G].  -> edge_index int64 [2,E], n_edges [G], GraphCSR"""
-    st = radius_graph_count(pos, n_nodes_per_graph, r_max)
+    st = radius_graph_count(pos, n_nodes_per_graph, r_max, criteria, data)
     return radius_graph_finish(st)
 
 
 def radius_graph_finish(st):
     edge_index, rev = radius_graph_fill(st)
-    # symmetric graph: in-edges of n are the reversed out-edges; slot k of node n holds the
-    # edge (nbr -> n) whose id is rev[k]; out-grouping is the identity (edges sorted by source)
-    csr = GraphCSR(st.N, st.E, st.row_ptr, edge_index[1].to(torch.int32), rev, st.row_ptr, None)
+    if rev is None:                     # criteria edges: general grouping of an arbitrary (sorted) edge list
+        csr = build_csr(edge_index, st.N)
+    else:
+        # symmetric graph: in-edges of n are the reversed out-edges; slot k of node n holds the
+        # edge (nbr -> n) whose id is rev[k]; out-grouping is the identity (edges sorted by source)
+        csr = GraphCSR(st.N, st.E, st.row_ptr, edge_index[1].to(torch.int32), rev, st.row_ptr, None)
     edge_index._e3b_csr = csr
     return edge_index, edges_per_graph(st), csr
 

@@ -37,11 +37,19 @@ class FlatAdam:
         self.ema = self.param.clone() if ema_decay is not None else None
         self.ema_decay, self.ema_use_num_updates = ema_decay, ema_use_num_updates
         self.lr, self.betas, self.eps, self.weight_decay = float(lr), betas, float(eps), float(weight_decay)
-        self.n_steps = 0
+        self.n_steps = 0                                                   # calls of step() = updates of the moving average
+        # number of Adam updates actually APPLIED (a skipped step does not count, as in torch.optim.Adam): lives on
+        # the device because the skip flag does; two slots, read from one and written to the other each call
+        self._applied = torch.zeros(2, dtype=torch.int64, device=dev)
         self._skip = torch.zeros(1, dtype=torch.int32, device=dev)
         self._scale = torch.ones(1, dtype=torch.float32, device=dev)
         self._backup = None
         ops.WEIGHTS_EPOCH += 1
+
+    @property
+    def applied_steps(self):
+        """number of updates applied so far (host synchronisation; for logging / checkpoints)"""
+        return int(self._applied[self.n_steps % 2])
 
     def zero_grad(self):
         self.grad.zero_()
@@ -75,6 +83,7 @@ class FlatAdam:
             if skip_nonfinite:
                 self._skip.copy_((~torch.isfinite(norm)).to(torch.int32).reshape(1))
                 skip = self._skip
+        src, dst = self._applied[self.n_steps % 2:], self._applied[(self.n_steps + 1) % 2:]
         self.n_steps += 1
         decay = 0.0
         if self.ema is not None:
@@ -83,7 +92,7 @@ class FlatAdam:
                 decay = min(decay, (1 + self.n_steps) / (10 + self.n_steps))
         check(lib.e3b_adam_ema_step(ptr(self.param), ptr(self.grad), ptr(self.exp_avg), ptr(self.exp_avg_sq), ptr(self.ema),
                                     self.param.numel(), self.lr, self.betas[0], self.betas[1], self.eps, self.weight_decay,
-                                    self.n_steps, float(decay), ptr(scale), ptr(skip), stream()))
+                                    0, float(decay), ptr(scale), ptr(skip), ptr(src), ptr(dst), stream()))
         count_launch()
         ops.WEIGHTS_EPOCH += 1                                             # packed tensor-core weights must be rebuilt
 
@@ -98,3 +107,37 @@ class FlatAdam:
         self.param.copy_(self._backup)
         self._backup = None
         ops.WEIGHTS_EPOCH += 1
+
+    # -- checkpoints (reference Trainer.save: optimiser + EMA + progress; run/trainer.py:632-763) ----------------
+    def state_dict(self):
+        return {"param": self.param.clone(), "exp_avg": self.exp_avg.clone(), "exp_avg_sq": self.exp_avg_sq.clone(),
+                "ema": None if self.ema is None else self.ema.clone(), "n_steps": self.n_steps,
+                "applied_steps": self.applied_steps, "lr": self.lr}
+
+    def load_state_dict(self, state):
+        self.param.copy_(state["param"])
+        self.exp_avg.copy_(state["exp_avg"])
+        self.exp_avg_sq.copy_(state["exp_avg_sq"])
+        if self.ema is not None and state.get("ema") is not None:
+            self.ema.copy_(state["ema"])
+        self.n_steps = int(state["n_steps"])
+        self._applied.fill_(int(state["applied_steps"]))
+        self.lr = float(state.get("lr", self.lr))
+        ops.WEIGHTS_EPOCH += 1
+
+    def ema_state_dict(self, module):
+        """the module's state_dict with the averaged weights in place of the raw ones: the deployable model the
+        reference saves (Trainer.save_ema_model)"""
+        sd = {k: v.clone() for k, v in module.state_dict().items()}
+        if self.ema is None:
+            return sd
+        by_ptr = {}
+        o = 0
+        for p in self.params:
+            by_ptr[p.data_ptr()] = (o, p.numel(), p.shape)
+            o += p.numel()
+        for name, p in module.named_parameters():
+            if p.data_ptr() in by_ptr:
+                o, n, shape = by_ptr[p.data_ptr()]
+                sd[name] = self.ema[o:o + n].view(shape).clone()
+        return sd

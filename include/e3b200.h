@@ -72,6 +72,50 @@ E3B_API int e3b_radius_graph_fill(const float* pos, int64_t pos_stride, const in
                           int64_t n_nodes, float r_max, const int64_t* row_ptr, int64_t n_edges,
                           int64_t* edge_index /* [2,E] */, int32_t* rev /* [E] or NULL */, void* stream);
 
+/* Neighbour list with the `criteria` of the protein config evaluated inside the sweep (replaces the
+ * criteria(data, all_pairs) call of compute_edge.py:73-74 for e3_layers/configs/config_diffusion_CA.py:58-64):
+ * pair (a,b), a != b, same graph, is an edge iff   |pos[a]-pos[b]| < r_max
+ *      OR (segment != NULL and segment[a] == segment[b] and |a - b| < max_separation)
+ *      OR (p_random > 0 and u(a,b) < p_random),
+ * u(a,b) = uniforms[pair_ptr[g] + (a - first_g) * n_g + (b - first_g)] when `uniforms` is given (the reference's
+ * torch.rand over its all-pairs list, indexable so that a seeded run can be reproduced edge for edge), else a
+ * counter-based hash of (seed, a, b).  Same two phases and output order as e3b_radius_graph_*; the graph is not
+ * symmetric in general, so there is no `rev` (use e3b_csr_fill).  The struct holds DEVICE pointers.            */
+typedef struct {
+  const int64_t* segment;     /* [N] or NULL */
+  int64_t max_separation;
+  float p_random;
+  const float* uniforms;      /* [sum_g n_g^2] or NULL */
+  const int64_t* pair_ptr;    /* [G+1], exclusive scan of n_g^2; required with uniforms */
+  uint64_t seed;
+} e3b_pair_criteria;
+E3B_API int e3b_pair_graph_count(const float* pos, int64_t pos_stride, const int64_t* node_ptr, int32_t n_graphs,
+                                 int64_t n_nodes, float r_max, const e3b_pair_criteria* h_crit, int32_t* deg, void* stream);
+E3B_API int e3b_pair_graph_fill(const float* pos, int64_t pos_stride, const int64_t* node_ptr, int32_t n_graphs,
+                                int64_t n_nodes, float r_max, const e3b_pair_criteria* h_crit, const int64_t* row_ptr,
+                                int64_t n_edges, int64_t* edge_index, void* stream);
+
+/* Cell-list variant of e3b_radius_graph_* for large graphs (same predicate, same output, bit for bit).
+ *   bin  : graphs with >= min_nodes atoms get a uniform grid (cells >= 1.001 r_max, at most
+ *          cell_ptr[g+1]-cell_ptr[g] cells; the caller reserves about two cells per atom); writes grids
+ *          [G * E3B_CELL_GRID_BYTES], cell_of int32 [N] (-1 = graph not binned) and adds to the zeroed cell_count [C];
+ *   (caller: cell_start = exclusive scan of cell_count, int64 [C+1])
+ *   sort : atoms grouped by cell into sorted int32 [N] (cursor int32 [C], zeroed);
+ *   count / fill: as e3b_radius_graph_count / _fill; small graphs of the batch take the all-pairs loop.        */
+#define E3B_CELL_GRID_BYTES 48
+E3B_API int e3b_cell_graph_bin(const float* pos, int64_t pos_stride, const int64_t* node_ptr, int32_t n_graphs,
+                               int64_t n_nodes, float r_max, int64_t min_nodes, const int64_t* cell_ptr /* [G+1] */,
+                               void* grids, int32_t* cell_of, int32_t* cell_count, void* stream);
+E3B_API int e3b_cell_graph_sort(const int32_t* cell_of, int64_t n_nodes, const int64_t* cell_start, int32_t* cursor,
+                                int32_t* sorted, void* stream);
+E3B_API int e3b_cell_graph_count(const float* pos, int64_t pos_stride, const int64_t* node_ptr, int32_t n_graphs,
+                                 int64_t n_nodes, float r_max, const void* grids, const int64_t* cell_start,
+                                 const int32_t* sorted, int32_t* deg, void* stream);
+E3B_API int e3b_cell_graph_fill(const float* pos, int64_t pos_stride, const int64_t* node_ptr, int32_t n_graphs,
+                                int64_t n_nodes, float r_max, const void* grids, const int64_t* cell_start,
+                                const int32_t* sorted, const int64_t* row_ptr, int64_t n_edges, int64_t* edge_index,
+                                int32_t* rev /* [E] or NULL */, void* stream);
+
 /* Dst-grouped CSR of an arbitrary edge list (any order, e.g. with `criteria` edges or a
  * user-supplied edge_index).  The caller passes row_ptr = exclusive scan of the in-degree
  * (int64 [N+1]) and a zeroed int32 cursor[N]; the kernel fills, per destination node, the
@@ -291,13 +335,16 @@ E3B_API int e3b_layernorm_bwd(int dtype, const void* x, const void* gy, const vo
 /* ---------------------------------------------------------------------------------------
  * Optimiser step on a flat fp32 parameter buffer: Adam (torch.optim.Adam semantics: the reference's optimiser,
  * run/trainer.py:370-386, train.py:103-107) fused with the exponential moving average of the parameters
- * (torch_ema as used in run/trainer.py and run/sde_utils.py:232-248; `ema` may be NULL).  `step` >= 1 is the
- * number of this update (bias corrections).  grad_scale: optional DEVICE float multiplying the gradient
- * (clipping coefficient); skip: optional DEVICE int, non-zero = leave everything untouched (non-finite
- * gradients, run/sde_utils.py:240-246).                                                                     */
+ * (torch_ema as used in run/trainer.py and run/sde_utils.py:232-248; `ema` may be NULL).  grad_scale: optional
+ * DEVICE float multiplying the gradient (clipping coefficient); skip: optional DEVICE int, non-zero = the Adam
+ * update is skipped (non-finite gradients, run/sde_utils.py:240-246) while the moving average still advances.
+ * step_in / step_out: optional pair of DISTINCT DEVICE int64 scalars holding the number of updates applied so
+ * far (read from step_in, written to step_out; a skipped update does not count, as in torch.optim.Adam); when
+ * NULL, `step` >= 1 is the number of this update (bias corrections).                                          */
 E3B_API int e3b_adam_ema_step(void* param, const void* grad, void* exp_avg, void* exp_avg_sq, void* ema, int64_t n,
-                              float lr, float beta1, float beta2, float eps, float weight_decay, int64_t step,
-                              float ema_decay, const void* grad_scale, const void* skip, void* stream);
+                              float lr, double beta1, double beta2, float eps, float weight_decay, int64_t step,
+                              float ema_decay, const void* grad_scale, const void* skip, const void* step_in,
+                              void* step_out, void* stream);
 
 /* mul_ir <-> imu layout conversion of feature rows (blocks: mul, l). to_imu = 1: [u][m]->[m][u] */
 E3B_API int e3b_layout_convert(int dtype, const void* in, int64_t n, int32_t n_blocks, const int32_t* mul,

@@ -145,3 +145,81 @@ def test_pre_existing_edges_are_merged_and_attributes_remapped():
         assert torch.equal(data["_n_edges"].cpu(), ref_data["_n_edges"])
         if r_max < 100:
             assert out["edge_index"].shape[1] > bonds.shape[1]              # the radius part really added edges
+
+
+def test_pair_criteria_in_the_sweep_bit_exact_vs_oracle():
+    """ops.PairCriteria (the criteria of config_diffusion_CA.py:58-64) evaluated inside the neighbour-list kernel
+    (e3b_pair_graph_*): same edges, same order as the oracle's computeEdgeIndex fed the reference's own criteria
+    function with the same uniforms; the foreign-callable path of the product agrees too."""
+    from e3_layers.data import computeEdgeIndex
+
+    p = synthetic.protein_like(600, seed=7)
+    two = {k: torch.cat([p[k], p[k][:400]]) for k in ("CA", "chain_id")}           # two graphs, 600 + 400 residues
+    two["chain_id"][600:] += 10
+    n_nodes = torch.tensor([[600], [400]])
+    u = torch.rand(600 * 600 + 400 * 400, generator=torch.Generator().manual_seed(9))
+
+    def reference_criteria(data, edge_index):                                      # config_diffusion_CA.py:58-64, seeded
+        mask = (data["chain_id"][edge_index[0]] == data["chain_id"][edge_index[1]]).view(-1)
+        mask = torch.logical_and(mask, abs(edge_index[0] - edge_index[1]) < 5)
+        return torch.logical_or(mask, u.to(mask.device) < 0.02)
+
+    ref_data = {"CA": two["CA"], "chain_id": two["chain_id"], "_n_nodes": n_nodes}
+    d, _ = ref_layers.computeEdgeIndex(ref_data, {}, r_max=8.0 / 25.83, key="CA", criteria=reference_criteria)
+    crit = ops.PairCriteria(segment_key="chain_id", max_separation=5, p_random=0.02)
+    data = {"CA": two["CA"].to(DEV), "chain_id": two["chain_id"].to(DEV), "_n_nodes": n_nodes.to(DEV), "_pair_uniforms": u.to(DEV)}
+    out, _ = computeEdgeIndex(data, {}, r_max=8.0 / 25.83, key="CA", criteria=crit)
+    assert torch.equal(out["edge_index"].cpu(), d["edge_index"])
+    assert torch.equal(data["_n_edges"].cpu(), ref_data["_n_edges"])
+    _check_csr(out["edge_index"], ops.graph_of(out["edge_index"], 1000), 1000)
+    data2 = {k: v for k, v in data.items() if k != "_n_edges"}
+    out2, _ = computeEdgeIndex(data2, {}, r_max=8.0 / 25.83, key="CA", criteria=lambda dd, ei: crit(dd, ei))
+    assert torch.equal(out2["edge_index"], out["edge_index"])
+    # without explicit uniforms: hash RNG seeded from torch's CPU generator -> repeatable, right density, no self loops
+    data3 = {k: v for k, v in data.items() if k not in ("_n_edges", "_pair_uniforms")}
+    torch.manual_seed(4)
+    a, _ = computeEdgeIndex(dict(data3), {}, r_max=1e-6, key="CA", criteria=ops.PairCriteria(p_random=0.02))
+    torch.manual_seed(4)
+    b, _ = computeEdgeIndex(dict(data3), {}, r_max=1e-6, key="CA", criteria=ops.PairCriteria(p_random=0.02))
+    c, _ = computeEdgeIndex(dict(data3), {}, r_max=1e-6, key="CA", criteria=ops.PairCriteria(p_random=0.02))
+    assert torch.equal(a["edge_index"], b["edge_index"]) and not torch.equal(a["edge_index"], c["edge_index"])
+    n_pairs = 600 * 599 + 400 * 399
+    assert abs(a["edge_index"].shape[1] / n_pairs - 0.02) < 0.002
+    assert bool((a["edge_index"][0] != a["edge_index"][1]).all())
+    seg = torch.repeat_interleave(torch.arange(2, device=DEV), n_nodes.reshape(-1).to(DEV))
+    assert torch.equal(seg[a["edge_index"][0]], seg[a["edge_index"][1]])           # never across graphs
+
+
+@pytest.mark.parametrize("case", ["protein", "blob", "mixed"])
+def test_cell_list_bit_exact_vs_all_pairs(case, monkeypatch):
+    """the cell-list kernels (e3b_cell_graph_*) against the all-pairs sweep and the oracle: same edges, same order"""
+    if case == "protein":
+        p = synthetic.protein_like(3000, seed=2)
+        pos, n_nodes, r = p["CA"], torch.tensor([3000]), 8.0 / 25.83
+    elif case == "blob":                                      # dense: > 512 neighbours for many atoms (buffer overflow path)
+        g = torch.Generator().manual_seed(3)
+        pos, n_nodes, r = torch.rand(2500, 3, generator=g) * 4.0, torch.tensor([2500]), 1.9
+    else:                                                     # a large graph, a flat one (one cell thick) and small ones
+        g = torch.Generator().manual_seed(5)
+        big = torch.rand(2000, 3, generator=g) * 30.0
+        flat = torch.rand(1500, 3, generator=g) * torch.tensor([40.0, 40.0, 0.5])
+        small = synthetic.qm9_like(20, seed=1)
+        pos = torch.cat([big, small["pos"], flat, torch.zeros(1, 3)])
+        n_nodes = torch.cat([torch.tensor([2000]), small["_n_nodes"].reshape(-1), torch.tensor([1500, 1])])
+        r = 5.0
+    monkeypatch.setattr(ops, "CELL_MIN_NODES", 10 ** 9)
+    ei0, ne0, _ = ops.radius_graph(pos.to(DEV), n_nodes.to(DEV), r)
+    monkeypatch.setattr(ops, "CELL_MIN_NODES", 1024 if case != "mixed" else 64)
+    if case == "mixed":
+        # the dispatch looks at the mean graph size; force the cell path for this mixed batch
+        monkeypatch.setattr(ops, "_use_cells", lambda N, G: True)
+    ei1, ne1, csr = ops.radius_graph(pos.to(DEV), n_nodes.to(DEV), r)
+    assert torch.equal(ei1, ei0) and torch.equal(ne1, ne0)
+    _check_csr(ei1, csr, pos.shape[0])
+    if case == "protein":
+        data = {"pos": pos, "_n_nodes": n_nodes.view(-1, 1)}
+        d, _ = ref_layers.computeEdgeIndex(data, {}, r_max=r)
+        assert torch.equal(ei1.cpu(), d["edge_index"])
+    if case == "blob":
+        deg = torch.bincount(ei1[0])
+        assert int(deg.max()) > 512

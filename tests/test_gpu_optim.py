@@ -53,19 +53,55 @@ def test_flat_adam_matches_torch_adam_and_ema(clip, wd):
 
 
 def test_flat_adam_skips_nonfinite_step():
-    m = _mlp(3)
-    opt = optim.FlatAdam(m, lr=1e-2)
+    """a skipped step leaves parameters and moments alone, does NOT advance Adam's step count (torch.optim.Adam is
+    simply not called by the reference loop, run/sde_utils.py:240-246) and still moves the moving average"""
+    ref, m = _mlp(3), _mlp(3)
+    opt_ref = torch.optim.Adam(ref.parameters(), lr=1e-2)
+    opt = optim.FlatAdam(m, lr=1e-2, ema_decay=0.9, ema_use_num_updates=False)
     x = torch.randn(8, 7, device=DEV)
     opt.zero_grad()
     m(x).sum().backward()
-    opt.grad[3] = float("nan")
-    before = opt.param.clone()
-    opt.step(skip_nonfinite=True)
-    assert torch.equal(opt.param, before) and float(opt.exp_avg.abs().max()) == 0.0
+    opt.step()                                               # update 1
+    opt_ref.zero_grad()
+    ref(x).sum().backward()
+    opt_ref.step()
     opt.zero_grad()
     m(x).sum().backward()
-    opt.step(skip_nonfinite=True)
-    assert not torch.equal(opt.param, before)
+    opt.grad[3] = float("nan")
+    before, ema_before, avg_before = opt.param.clone(), opt.ema.clone(), opt.exp_avg.clone()
+    opt.step(skip_nonfinite=True)                            # skipped
+    assert torch.equal(opt.param, before) and torch.equal(opt.exp_avg, avg_before)
+    assert opt.applied_steps == 1 and opt.n_steps == 2
+    assert harness.rel_err(opt.ema, 0.9 * ema_before + 0.1 * before) < 1e-6 and not torch.equal(opt.ema, ema_before)
+    opt.zero_grad()
+    m(x).sum().backward()
+    opt.step(skip_nonfinite=True)                            # update 2: bias corrections of step 2, not 3
+    opt_ref.zero_grad()
+    ref(x).sum().backward()
+    opt_ref.step()
+    assert opt.applied_steps == 2
+    for a, b in zip(m.parameters(), ref.parameters()):
+        assert harness.rel_err(a, b) < 2e-6
+
+
+def test_flat_adam_state_round_trip():
+    a, b = _mlp(5), _mlp(6)
+    oa, ob = optim.FlatAdam(a, lr=1e-2, ema_decay=0.99), optim.FlatAdam(b, lr=1e-3, ema_decay=0.99)
+    x = torch.randn(8, 7, device=DEV)
+    for _ in range(3):
+        oa.zero_grad()
+        a(x).sum().backward()
+        oa.step()
+    ob.load_state_dict(oa.state_dict())
+    assert ob.n_steps == 3 and ob.applied_steps == 3 and ob.lr == 1e-2
+    for o, model in ((oa, a), (ob, b)):
+        o.zero_grad()
+        model(x).sum().backward()
+        o.step()
+    assert torch.equal(oa.param, ob.param) and torch.equal(oa.ema, ob.ema)
+    sd = oa.ema_state_dict(a)
+    flat = torch.cat([sd[k].reshape(-1) for k, _ in a.named_parameters()])
+    assert torch.equal(flat, oa.ema)
 
 
 def test_flat_adam_drives_the_fused_blocks():

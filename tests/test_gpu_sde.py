@@ -66,6 +66,29 @@ def test_graph_replay_equals_eager_loop():
     assert torch.isfinite(a["pos"]).all() and not torch.equal(a["pos"], b["pos"])
 
 
+def test_graph_sampler_on_a_batch_without_t():
+    """dataset batches (qm9 ...) carry no 't': the sampler assigns it itself (reference sde_sampling.py:231-236), also
+    on the CUDA-graph path (the set of graph inputs was recorded before 't' existed -> KeyError)"""
+    meta = {"config": "config_diffusion", "seed": 4}
+    inputs = {k: v for k, v in synthetic.diffusion_like(8, seed=5).items() if k != "t"}
+    model = product_harness.build_product(meta, torch.float32, DEV)
+    outs = []
+    for graph in (False, True):
+        sde = VPSDE({"pos": 3}, N=100)
+        sde.randn_like = lambda x: 0.9 * torch.cos(11.0 * x + 0.3 * torch.arange(x.shape[0], device=x.device,
+                                                                                 dtype=x.dtype).view(-1, 1))
+        sampler = get_pc_sampler(sde, EulerMaruyamaPredictor, LangevinCorrector, lambda b: b, snr=0.16, n_steps=1,
+                                 max_iterations=4, graph=graph)
+        batch = product_batch(inputs, torch.float32, DEV)
+        assert "t" not in batch
+        torch.manual_seed(0)
+        out, nfe = sampler(model, batch)
+        assert nfe == 8 and torch.isfinite(out["pos"]).all()
+        outs.append(out["pos"])
+    # the prior draw differs between the two runs unless seeded identically: both were seeded with 0 above
+    assert harness.rel_err(outs[1], outs[0]) < 1e-5
+
+
 def test_protein_sampler_rebuilds_edges_and_score_matching_step():
     cfg = configs.config_diffusion_CA()
     model = reseed_parameters(build(cfg.model_config), 1).to(DEV).eval()

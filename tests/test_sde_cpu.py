@@ -98,3 +98,35 @@ def test_step_fn_follows_the_reference_quirks(monkeypatch):
         assert val == val and torch.equal(flat(), p2)             # evaluation on the EMA weights leaves the live ones alone
     finally:
         torch.set_default_dtype(torch.float32)
+
+
+def test_ema_decay_warms_up_like_the_reference():
+    """score_sde_pytorch models/ema.py (what reference train.py:103 builds): use_num_updates=True by default, decay =
+    min(decay, (1 + n) / (10 + n)); parameters without requires_grad are not tracked; state round-trips."""
+    from e3_layers.run import ExponentialMovingAverage
+
+    w = torch.nn.Parameter(torch.zeros(3))
+    frozen = torch.nn.Parameter(torch.ones(2), requires_grad=False)
+    ema = ExponentialMovingAverage([w, frozen], decay=0.9999)
+    assert len(ema.shadow) == 1
+    ref = torch.zeros(3)
+    for n in range(1, 30):
+        with torch.no_grad():
+            w += 1.0
+        ema.update([w, frozen])
+        d = min(0.9999, (1 + n) / (10 + n))
+        ref = d * ref + (1 - d) * w.detach()
+        assert abs(ema.current_decay() - d) < 1e-15
+        assert torch.allclose(ema.shadow[0], ref, atol=1e-6)
+    assert float(ema.shadow[0][0]) > 10.0            # a fixed 0.9999 would still sit at ~0.04
+    fixed = ExponentialMovingAverage([w], decay=0.9999, use_num_updates=False)
+    fixed.update([w])
+    assert fixed.current_decay() == 0.9999
+    other = ExponentialMovingAverage([torch.nn.Parameter(torch.zeros(3)), frozen], decay=0.5)
+    other.load_state_dict(ema.state_dict())
+    assert other.num_updates == 29 and other.decay == 0.9999 and torch.equal(other.shadow[0], ema.shadow[0])
+    ema.store([w, frozen])
+    ema.copy_to([w, frozen])
+    assert torch.equal(w.detach(), ema.shadow[0]) and torch.equal(frozen, torch.ones(2))
+    ema.restore([w, frozen])
+    assert float(w[0]) == 29.0

@@ -122,14 +122,18 @@ def main(rank, flags):
     target_keys = list(loss_coeffs)
     setSeed(flags.seed)                                          # identical initial weights on every rank
     model = build(config.model_config).to(dev).train()
-    if flags.resume_from:
-        state = torch.load(flags.resume_from, map_location=dev)
-        model.load_state_dict({(k[7:] if k.startswith("module.") else k): v for k, v in state.items()})
+    resume = _load_checkpoint(flags.resume_from, dev)
+    if resume is not None:
+        model.load_state_dict(_strip_module(resume["model"]))
     parallel.broadcast_parameters(model)
     # flat parameter / gradient buffers: one all-reduce, one fused Adam + EMA kernel per step (e3b200.optim)
     opt = optim.FlatAdam(model, lr=float(config.learning_rate),
                          ema_decay=float(config.ema_decay) if getattr(config, "use_ema", False) else None,
                          ema_use_num_updates=bool(getattr(config, "ema_use_num_updates", True)))
+    first_step = 0
+    if resume is not None and resume.get("optimizer") is not None:     # full trainer state: moments, EMA, progress
+        opt.load_state_dict(resume["optimizer"])
+        first_step = int(resume.get("step", 0))
     r_max = float(config.model_config.r_max)
 
     data = load_data(flags, config, target_keys)
@@ -141,7 +145,9 @@ def main(rank, flags):
     attrs = {"pos": ("node", "1x1o"), "species": ("node", "1x0e"), "_n_nodes": ("graph", "1x0e")}
     out_dir = os.path.join(flags.workdir, flags.name)
     t0 = time.time()
-    for step in range(flags.steps):
+    for _ in range(first_step):                                  # replay the data order up to the restored step
+        torch.randperm(G, generator=gen)
+    for step in range(first_step, flags.steps):
         pick = torch.randperm(G, generator=gen)[:bs].sort().values
         node_idx = torch.cat([torch.arange(int(starts[g]), int(starts[g] + n_all[g])) for g in pick])
         host = {k: (v[node_idx] if v.shape[0] == int(n_all.sum()) else v[pick]) for k, v in data.items()}
@@ -170,10 +176,34 @@ def main(rank, flags):
             if rank == 0:
                 logging.info("step %d loss %.6g mae %.6g (%.1f s)", step, float(scal[0]), float(scal[1]), time.time() - t0)
         if rank == 0 and ((step + 1) % flags.save_period == 0 or step == flags.steps - 1):
+            # reference Trainer.save (run/trainer.py:632-763): trainer.pt = everything needed to resume (raw weights,
+            # optimiser moments, EMA, progress); model.pt = the deployable weights = the EMA average when it is kept
             os.makedirs(out_dir, exist_ok=True)
-            torch.save(model.state_dict(), os.path.join(out_dir, "model.pt"))
+            _atomic_save({"model": model.state_dict(), "optimizer": opt.state_dict(), "step": step + 1,
+                          "config": flags.config}, os.path.join(out_dir, "trainer.pt"))
+            _atomic_save(opt.ema_state_dict(model), os.path.join(out_dir, "model.pt"))
     if world > 1:
         dist.destroy_process_group()
+
+
+def _strip_module(sd):
+    return {(k[7:] if k.startswith("module.") else k): v for k, v in sd.items()}
+
+
+def _load_checkpoint(path, dev):
+    """--resume_from takes a trainer.pt (full state) or a bare state_dict (weights only, reference inference.py:46-53)"""
+    if not path:
+        return None
+    state = torch.load(path, map_location=dev, weights_only=False)
+    if isinstance(state, dict) and "model" in state and isinstance(state["model"], dict):
+        return state
+    return {"model": state}
+
+
+def _atomic_save(obj, path):
+    tmp = path + ".tmp"
+    torch.save(obj, tmp)
+    os.replace(tmp, path)                                        # the reference renames a finished temp file too
 
 
 def train_diffusion(config, flags, rank, world, dev):
@@ -187,9 +217,9 @@ def train_diffusion(config, flags, rank, world, dev):
 
     setSeed(flags.seed)
     model = build(config.model_config).to(dev).train()
-    if flags.resume_from:
-        state = torch.load(flags.resume_from, map_location=dev)
-        model.load_state_dict({(k[7:] if k.startswith("module.") else k): v for k, v in state.items()})
+    resume = _load_checkpoint(flags.resume_from, dev)
+    if resume is not None:
+        model.load_state_dict(_strip_module(resume["model"]))
     parallel.broadcast_parameters(model)
     keys = getattr(config, "diffusion_keys", None)
     keys = dict(keys.items()) if keys is not None and hasattr(keys, "items") else {"pos": 3}
@@ -197,6 +227,10 @@ def train_diffusion(config, flags, rank, world, dev):
     opt = torch.optim.Adam(model.parameters(), lr=float(config.learning_rate))
     flat = parallel.FlatGradients(model.parameters())
     state = {"model": model, "optimizer": opt, "ema": ExponentialMovingAverage(model.parameters(), decay=flags.ema_rate), "step": 0}
+    if resume is not None and resume.get("optimizer") is not None:     # reference restore_checkpoint: optimizer, ema, step
+        opt.load_state_dict(resume["optimizer"])
+        state["ema"].load_state_dict(resume["ema"])
+        state["step"] = int(resume["step"])
     clip = getattr(config, "grad_clid_norm", None)
     step_fn = get_step_fn(sde, train=True, optimizer=opt, reduce_mean=True, grad_clid_norm=clip,
                           grad_acc=int(getattr(config, "grad_acc", 1)), grad_sync=flat.all_reduce if world > 1 else None)
@@ -214,7 +248,7 @@ def train_diffusion(config, flags, rank, world, dev):
         pool.append({k: v.to(dev) for k, v in b.items()})
     out_dir = os.path.join(flags.workdir, flags.name)
     t0, window = time.time(), []
-    for step in range(flags.steps):
+    for step in range(state["step"], flags.steps):
         b = pool[step % len(pool)]
         batch = Batch({k: attrs_of[k] for k in b if k in attrs_of}, **{k: v.clone() for k, v in b.items()})
         loss, losses = step_fn(state, batch)
@@ -223,8 +257,16 @@ def train_diffusion(config, flags, rank, world, dev):
             logging.info("step %d training_loss %.5e (%.1f s)", step, sum(window) / len(window), time.time() - t0)
             window = []
         if rank == 0 and ((step + 1) % flags.save_period == 0 or step == flags.steps - 1):
+            # reference save_checkpoint(state) (utils/saveload.py:432-454): {optimizer, model, ema, step}; model.pt holds
+            # the EMA weights, which are the ones the reference samples and validates with
             os.makedirs(out_dir, exist_ok=True)
-            torch.save(model.state_dict(), os.path.join(out_dir, "model.pt"))
+            _atomic_save({"model": model.state_dict(), "optimizer": opt.state_dict(), "ema": state["ema"].state_dict(),
+                          "step": state["step"], "config": flags.config}, os.path.join(out_dir, "checkpoint.pt"))
+            ema = state["ema"]
+            ema.store(model.parameters())
+            ema.copy_to(model.parameters())
+            _atomic_save(model.state_dict(), os.path.join(out_dir, "model.pt"))
+            ema.restore(model.parameters())
     if world > 1:
         dist.destroy_process_group()
 
