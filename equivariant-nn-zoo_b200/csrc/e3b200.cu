@@ -113,11 +113,12 @@ __global__ void __launch_bounds__(256) radius_graph_kernel(const float* __restri
   if (!FILL && lane == 0) deg[a] = count;
 }
 
-// rev[e] = index of the reversed edge (b, a): binary search for a among b's sorted neighbours
+// rev[e] = index of the reversed edge (b, a): binary search for a among b's sorted neighbours.
+// `count` edges are visited, `n_edges` is the row pitch of edge_index; nbr32 (optional) receives int32(b).
 __global__ void reverse_edge_kernel(const int64_t* __restrict__ edge_index, const int64_t* __restrict__ row_ptr,
-                                    int64_t n_edges, int32_t* __restrict__ rev) {
+                                    int64_t count, int64_t n_edges, int32_t* __restrict__ rev, int32_t* __restrict__ nbr32) {
   const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (e >= n_edges) return;
+  if (e >= count) return;
   const int64_t a = edge_index[e], b = edge_index[n_edges + e];
   int64_t lo = row_ptr[b], hi = row_ptr[b + 1] - 1;
   int64_t found = -1;
@@ -128,6 +129,41 @@ __global__ void reverse_edge_kernel(const int64_t* __restrict__ edge_index, cons
     if (v < a) lo = mid + 1; else hi = mid - 1;
   }
   rev[e] = (int32_t)found;
+  if (nbr32) nbr32[e] = (int32_t)b;
+}
+
+// Bucketed edge count (CUDA-graph replay of batches with different sizes): the last n_pad atoms of the batch are
+// padding atoms in a graph of their own, laid out as isolated pairs (2p, 2p + 1) (an odd last one has no partner).
+// The natural radius graph gives every paired atom one neighbour; here the tail of row_ptr is rewritten so that the edge
+// list has exactly n_total entries: the P = n_total - natural missing ones are parallel copies of the pair edges,
+// spread evenly over the pairs (P / 2 per direction).  One thread per padding atom writes its whole row.
+__global__ void pad_rows_kernel(int64_t* __restrict__ row_ptr, int64_t n_real, int64_t n_pad, int64_t n_total,
+                                int64_t* __restrict__ edge_index, int32_t* __restrict__ rev, int32_t* __restrict__ nbr32) {
+  const int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= n_pad) return;
+  const int64_t pairs = n_pad >> 1;
+  const int64_t e_real = row_ptr[n_real];                 // never rewritten (start of the first padding row)
+  const int64_t half = (n_total - e_real - 2 * pairs) >> 1;   // extra edges per direction
+  const int64_t base = pairs ? half / pairs : 0, rem = pairs ? half % pairs : 0;
+  const int64_t p = j >> 1, s = j & 1;
+  int64_t start, deg = 0, partner_start = 0;
+  if (p < pairs) {
+    const int64_t before = 2 * (p * (1 + base) + (p < rem ? p : rem));
+    deg = 1 + base + (p < rem ? 1 : 0);
+    start = e_real + before + s * deg;
+    partner_start = e_real + before + (1 - s) * deg;
+  } else {
+    start = n_total;                                        // unpaired last atom: empty row
+  }
+  if (j > 0) row_ptr[n_real + j] = start;
+  if (j == n_pad - 1) row_ptr[n_real + n_pad] = n_total;
+  const int64_t a = n_real + j, b = n_real + (j ^ 1);
+  for (int64_t i = 0; i < deg; ++i) {
+    edge_index[start + i] = a;
+    edge_index[n_total + start + i] = b;
+    rev[start + i] = (int32_t)(partner_start + i);
+    if (nbr32) nbr32[start + i] = (int32_t)b;
+  }
 }
 
 extern "C" int e3b_radius_graph_count(const float* pos, int64_t pos_stride, const int64_t* node_ptr, int32_t n_graphs,
@@ -149,10 +185,39 @@ extern "C" int e3b_radius_graph_fill(const float* pos, int64_t pos_stride, const
   int rc = check_launch("radius_graph_fill");
   if (rc) return rc;
   if (rev) {
-    reverse_edge_kernel<<<blocks_for(n_edges, 256), 256, 0, (cudaStream_t)stream>>>(edge_index, row_ptr, n_edges, rev);
+    reverse_edge_kernel<<<blocks_for(n_edges, 256), 256, 0, (cudaStream_t)stream>>>(edge_index, row_ptr, n_edges, n_edges, rev,
+                                                                                  nullptr);
     rc = check_launch("radius_graph_reverse");
   }
   return rc;
+}
+
+extern "C" int e3b_radius_graph_fill_padded(const float* pos, int64_t pos_stride, const int64_t* node_ptr, int32_t n_graphs,
+                                            int64_t n_nodes, int64_t n_pad, float r_max, int64_t* row_ptr,
+                                            int64_t n_edges_natural, int64_t n_edges_total, int64_t* edge_index, int32_t* rev,
+                                            int32_t* nbr32, void* stream) {
+  if (!pos || !node_ptr || !row_ptr || !edge_index || !rev) return fail(E3B_ERR_INVALID, "radius_graph_fill_padded: null argument");
+  const int64_t pairs = n_pad / 2, n_real = n_nodes - n_pad, e_real = n_edges_natural - 2 * pairs;
+  if (n_pad < 0 || n_real < 0 || n_graphs < 2 || e_real < 0 || n_edges_total < n_edges_natural ||
+      ((n_edges_total - n_edges_natural) & 1) || (n_edges_total > n_edges_natural && pairs == 0))
+    return fail(E3B_ERR_INVALID, "radius_graph_fill_padded: need >= 1 padding pair and an even number of extra edges");
+  cudaStream_t s = (cudaStream_t)stream;
+  if (n_pad) {
+    pad_rows_kernel<<<blocks_for(n_pad, 128), 128, 0, s>>>(row_ptr, n_real, n_pad, n_edges_total, edge_index, rev, nbr32);
+    int rc = check_launch("radius_graph_pad_rows");
+    if (rc) return rc;
+  }
+  if (n_real && e_real) {
+    // the real atoms: graphs 0 .. n_graphs - 2; edge_index has row pitch n_edges_total
+    radius_graph_kernel<true><<<blocks_for(n_real, 8), 256, 0, s>>>(pos, pos_stride, node_ptr, n_graphs - 1, n_real, r_max,
+                                                                     nullptr, row_ptr, n_edges_total, edge_index);
+    int rc = check_launch("radius_graph_fill");
+    if (rc) return rc;
+    reverse_edge_kernel<<<blocks_for(e_real, 256), 256, 0, s>>>(edge_index, row_ptr, e_real, n_edges_total, rev, nbr32);
+    rc = check_launch("radius_graph_reverse");
+    if (rc) return rc;
+  }
+  return E3B_OK;
 }
 
 // ------------------------------------------------------------------------------------------
@@ -467,7 +532,8 @@ extern "C" int e3b_cell_graph_fill(const float* pos, int64_t pos_stride, const i
   int rc = check_launch("cell_graph_fill");
   if (rc) return rc;
   if (rev) {
-    reverse_edge_kernel<<<blocks_for(n_edges, 256), 256, 0, (cudaStream_t)stream>>>(edge_index, row_ptr, n_edges, rev);
+    reverse_edge_kernel<<<blocks_for(n_edges, 256), 256, 0, (cudaStream_t)stream>>>(edge_index, row_ptr, n_edges, n_edges, rev,
+                                                                                  nullptr);
     rc = check_launch("radius_graph_reverse");
   }
   return rc;

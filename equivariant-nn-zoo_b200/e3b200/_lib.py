@@ -59,6 +59,8 @@ SIGNATURES = {
     "e3b_struct_size": (c_i64, [c_int]),
     "e3b_radius_graph_count": (c_int, [c_vp, c_i64, c_vp, c_i32, c_i64, c_f32, c_vp, c_vp]),
     "e3b_radius_graph_fill": (c_int, [c_vp, c_i64, c_vp, c_i32, c_i64, c_f32, c_vp, c_i64, c_vp, c_vp, c_vp]),
+    "e3b_radius_graph_fill_padded": (c_int, [c_vp, c_i64, c_vp, c_i32, c_i64, c_i64, c_f32, c_vp, c_i64, c_i64, c_vp, c_vp, c_vp,
+                                             c_vp]),
     "e3b_pair_graph_count": (c_int, [c_vp, c_i64, c_vp, c_i32, c_i64, c_f32, ctypes.POINTER(PairCriteriaStruct), c_vp, c_vp]),
     "e3b_pair_graph_fill": (c_int, [c_vp, c_i64, c_vp, c_i32, c_i64, c_f32, ctypes.POINTER(PairCriteriaStruct), c_vp, c_i64, c_vp,
                                     c_vp]),

@@ -279,6 +279,31 @@ def radius_graph_fill(st, edge_index=None, rev=None):
     return edge_index, rev
 
 
+def padding_positions(n, r_max, device):
+    """[n, 3] positions of n padding atoms for `radius_graph_fill_padded`: isolated pairs (2p, 2p + 1), the two atoms
+    of a pair min(1, r_max / 2) apart, pairs 3 r_max apart (they form a graph of their own, so where they sit relative to
+    the real atoms does not matter)."""
+    j = torch.arange(n, device=device)
+    pos = torch.zeros(n, 3, dtype=torch.float32, device=device)
+    pos[:, 0] = (j // 2).float() * (3.0 * float(r_max))
+    pos[:, 1] = (j % 2).float() * min(1.0, 0.5 * float(r_max))
+    return pos
+
+
+def radius_graph_fill_padded(st, n_pad, n_edges_total, edge_index, rev, nbr32=None):
+    """phase 2 for a batch whose last `n_pad` atoms are padding pairs (see `padding_positions`): fills the caller's
+    buffers with exactly `n_edges_total` edges (include/e3b200.h: e3b_radius_graph_fill_padded) and rewrites the padding
+    rows of st.row_ptr; st.E becomes n_edges_total."""
+    lib = _lib.load()
+    assert st.crit is None and st.cells is None, "bucketed padding is for the plain radius graph"
+    assert edge_index.shape == (2, n_edges_total) and edge_index.is_contiguous() and rev.shape == (n_edges_total,)
+    check(lib.e3b_radius_graph_fill_padded(ptr(st.pos), 3, ptr(st.node_ptr), st.G, st.N, n_pad, st.r_max, ptr(st.row_ptr), st.E,
+                                           n_edges_total, ptr(edge_index), ptr(rev), ptr(nbr32), stream()))
+    count_launch(3)
+    st.E = n_edges_total
+    return edge_index, rev
+
+
 def edges_per_graph(st):
     g = st.row_ptr[st.node_ptr]
     return (g[1:] - g[:-1]).view(-1, 1)

@@ -44,6 +44,7 @@ class FlatAdam:
         self._skip = torch.zeros(1, dtype=torch.int32, device=dev)
         self._scale = torch.ones(1, dtype=torch.float32, device=dev)
         self._backup = None
+        self._buckets = None
         ops.WEIGHTS_EPOCH += 1
 
     @property
@@ -64,10 +65,49 @@ class FlatAdam:
             yield self.grad[o:o + n].view(p.shape)
             o += n
 
+    def enable_overlap(self, bucket_bytes=2 << 20):
+        """Issue the gradient all-reduce bucket by bucket DURING the backward pass: the flat buffer is cut into
+        contiguous ranges of about `bucket_bytes` (parameters are laid out in forward order, the backward finalises them
+        roughly back to front); a post-accumulate hook per parameter counts arrivals and, when a bucket is complete,
+        launches its asynchronous all-reduce -- NCCL runs it on its own stream, ordered after the gradient kernels
+        issued so far, while the rest of the backward keeps the compute stream busy.  `all_reduce()` then only issues
+        what is left, waits and scales.  (reference: DistributedDataParallel's bucketed hooks, run/trainer.py:138-139)"""
+        if self._buckets is not None:
+            return
+        self._buckets, self._bucket_of = [], {}
+        o = start = 0
+        members = []
+        for i, p in enumerate(self.params):
+            members.append(i)
+            o += p.numel()
+            if (o - start) * 4 >= bucket_bytes or i == len(self.params) - 1:
+                self._buckets.append({"lo": start, "hi": o, "n": len(members), "seen": 0, "work": None})
+                for m in members:
+                    self._bucket_of[m] = len(self._buckets) - 1
+                start, members = o, []
+        for i, p in enumerate(self.params):
+            p.register_post_accumulate_grad_hook(lambda _p, i=i: self._arrived(i))
+
+    def _arrived(self, i):
+        if not (dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1):
+            return
+        b = self._buckets[self._bucket_of[i]]
+        b["seen"] += 1
+        if b["seen"] == b["n"] and b["work"] is None:
+            b["work"] = dist.all_reduce(self.grad[b["lo"]:b["hi"]], op=dist.ReduceOp.SUM, async_op=True)
+
     def all_reduce(self):
         """averages the gradient buffer over the ranks (NCCL over NVLink on the GPU box, gloo in the CPU tests)"""
         if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
-            dist.all_reduce(self.grad, op=dist.ReduceOp.SUM)
+            if self._buckets is None:
+                dist.all_reduce(self.grad, op=dist.ReduceOp.SUM)
+            else:
+                for b in self._buckets:                   # same order on every rank: buckets whose hooks did not all fire
+                    if b["work"] is None:                 # (parameters without a gradient this step) go now
+                        b["work"] = dist.all_reduce(self.grad[b["lo"]:b["hi"]], op=dist.ReduceOp.SUM, async_op=True)
+                for b in self._buckets:
+                    b["work"].wait()
+                    b["work"], b["seen"] = None, 0
             self.grad /= dist.get_world_size()
 
     def step(self, max_grad_norm=None, skip_nonfinite=False):

@@ -72,6 +72,20 @@ E3B_API int e3b_radius_graph_fill(const float* pos, int64_t pos_stride, const in
                           int64_t n_nodes, float r_max, const int64_t* row_ptr, int64_t n_edges,
                           int64_t* edge_index /* [2,E] */, int32_t* rev /* [E] or NULL */, void* stream);
 
+/* Bucketed edge count, for replaying one captured CUDA graph over batches of different sizes (the reference has no
+ * counterpart: its eager PyTorch path re-allocates per batch, data/compute_edge.py:56-75).  The caller appends n_pad
+ * padding atoms to the batch as the LAST graph, laid out as isolated pairs (2p, 2p+1) closer than r_max (an odd last
+ * atom stays alone), runs e3b_radius_graph_count + scan over the padded batch (n_edges_natural = row_ptr[N]) and picks
+ * n_edges_total >= n_edges_natural (same parity).  This call rewrites the padding rows of row_ptr so that the edge
+ * list has exactly n_edges_total entries -- the missing ones are parallel copies of the pair edges, spread evenly
+ * over the pairs -- and fills edge_index [2, n_edges_total], rev and (optionally) nbr32 = int32(edge_index[1]).
+ * Real atoms get exactly the edges e3b_radius_graph_fill gives them, in the same order.                       */
+E3B_API int e3b_radius_graph_fill_padded(const float* pos, int64_t pos_stride, const int64_t* node_ptr, int32_t n_graphs,
+                                         int64_t n_nodes /* incl. padding */, int64_t n_pad, float r_max,
+                                         int64_t* row_ptr /* [N+1], in/out */, int64_t n_edges_natural,
+                                         int64_t n_edges_total, int64_t* edge_index, int32_t* rev,
+                                         int32_t* nbr32 /* [n_edges_total] or NULL */, void* stream);
+
 /* Neighbour list with the `criteria` of the protein config evaluated inside the sweep (replaces the
  * criteria(data, all_pairs) call of compute_edge.py:73-74 for e3_layers/configs/config_diffusion_CA.py:58-64):
  * pair (a,b), a != b, same graph, is an edge iff   |pos[a]-pos[b]| < r_max

@@ -131,6 +131,69 @@ def test_graphed_evaluator_matches_eager():
     assert harness.rel_err(got["forces"], eager["forces"]) < 1e-5 and ev.misses == 2
 
 
+def test_bucketed_evaluator_distinct_batches():
+    """Bucketed padding (e3b200.graphed): DIFFERENT batches (different atom and edge counts) replay one captured graph;
+    real atoms keep exactly their neighbours, so energies and forces equal the unpadded eager evaluation."""
+    from e3b200.graphed import GraphedEvaluator
+
+    meta = {"config": "config_energy_force", "seed": 8}
+    model = product_harness.build_product(meta, torch.float32, DEV)
+    ev = GraphedEvaluator(model, r_max=5.0, node_bucket=256, edge_bucket=4096, min_pad_nodes=16)
+    shapes = set()
+    for seed in (11, 12, 13, 14, 11):
+        v = synthetic.qm9_like(24, seed=seed)
+        eager = product_harness.run_product(model, v, torch.float32, DEV, pre_edge={"r_max": 5.0})
+        shapes.add((eager["pos"].shape[0], eager["edge_index"].shape[1]))
+        got = ev({k: t.to(DEV) for k, t in v.items()})
+        assert got["energy"].shape == eager["energy"].shape and got["forces"].shape == eager["forces"].shape
+        assert harness.rel_err(got["energy"], eager["energy"]) < 1e-6, seed
+        assert harness.rel_err(got["forces"], eager["forces"]) < 1e-6, seed
+    assert len(shapes) >= 4                       # the batches really differ ...
+    assert ev.misses <= 2 and ev.hits >= 3        # ... and still share at most two captures
+    # new weights: the stale captures are dropped and re-captured, never replayed
+    with torch.no_grad():
+        for p_ in model.parameters():
+            p_.mul_(1.01)
+    v = synthetic.qm9_like(24, seed=11)
+    eager = product_harness.run_product(model, v, torch.float32, DEV, pre_edge={"r_max": 5.0})
+    got = ev({k: t.to(DEV) for k, t in v.items()})
+    assert harness.rel_err(got["forces"], eager["forces"]) < 1e-6
+
+
+def test_padded_neighbour_list():
+    """e3b_radius_graph_fill_padded: real atoms get exactly the edges of the plain radius graph, the padding rows are
+    consistent (sorted edge list, row_ptr, reversed-edge index) and the total is the requested one"""
+    from e3b200 import ops
+
+    v = synthetic.qm9_like(9, seed=3)
+    pos, nn = v["pos"].to(DEV), v["_n_nodes"].reshape(-1).to(DEV)
+    ei0, _, _ = ops.radius_graph(pos, nn, 5.0)
+    N = pos.shape[0]
+    for n_pad, extra in ((8, 0), (8, 38), (7, 10), (2, 64)):
+        ppos = torch.cat([pos, ops.padding_positions(n_pad, 5.0, DEV)])
+        pnn = torch.cat([nn, torch.tensor([n_pad], device=DEV)])
+        st = ops.radius_graph_count(ppos, pnn, 5.0)
+        assert st.E == ei0.shape[1] + 2 * (n_pad // 2)
+        Et = st.E + extra
+        ei = torch.empty(2, Et, dtype=torch.int64, device=DEV)
+        rev = torch.empty(Et, dtype=torch.int32, device=DEV)
+        nbr = torch.empty(Et, dtype=torch.int32, device=DEV)
+        ops.radius_graph_fill_padded(st, n_pad, Et, ei, rev, nbr)
+        E0 = ei0.shape[1]
+        assert torch.equal(ei[:, :E0], ei0)
+        assert int(st.row_ptr[-1]) == Et and int(st.row_ptr[N]) == E0
+        key = ei[0] * (N + n_pad) + ei[1]
+        assert bool((key[1:] >= key[:-1]).all())                      # sorted (parallel edges are equal keys)
+        assert bool((ei[:, E0:] >= N).all())
+        deg = st.row_ptr[1:] - st.row_ptr[:-1]
+        assert torch.equal(torch.bincount(ei[0], minlength=N + n_pad), deg)
+        assert torch.equal(nbr.long(), ei[1])
+        r = rev.long()
+        assert torch.equal(ei[0][r], ei[1]) and torch.equal(ei[1][r], ei[0]) and torch.equal(r[r], torch.arange(Et, device=DEV))
+        pd = deg[N:N + 2 * (n_pad // 2)]
+        assert int(pd.max()) - int(pd.min()) <= 1                     # spread evenly over the pairs
+
+
 def test_ragged_batch_with_isolated_atoms():
     """single-atom molecules (no edges at all) and a far-apart pair inside an ordinary batch: empty CSR segments
     through every kernel, fp32 product vs fp64 oracle, forces of isolated atoms exactly zero"""

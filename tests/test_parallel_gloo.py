@@ -112,3 +112,62 @@ def test_flat_adam_buffers_allreduce_world2():
     assert a0 and a1 and loud0 and loud1
     assert g0 == g1 and torch.allclose(torch.tensor(g0), (torch.tensor(l0) + torch.tensor(l1)) / 2)
     assert sum(v0, []) == g0                                     # the parameters' .grad ARE the buffer
+
+
+def _worker_overlap(rank, world, port, q):
+    from e3b200 import optim
+
+    os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        torch.manual_seed(0)
+        net = torch.nn.Sequential(torch.nn.Linear(6, 7), torch.nn.Tanh(), torch.nn.Linear(7, 5), torch.nn.Tanh(),
+                                  torch.nn.Linear(5, 2))
+        unused = torch.nn.Linear(3, 3)                           # parameters that never receive a gradient
+        holder = torch.nn.ModuleList([net, unused])
+        parallel.broadcast_parameters(holder)
+        opt = optim.FlatAdam(holder, lr=1e-2)
+        opt.enable_overlap(bucket_bytes=128)                     # several buckets, all-reduce issued from gradient hooks
+        res = []
+        for it in range(2):                                      # second pass: counters were reset
+            x = torch.full((4, 6), float(rank + 1 + it))
+            opt.zero_grad()
+            net(x).sum().backward()
+            issued = sum(b["work"] is not None for b in opt._buckets)
+            opt.all_reduce()
+            res.append((issued, opt.grad.tolist()))
+        # reference: the same two passes, plain all-reduce of the local gradient
+        ref = []
+        for it in range(2):
+            x = torch.full((4, 6), float(rank + 1 + it))
+            opt.zero_grad()
+            for b in opt._buckets:
+                b["n"] = 10 ** 9                                 # hooks never complete a bucket
+            net(x).sum().backward()
+            assert all(b["work"] is None for b in opt._buckets)
+            opt.all_reduce()
+            ref.append(opt.grad.tolist())
+        q.put((rank, len(opt._buckets), res, ref))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_flat_adam_overlapped_allreduce_world2():
+    """bucketed all-reduce issued from post-accumulate hooks during backward == one all-reduce after it"""
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29811 + os.getpid() % 200
+    procs = [ctx.Process(target=_worker_overlap, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = sorted(q.get(timeout=120) for _ in range(2))
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    (_, nb0, r0, ref0), (_, nb1, r1, ref1) = res
+    assert nb0 == nb1 and nb0 >= 3
+    for (issued0, g0), (issued1, g1), e0 in zip(r0, r1, ref0):
+        assert issued0 == issued1 and 1 <= issued0 < nb0          # some buckets went during backward, the unused one after
+        assert g0 == g1
+        assert torch.allclose(torch.tensor(g0), torch.tensor(e0))
+    assert ref0 == ref1
