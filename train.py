@@ -93,9 +93,48 @@ def load_data(flags, config, target_keys):
     return data
 
 
+ATTRS = {"pos": ("node", "1x1o"), "species": ("node", "1x0e"), "_n_nodes": ("graph", "1x0e"),
+         "energy": ("graph", "1x0e"), "total_energy": ("graph", "1x0e"), "forces": ("node", "1x1o"), "dipole": ("node", "1x1o")}
+
+
+def make_pipeline(data, target_keys, batch_size, r_max, seed, rank, world, dev, resident=None):
+    """dataset -> device (e3_layers.data.DevicePipeline): the concatenated host tensors go to HBM once (or stay pinned
+    and are streamed by the copy engine), every batch is cut out by vectorised gathers and the neighbour list is built
+    on the GPU as a preprocess with the layer contract -- no DataLoader workers (reference dataloader.py:86-105)"""
+    from functools import partial
+
+    from e3_layers.data import CondensedDataset, DevicePipeline, computeEdgeIndex
+
+    attrs = {k: ATTRS[k] for k in data if k in ATTRS}
+    ds = CondensedDataset(data=data, attrs=attrs, preprocess=[partial(computeEdgeIndex, r_max=r_max)])
+    gen = torch.Generator().manual_seed(seed)                     # same order on every rank; each takes its shard
+    return DevicePipeline(ds, batch_size=batch_size, shuffle=True, drop_last=True, generator=gen, device=dev,
+                          rank=rank, world_size=world, resident=resident)
+
+
+def train_step(model, opt, batch, target_keys, loss_coeffs):
+    """one optimiser step on a device batch that carries its targets; -> (loss, mae) as device scalars"""
+    from e3_layers.data import Batch
+
+    targets = {k: batch.data.pop(k) for k in target_keys}
+    for k in target_keys:
+        batch.attrs.pop(k, None)
+    out = model(Batch(batch.attrs, **batch.data))
+    loss, mae = 0.0, 0.0                                         # reference run/loss.py:274-287: sum of coeff * mean loss
+    for k in target_keys:
+        coeff, kind = loss_coeffs[k][0], loss_coeffs[k][1]
+        diff = out[k] - targets[k]
+        loss = loss + coeff * (diff.abs().mean() if kind == "L1Loss" else (diff ** 2).mean())
+        mae = mae + diff.detach().abs().mean()
+    opt.zero_grad()
+    loss.backward()
+    opt.all_reduce()
+    opt.step()
+    return loss.detach(), mae
+
+
 def main(rank, flags):
     from e3_layers import configs
-    from e3_layers.data import Batch, computeEdgeIndex
     from e3_layers.utils import build, setSeed
     from e3b200 import optim, parallel
 
@@ -137,39 +176,14 @@ def main(rank, flags):
     r_max = float(config.model_config.r_max)
 
     data = load_data(flags, config, target_keys)
-    n_all = data["_n_nodes"].reshape(-1)
-    G = n_all.numel()
-    bs = int(config.batch_size) * world                          # global batch; every rank takes its shard
-    gen = torch.Generator().manual_seed(flags.seed)              # same permutation on every rank
-    starts = torch.cumsum(n_all, 0) - n_all
-    attrs = {"pos": ("node", "1x1o"), "species": ("node", "1x0e"), "_n_nodes": ("graph", "1x0e")}
+    pipe = make_pipeline(data, target_keys, int(config.batch_size), r_max, flags.seed, rank, world, dev)
+    batches = pipe.endless(skip=first_step)                      # a resumed run replays the data order up to its step
     out_dir = os.path.join(flags.workdir, flags.name)
     t0 = time.time()
-    for _ in range(first_step):                                  # replay the data order up to the restored step
-        torch.randperm(G, generator=gen)
     for step in range(first_step, flags.steps):
-        pick = torch.randperm(G, generator=gen)[:bs].sort().values
-        node_idx = torch.cat([torch.arange(int(starts[g]), int(starts[g] + n_all[g])) for g in pick])
-        host = {k: (v[node_idx] if v.shape[0] == int(n_all.sum()) else v[pick]) for k, v in data.items()}
-        mine = parallel.shard_batch(host, rank, world)
-        targets = {k: mine.pop(k).to(dev) for k in target_keys}
-        batch = Batch(dict(attrs), **{k: v.to(dev) for k, v in mine.items()})
-        d, a = computeEdgeIndex(batch.data, batch.attrs, r_max=r_max)
-        batch.update(d)
-        batch.attrs.update(a)
-        out = model(Batch(batch.attrs, **batch.data))
-        loss, mae = 0.0, 0.0                                     # reference run/loss.py:274-287: sum of coeff * mean loss
-        for k in target_keys:
-            coeff, kind = loss_coeffs[k][0], loss_coeffs[k][1]
-            diff = out[k] - targets[k]
-            loss = loss + coeff * (diff.abs().mean() if kind == "L1Loss" else (diff ** 2).mean())
-            mae = mae + diff.detach().abs().mean()
-        opt.zero_grad()
-        loss.backward()
-        opt.all_reduce()
-        opt.step()
+        loss, mae = train_step(model, opt, next(batches), target_keys, loss_coeffs)
         if step % flags.log_period == 0 or step == flags.steps - 1:
-            scal = torch.stack([loss.detach(), torch.as_tensor(mae, device=dev)])
+            scal = torch.stack([loss, torch.as_tensor(mae, device=dev)])
             if world > 1:                                        # logging scalars: averaged over the ranks on log steps only
                 dist.all_reduce(scal)
                 scal /= world
