@@ -46,6 +46,7 @@ extern "C" int64_t e3b_struct_size(int which) {
     case 1: return (int64_t)sizeof(e3b_gate_desc);
     case 2: return (int64_t)sizeof(e3b_gemm_problem);
     case 3: return (int64_t)sizeof(e3b_gemm_pack_desc);
+    case 4: return (int64_t)sizeof(e3b_wgrad_problem);
     default: return -1;
   }
 }

@@ -44,12 +44,20 @@ class GemmPackDesc(ctypes.Structure):
                 ("K", c_i32), ("dst", c_vp)]
 
 
+class WgradProblem(ctypes.Structure):
+    _fields_ = [("A", c_vp), ("a_s1", c_i64), ("a_s2", c_i64), ("a_d", c_i32), ("B", c_vp), ("b_s1", c_i64), ("b_s2", c_i64),
+                ("b_d", c_i32), ("aux", c_vp), ("aux_ld", c_i64), ("aux_d", c_i32), ("V", c_i32), ("C", c_vp), ("c_s1", c_i64),
+                ("c_s2", c_i64), ("c_s3", c_i64), ("c_d", c_i32), ("R", c_i64), ("K1", c_i32), ("K2", c_i32), ("alpha", c_f32),
+                ("accumulate", c_i32)]
+
+
 class PairCriteriaStruct(ctypes.Structure):
     _fields_ = [("segment", c_vp), ("max_separation", c_i64), ("p_random", c_f32), ("uniforms", c_vp), ("pair_ptr", c_vp),
                 ("seed", ctypes.c_uint64)]
 
 
 E3B_GEMM_MAX_GROUP = 8
+E3B_WGRAD_MAX_GROUP = 8
 CELL_GRID_BYTES = 48
 
 # name -> (restype, argtypes); must list EVERY symbol include/e3b200.h declares
@@ -92,6 +100,8 @@ SIGNATURES = {
     "e3b_gemm_packed_floats": (c_i64, [c_i32, c_i32]),
     "e3b_gemm_pack": (c_int, [ctypes.POINTER(GemmPackDesc), c_i32, c_vp]),
     "e3b_gemm_run": (c_int, [ctypes.POINTER(GemmProblem), c_i32, c_vp]),
+    "e3b_wgrad_workspace_floats": (c_i64, [ctypes.POINTER(WgradProblem), c_i32]),
+    "e3b_wgrad_run": (c_int, [ctypes.POINTER(WgradProblem), c_i32, c_vp, c_vp]),
     "e3b_layernorm_fwd": (c_int, [c_int, c_vp, c_i64, c_i32, c_vp, c_vp, c_vp, c_f64, c_vp, c_vp, c_vp]),
     "e3b_layernorm_bwd_blocks": (c_i64, [c_i64]),
     "e3b_layernorm_bwd": (c_int, [c_int, c_vp, c_vp, c_vp, c_i64, c_i32, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp]),
@@ -118,7 +128,7 @@ def load():
             fn.argtypes = args
         if lib.e3b_abi_version() != 1:
             raise RuntimeError("libe3b200.so ABI version mismatch")
-        for which, st in enumerate((TpDesc, GateDesc, GemmProblem, GemmPackDesc)):
+        for which, st in enumerate((TpDesc, GateDesc, GemmProblem, GemmPackDesc, WgradProblem)):
             if lib.e3b_struct_size(which) != ctypes.sizeof(st):
                 raise RuntimeError(f"libe3b200.so struct layout mismatch for {st.__name__}")
         _lib = lib

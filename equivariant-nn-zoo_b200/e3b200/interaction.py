@@ -337,24 +337,40 @@ class _Interaction(torch.autograd.Function):
 
 
 def _param_grads(fi, needs, x_imu, attrs, h, gz, mid, g_cv, g_xl, need_attrs):
+    """parameter gradients of one block: reductions over all edges / nodes on the split-K tcgen05 kernel
+    (csrc/wgrad_tf32x3.cu), written straight into the flat weight layouts; the attribute gradient (a per-node
+    quantity) stays a torch contraction"""
     conv = fi.conv
     n_fc = conv.fc.n_layers
     out = []
-    N = x_imu.shape[0]
+    N, dev = x_imu.shape[0], x_imu.device
+    probs = []
     for i in range(n_fc):
-        out.append((h[i].t() @ gz[i + 1]) * (1.0 / math.sqrt(fi.hs[i])) if needs[7 + i] else None)
+        if not needs[7 + i]:
+            out.append(None)
+            continue
+        K1, K2 = fi.hs[i], fi.hs[i + 1]
+        a, b = h[i], gz[i + 1]
+        if K1 % 4 == 0 and K2 % 4 == 0 and a.is_contiguous() and b.is_contiguous():
+            gw_i = torch.empty(K1, K2, dtype=torch.float32, device=dev)
+            probs.append(ops.wgrad_problem(a, b, gw_i, a.shape[0], K1, K2, alpha=1.0 / math.sqrt(K1)))
+        else:
+            gw_i = (a.t() @ b) * (1.0 / math.sqrt(K1))
+        out.append(gw_i)
     # linear_1: dW[u, w] = alpha sum_{z, m} x[z, m, u] g_xl[z, m, w]
     lin1 = conv.linear_1
     g = None
-    if needs[7 + n_fc] and g_xl is not None:
+    if needs[7 + n_fc]:
         g = torch.zeros_like(lin1.weight)
-        for i, o, off, alpha in lin1.paths:
-            bi, bo = fi.feat_in[i], fi.feat_in[o]
-            a = x_imu[:, fi.x_off[i]:fi.x_off[i] + bi.dim].reshape(-1, bi.mul)
-            b = g_xl[:, fi.x_off[o]:fi.x_off[o] + bo.dim].reshape(-1, bo.mul)
-            g[off:off + bi.mul * bo.mul] += (alpha * (a.t() @ b)).reshape(-1)
-    elif needs[7 + n_fc]:
-        g = torch.zeros_like(lin1.weight)
+        if g_xl is not None:
+            seen = set()
+            for i, o, off, alpha in lin1.paths:
+                bi, bo = fi.feat_in[i], fi.feat_in[o]
+                probs.append(ops.wgrad_problem(x_imu, g_xl, g, N * bi.ir.dim, bi.mul, bo.mul, a_off=fi.x_off[i],
+                                               a_rows=(fi.Din, bi.mul, bi.ir.dim), b_off=fi.x_off[o],
+                                               b_rows=(fi.Din, bo.mul, bo.ir.dim), c_off=off, alpha=alpha))
+                assert off not in seen
+                seen.add(off)
     out.append(g)
     # post linear: dW[kk, w] = alpha' sum_{z, k} mid[z, k, kk] g_cv[z, k, w]
     post = conv.tp.linear
@@ -363,26 +379,31 @@ def _param_grads(fi, needs, x_imu, attrs, h, gz, mid, g_cv, g_xl, need_attrs):
         g = torch.zeros_like(post.weight)
         for i, o, off, alpha in post.paths:
             bi, bo = fi.mid[i], fi.conv_out[o]
-            a = mid[:, fi.m_off[i]:fi.m_off[i] + bi.dim].reshape(-1, bi.mul)
-            b = g_cv[:, fi.c_off[o]:fi.c_off[o] + bo.dim].reshape(-1, bo.mul)
-            g[off:off + bi.mul * bo.mul] += (alpha * fi.inv_sqrt_avg * (a.t() @ b)).reshape(-1)
+            probs.append(ops.wgrad_problem(mid, g_cv, g, N * bi.ir.dim, bi.mul, bo.mul, a_off=fi.m_off[i],
+                                           a_rows=(fi.Dmid, bi.mul, bi.ir.dim), b_off=fi.c_off[o],
+                                           b_rows=(fi.Dconv, bo.mul, bo.ir.dim), c_off=off, alpha=alpha * fi.inv_sqrt_avg))
     out.append(g)
     # self-connection: dW[u, v, w] = alpha sum_{z, m} x[z, m, u] a[z, v] g[z, m, w];  da[z, v] likewise
     sc = conv.sc
     g = torch.zeros_like(sc.weight) if needs[9 + n_fc] else None
     g_attrs = torch.zeros_like(attrs) if need_attrs else None
-    if g is not None or g_attrs is not None:
-        V = fi.V
+    V = fi.V
+    if g is not None:
+        for i1, i2, o, off, alpha in sc.paths:
+            bi, bo = fi.feat_in[i1], fi.conv_out[o]
+            probs.append(ops.wgrad_problem(x_imu, g_cv, g, N * bi.ir.dim, bi.mul, bo.mul, a_off=fi.x_off[i1],
+                                           a_rows=(fi.Din, bi.mul, bi.ir.dim), b_off=fi.c_off[o],
+                                           b_rows=(fi.Dconv, bo.mul, bo.ir.dim), aux=attrs, aux_d=bi.ir.dim, c_off=off,
+                                           c_rows=(bo.mul, V * bo.mul, bi.mul), alpha=alpha))
+    ops.wgrad_run(probs, dev)
+    if g_attrs is not None:
         for i1, i2, o, off, alpha in sc.paths:
             bi, bo = fi.feat_in[i1], fi.conv_out[o]
             xa = x_imu[:, fi.x_off[i1]:fi.x_off[i1] + bi.dim].reshape(N, bi.ir.dim, bi.mul)
             gb = g_cv[:, fi.c_off[o]:fi.c_off[o] + bo.dim].reshape(N, bi.ir.dim, bo.mul)
             t = torch.einsum("zmu,zmw->zuw", xa, gb)                     # [z, u, w]
-            if g is not None:
-                g[off:off + bi.mul * V * bo.mul] += (alpha * torch.einsum("zuw,zv->uvw", t, attrs)).reshape(-1)
-            if g_attrs is not None:
-                W = sc.weight[off:off + bi.mul * V * bo.mul].reshape(bi.mul, V, bo.mul)
-                g_attrs += alpha * torch.einsum("zuw,uvw->zv", t, W)
+            W = sc.weight[off:off + bi.mul * V * bo.mul].reshape(bi.mul, V, bo.mul)
+            g_attrs += alpha * torch.einsum("zuw,uvw->zv", t, W)
     out.append(g)
     return out, g_attrs
 

@@ -1010,6 +1010,69 @@ def gemm_tf32x3(A, B, C, M, N, K, a_rows=None, c_rows=None, c_col_stride=1, alph
 
 
 # ------------------------------------------------------------------------------------------
+# Weight gradients: reductions over all rows, C[m, n] = alpha sum_r A'[r, m] B[r, n] (csrc/wgrad_tf32x3.cu)
+_WGRAD_WS = {}
+
+
+def wgrad_problem(A, B, C, R, K1, K2, a_off=0, a_rows=None, b_off=0, b_rows=None, c_off=0, c_rows=None, c_col_stride=1,
+                  alpha=1.0, accumulate=False, aux=None, aux_d=1):
+    """One problem of a grouped weight-gradient launch.  A / B / C are fp32 CUDA tensors used as raw storage (element
+    offsets *_off); ``a_rows`` / ``b_rows`` = (s1, s2, d): row r starts at base + (r // d) * s1 + (r % d) * s2 (default:
+    dense rows of K1 / K2 floats); ``c_rows`` = (s1, s2, d) addresses output row m likewise (default: dense [M, K2]).
+    With ``aux`` [*, V] the rows of A are expanded to (v, u): A'[r, v * K1 + u] = A[r, u] * aux[r // aux_d, v]."""
+    g = _lib.WgradProblem()
+    V = aux.shape[1] if aux is not None else 0
+    a_s1, a_s2, a_d = a_rows if a_rows is not None else (K1, 0, 1)
+    b_s1, b_s2, b_d = b_rows if b_rows is not None else (K2, 0, 1)
+    c_s1, c_s2, c_d = c_rows if c_rows is not None else (K2 * c_col_stride, 0, 1)
+    g.A, g.a_s1, g.a_s2, g.a_d = A.data_ptr() + 4 * a_off, a_s1, a_s2, a_d
+    g.B, g.b_s1, g.b_s2, g.b_d = B.data_ptr() + 4 * b_off, b_s1, b_s2, b_d
+    if aux is not None:
+        assert aux.dtype == torch.float32 and aux.stride(1) == 1
+        g.aux, g.aux_ld, g.aux_d, g.V = aux.data_ptr(), aux.stride(0), aux_d, V
+    else:
+        g.aux, g.aux_ld, g.aux_d, g.V = None, 0, 1, 0
+    g.C, g.c_s1, g.c_s2, g.c_s3, g.c_d = C.data_ptr() + 4 * c_off, c_s1, c_s2, c_col_stride, c_d
+    g.R, g.K1, g.K2, g.alpha, g.accumulate = R, K1, K2, float(alpha), int(bool(accumulate))
+    return g
+
+
+def wgrad_supported(*tensors, widths=()):
+    return (all(t is not None and t.is_cuda and t.dtype == torch.float32 for t in tensors)
+            and all(w % 4 == 0 and w > 0 for w in widths))
+
+
+def wgrad_run(problems, device):
+    """launches the problems (built by wgrad_problem), <= 8 per kernel pair"""
+    lib = _lib.load()
+    group = [g for g in problems if g.R and g.K1 and g.K2]
+    if group:
+        for lo in range(0, len(group), _lib.E3B_WGRAD_MAX_GROUP):
+            chunk = group[lo:lo + _lib.E3B_WGRAD_MAX_GROUP]
+            arr = (_lib.WgradProblem * len(chunk))(*chunk)
+            need = lib.e3b_wgrad_workspace_floats(arr, len(chunk))
+            if need < 0:
+                raise RuntimeError("libe3b200: unsupported weight-gradient problem (alignment / widths)")
+            key = (device.index, torch.cuda.current_stream(device).cuda_stream)
+            ws = _WGRAD_WS.get(key)
+            if ws is None or ws.numel() < need:
+                ws = torch.empty(max(need, 1 << 20), dtype=torch.float32, device=device)
+                _WGRAD_WS[key] = ws
+            check(lib.e3b_wgrad_run(arr, len(chunk), ptr(ws), stream()))
+            count_launch(2)
+
+
+def k_wgrad(x, g, alpha=1.0):
+    """alpha * x^T @ g for x [R, K1], g [R, K2] (row-major, contiguous) on the tensor cores -> [K1, K2]"""
+    require_cuda(x, g)
+    R, K1 = x.shape
+    K2 = g.shape[1]
+    out = torch.empty(K1, K2, dtype=torch.float32, device=x.device)
+    wgrad_run([wgrad_problem(x, g, out, R, K1, K2, alpha=alpha)], x.device)
+    return out
+
+
+# ------------------------------------------------------------------------------------------
 # Dense map with a small weight matrix as a differentiable node on the tensor cores (second-order mode):
 # products of the form [many rows, K] x [K, N] run on the tcgen05 3xTF32 kernel, whichever argument the
 # weight is; the weight gradient (a reduction over the rows) is a library GEMM.  The backward is made of the
@@ -1053,7 +1116,11 @@ class _Dense(torch.autograd.Function):
             gx = _Dense.apply(gy, W, ctx.alpha, not ctx.trans) if N % 4 == 0 else \
                 ctx.alpha * (gy @ (W if ctx.trans else W.t()))
         if ctx.needs_input_grad[1] and needs_grad_now(W):
-            gW = ctx.alpha * (gy.t() @ x if ctx.trans else x.t() @ gy)
+            a, b = (gy, x) if ctx.trans else (x, gy)
+            if not torch.is_grad_enabled() and wgrad_supported(a, b, widths=(a.shape[1], b.shape[1])) and a.is_contiguous():
+                gW = k_wgrad(a, b, ctx.alpha)          # split-K tcgen05 reduction over all rows
+            else:                                      # a graph of this gradient is being recorded: plain torch
+                gW = ctx.alpha * (a.t() @ b)
         return gx, gW, None, None
 
 
@@ -1143,12 +1210,45 @@ def k_sc(spec, src, attrs, W, to_out):
     return dst
 
 
+def _sc_weight_grad_kernel(spec, x, a, W, g):
+    """dW of a block-wise linear map (V == 0: dW[u, w]) or of the self-connection (dW[u, v, w] = alpha sum_{z, d}
+    x[z, d, u] a[z, v] g[z, d, w]) on the split-K tcgen05 kernel: one problem per irreps path, written straight into the
+    flat weight layout; the (x, a) outer product is formed by the kernel's loader."""
+    N, V = x.shape[0], spec.V
+    covered = sum(spec.irreps_in[i].mul * max(V, 1) * spec.irreps_out[o].mul for i, o, _, _ in spec.paths)
+    disjoint = len({off for _, _, off, _ in spec.paths}) == len(spec.paths)
+    gW = torch.empty_like(W) if covered == W.numel() and disjoint else torch.zeros_like(W)
+    probs, seen = [], set()
+    for i, o, off, alpha in spec.paths:
+        bi, bo = spec.irreps_in[i], spec.irreps_out[o]
+        d = bi.ir.dim
+        kw = dict(a_off=spec.x_off[i], a_rows=(spec.Din, bi.mul, d), b_off=spec.c_off[o], b_rows=(spec.Dout, bo.mul, d),
+                  c_off=off, alpha=alpha, accumulate=off in seen)
+        if V:
+            kw.update(aux=a, aux_d=d, c_rows=(bo.mul, V * bo.mul, bi.mul))       # row m = v * m1 + u of the kernel -> W[u, v, :]
+        probs.append(wgrad_problem(x, g, gW, N * d, bi.mul, bo.mul, **kw))
+        seen.add(off)
+    # problems accumulating into a block written by an earlier one must run after it: one launch per "wave"
+    first = [p for p in probs if not p.accumulate]
+    later = [p for p in probs if p.accumulate]
+    wgrad_run(first, x.device)
+    for p in later:
+        wgrad_run([p], x.device)
+    return gW
+
+
 def _sc_reductions(spec, x, a, W, g, want_a, want_W):
     """d/da and d/dW of <g, S(x, a, W)>:  t[z,u,w] = sum_d x[z,d,u] g[z,d,w] per path first (4x fewer flops than
     going through the (u,v) outer product), then ONE skinny GEMM over all paths for each of the two results
     (a^T T and T Wcat): they are bound by reading T once instead of once per path.  Plain torch contractions,
     so the graph of these gradients can be differentiated again by torch."""
     N, V = x.shape[0], spec.V
+    if (want_W and not torch.is_grad_enabled() and spec.ok and wgrad_supported(x, g, W)
+            and x.is_contiguous() and g.is_contiguous() and (V == 0 or (a.is_contiguous() and a.shape[1] == V))):
+        gW = _sc_weight_grad_kernel(spec, x, a, W, g)
+        if not want_a:
+            return None, gW
+        return _sc_reductions(spec, x, a, W, g, True, False)[0], gW
     if V == 0:                      # plain linear map: dW[u, w] = alpha sum_{z,d} x[z,d,u] g[z,d,w] per block pair
         pieces = []
         for i, o, off, alpha in spec.paths:

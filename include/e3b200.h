@@ -48,7 +48,7 @@ typedef enum {
 E3B_API int e3b_abi_version(void);
 E3B_API const char* e3b_last_error(void);
 /* sizeof of the ABI structs as compiled (0 e3b_tp_desc, 1 e3b_gate_desc, 2 e3b_gemm_problem,
- * 3 e3b_gemm_pack_desc) so that a binding can verify its own struct layout; -1 otherwise */
+ * 3 e3b_gemm_pack_desc, 4 e3b_wgrad_problem) so that a binding can verify its own struct layout; -1 otherwise */
 E3B_API int64_t e3b_struct_size(int which);
 
 /* ---------------------------------------------------------------------------------------
@@ -331,6 +331,43 @@ E3B_API int e3b_gemm_tile_n(int32_t N, int32_t K);
 E3B_API int64_t e3b_gemm_packed_floats(int32_t N, int32_t K);
 E3B_API int e3b_gemm_pack(const e3b_gemm_pack_desc* descs, int32_t n, void* stream);
 E3B_API int e3b_gemm_run(const e3b_gemm_problem* problems, int32_t n, void* stream);
+
+/* ---------------------------------------------------------------------------------------
+ * Weight gradients on the tcgen05 tensor cores (3xTF32, fp32 accumulate, deterministic split-K): the
+ * reductions over all rows that autograd produces for e3nn o3.Linear / nn.FullyConnectedNet /
+ * o3.FullyConnectedTensorProduct weights (reference: the torch.einsum / matmul backward behind
+ * nn/message_passing.py:58-63,74-87 and nn/pointwise.py:87-92 when nn/output.py:39-43 or a loss is differentiated).
+ *
+ *   C[m, n] (+)= alpha * sum_{r < R} A'[r, m] * B[r, n]
+ *   V == 0:  A'[r, m] = A[r, m],                                   m < K1
+ *   V  > 0:  A'[r, v * K1 + u] = A[r, u] * aux[(r / aux_d) * aux_ld + v],  m = v * K1 + u < V * K1
+ *            (self-connection weights W[u, v, w]: the feature x attribute outer product is formed in the loader)
+ * Row r of A starts at A + (r / a_d) * a_s1 + (r % a_d) * a_s2 (K1 contiguous floats), of B likewise (K2
+ * contiguous floats); C[m, n] is at C + (m / c_d) * c_s1 + (m % c_d) * c_s2 + n * c_s3.  K1, K2, the row strides
+ * and the bases of A and B must be multiples of 4 floats; R < 2^31.
+ * Up to E3B_WGRAD_MAX_GROUP problems per launch; the caller provides a workspace of
+ * e3b_wgrad_workspace_floats() floats (partial tiles, summed in a fixed order by a second kernel).             */
+#define E3B_WGRAD_MAX_GROUP 8
+typedef struct {
+  const float* A;
+  int64_t a_s1, a_s2;
+  int32_t a_d;
+  const float* B;
+  int64_t b_s1, b_s2;
+  int32_t b_d;
+  const float* aux;
+  int64_t aux_ld;
+  int32_t aux_d, V;
+  float* C;
+  int64_t c_s1, c_s2, c_s3;
+  int32_t c_d;
+  int64_t R;
+  int32_t K1, K2;
+  float alpha;
+  int32_t accumulate;
+} e3b_wgrad_problem;
+E3B_API int64_t e3b_wgrad_workspace_floats(const e3b_wgrad_problem* problems, int32_t n);   /* -1: invalid / unsupported */
+E3B_API int e3b_wgrad_run(const e3b_wgrad_problem* problems, int32_t n, float* workspace, void* stream);
 
 /* ---------------------------------------------------------------------------------------
  * LayerNormalization.  Replaces nn/pointwise.py:32-51 (used when normalize=True,

@@ -24,6 +24,7 @@ def main():
     ap.add_argument("--graphs", type=int, default=512)
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=2)
+    ap.add_argument("--profile", default=None, help="write a torch profiler table of 3 steps to this file")
     a = ap.parse_args()
     import product_harness
     from e3_layers.data import Batch, computeEdgeIndex
@@ -85,6 +86,15 @@ def main():
                           "train_atoms_per_s": float(atoms) / (ms * 1e-3), "libe3b200_launches_per_step":
                           (_lib.launch_count - n0) / a.steps, "peak_mem_gb": torch.cuda.max_memory_allocated() / 1e9,
                           "losses": losses}))
+    if a.profile and rank == 0:
+        from torch.profiler import ProfilerActivity, profile
+        with profile(activities=[ProfilerActivity.CPU, ProfilerActivity.CUDA]) as prof:
+            for _ in range(3):
+                step()
+            torch.cuda.synchronize()
+        with open(a.profile, "w") as f:
+            f.write("# torch profiler, 3 training steps of config_energy_force at W2 (tools/bench_train.py --profile)\n")
+            f.write(prof.key_averages().table(sort_by="self_cuda_time_total", row_limit=45, max_name_column_width=70))
     if world > 1:
         dist.destroy_process_group()
 
