@@ -6,7 +6,7 @@ from e3b200 import ops
 from e3b200.irreps import Irreps
 
 from ..utils import ConfigDict, build
-from .sequential import Module
+from .sequential import Module, strip_reference_state
 
 
 class GradientOutput(Module):
@@ -23,6 +23,10 @@ class GradientOutput(Module):
         self.init_irreps(x=x, y=y, gradients=gradients, output_keys=["gradients"])
         assert Irreps(self.irreps_in["y"]).lmax == 0
         self.func = build(func, **kwargs) if isinstance(func, (dict, ConfigDict)) else func
+
+    def load_state_dict(self, state_dict, strict=True, **kwargs):
+        """accepts the reference's checkpoints as they are (``sequential.strip_reference_state``)"""
+        return super().load_state_dict(strip_reference_state(state_dict, set(self.state_dict().keys())), strict=strict, **kwargs)
 
     def forward(self, data):
         create_graph = bool(self.training and torch.is_grad_enabled())

@@ -39,6 +39,23 @@ class Module(torch.nn.Module):
         return keyMap(obj, self.output_key_mapping)
 
 
+def strip_reference_state(state, own_keys=None):
+    """A checkpoint written by the reference (e3nn 0.4.4 modules under DistributedDataParallel) carries keys this
+    implementation has no use for: the ``module.`` prefix of DDP (reference ``inference.py:46-53`` strips it too), the
+    Wigner-3j constants and generated sub-modules of e3nn's compiled tensor products / linear maps
+    (``..._compiled_main_left_right._w3j_1_1_0`` etc.), and buffers of e3nn layers that are pure functions here.  They
+    are dropped; every parameter and every buffer this model owns must still be present (strict loading)."""
+    out = {}
+    for k, v in state.items():
+        k = k[7:] if k.startswith("module.") else k
+        if "_compiled_main" in k or "._w3j_" in k or k.rsplit(".", 1)[-1].startswith("_w3j_"):
+            continue
+        if own_keys is not None and k not in own_keys and k.rsplit(".", 1)[-1] in ("output_mask", "_zeros", "cst"):
+            continue
+        out[k] = v
+    return out
+
+
 class SequentialGraphNetwork(torch.nn.Sequential):
     """Runs (key, layer) pairs over one shared dict; a layer is a ``Module`` built from a config
     node or any callable ``f(data, attrs)``.  ``jit`` in the config is accepted and ignored (the
@@ -57,6 +74,10 @@ class SequentialGraphNetwork(torch.nn.Sequential):
             self.layers.append((key, layer))
         self.layer_configs = config["layers"]
         super().__init__(built)
+
+    def load_state_dict(self, state_dict, strict=True, **kwargs):
+        """accepts the reference's checkpoints as they are (see ``strip_reference_state``)"""
+        return super().load_state_dict(strip_reference_state(state_dict, set(self.state_dict().keys())), strict=strict, **kwargs)
 
     def forward(self, batch):
         data, attrs = batch.data, batch.attrs
