@@ -34,6 +34,7 @@ template <typename T> __device__ __forceinline__ T warp_sum(T v) {
 #define TP_THREADS 128
 #define TPP_STAGES 3     // shared-memory ring depth of the pipelined forward kernel
 #define TPP_MAXSEG 256   // edges of one destination segment staged per index chunk
+#define TPP_GXBUF 3      // staging rows of the backward kernel's node-reduction mode (TMA reduce-add in flight)
 
 #if defined(__CUDACC__) && !defined(E3B_HOST_EMU)
 // ---- mbarrier + TMA bulk-copy primitives (sm_90+; SASS: SYNCS / UBLKCP) ---------------------
@@ -65,6 +66,15 @@ __device__ __forceinline__ void tpp_issue(float* stage, uint64_t* bar, const flo
   bulk_g2s(stage, w_row, (uint32_t)row_w * 4u, bar);
   bulk_g2s(stage + row_w, x_row, (uint32_t)row_x * 4u, bar);
 }
+// ---- TMA reduce-add of a shared-memory row into global memory (sm_90+; SASS: UBLKRED), bulk async groups
+__device__ __forceinline__ void bulk_reduce_add_f32(float* gdst, const float* ssrc, uint32_t bytes) {
+  asm volatile("cp.reduce.async.bulk.global.shared::cta.bulk_group.add.f32 [%0], [%1], %2;" ::"l"(gdst), "r"(smem_u32(ssrc)),
+               "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+template <int N> __device__ __forceinline__ void bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory"); }
+__device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 bool e3b_tp_pipelined_enabled();
 #endif
 
@@ -77,6 +87,7 @@ struct TpArgs {
   const T* gy;   // [N, y_dim]   (backward)
   T* y;          // [N, y_dim]
   T* gx_edge;    // [E, x_dim]   (backward, may be null)
+  T* gx_node;    // [N, x_dim]   (backward, pipelined kernels only, may be null): d/dx reduced into the SOURCE node's row
   T* gsh;        // [E, n_part, sh_dim] (backward, may be null)
   T* gw;         // [E, w_dim]   (backward)
   const int64_t* in_ptr;

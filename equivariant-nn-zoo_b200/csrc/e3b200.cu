@@ -1052,7 +1052,7 @@ static TpArgs<T> make_args(const e3b_tp_plan* p, int64_t n_nodes, const void* x,
                            void* gx_edge, void* gsh, void* gw) {
   TpArgs<T> a;
   a.x = (const T*)x; a.sh = (const T*)sh; a.w = (const T*)w; a.gy = (const T*)gy;
-  a.y = (T*)y; a.gx_edge = (T*)gx_edge; a.gsh = (T*)gsh; a.gw = (T*)gw;
+  a.y = (T*)y; a.gx_edge = (T*)gx_edge; a.gx_node = nullptr; a.gsh = (T*)gsh; a.gw = (T*)gw;
   a.in_ptr = in_ptr; a.in_nbr = in_nbr; a.in_eid = in_eid;
   a.n_nodes = n_nodes;
   a.x_dim = p->x_dim; a.sh_dim = p->sh_dim; a.w_dim = p->w_dim; a.y_dim = p->y_dim;
@@ -1082,6 +1082,24 @@ extern "C" int e3b_tpconv_fwd(const e3b_tp_plan* plan, int dtype, int64_t n_node
                                                    nullptr, nullptr);
                  tp_generic_fwd_kernel<T><<<blocks_for(threads, 128), 128, 0, st>>>(g, a);)
   return check_launch("tpconv_fwd (generic)");
+}
+
+bool e3b_tp_pipelined_enabled();   // tp_fast.cu
+
+extern "C" int e3b_tpconv_bwd_nodes(const e3b_tp_plan* plan, int64_t n_nodes, int64_t n_edges, const float* x, const float* sh,
+                                    const float* w, const float* gy, const int64_t* in_ptr, const int32_t* in_nbr,
+                                    const int32_t* in_eid, float* gx_node, float* gsh, float* gw, void* stream) {
+  if (!plan) return fail(E3B_ERR_INVALID, "tpconv_bwd_nodes: null plan");
+  if (!plan->gen || (plan->desc.mul != 64 && plan->desc.mul != 32) || !e3b_tp_pipelined_enabled())
+    return fail(E3B_ERR_UNSUPPORTED, "tpconv_bwd_nodes: needs a generated structure with multiplicity 32 or 64");
+  if (n_nodes == 0 || n_edges == 0) return E3B_OK;
+  if (!x || !sh || !w || !gy || !in_ptr || !in_nbr || !gw || !gx_node) return fail(E3B_ERR_INVALID, "tpconv_bwd_nodes: null argument");
+  if ((reinterpret_cast<uintptr_t>(gx_node) & 15) || ((plan->x_dim * 4) & 15))
+    return fail(E3B_ERR_INVALID, "tpconv_bwd_nodes: gx_node rows must be 16-byte aligned");
+  TpArgs<float> a = make_args<float>(plan, n_nodes, x, sh, w, gy, in_ptr, in_nbr, in_eid, nullptr, nullptr, gsh, gw);
+  a.gx_node = gx_node;
+  plan->gen->bwd(a, 0, (cudaStream_t)stream);
+  return check_launch("tpconv_bwd_nodes (generated)");
 }
 
 extern "C" int e3b_tpconv_bwd(const e3b_tp_plan* plan, int dtype, int64_t n_nodes, int64_t n_edges, const void* x,

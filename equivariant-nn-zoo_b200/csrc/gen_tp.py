@@ -86,7 +86,7 @@ def emit_structure(E, sid, st):
                     out.append((b, s, ps))
         return out
 
-    def emit_bwd_body(blocks, xl, wl, yl):
+    def emit_bwd_body(blocks, xl, wl, yl, stage_gx=False):
             used_s = sorted({s for (b, s, ps) in pairs_of(blocks)})
             for s in used_s:
                 for j in range(st.irreps_sh[s].ir.dim):
@@ -139,6 +139,11 @@ def emit_structure(E, sid, st):
                 for i in range(d1):
                     E(f"      gxr[{xoff[b] + i} * mul] = gx_{b}_{i};")
                 E("    }")
+                if stage_gx:     # node-reduction mode: the edge's gradient row is staged in shared memory for one TMA reduce-add
+                    E("    if (a.gx_node != nullptr) {")
+                    for i in range(d1):
+                        E(f"      gxs[{xoff[b] + i} * mul + u] = gx_{b}_{i};")
+                    E("    }")
             E("    if (a.gsh != nullptr) {")
             E("      T* __restrict__ gsr = a.gsh + (eid * a.n_part + part) * a.sh_dim;")
             for s in range(len(st.irreps_sh)):
@@ -380,6 +385,7 @@ def emit_structure(E, sid, st):
     E("  int* s_src = reinterpret_cast<int*>(stages + TPP_STAGES * STAGE);")
     E("  int* s_eid = s_src + TPP_MAXSEG;")
     E("  uint64_t* full = reinterpret_cast<uint64_t*>(s_eid + TPP_MAXSEG);")
+    E("  float* gx_stage = reinterpret_cast<float*>(full + TPP_STAGES + (TPP_STAGES & 1));   // 16-byte aligned; only with a.gx_node")
     E("  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;")
     E("  const int64_t node = blockIdx.x;")
     E(f"  const int chunk = warp / G, group = warp - chunk * G, part = warp;")
@@ -423,20 +429,33 @@ def emit_structure(E, sid, st):
         E("        const T* __restrict__ sw = stages + s * STAGE + u;")
         E("        const T* __restrict__ sx = sw + ROW_W;")
         E("        T* __restrict__ gwr = a.gw + eid * w_dim + u;")
+        E("        float* gxs = gx_stage + (it % TPP_GXBUF) * ROW_X;")
         E("        {")
         emit_bwd_body(blocks, lambda b, i: f"sx[{xoff[b] + i} * MUL]", lambda pi: f"sw[{pi} * MUL]",
-                      lambda s_, j: f"__shfl_sync(0xffffffffu, Ycur, {soff[s_] + j})")
+                      lambda s_, j: f"__shfl_sync(0xffffffffu, Ycur, {soff[s_] + j})", stage_gx=True)
+        E("        }")
+        E("        if (a.gx_node != nullptr) {")
+        E("          fence_proxy_async();                       // the staged row -> visible to the TMA engine")
+        E("          if (tid == 0) bulk_wait_read<TPP_GXBUF - 2>();   // the buffer of the NEXT edge has been read out")
         E("        }")
         E("        Ycur = Ynext;")
         E("        __syncthreads();")
-        E("        if (tid == 0 && i + TPP_STAGES < n)")
-        E("          tpp_issue(stages + s * STAGE, &full[s], a.w + (int64_t)s_eid[i + TPP_STAGES] * ROW_W, ROW_W,")
-        E("                    a.x + (int64_t)s_src[i + TPP_STAGES] * ROW_X, ROW_X);")
+        E("        if (tid == 0) {")
+        E("          if (a.gx_node != nullptr) {                // d/dx of this edge += into its source node's row (L2 reduction)")
+        E("            bulk_reduce_add_f32(a.gx_node + (int64_t)s_src[i] * ROW_X, gxs, ROW_X * 4u);")
+        E("            bulk_commit();")
+        E("          }")
+        E("          if (i + TPP_STAGES < n)")
+        E("            tpp_issue(stages + s * STAGE, &full[s], a.w + (int64_t)s_eid[i + TPP_STAGES] * ROW_W, ROW_W,")
+        E("                      a.x + (int64_t)s_src[i + TPP_STAGES] * ROW_X, ROW_X);")
+        E("        }")
         E("      }")
         E("    }")
         E("  } break;")
     E("  }")
+    E("  if (a.gx_node != nullptr && tid == 0) bulk_wait_all();   // the staging buffers must outlive the reductions reading them")
     E("}")
+    E(f"static size_t tpbp_smem_S{sid}(int mul, bool reduce) {{ return ((tpfp_smem_S{sid}(mul) + 15) & ~(size_t)15) + 16 + (reduce ? (size_t)TPP_GXBUF * {xdim} * mul * 4 : 0); }}")
     E("#endif  // __CUDACC__")
     E()
 
@@ -500,7 +519,7 @@ def emit_tables(st_list):
             E(f"static void launch_tp{kind}_S{sid}(const TpArgs<float>& a, int64_t grid, cudaStream_t s) {{")
             if kind == "b":
                 E(f"  if ((a.mul == 64 || a.mul == 32) && e3b_tp_pipelined_enabled()) {{")
-                E(f"    const size_t smem = tpfp_smem_S{sid}(a.mul);")
+                E(f"    const size_t smem = tpbp_smem_S{sid}(a.mul, a.gx_node != nullptr);")
                 E(f"    if (a.mul == 64) {{ if (smem > 48 * 1024) cudaFuncSetAttribute(tpbp_S{sid}<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);")
                 E(f"      tpbp_S{sid}<64><<<(unsigned)a.n_nodes, 32 * {Gs[sid]} * 2, smem, s>>>(a); }}")
                 E(f"    else {{ if (smem > 48 * 1024) cudaFuncSetAttribute(tpbp_S{sid}<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);")

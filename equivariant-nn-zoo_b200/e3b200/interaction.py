@@ -262,13 +262,21 @@ class _Interaction(torch.autograd.Function):
         fast = plan.specialized
         alloc = torch.empty if fast else torch.zeros
         n_part = plan.n_part_f32 if fast else 1
-        gx_edge = alloc(E, plan.x_dim, dtype=torch.float32, device=dev) if need_x else None
+        # d/dx per source node: reduced inside the kernel (TMA reduce-add of each edge's row into its source's row, no
+        # per-edge buffer, no segment sum) unless bit-reproducible gradients are asked for (E3B_DETERMINISTIC=1)
+        in_kernel = bool(need_x and fast and E and plan.structure.uniform_mul in (32, 64) and not ops.DETERMINISTIC)
+        gx_edge = alloc(E, plan.x_dim, dtype=torch.float32, device=dev) if need_x and not in_kernel else None
+        g_xl = torch.zeros(N, fi.Din, dtype=torch.float32, device=dev) if in_kernel else None
         gsh_part = alloc(E, n_part, plan.sh_dim, dtype=torch.float32, device=dev) if need_Y else None
         gw = new(E, plan.w_dim)
         if E:
             end = ops._timed(("bwd", len(plan.structure.paths), plan.structure.uniform_mul, plan.x_dim, plan.y_dim, N, E))
-            check(lib.e3b_tpconv_bwd(plan.handle, 0, N, E, ptr(xl), ptr(Y), ptr(w), ptr(g_mid), ptr(csr.in_ptr),
-                                     ptr(csr.in_nbr), ptr(csr.in_eid), ptr(gx_edge), ptr(gsh_part), ptr(gw), stream()))
+            if in_kernel:
+                check(lib.e3b_tpconv_bwd_nodes(plan.handle, N, E, ptr(xl), ptr(Y), ptr(w), ptr(g_mid), ptr(csr.in_ptr),
+                                               ptr(csr.in_nbr), ptr(csr.in_eid), ptr(g_xl), ptr(gsh_part), ptr(gw), stream()))
+            else:
+                check(lib.e3b_tpconv_bwd(plan.handle, 0, N, E, ptr(xl), ptr(Y), ptr(w), ptr(g_mid), ptr(csr.in_ptr),
+                                         ptr(csr.in_nbr), ptr(csr.in_eid), ptr(gx_edge), ptr(gsh_part), ptr(gw), stream()))
             if end is not None:
                 end.record()
             count_launch()
@@ -291,12 +299,13 @@ class _Interaction(torch.autograd.Function):
             gz[i] = out
         g_er = gz[0] if need_er else None
         # ---- d/dx: linear_1 transposed on the reduced edge gradient + self-connection transposed
-        g_x = g_xl = None
+        g_x = None
         if need_x:
-            g_xl = new(N, fi.Din)
-            with ops.stage("b.segment_sum"):
-                check(lib.e3b_segment_sum(0, ptr(gx_edge), plan.x_dim, ptr(csr.out_ptr), ptr(csr.out_eid), N, ptr(g_xl), stream()))
-            count_launch()
+            if not in_kernel:
+                g_xl = new(N, fi.Din)
+                with ops.stage("b.segment_sum"):
+                    check(lib.e3b_segment_sum(0, ptr(gx_edge), plan.x_dim, ptr(csr.out_ptr), ptr(csr.out_eid), N, ptr(g_xl), stream()))
+                count_launch()
             g_x = new(N, fi.Din)
             probs, written = [], set()
             for q, (i, o, off, alpha) in enumerate(lin1.paths):

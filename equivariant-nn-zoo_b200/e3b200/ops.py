@@ -22,6 +22,11 @@ _SECOND_ORDER = 0
 WEIGHTS_EPOCH = 0
 
 
+# E3B_DETERMINISTIC=1: bit-reproducible gradients everywhere (the evaluation-mode backward of the fused block then writes
+# the per-edge d/dx rows and reduces them with the segment-sum kernel instead of TMA reduce-adds in the kernel)
+DETERMINISTIC = __import__("os").environ.get("E3B_DETERMINISTIC", "0") == "1"
+
+
 class second_order:
     def __enter__(self):
         global _SECOND_ORDER

@@ -231,6 +231,15 @@ E3B_API int e3b_tpconv_bwd(const e3b_tp_plan* plan, int dtype, int64_t n_nodes, 
 
 /* out[n, :] = sum_{k in [ptr[n], ptr[n+1])} src[ids ? ids[k] : k, :]  (rows of `width` scalars).
  * Replaces torch_runstats scatter at nn/message_passing.py:109 / nn/output.py:69 (Pooling). */
+/* Backward with d/dx reduced per SOURCE node inside the kernel (fp32 only; generated structures with multiplicity 32 / 64):
+ * every edge's gradient row is staged in shared memory and added into gx_node[src] by one TMA reduce-add
+ * (cp.reduce.async.bulk), so neither the [E, x_dim] per-edge buffer nor the segment sum of e3b_tpconv_bwd's caller is needed.
+ * gx_node [N, x_dim] must be ZEROED by the caller; the order of the additions into a row is not fixed (results repeat to
+ * fp32 rounding, ~1e-7 relative, not bit for bit) -- callers that need bit-reproducible gradients use e3b_tpconv_bwd.   */
+E3B_API int e3b_tpconv_bwd_nodes(const e3b_tp_plan* plan, int64_t n_nodes, int64_t n_edges, const float* x, const float* sh,
+                                 const float* w, const float* gy, const int64_t* in_ptr, const int32_t* in_nbr,
+                                 const int32_t* in_eid, float* gx_node, float* gsh /* [E, n_part, sh_dim] or NULL */,
+                                 float* gw, void* stream);
 E3B_API int e3b_segment_sum(int dtype, const void* src, int64_t width, const int64_t* ptr, const int32_t* ids,
                     int64_t n_out, void* out, void* stream);
 

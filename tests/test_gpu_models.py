@@ -194,6 +194,30 @@ def test_padded_neighbour_list():
         assert int(pd.max()) - int(pd.min()) <= 1                     # spread evenly over the pairs
 
 
+def test_in_kernel_node_reduction_matches_deterministic_path():
+    """evaluation-mode backward: d/dx reduced per source node by TMA reduce-adds inside the tensor-product kernel
+    (e3b_tpconv_bwd_nodes) == per-edge rows + segment-sum kernel (E3B_DETERMINISTIC=1), to fp32 rounding"""
+    from e3b200 import ops
+
+    meta = {"config": "config_energy_force", "seed": 3}
+    model = product_harness.build_product(meta, torch.float32, DEV)
+    inputs = synthetic.qm9_like(40, seed=21)
+    outs = {}
+    for det in (True, False, False):
+        ops.DETERMINISTIC = det
+        try:
+            o = product_harness.run_product(model, inputs, torch.float32, DEV, pre_edge={"r_max": 5.0})
+        finally:
+            ops.DETERMINISTIC = False
+        outs.setdefault(det, []).append((o["energy"].clone(), o["forces"].clone()))
+    (e_det, f_det), (e_a, f_a), (e_b, f_b) = outs[True][0], outs[False][0], outs[False][1]
+    assert torch.equal(e_det, e_a)                                   # the forward pass is the same code
+    assert harness.rel_err(f_a, f_det) < 2e-6 and harness.rel_err(f_b, f_a) < 2e-6
+    oracle = harness.build_oracle(meta, torch.float64)
+    ref = harness.run_oracle(oracle, inputs, torch.float64, pre_edge={"r_max": 5.0})
+    assert harness.rel_err(f_a, ref["forces"]) < 1e-5
+
+
 def test_ragged_batch_with_isolated_atoms():
     """single-atom molecules (no edges at all) and a far-apart pair inside an ordinary batch: empty CSR segments
     through every kernel, fp32 product vs fp64 oracle, forces of isolated atoms exactly zero"""
