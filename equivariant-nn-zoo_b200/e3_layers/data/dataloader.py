@@ -112,6 +112,9 @@ class DevicePipeline:
     def endless(self, skip=0):
         """batches for ever, epoch after epoch (reference ``autoReset``); ``skip`` batches are drawn but not built
         (resuming a run replays the data order without touching the data)"""
+        if len(self) == 0:
+            raise ValueError(f"no batch can be formed: {self.n_graphs} graphs, batch_size {self.batch_size} x {self.world} "
+                             f"rank(s), drop_last={self.drop_last}")
         while True:
             todo = list(self.batches_of_indices())
             if skip >= len(todo):

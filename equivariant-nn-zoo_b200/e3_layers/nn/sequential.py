@@ -74,6 +74,11 @@ class SequentialGraphNetwork(torch.nn.Sequential):
             self.layers.append((key, layer))
         self.layer_configs = config["layers"]
         super().__init__(built)
+        # the interaction blocks of one network share work that depends on the edges only (their radial hidden layers run
+        # as one grouped launch per layer, e3b200.interaction._RadialHidden)
+        blocks = [m for m in built.values() if type(m).__name__ == "MessagePassing"]
+        for m in blocks:
+            object.__setattr__(m, "_e3b_group", blocks)
 
     def load_state_dict(self, state_dict, strict=True, **kwargs):
         """accepts the reference's checkpoints as they are (see ``strip_reference_state``)"""

@@ -5,7 +5,9 @@ Forward, per layer (every step is a libe3b200 kernel; feature rows stay in the c
 "imu" layout between the kernels, so no transposes or concatenations are materialised):
 
     x_l   = linear_1(x)                               grouped tcgen05 GEMM (irreps blocks = problems)
-    h, w  = radial MLP(edge_radial)                   tcgen05 GEMMs, ssp fused in the epilogue
+    h     = radial MLP hidden layers(edge_radial)     ONE node for all blocks of the network (`_RadialHidden`):
+                                                      layer i of every block in one grouped tcgen05 launch
+    w     = h @ W_last                                tcgen05 GEMM
     mid   = sum_{e -> n} w_e * (x_l[src] (x) Y_e)     fused gather / CG product / segmented sum
     conv  = linear(mid) / sqrt(avg_num_neighbors)     grouped tcgen05 GEMM (after the reduction)
     conv += sc(x, node_attrs)                         grouped tcgen05 GEMM, attribute contraction in the epilogue
@@ -75,9 +77,22 @@ class FusedInteraction:
 
     # -- packed weights -------------------------------------------------------------------------
     def _params(self):
+        """every parameter the packed weights depend on"""
         c = self.conv
         return [getattr(c.fc, f"layer{i}").weight for i in range(c.fc.n_layers)] + [c.linear_1.weight, c.tp.linear.weight,
                                                                                    c.sc.weight]
+
+    def _hidden_params(self):
+        c = self.conv
+        return [getattr(c.fc, f"layer{i}").weight for i in range(c.fc.n_layers - 1)]
+
+    def _block_params(self):
+        """parameters whose gradients the block's own autograd node produces: last radial layer, linear_1, post linear, sc"""
+        c = self.conv
+        return [getattr(c.fc, f"layer{c.fc.n_layers - 1}").weight, c.linear_1.weight, c.tp.linear.weight, c.sc.weight]
+
+    def hidden_signature(self):
+        return (tuple(self.hs[:-1]), float(self.fc.cst))
 
     def packs(self, role):
         """role 'fwd' | 'bwd' -> dict of PackedWeight lists, repacked only when a parameter changed"""
@@ -122,17 +137,119 @@ class FusedInteraction:
 _waves = ops.gemm_waves
 
 
+class _RadialHidden(torch.autograd.Function):
+    """The hidden layers of the radial MLPs of ALL interaction blocks of a network as one autograd node.  They depend on
+    the edge lengths only, not on the node features, so layer i of every block runs in ONE grouped tcgen05 launch
+    (forward: 3 launches instead of 15 for a 5-block network; backward likewise -- autograd calls this node's backward
+    once, after every block has delivered its gradient).  Contract with `_Interaction` (both private): output b is the
+    last hidden activation of block b; the gradient that comes back for it is already multiplied by the activation
+    derivative at that output (fused in the epilogue of the block's last-layer backward GEMM)."""
+
+    @staticmethod
+    def forward(ctx, er, fis, *weights):
+        ctx.set_materialize_grads(False)
+        er = er.contiguous()
+        E, dev = er.shape[0], er.device
+        hs, cst = fis[0].hs, fis[0].fc.cst
+        n_hid = len(hs) - 2
+        h = [[er] for _ in fis]
+        with ops.stage("f.mlp_hidden"):
+            for i in range(n_hid):
+                probs = []
+                for b, fi in enumerate(fis):
+                    out = torch.empty(E, hs[i + 1], dtype=torch.float32, device=dev)
+                    src = h[b][-1]
+                    probs.append(ops.gemm_problem(src, fi.packs("fwd")["fc"][i], out, E, a_rows=(src.stride(0), 0, 1),
+                                                  alpha=1.0 / math.sqrt(hs[i]), epilogue=2, act_cst=cst))
+                    h[b].append(out)
+                ops.gemm_run(probs)
+        ctx.fis, ctx.n_hid = fis, n_hid
+        ctx.save_for_backward(*[t for hb in h for t in hb])
+        return tuple(hb[-1] for hb in h)
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, *g_out):
+        fis, n_hid = ctx.fis, ctx.n_hid
+        saved = ctx.saved_tensors
+        L = len(fis)
+        h = [list(saved[b * (n_hid + 1):(b + 1) * (n_hid + 1)]) for b in range(L)]
+        hs, cst = fis[0].hs, fis[0].fc.cst
+        E, dev = h[0][0].shape[0], h[0][0].device
+        need_er = ctx.needs_input_grad[0]
+        need_w = [ctx.needs_input_grad[2 + k] for k in range(L * n_hid)]
+        need_params = any(need_w) and not ops.positions_only_active()
+        live = [b for b in range(L) if g_out[b] is not None]
+        if not live or not (need_er or need_params):
+            return (None, None) + (None,) * (L * n_hid)
+        gz = [[None] * (n_hid + 1) for _ in range(L)]
+        for b in live:
+            gz[b][n_hid] = g_out[b].contiguous()
+        lo = 0 if need_er else 1
+        with ops.stage("b.mlp_hidden"):
+            for i in range(n_hid - 1, lo - 1, -1):
+                probs = []
+                for b in live:
+                    out = torch.empty(E, hs[i], dtype=torch.float32, device=dev)
+                    probs.append(ops.gemm_problem(gz[b][i + 1], fis[b].packs("bwd")["fc"][i], out, E, alpha=1.0 / math.sqrt(hs[i]),
+                                                  epilogue=3 if i > 0 else 0, H=h[b][i] if i > 0 else None, act_cst=cst))
+                    gz[b][i] = out
+                ops.gemm_run(probs)
+        g_er = None
+        if need_er:
+            g_er = gz[live[0]][0]
+            for b in live[1:]:
+                g_er = g_er + gz[b][0]
+        g_w = [None] * (L * n_hid)
+        if need_params:
+            probs = []
+            for b in live:
+                for i in range(n_hid):
+                    if not need_w[b * n_hid + i]:
+                        continue
+                    K1, K2 = hs[i], hs[i + 1]
+                    a, g = h[b][i], gz[b][i + 1]
+                    if K1 % 4 == 0 and K2 % 4 == 0 and a.is_contiguous():
+                        out = torch.empty(K1, K2, dtype=torch.float32, device=dev)
+                        probs.append(ops.wgrad_problem(a, g, out, E, K1, K2, alpha=1.0 / math.sqrt(K1)))
+                    else:
+                        out = (a.t() @ g) * (1.0 / math.sqrt(K1))
+                    g_w[b * n_hid + i] = out
+            ops.wgrad_run(probs, dev)
+        return (g_er, None, *g_w)
+
+
+def radial_hidden(er, fi, group):
+    """last hidden activation of block `fi`'s radial MLP; computed for every compatible block of `group` at the first
+    request and remembered on the `edge_radial` tensor object (a new one every forward pass)"""
+    cache = getattr(er, "_e3b_rh", None)
+    if cache is None or id(fi) not in cache:
+        sig = fi.hidden_signature()
+        fis = [fi]
+        for m in (group or []):
+            f2 = m.fused
+            if f2 is not fi and f2.reason is None and f2.hidden_signature() == sig and (cache is None or id(f2) not in cache):
+                fis.append(f2)
+        weights = [w for f2 in fis for w in f2._hidden_params()]
+        outs = _RadialHidden.apply(er, tuple(fis), *weights)
+        cache = dict(cache or {})
+        for f2, o in zip(fis, outs):
+            cache[id(f2)] = o
+        er._e3b_rh = cache
+    return cache[id(fi)]
+
+
 class _Interaction(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, x_mi, x_imu, attrs, er, Y, fi, csr, *params):
+    def forward(ctx, x_mi, x_imu, attrs, h_last, Y, fi, csr, *params):
         lib = _lib.load()
         ctx.set_materialize_grads(False)
         conv = fi.conv
         src_is_imu = x_imu is not None
         if x_imu is None:
             x_imu = x_mi.contiguous() if fi.all_scalar_in else ops.layout_convert(x_mi, fi.feat_in, True)
-        x_imu, attrs, er, Y = x_imu.contiguous(), attrs.contiguous(), er.contiguous(), Y.contiguous()
-        N, E = x_imu.shape[0], er.shape[0]
+        x_imu, attrs, h_last, Y = x_imu.contiguous(), attrs.contiguous(), h_last.contiguous(), Y.contiguous()
+        N, E = x_imu.shape[0], h_last.shape[0]
         dev = x_imu.device
         P = fi.packs("fwd")
         new = lambda *s: torch.empty(*s, dtype=torch.float32, device=dev)
@@ -151,17 +268,13 @@ class _Interaction(torch.autograd.Function):
         with ops.stage("f.linear_1"):
             for wave in _waves(probs):
                 ops.gemm_run(wave)
-        # ---- radial MLP
+        # ---- last layer of the radial MLP (the hidden layers are the shared `_RadialHidden` node)
         hs = fi.hs
-        h = [er]
-        for i in range(conv.fc.n_layers):
-            last = i == conv.fc.n_layers - 1
-            out = new(E, hs[i + 1])
-            with ops.stage("f.mlp_last" if last else "f.mlp_hidden"):
-                ops.gemm_run([ops.gemm_problem(h[-1], P["fc"][i], out, E, a_rows=(h[-1].stride(0), 0, 1),
-                                               alpha=1.0 / math.sqrt(hs[i]), epilogue=0 if last else 2, act_cst=conv.fc.cst)])
-            h.append(out)
-        w = h[-1]
+        n_fc = conv.fc.n_layers
+        w = new(E, hs[-1])
+        with ops.stage("f.mlp_last"):
+            ops.gemm_run([ops.gemm_problem(h_last, P["fc"][n_fc - 1], w, E, a_rows=(h_last.stride(0), 0, 1),
+                                           alpha=1.0 / math.sqrt(hs[-2]), epilogue=0, act_cst=conv.fc.cst)])
         # ---- fused gather + CG tensor product + segmented sum
         plan = conv.tp.plan
         mid = new(N, plan.y_dim)
@@ -210,8 +323,7 @@ class _Interaction(torch.autograd.Function):
         # (fine-tuning under model.eval(), gradient diagnostics); the one pass that must not pay for them -- the
         # position gradient of an energy+force evaluation -- is marked by GradientOutput with ops.positions_only
         ctx.want_params = bool(any(p.requires_grad for p in params))
-        ctx.save_for_backward(x_imu, attrs, Y, xl, cv, *h, mid if ctx.want_params else None)
-        ctx.n_h = len(h)
+        ctx.save_for_backward(x_imu, attrs, Y, xl, cv, h_last, w, mid if ctx.want_params else None)
         return out_mi, out_imu
 
     @staticmethod
@@ -221,15 +333,12 @@ class _Interaction(torch.autograd.Function):
         fi, csr = ctx.fi, ctx.csr
         conv = fi.conv
         saved = ctx.saved_tensors
-        x_imu, attrs, Y, xl, cv = saved[:5]
-        h = list(saved[5:5 + ctx.n_h])
-        mid = saved[5 + ctx.n_h]
-        er, w = h[0], h[-1]
-        N, E = x_imu.shape[0], er.shape[0]
+        x_imu, attrs, Y, xl, cv, h_last, w, mid = saved
+        N, E = x_imu.shape[0], h_last.shape[0]
         dev = x_imu.device
         new = lambda *s: torch.empty(*s, dtype=torch.float32, device=dev)
         need_x = ctx.needs_input_grad[0] or ctx.needs_input_grad[1]
-        need_attrs, need_er, need_Y = ctx.needs_input_grad[2], ctx.needs_input_grad[3], ctx.needs_input_grad[4]
+        need_attrs, need_h, need_Y = ctx.needs_input_grad[2], ctx.needs_input_grad[3], ctx.needs_input_grad[4]
         pos_only = ops.positions_only_active()          # parameters never depend on the positions
         need_params = ctx.want_params and any(ctx.needs_input_grad[7:]) and not pos_only
         need_attrs = need_attrs and ops.needs_grad_now(attrs)
@@ -263,8 +372,10 @@ class _Interaction(torch.autograd.Function):
         alloc = torch.empty if fast else torch.zeros
         n_part = plan.n_part_f32 if fast else 1
         # d/dx per source node: reduced inside the kernel (TMA reduce-add of each edge's row into its source's row, no
-        # per-edge buffer, no segment sum) unless bit-reproducible gradients are asked for (E3B_DETERMINISTIC=1)
-        in_kernel = bool(need_x and fast and E and plan.structure.uniform_mul in (32, 64) and not ops.DETERMINISTIC)
+        # per-edge buffer, no segment sum) in the evaluation pass; passes that produce parameter gradients (training) and
+        # E3B_DETERMINISTIC=1 keep the bit-reproducible per-edge rows + segment sum
+        in_kernel = bool(need_x and fast and E and plan.structure.uniform_mul in (32, 64) and not need_params
+                         and not ops.DETERMINISTIC)
         gx_edge = alloc(E, plan.x_dim, dtype=torch.float32, device=dev) if need_x and not in_kernel else None
         g_xl = torch.zeros(N, fi.Din, dtype=torch.float32, device=dev) if in_kernel else None
         gsh_part = alloc(E, n_part, plan.sh_dim, dtype=torch.float32, device=dev) if need_Y else None
@@ -284,20 +395,17 @@ class _Interaction(torch.autograd.Function):
         if need_Y:
             with ops.stage("b.gsh_sum"):
                 g_Y = gsh_part.sum(1) if n_part > 1 else gsh_part.view(E, plan.sh_dim)
-        # ---- radial MLP backward (data path): g_z_i = (g_z_{i+1} W_i^T) * act'(z_i), derivative from the stored h_i
+        # ---- last radial layer backward (data path): the gradient handed to the shared hidden node is already
+        # multiplied by the activation derivative at h_last (epilogue 3), see `_RadialHidden`
         hs = fi.hs
-        gz = [None] * (conv.fc.n_layers + 1)       # gz[i] = gradient wrt the INPUT of layer i (after its activation derivative)
-        gz[conv.fc.n_layers] = gw
-        lo = 0 if need_er else 1
-        for i in range(conv.fc.n_layers - 1, lo - 1, -1):
-            if not (need_er or need_params):
-                break
-            out = new(E, hs[i])
-            with ops.stage("b.mlp_last" if i == conv.fc.n_layers - 1 else "b.mlp_hidden"):
-                ops.gemm_run([ops.gemm_problem(gz[i + 1], P["fc"][i], out, E, alpha=1.0 / math.sqrt(hs[i]),
-                                               epilogue=3 if i > 0 else 0, H=h[i] if i > 0 else None, act_cst=conv.fc.cst)])
-            gz[i] = out
-        g_er = gz[0] if need_er else None
+        n_fc = conv.fc.n_layers
+        g_h = None
+        if need_h:
+            g_h = new(E, hs[-2])
+            with ops.stage("b.mlp_last"):
+                ops.gemm_run([ops.gemm_problem(gw, P["fc"][n_fc - 1], g_h, E, alpha=1.0 / math.sqrt(hs[-2]),
+                                               epilogue=3 if n_fc > 1 else 0, H=h_last if n_fc > 1 else None,
+                                               act_cst=conv.fc.cst)])
         # ---- d/dx: linear_1 transposed on the reduced edge gradient + self-connection transposed
         g_x = None
         if need_x:
@@ -335,37 +443,35 @@ class _Interaction(torch.autograd.Function):
         g_params = [None] * len(ctx.needs_input_grad[7:])
         g_attrs = None
         if need_params or need_attrs:
-            g_params, g_attrs = _param_grads(fi, ctx.needs_input_grad, x_imu, attrs, h, gz, mid, g_cv, g_xl, need_attrs)
+            g_params, g_attrs = _param_grads(fi, ctx.needs_input_grad, x_imu, attrs, h_last, gw, mid, g_cv, g_xl, need_attrs)
         g_x_mi = g_x_imu = None
         if need_x:
             if ctx.src_is_imu:
                 g_x_imu = g_x
             else:
                 g_x_mi = g_x if fi.all_scalar_in else ops.layout_convert(g_x, fi.feat_in, False)
-        return (g_x_mi, g_x_imu, g_attrs, g_er, g_Y, None, None, *g_params)
+        return (g_x_mi, g_x_imu, g_attrs, g_h, g_Y, None, None, *g_params)
 
 
-def _param_grads(fi, needs, x_imu, attrs, h, gz, mid, g_cv, g_xl, need_attrs):
-    """parameter gradients of one block: reductions over all edges / nodes on the split-K tcgen05 kernel
-    (csrc/wgrad_tf32x3.cu), written straight into the flat weight layouts; the attribute gradient (a per-node
-    quantity) stays a torch contraction"""
+def _param_grads(fi, needs, x_imu, attrs, h_last, gw, mid, g_cv, g_xl, need_attrs):
+    """parameter gradients of one block (last radial layer, linear_1, post linear, self-connection): reductions over all
+    edges / nodes on the split-K tcgen05 kernel (csrc/wgrad_tf32x3.cu), written straight into the flat weight layouts;
+    the attribute gradient (a per-node quantity) stays a torch contraction"""
     conv = fi.conv
-    n_fc = conv.fc.n_layers
+    n_fc = 1                                           # parameters of this node: [fc last, linear_1, post, sc]
     out = []
     N, dev = x_imu.shape[0], x_imu.device
     probs = []
-    for i in range(n_fc):
-        if not needs[7 + i]:
-            out.append(None)
-            continue
-        K1, K2 = fi.hs[i], fi.hs[i + 1]
-        a, b = h[i], gz[i + 1]
-        if K1 % 4 == 0 and K2 % 4 == 0 and a.is_contiguous() and b.is_contiguous():
-            gw_i = torch.empty(K1, K2, dtype=torch.float32, device=dev)
-            probs.append(ops.wgrad_problem(a, b, gw_i, a.shape[0], K1, K2, alpha=1.0 / math.sqrt(K1)))
+    if needs[7]:
+        K1, K2 = fi.hs[-2], fi.hs[-1]
+        if K1 % 4 == 0 and K2 % 4 == 0:
+            gw_last = torch.empty(K1, K2, dtype=torch.float32, device=dev)
+            probs.append(ops.wgrad_problem(h_last, gw, gw_last, h_last.shape[0], K1, K2, alpha=1.0 / math.sqrt(K1)))
         else:
-            gw_i = (a.t() @ b) * (1.0 / math.sqrt(K1))
-        out.append(gw_i)
+            gw_last = (h_last.t() @ gw) * (1.0 / math.sqrt(K1))
+        out.append(gw_last)
+    else:
+        out.append(None)
     # linear_1: dW[u, w] = alpha sum_{z, m} x[z, m, u] g_xl[z, m, w]
     lin1 = conv.linear_1
     g = None
@@ -417,11 +523,13 @@ def _param_grads(fi, needs, x_imu, attrs, h, gz, mid, g_cv, g_xl, need_attrs):
     return out, g_attrs
 
 
-def interaction(fi, x, attrs, er, Y, csr):
+def interaction(fi, x, attrs, er, Y, csr, group=None):
     """-> (out mul_ir, out imu).  `x` is the mul_ir feature tensor; if it carries the imu twin written by the
-    previous block's gate (attribute ``_e3b_imu``) that one is consumed instead, so no layout pass runs."""
+    previous block's gate (attribute ``_e3b_imu``) that one is consumed instead, so no layout pass runs.  `group`: the
+    interaction blocks of the same network (their radial hidden layers run together, see `_RadialHidden`)."""
     twin = getattr(x, "_e3b_imu", None)
-    params = fi._params()
+    params = fi._block_params()
+    h_last = radial_hidden(er, fi, group) if fi.conv.fc.n_layers > 1 else er
     if twin is not None:
-        return _Interaction.apply(None, twin, attrs, er, Y, fi, csr, *params)
-    return _Interaction.apply(x, None, attrs, er, Y, fi, csr, *params)
+        return _Interaction.apply(None, twin, attrs, h_last, Y, fi, csr, *params)
+    return _Interaction.apply(x, None, attrs, h_last, Y, fi, csr, *params)

@@ -68,6 +68,14 @@ def test_endless_skip_replays_the_order():
         assert torch.equal(next(it2)["pos"], want)
 
 
+def test_endless_refuses_an_empty_epoch():
+    ds = CondensedDataset(data=synthetic.qm9_like(3, seed=3), attrs=dict(ATTRS_MOL))
+    p = DevicePipeline(ds, batch_size=8, drop_last=True, device="cpu")
+    assert len(p) == 0 and list(p) == []
+    with pytest.raises(ValueError):
+        next(p.endless())
+
+
 def test_preprocess_contract_is_merged_not_replaced():
     """a layer-style function returning only its NEW tensors keeps the item's other tensors
     (the reference loses them: dataset.py:115-117 with compute_edge.py:110-113)"""

@@ -108,6 +108,7 @@ def make_pipeline(data, target_keys, batch_size, r_max, seed, rank, world, dev, 
     attrs = {k: ATTRS[k] for k in data if k in ATTRS}
     ds = CondensedDataset(data=data, attrs=attrs, preprocess=[partial(computeEdgeIndex, r_max=r_max)])
     gen = torch.Generator().manual_seed(seed)                     # same order on every rank; each takes its shard
+    batch_size = max(1, min(batch_size, int(data["_n_nodes"].shape[0]) // world))    # a dataset smaller than one batch
     return DevicePipeline(ds, batch_size=batch_size, shuffle=True, drop_last=True, generator=gen, device=dev,
                           rank=rank, world_size=world, resident=resident)
 
