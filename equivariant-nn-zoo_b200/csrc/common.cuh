@@ -93,6 +93,8 @@ struct TpArgs {
   const int64_t* in_ptr;
   const int32_t* in_nbr;
   const int32_t* in_eid;
+  const int32_t* w_idx;   // [E] or null: row of w (forward and backward read) of edge id e -- edges that share a weight row
+                          // (the two directions of an undirected edge); pipelined kernels only
   int64_t n_nodes;
   int64_t x_dim, sh_dim, w_dim, y_dim;
   int32_t mul, n_chunks, n_part;

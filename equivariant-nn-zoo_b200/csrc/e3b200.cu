@@ -221,6 +221,36 @@ extern "C" int e3b_radius_graph_fill_padded(const float* pos, int64_t pos_stride
   return E3B_OK;
 }
 
+// Undirected-edge bookkeeping of the radial MLP: out[u, k] = (g[canon[u], k] + g[rev[canon[u]], k]) * d/dz[cst ssp](z)
+// with the derivative evaluated from the stored activation h[u, k] = cst * ssp(z) (h == null: factor 1).
+__global__ void pair_sum_act_kernel(const float* __restrict__ g, const int64_t* __restrict__ canon, const int32_t* __restrict__ rev,
+                                    const float* __restrict__ h, float cst, int64_t n_unique, int width, float* __restrict__ out) {
+  const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;      // one float4 per thread
+  const int w4 = width >> 2;
+  if (idx >= n_unique * w4) return;
+  const int64_t u = idx / w4;
+  const int c = (int)(idx - u * w4) * 4;
+  const int64_t e = canon[u], r = rev[e];
+  const float4 a = *reinterpret_cast<const float4*>(g + e * width + c), b = *reinterpret_cast<const float4*>(g + r * width + c);
+  float4 o = make_float4(a.x + b.x, a.y + b.y, a.z + b.z, a.w + b.w);
+  if (h) {
+    const float4 hv = *reinterpret_cast<const float4*>(h + u * width + c);
+    const float ic = 1.f / cst;
+    o.x *= cst * (1.f - 0.5f * __expf(-hv.x * ic)); o.y *= cst * (1.f - 0.5f * __expf(-hv.y * ic));
+    o.z *= cst * (1.f - 0.5f * __expf(-hv.z * ic)); o.w *= cst * (1.f - 0.5f * __expf(-hv.w * ic));
+  }
+  *reinterpret_cast<float4*>(out + u * width + c) = o;
+}
+
+extern "C" int e3b_pair_sum_act(const float* g, const int64_t* canon, const int32_t* rev, const float* h, float cst,
+                                int64_t n_unique, int32_t width, float* out, void* stream) {
+  if (n_unique == 0) return E3B_OK;
+  if (!g || !canon || !rev || !out || width <= 0 || (width & 3)) return fail(E3B_ERR_INVALID, "pair_sum_act: bad argument");
+  pair_sum_act_kernel<<<blocks_for(n_unique * (width / 4), 256), 256, 0, (cudaStream_t)stream>>>(g, canon, rev, h, cst, n_unique,
+                                                                                                 width, out);
+  return check_launch("pair_sum_act");
+}
+
 // ------------------------------------------------------------------------------------------
 // Neighbour list with pair predicates evaluated inside the sweep (the `criteria` callable of
 // config_diffusion_CA.py:58-64: same chain and |a - b| < 5, OR a Bernoulli(p) draw per ordered pair) and, for
@@ -1053,7 +1083,7 @@ static TpArgs<T> make_args(const e3b_tp_plan* p, int64_t n_nodes, const void* x,
   TpArgs<T> a;
   a.x = (const T*)x; a.sh = (const T*)sh; a.w = (const T*)w; a.gy = (const T*)gy;
   a.y = (T*)y; a.gx_edge = (T*)gx_edge; a.gx_node = nullptr; a.gsh = (T*)gsh; a.gw = (T*)gw;
-  a.in_ptr = in_ptr; a.in_nbr = in_nbr; a.in_eid = in_eid;
+  a.in_ptr = in_ptr; a.in_nbr = in_nbr; a.in_eid = in_eid; a.w_idx = nullptr;
   a.n_nodes = n_nodes;
   a.x_dim = p->x_dim; a.sh_dim = p->sh_dim; a.w_dim = p->w_dim; a.y_dim = p->y_dim;
   a.mul = p->desc.mul;
@@ -1086,11 +1116,30 @@ extern "C" int e3b_tpconv_fwd(const e3b_tp_plan* plan, int dtype, int64_t n_node
 
 bool e3b_tp_pipelined_enabled();   // tp_fast.cu
 
+static bool pipelined_plan(const e3b_tp_plan* plan) {
+  return plan->gen && (plan->desc.mul == 64 || plan->desc.mul == 32) && e3b_tp_pipelined_enabled();
+}
+
+extern "C" int e3b_tpconv_fwd_shared(const e3b_tp_plan* plan, int64_t n_nodes, int64_t n_edges, const float* x, const float* sh,
+                                     const float* w, const int32_t* w_idx, const int64_t* in_ptr, const int32_t* in_nbr,
+                                     const int32_t* in_eid, float* y, void* stream) {
+  if (!plan) return fail(E3B_ERR_INVALID, "tpconv_fwd_shared: null plan");
+  if (!pipelined_plan(plan))
+    return fail(E3B_ERR_UNSUPPORTED, "tpconv_fwd_shared: needs a generated structure with multiplicity 32 or 64");
+  if (n_nodes == 0) return E3B_OK;
+  if (!x || !in_ptr || !y || !w_idx || (n_edges > 0 && (!sh || !w || !in_nbr))) return fail(E3B_ERR_INVALID, "tpconv_fwd_shared: null argument");
+  TpArgs<float> a = make_args<float>(plan, n_nodes, x, sh, w, nullptr, in_ptr, in_nbr, in_eid, y, nullptr, nullptr, nullptr);
+  a.w_idx = w_idx;
+  plan->gen->fwd(a, 0, (cudaStream_t)stream);
+  return check_launch("tpconv_fwd_shared (generated)");
+}
+
 extern "C" int e3b_tpconv_bwd_nodes(const e3b_tp_plan* plan, int64_t n_nodes, int64_t n_edges, const float* x, const float* sh,
-                                    const float* w, const float* gy, const int64_t* in_ptr, const int32_t* in_nbr,
-                                    const int32_t* in_eid, float* gx_node, float* gsh, float* gw, void* stream) {
+                                    const float* w, const int32_t* w_idx, const float* gy, const int64_t* in_ptr,
+                                    const int32_t* in_nbr, const int32_t* in_eid, float* gx_node, float* gsh, float* gw,
+                                    void* stream) {
   if (!plan) return fail(E3B_ERR_INVALID, "tpconv_bwd_nodes: null plan");
-  if (!plan->gen || (plan->desc.mul != 64 && plan->desc.mul != 32) || !e3b_tp_pipelined_enabled())
+  if (!pipelined_plan(plan))
     return fail(E3B_ERR_UNSUPPORTED, "tpconv_bwd_nodes: needs a generated structure with multiplicity 32 or 64");
   if (n_nodes == 0 || n_edges == 0) return E3B_OK;
   if (!x || !sh || !w || !gy || !in_ptr || !in_nbr || !gw || !gx_node) return fail(E3B_ERR_INVALID, "tpconv_bwd_nodes: null argument");
@@ -1098,6 +1147,7 @@ extern "C" int e3b_tpconv_bwd_nodes(const e3b_tp_plan* plan, int64_t n_nodes, in
     return fail(E3B_ERR_INVALID, "tpconv_bwd_nodes: gx_node rows must be 16-byte aligned");
   TpArgs<float> a = make_args<float>(plan, n_nodes, x, sh, w, gy, in_ptr, in_nbr, in_eid, nullptr, nullptr, gsh, gw);
   a.gx_node = gx_node;
+  a.w_idx = w_idx;
   plan->gen->bwd(a, 0, (cudaStream_t)stream);
   return check_launch("tpconv_bwd_nodes (generated)");
 }

@@ -277,7 +277,8 @@ def emit_structure(E, sid, st):
     E("  float* stages = reinterpret_cast<float*>(tpp_smem);")
     E("  int* s_src = reinterpret_cast<int*>(stages + TPP_STAGES * STAGE);")
     E("  int* s_eid = s_src + TPP_MAXSEG;")
-    E("  uint64_t* full = reinterpret_cast<uint64_t*>(s_eid + TPP_MAXSEG);")
+    E("  int* s_wid = s_eid + TPP_MAXSEG;    // row of the weight tensor per slot (= edge id unless a.w_idx shares rows)")
+    E("  uint64_t* full = reinterpret_cast<uint64_t*>(s_wid + TPP_MAXSEG);")
     E("  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;")
     E("  const int64_t node = blockIdx.x;")
     E(f"  const int chunk = warp / G, group = warp - chunk * G;")
@@ -304,14 +305,16 @@ def emit_structure(E, sid, st):
         E("      __syncthreads();   // previous chunk fully consumed (also orders the barrier init)")
         E("      for (int i = tid; i < n; i += NT) {")
         E("        s_src[i] = a.in_nbr[c0 + i];")
-        E("        s_eid[i] = a.in_eid ? a.in_eid[c0 + i] : (int)(c0 + i);")
+        E("        const int eid_i = a.in_eid ? a.in_eid[c0 + i] : (int)(c0 + i);")
+        E("        s_eid[i] = eid_i;")
+        E("        s_wid[i] = a.w_idx ? a.w_idx[eid_i] : eid_i;")
         E("      }")
         E("      __syncthreads();")
         E("      if (tid == 0) {")
         E("        const int pre = n < TPP_STAGES ? n : TPP_STAGES;")
         E("        for (int j = 0; j < pre; ++j) {")
         E("          const uint32_t s = (it + j) % TPP_STAGES;")
-        E("          tpp_issue(stages + s * STAGE, &full[s], a.w + (int64_t)s_eid[j] * ROW_W, ROW_W, a.x + (int64_t)s_src[j] * ROW_X, ROW_X);")
+        E("          tpp_issue(stages + s * STAGE, &full[s], a.w + (int64_t)s_wid[j] * ROW_W, ROW_W, a.x + (int64_t)s_src[j] * ROW_X, ROW_X);")
         E("        }")
         E("      }")
         E("      T Ycur = (lane < SH_DIM) ? ldg(a.sh + (int64_t)s_eid[0] * SH_DIM + lane) : T(0);")
@@ -359,7 +362,7 @@ def emit_structure(E, sid, st):
         E("        Ycur = Ynext;")
         E("        __syncthreads();   // every warp is done with stage s")
         E("        if (tid == 0 && i + TPP_STAGES < n)")
-        E("          tpp_issue(stages + s * STAGE, &full[s], a.w + (int64_t)s_eid[i + TPP_STAGES] * ROW_W, ROW_W,")
+        E("          tpp_issue(stages + s * STAGE, &full[s], a.w + (int64_t)s_wid[i + TPP_STAGES] * ROW_W, ROW_W,")
         E("                    a.x + (int64_t)s_src[i + TPP_STAGES] * ROW_X, ROW_X);")
         E("      }")
         E("    }")
@@ -371,7 +374,7 @@ def emit_structure(E, sid, st):
         E("  } break;")
     E("  }")
     E("}")
-    E(f"static size_t tpfp_smem_S{sid}(int mul) {{ return (size_t)TPP_STAGES * ({n_paths} + {xdim}) * mul * 4 + 2 * TPP_MAXSEG * 4 + TPP_STAGES * 8; }}")
+    E(f"static size_t tpfp_smem_S{sid}(int mul) {{ return (size_t)TPP_STAGES * ({n_paths} + {xdim}) * mul * 4 + 3 * TPP_MAXSEG * 4 + TPP_STAGES * 8; }}")
     # ---- pipelined backward: same ring; gy of the node lives in registers, gw / gx_edge / gsh
     # partials are stored directly (fire-and-forget)
     E(f"template <int MUL> __global__ void __launch_bounds__(32 * {G} * (MUL / 32)) tpbp_S{sid}(const TpArgs<float> a) {{")
@@ -384,7 +387,8 @@ def emit_structure(E, sid, st):
     E("  float* stages = reinterpret_cast<float*>(tpp_smem);")
     E("  int* s_src = reinterpret_cast<int*>(stages + TPP_STAGES * STAGE);")
     E("  int* s_eid = s_src + TPP_MAXSEG;")
-    E("  uint64_t* full = reinterpret_cast<uint64_t*>(s_eid + TPP_MAXSEG);")
+    E("  int* s_wid = s_eid + TPP_MAXSEG;    // row of the weight tensor per slot (= edge id unless a.w_idx shares rows)")
+    E("  uint64_t* full = reinterpret_cast<uint64_t*>(s_wid + TPP_MAXSEG);")
     E("  float* gx_stage = reinterpret_cast<float*>(full + TPP_STAGES + (TPP_STAGES & 1));   // 16-byte aligned; only with a.gx_node")
     E("  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;")
     E("  const int64_t node = blockIdx.x;")
@@ -409,14 +413,16 @@ def emit_structure(E, sid, st):
         E("      __syncthreads();")
         E("      for (int i = tid; i < n; i += NT) {")
         E("        s_src[i] = a.in_nbr[c0 + i];")
-        E("        s_eid[i] = a.in_eid ? a.in_eid[c0 + i] : (int)(c0 + i);")
+        E("        const int eid_i = a.in_eid ? a.in_eid[c0 + i] : (int)(c0 + i);")
+        E("        s_eid[i] = eid_i;")
+        E("        s_wid[i] = a.w_idx ? a.w_idx[eid_i] : eid_i;")
         E("      }")
         E("      __syncthreads();")
         E("      if (tid == 0) {")
         E("        const int pre = n < TPP_STAGES ? n : TPP_STAGES;")
         E("        for (int j = 0; j < pre; ++j) {")
         E("          const uint32_t s = (it + j) % TPP_STAGES;")
-        E("          tpp_issue(stages + s * STAGE, &full[s], a.w + (int64_t)s_eid[j] * ROW_W, ROW_W, a.x + (int64_t)s_src[j] * ROW_X, ROW_X);")
+        E("          tpp_issue(stages + s * STAGE, &full[s], a.w + (int64_t)s_wid[j] * ROW_W, ROW_W, a.x + (int64_t)s_src[j] * ROW_X, ROW_X);")
         E("        }")
         E("      }")
         E("      T Ycur = (lane < SH_DIM) ? ldg(a.sh + (int64_t)s_eid[0] * SH_DIM + lane) : T(0);")
@@ -446,7 +452,7 @@ def emit_structure(E, sid, st):
         E("            bulk_commit();")
         E("          }")
         E("          if (i + TPP_STAGES < n)")
-        E("            tpp_issue(stages + s * STAGE, &full[s], a.w + (int64_t)s_eid[i + TPP_STAGES] * ROW_W, ROW_W,")
+        E("            tpp_issue(stages + s * STAGE, &full[s], a.w + (int64_t)s_wid[i + TPP_STAGES] * ROW_W, ROW_W,")
         E("                      a.x + (int64_t)s_src[i + TPP_STAGES] * ROW_X, ROW_X);")
         E("        }")
         E("      }")

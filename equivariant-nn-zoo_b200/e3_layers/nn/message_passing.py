@@ -137,7 +137,8 @@ class MessagePassing(Module):
             edge_index = data["edge_index"]
             csr = ops.graph_of(edge_index, skip.shape[0])
             out, out_imu = interaction.interaction(self.fused, skip, data["node_attrs"], data["edge_radial"],
-                                                   data["edge_spherical"], csr, group=getattr(self, "_e3b_group", None))
+                                                   data["edge_spherical"], csr, group=getattr(self, "_e3b_group", None),
+                                                   edge_index=edge_index)
             out._e3b_imu = out_imu       # the next block gathers from the channel-fastest twin
         else:
             # fp64 correctness mode / irregular irreps / second-order mode (graph of the gradient): the same

@@ -90,7 +90,9 @@ SIGNATURES = {
     "e3b_tp_plan_dims": (c_int, [c_vp] + [ctypes.POINTER(c_i32)] * 5),
     "e3b_tpconv_fwd": (c_int, [c_vp, c_int, c_i64, c_i64, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp]),
     "e3b_tpconv_bwd": (c_int, [c_vp, c_int, c_i64, c_i64, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp]),
-    "e3b_tpconv_bwd_nodes": (c_int, [c_vp, c_i64, c_i64] + [c_vp] * 11),
+    "e3b_tpconv_bwd_nodes": (c_int, [c_vp, c_i64, c_i64] + [c_vp] * 12),
+    "e3b_tpconv_fwd_shared": (c_int, [c_vp, c_i64, c_i64] + [c_vp] * 9),
+    "e3b_pair_sum_act": (c_int, [c_vp, c_vp, c_vp, c_vp, c_f32, c_i64, c_i32, c_vp, c_vp]),
     "e3b_segment_sum": (c_int, [c_int, c_vp, c_i64, c_vp, c_vp, c_i64, c_vp, c_vp]),
     "e3b_gate_fwd": (c_int, [ctypes.POINTER(GateDesc), c_int, c_vp, c_i64, c_vp, c_vp]),
     "e3b_gate_bwd": (c_int, [ctypes.POINTER(GateDesc), c_int, c_vp, c_vp, c_i64, c_vp, c_vp]),

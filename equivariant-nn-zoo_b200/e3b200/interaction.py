@@ -219,6 +219,37 @@ class _RadialHidden(torch.autograd.Function):
         return (g_er, None, *g_w)
 
 
+SHARED_W = __import__("os").environ.get("E3B_SHARED_W", "1") != "0"
+
+
+class _Undirected:
+    """undirected-edge view of a symmetric radius graph: uid [E] int32 (row of the shared tensors for edge e), canon [E/2]
+    int64 (the direction src < dst of every undirected edge), rev [E] int32, er_u = edge_radial[canon]"""
+    __slots__ = ("uid", "canon", "rev", "er_u")
+
+
+def undirected(er, edge_index, csr):
+    """The radial embedding is a function of the edge LENGTH, so the two directions of an edge of the radius graph have
+    bit-identical rows: everything downstream of it that does not see the direction (the whole radial MLP, i.e. the
+    per-edge weights) is evaluated once per undirected edge.  Built once per forward pass, remembered on `er`."""
+    u = getattr(er, "_e3b_und", None)
+    if u is None:
+        E = er.shape[0]
+        src, dst = edge_index[0], edge_index[1]
+        flag = src < dst
+        rank = torch.cumsum(flag, 0, dtype=torch.int32) - 1                 # index among the canonical directions
+        rev = csr.in_eid
+        uid = torch.where(flag, rank, rank[rev.long()])
+        idx = torch.arange(E, device=er.device)
+        canon = torch.zeros(E // 2 + 1, dtype=torch.int64, device=er.device)
+        canon.scatter_(0, torch.where(flag, rank, torch.full_like(rank, E // 2)).long(), idx)
+        u = _Undirected()
+        u.uid, u.canon, u.rev = uid.contiguous(), canon[:E // 2].contiguous(), rev
+        u.er_u = er.index_select(0, u.canon)
+        er._e3b_und = u
+    return u
+
+
 def radial_hidden(er, fi, group):
     """last hidden activation of block `fi`'s radial MLP; computed for every compatible block of `group` at the first
     request and remembered on the `edge_radial` tensor object (a new one every forward pass)"""
@@ -241,7 +272,7 @@ def radial_hidden(er, fi, group):
 
 class _Interaction(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, x_mi, x_imu, attrs, h_last, Y, fi, csr, *params):
+    def forward(ctx, x_mi, x_imu, attrs, h_last, Y, fi, csr, und, *params):
         lib = _lib.load()
         ctx.set_materialize_grads(False)
         conv = fi.conv
@@ -249,7 +280,7 @@ class _Interaction(torch.autograd.Function):
         if x_imu is None:
             x_imu = x_mi.contiguous() if fi.all_scalar_in else ops.layout_convert(x_mi, fi.feat_in, True)
         x_imu, attrs, h_last, Y = x_imu.contiguous(), attrs.contiguous(), h_last.contiguous(), Y.contiguous()
-        N, E = x_imu.shape[0], h_last.shape[0]
+        N, E, Ew = x_imu.shape[0], Y.shape[0], h_last.shape[0]       # directed edges, rows of the weight tensor
         dev = x_imu.device
         P = fi.packs("fwd")
         new = lambda *s: torch.empty(*s, dtype=torch.float32, device=dev)
@@ -271,16 +302,20 @@ class _Interaction(torch.autograd.Function):
         # ---- last layer of the radial MLP (the hidden layers are the shared `_RadialHidden` node)
         hs = fi.hs
         n_fc = conv.fc.n_layers
-        w = new(E, hs[-1])
+        w = new(Ew, hs[-1])
         with ops.stage("f.mlp_last"):
-            ops.gemm_run([ops.gemm_problem(h_last, P["fc"][n_fc - 1], w, E, a_rows=(h_last.stride(0), 0, 1),
+            ops.gemm_run([ops.gemm_problem(h_last, P["fc"][n_fc - 1], w, Ew, a_rows=(h_last.stride(0), 0, 1),
                                            alpha=1.0 / math.sqrt(hs[-2]), epilogue=0, act_cst=conv.fc.cst)])
         # ---- fused gather + CG tensor product + segmented sum
         plan = conv.tp.plan
         mid = new(N, plan.y_dim)
         end = ops._timed(("fwd", len(plan.structure.paths), plan.structure.uniform_mul, plan.x_dim, plan.y_dim, N, E))
-        check(lib.e3b_tpconv_fwd(plan.handle, 0, N, E, ptr(xl), ptr(Y), ptr(w), ptr(csr.in_ptr), ptr(csr.in_nbr),
-                                 ptr(csr.in_eid), ptr(mid), stream()))
+        if und is not None:
+            check(lib.e3b_tpconv_fwd_shared(plan.handle, N, E, ptr(xl), ptr(Y), ptr(w), ptr(und.uid), ptr(csr.in_ptr),
+                                            ptr(csr.in_nbr), ptr(csr.in_eid), ptr(mid), stream()))
+        else:
+            check(lib.e3b_tpconv_fwd(plan.handle, 0, N, E, ptr(xl), ptr(Y), ptr(w), ptr(csr.in_ptr), ptr(csr.in_nbr),
+                                     ptr(csr.in_eid), ptr(mid), stream()))
         if end is not None:
             end.record()
         count_launch()
@@ -318,7 +353,7 @@ class _Interaction(torch.autograd.Function):
         with ops.stage("f.gate"):
             check(lib.e3b_gate_imu_fwd(ctypes.byref(fi.gate.desc), 0, ptr(cv), N, ptr(out_mi), ptr(out_imu), stream()))
         count_launch()
-        ctx.fi, ctx.csr, ctx.src_is_imu = fi, csr, src_is_imu
+        ctx.fi, ctx.csr, ctx.src_is_imu, ctx.und = fi, csr, src_is_imu, und
         # parameter gradients are produced whenever a parameter requires them, in training AND in evaluation mode
         # (fine-tuning under model.eval(), gradient diagnostics); the one pass that must not pay for them -- the
         # position gradient of an energy+force evaluation -- is marked by GradientOutput with ops.positions_only
@@ -334,16 +369,17 @@ class _Interaction(torch.autograd.Function):
         conv = fi.conv
         saved = ctx.saved_tensors
         x_imu, attrs, Y, xl, cv, h_last, w, mid = saved
-        N, E = x_imu.shape[0], h_last.shape[0]
+        und = ctx.und
+        N, E, Ew = x_imu.shape[0], Y.shape[0], h_last.shape[0]
         dev = x_imu.device
         new = lambda *s: torch.empty(*s, dtype=torch.float32, device=dev)
         need_x = ctx.needs_input_grad[0] or ctx.needs_input_grad[1]
         need_attrs, need_h, need_Y = ctx.needs_input_grad[2], ctx.needs_input_grad[3], ctx.needs_input_grad[4]
         pos_only = ops.positions_only_active()          # parameters never depend on the positions
-        need_params = ctx.want_params and any(ctx.needs_input_grad[7:]) and not pos_only
+        need_params = ctx.want_params and any(ctx.needs_input_grad[8:]) and not pos_only
         need_attrs = need_attrs and ops.needs_grad_now(attrs)
         if g_mi is None and g_imu is None:
-            return (None,) * (7 + len(ctx.needs_input_grad[7:]))
+            return (None,) * (8 + len(ctx.needs_input_grad[8:]))
         P = fi.packs("bwd")
         # ---- gate
         g_cv = new(N, fi.Dconv)
@@ -374,8 +410,8 @@ class _Interaction(torch.autograd.Function):
         # d/dx per source node: reduced inside the kernel (TMA reduce-add of each edge's row into its source's row, no
         # per-edge buffer, no segment sum) in the evaluation pass; passes that produce parameter gradients (training) and
         # E3B_DETERMINISTIC=1 keep the bit-reproducible per-edge rows + segment sum
-        in_kernel = bool(need_x and fast and E and plan.structure.uniform_mul in (32, 64) and not need_params
-                         and not ops.DETERMINISTIC)
+        in_kernel = bool(need_x and fast and E and plan.structure.uniform_mul in (32, 64)
+                         and ((not need_params and not ops.DETERMINISTIC) or und is not None))
         gx_edge = alloc(E, plan.x_dim, dtype=torch.float32, device=dev) if need_x and not in_kernel else None
         g_xl = torch.zeros(N, fi.Din, dtype=torch.float32, device=dev) if in_kernel else None
         gsh_part = alloc(E, n_part, plan.sh_dim, dtype=torch.float32, device=dev) if need_Y else None
@@ -383,8 +419,9 @@ class _Interaction(torch.autograd.Function):
         if E:
             end = ops._timed(("bwd", len(plan.structure.paths), plan.structure.uniform_mul, plan.x_dim, plan.y_dim, N, E))
             if in_kernel:
-                check(lib.e3b_tpconv_bwd_nodes(plan.handle, N, E, ptr(xl), ptr(Y), ptr(w), ptr(g_mid), ptr(csr.in_ptr),
-                                               ptr(csr.in_nbr), ptr(csr.in_eid), ptr(g_xl), ptr(gsh_part), ptr(gw), stream()))
+                check(lib.e3b_tpconv_bwd_nodes(plan.handle, N, E, ptr(xl), ptr(Y), ptr(w), ptr(und.uid) if und is not None else None,
+                                               ptr(g_mid), ptr(csr.in_ptr), ptr(csr.in_nbr), ptr(csr.in_eid), ptr(g_xl),
+                                               ptr(gsh_part), ptr(gw), stream()))
             else:
                 check(lib.e3b_tpconv_bwd(plan.handle, 0, N, E, ptr(xl), ptr(Y), ptr(w), ptr(g_mid), ptr(csr.in_ptr),
                                          ptr(csr.in_nbr), ptr(csr.in_eid), ptr(gx_edge), ptr(gsh_part), ptr(gw), stream()))
@@ -400,12 +437,22 @@ class _Interaction(torch.autograd.Function):
         hs = fi.hs
         n_fc = conv.fc.n_layers
         g_h = None
-        if need_h:
+        if need_h and und is None:
             g_h = new(E, hs[-2])
             with ops.stage("b.mlp_last"):
                 ops.gemm_run([ops.gemm_problem(gw, P["fc"][n_fc - 1], g_h, E, alpha=1.0 / math.sqrt(hs[-2]),
                                                epilogue=3 if n_fc > 1 else 0, H=h_last if n_fc > 1 else None,
                                                act_cst=conv.fc.cst)])
+        elif need_h:
+            # shared weight rows: the GEMM is linear, so it runs on the directed gradient rows and the two directions of every
+            # undirected edge are folded afterwards on the small [E, 64] result, with the activation derivative in the same pass
+            g_dir = new(E, hs[-2])
+            with ops.stage("b.mlp_last"):
+                ops.gemm_run([ops.gemm_problem(gw, P["fc"][n_fc - 1], g_dir, E, alpha=1.0 / math.sqrt(hs[-2]), epilogue=0)])
+                g_h = new(Ew, hs[-2])
+                check(lib.e3b_pair_sum_act(ptr(g_dir), ptr(und.canon), ptr(und.rev), ptr(h_last), float(conv.fc.cst), Ew,
+                                           hs[-2], ptr(g_h), stream()))
+                count_launch()
         # ---- d/dx: linear_1 transposed on the reduced edge gradient + self-connection transposed
         g_x = None
         if need_x:
@@ -440,17 +487,18 @@ class _Interaction(torch.autograd.Function):
                 for wave in _waves(sc_probs):
                     ops.gemm_run(wave)
         # ---- parameter / attribute gradients (training only): library GEMMs on the saved activations
-        g_params = [None] * len(ctx.needs_input_grad[7:])
+        g_params = [None] * len(ctx.needs_input_grad[8:])
         g_attrs = None
         if need_params or need_attrs:
-            g_params, g_attrs = _param_grads(fi, ctx.needs_input_grad, x_imu, attrs, h_last, gw, mid, g_cv, g_xl, need_attrs)
+            gw_rows = gw if und is None else gw.index_select(0, und.canon) + gw.index_select(0, und.rev.long().index_select(0, und.canon))
+            g_params, g_attrs = _param_grads(fi, ctx.needs_input_grad[1:], x_imu, attrs, h_last, gw_rows, mid, g_cv, g_xl, need_attrs)
         g_x_mi = g_x_imu = None
         if need_x:
             if ctx.src_is_imu:
                 g_x_imu = g_x
             else:
                 g_x_mi = g_x if fi.all_scalar_in else ops.layout_convert(g_x, fi.feat_in, False)
-        return (g_x_mi, g_x_imu, g_attrs, g_h, g_Y, None, None, *g_params)
+        return (g_x_mi, g_x_imu, g_attrs, g_h, g_Y, None, None, None, *g_params)
 
 
 def _param_grads(fi, needs, x_imu, attrs, h_last, gw, mid, g_cv, g_xl, need_attrs):
@@ -523,13 +571,21 @@ def _param_grads(fi, needs, x_imu, attrs, h_last, gw, mid, g_cv, g_xl, need_attr
     return out, g_attrs
 
 
-def interaction(fi, x, attrs, er, Y, csr, group=None):
+def interaction(fi, x, attrs, er, Y, csr, group=None, edge_index=None):
     """-> (out mul_ir, out imu).  `x` is the mul_ir feature tensor; if it carries the imu twin written by the
     previous block's gate (attribute ``_e3b_imu``) that one is consumed instead, so no layout pass runs.  `group`: the
-    interaction blocks of the same network (their radial hidden layers run together, see `_RadialHidden`)."""
+    interaction blocks of the same network (their radial hidden layers run together, see `_RadialHidden`).  On a
+    symmetric radius graph in evaluation mode the radial MLP runs once per UNDIRECTED edge (`undirected`)."""
     twin = getattr(x, "_e3b_imu", None)
     params = fi._block_params()
-    h_last = radial_hidden(er, fi, group) if fi.conv.fc.n_layers > 1 else er
+    E = er.shape[0]
+    und = None
+    if (SHARED_W and not ops.DETERMINISTIC and edge_index is not None and not fi.mp.training and E > 0 and E % 2 == 0 and csr.out_eid is None
+            and csr.in_eid is not None and fi.conv.tp.plan.specialized and fi.structure.uniform_mul in (32, 64)
+            and fi.conv.fc.n_layers > 1 and fi.hs[-2] % 4 == 0):
+        und = undirected(er, edge_index, csr)
+    src = und.er_u if und is not None else er
+    h_last = radial_hidden(src, fi, group) if fi.conv.fc.n_layers > 1 else er
     if twin is not None:
-        return _Interaction.apply(None, twin, attrs, h_last, Y, fi, csr, *params)
-    return _Interaction.apply(x, None, attrs, h_last, Y, fi, csr, *params)
+        return _Interaction.apply(None, twin, attrs, h_last, Y, fi, csr, und, *params)
+    return _Interaction.apply(x, None, attrs, h_last, Y, fi, csr, und, *params)

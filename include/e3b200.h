@@ -237,9 +237,23 @@ E3B_API int e3b_tpconv_bwd(const e3b_tp_plan* plan, int dtype, int64_t n_nodes, 
  * gx_node [N, x_dim] must be ZEROED by the caller; the order of the additions into a row is not fixed (results repeat to
  * fp32 rounding, ~1e-7 relative, not bit for bit) -- callers that need bit-reproducible gradients use e3b_tpconv_bwd.   */
 E3B_API int e3b_tpconv_bwd_nodes(const e3b_tp_plan* plan, int64_t n_nodes, int64_t n_edges, const float* x, const float* sh,
-                                 const float* w, const float* gy, const int64_t* in_ptr, const int32_t* in_nbr,
-                                 const int32_t* in_eid, float* gx_node, float* gsh /* [E, n_part, sh_dim] or NULL */,
-                                 float* gw, void* stream);
+                                 const float* w, const int32_t* w_idx /* [E] or NULL, see e3b_tpconv_fwd_shared */,
+                                 const float* gy, const int64_t* in_ptr, const int32_t* in_nbr, const int32_t* in_eid,
+                                 float* gx_node, float* gsh /* [E, n_part, sh_dim] or NULL */, float* gw, void* stream);
+/* Forward with SHARED weight rows: edge e reads w[w_idx[e]] instead of w[e].  The radial weights are a function of the edge
+ * LENGTH (nn/message_passing.py:93 on nn/embedding.py:181-219), so the two directions of an undirected edge of the radius
+ * graph carry bit-identical rows: the radial MLP is evaluated once per undirected edge ([E/2, W] rows, half the GEMM work and
+ * half the HBM write) and both directions read the same row (the second read usually hits L2).  Same restrictions as
+ * e3b_tpconv_bwd_nodes (fp32, generated structures with multiplicity 32 / 64).                                          */
+E3B_API int e3b_tpconv_fwd_shared(const e3b_tp_plan* plan, int64_t n_nodes, int64_t n_edges, const float* x, const float* sh,
+                                  const float* w, const int32_t* w_idx, const int64_t* in_ptr, const int32_t* in_nbr,
+                                  const int32_t* in_eid, float* y, void* stream);
+/* out[u, k] = (g[canon[u], k] + g[rev[canon[u]], k]) * d/dz[cst * ssp](z), derivative from the stored activation
+ * h[u, k] = cst * ssp(z) (h == NULL: factor 1): folds the gradients of the two directions of every undirected edge and
+ * applies the activation derivative of the last hidden radial layer in one pass.  width % 4 == 0.                       */
+E3B_API int e3b_pair_sum_act(const float* g /* [E, width] */, const int64_t* canon /* [n_unique] */, const int32_t* rev /* [E] */,
+                             const float* h /* [n_unique, width] or NULL */, float cst, int64_t n_unique, int32_t width,
+                             float* out /* [n_unique, width] */, void* stream);
 E3B_API int e3b_segment_sum(int dtype, const void* src, int64_t width, const int64_t* ptr, const int32_t* ids,
                     int64_t n_out, void* out, void* stream);
 
