@@ -549,7 +549,7 @@ def run_ours(args, wl):
         _, n_paths, mul, x_dim, y_dim, N0, E0 = rows[0][1]
         ach = alg / (tt * 1e-3) / 1e9
         traffic = None     # dram bytes per launch of the same kernel from the committed ncu --set full capture
-        for name in ("r2_tpfp_traffic.json", "r1_tpfp_S3_traffic.json"):
+        for name in ("r2_tpfp_traffic.json",):
             tpath = os.path.join(ROOT, "profiles", name)
             if traffic is None and wl.name == "W2" and os.path.exists(tpath):
                 with open(tpath) as fh:
@@ -557,6 +557,9 @@ def run_ours(args, wl):
                 if (tj.get("n_edges"), tj.get("n_nodes")) in {(tag[6], tag[5]) for _, tag in rows}:
                     traffic = tj["traffic_bytes_per_launch"]
         roof = {"kernel": f"tpfp (fused gather + uvu CG tensor product + segmented sum, {n_paths} paths, mul {mul})",
+                "note": "algorithmic bytes = SURVEY 8d per directed edge (one weight row per edge); since round 2 the two directions of "
+                        "an undirected edge read ONE shared weight row (the second read mostly hits L2), so `traffic` (ncu DRAM bytes) "
+                        "is below the algorithmic figure and `frac` can exceed what HBM alone would allow",
                 "bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": traffic,
                 "peak_source": peak_src, "timing": timing_how,
                 "algorithmic_bytes_per_launch": alg / len(rows), "avg_launch_ms": tt / len(rows),
