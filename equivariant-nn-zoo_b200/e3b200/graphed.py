@@ -14,7 +14,10 @@ real graphs are bit-identical to the unpadded evaluation; the outputs are sliced
 padding work (a few per cent of the atoms and edges) is real work inside the timed step.
 
 Without buckets the exact shapes are the key: batched inference over fixed molecules and the diffusion sampler (fixed
-complete graphs) hit every time, anything else misses and runs eagerly.  The evaluator is always safe to use: training
+complete graphs) hit every time, anything else misses and runs eagerly.  Batches that bring their own edge list (complete
+graphs, bond lists) or whose model builds it as a layer take the same route without any host synchronisation
+(``_call_given_topology``; the model must then have static shapes for fixed inputs, which rules out a neighbour-list layer
+with random pair criteria).  The evaluator is always safe to use: training
 mode, edge-typed inputs or a full cache simply run the model eagerly."""
 import torch
 
@@ -145,6 +148,8 @@ class GraphedEvaluator:
         """tensors: dict(pos [N,3] f32, species [N,1] i64, _n_nodes [G,1] i64, ...) on the GPU.
         -> dict of output tensors (owned by the evaluator until the next call)"""
         eager = self.model.training or (self.grad and not torch.is_grad_enabled())
+        if "edge_index" in tensors or self.r_max <= 0:
+            return self._call_given_topology(tensors, eager)
         if self.bucketed and not eager and all(self._kind(k) in ("node", "graph") for k in tensors):
             return self._call_bucketed(tensors)
         pos = tensors["pos"]
@@ -176,6 +181,59 @@ class GraphedEvaluator:
         e.graph.replay()
         _lib.count_launch(e.launches)
         return e.out
+
+    def _call_given_topology(self, tensors, eager):
+        """the batch brings its own edge list (complete graphs of the diffusion configs, bond lists) or the model builds
+        its own (neighbour list as a model layer): no host synchronisation at all, one capture per input shape signature;
+        the inputs are copied into the capture's static buffers"""
+        if eager:
+            self.eager += 1
+            return self._run_plain(tensors)
+        tag = self._weights_tag()
+        key = tuple((k, tuple(v.shape)) for k, v in sorted(tensors.items()))
+        e = self._lookup(key, tag)
+        if e is None:
+            self.misses += 1
+            if not self._room(tag):
+                self.eager += 1
+                return self._run_plain(tensors)
+            e = _Entry()
+            e.tag = tag
+            self._tick += 1
+            e.tick = self._tick
+            e.static_in = {k: v.clone() for k, v in tensors.items()}
+            e.csr = e.edge_index = e.n_edges = None
+            side = torch.cuda.Stream()
+            side.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(side):
+                self._run_plain(e.static_in)
+            torch.cuda.current_stream().wait_stream(side)
+            e.graph = torch.cuda.CUDAGraph()
+            if self._pool is None or not self.cache:
+                self._pool = torch.cuda.graph_pool_handle()
+            n0 = _lib.launch_count
+            with torch.cuda.graph(e.graph, pool=self._pool):
+                e.out = self._run_plain(e.static_in)
+            e.launches = _lib.launch_count - n0
+            self.cache[key] = e
+        else:
+            self.hits += 1
+            for k, v in tensors.items():
+                e.static_in[k].copy_(v, non_blocking=True)
+        e.graph.replay()
+        _lib.count_launch(e.launches)
+        return e.out
+
+    def _run_plain(self, tensors):
+        from e3_layers.data import Batch
+
+        batch = Batch(dict(self.attrs), **dict(tensors))        # (a fresh dict: the model's layers add their keys to it)
+        if self.grad:
+            out = self.model(batch)
+        else:
+            with torch.no_grad():
+                out = self.model(batch)
+        return {k: out[k] for k in self.out_keys}
 
     def _call_bucketed(self, tensors):
         stage, N, G, n_pad = self._pad_inputs(tensors)

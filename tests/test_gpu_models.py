@@ -160,6 +160,29 @@ def test_bucketed_evaluator_distinct_batches():
     assert harness.rel_err(got["forces"], eager["forces"]) < 1e-6
 
 
+def test_graphed_evaluator_given_topology():
+    """batches that bring their edge list (config_diffusion: complete graphs + bond types + t): the whole score evaluation is
+    one captured graph per input shape, replays honour new inputs"""
+    from e3b200.graphed import GraphedEvaluator
+
+    meta = {"config": "config_diffusion", "seed": 4, "spec": ""}
+    model = product_harness.build_product(meta, torch.float32, DEV)
+    a = synthetic.diffusion_like(6, seed=1)
+    ev = GraphedEvaluator(model, r_max=0.0, attrs=harness.attrs_for(a), out_keys=("score",), grad=False)
+    b = dict(a)
+    b["pos"] = a["pos"] * 0.9
+    b["t"] = a["t"] * 0.5 + 0.1
+    for v in (a, b, synthetic.diffusion_like(4, seed=2)):
+        dev_in = {k: t.to(DEV) for k, t in v.items()}
+        ei = dev_in.pop("edge_index")
+        with torch.no_grad():
+            eager = product_harness.run_product(model, {k: t for k, t in v.items() if k != "edge_index"}, torch.float32, DEV,
+                                                edge_index=v["edge_index"])
+        got = ev(dict(dev_in, edge_index=ei))
+        assert harness.rel_err(got["score"], eager["score"]) < 1e-6
+    assert ev.misses == 2 and ev.hits == 1
+
+
 def test_padded_neighbour_list():
     """e3b_radius_graph_fill_padded: real atoms get exactly the edges of the plain radius graph, the padding rows are
     consistent (sorted edge list, row_ptr, reversed-edge index) and the total is the requested one"""
