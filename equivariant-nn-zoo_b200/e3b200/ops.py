@@ -1030,6 +1030,15 @@ def wgrad_problem(A, B, C, R, K1, K2, a_off=0, a_rows=None, b_off=0, b_rows=None
     a_s1, a_s2, a_d = a_rows if a_rows is not None else (K1, 0, 1)
     b_s1, b_s2, b_d = b_rows if b_rows is not None else (K2, 0, 1)
     c_s1, c_s2, c_d = c_rows if c_rows is not None else (K2 * c_col_stride, 0, 1)
+    # The kernel's tile is 128 (rows of C, operand A) x 64 (columns, operand B).  A narrow A with a wide B -- dW of the
+    # last radial layer: [E, 64]^T [E, 1920] -- would use half of every A tile and convert the narrow operand once per
+    # column tile; with the operands exchanged (C written transposed through its strides) the same product takes half
+    # the tiles, all of them full.
+    tiles = lambda k1, k2: -(-k1 // 128) * -(-k2 // 64)
+    if aux is None and c_d == 1 and tiles(K2, K1) < tiles(K1, K2):
+        A, B, a_off, b_off, K1, K2 = B, A, b_off, a_off, K2, K1
+        (a_s1, a_s2, a_d), (b_s1, b_s2, b_d) = (b_s1, b_s2, b_d), (a_s1, a_s2, a_d)
+        c_s1, c_s2, c_col_stride = c_col_stride, 0, c_s1            # C^T[m', n'] = C[n', m']
     g.A, g.a_s1, g.a_s2, g.a_d = A.data_ptr() + 4 * a_off, a_s1, a_s2, a_d
     g.B, g.b_s1, g.b_s2, g.b_d = B.data_ptr() + 4 * b_off, b_s1, b_s2, b_d
     if aux is not None:
