@@ -24,6 +24,7 @@ def computeEdgeVector(data, attrs, key="pos", with_lengths=True):
     vec, length = ops.edge_vectors(pos, ei, csr)
     data["edge_vector"] = vec
     if with_lengths:
+        length._e3b_edge_length = True       # provenance tag: |pos[dst] - pos[src]|, identical for the two directions
         data["edge_length"] = length
     return data, attrs
 

@@ -97,7 +97,12 @@ class RadialBasisEncoding(Module):
         b = self.basis
         emb = ops.radial_basis(x.reshape(-1), b.bessel_weights, b.r_max, b.r_min, b.one_over_r, self.cutoff_kind,
                                self.cutoff.p)
-        return ({"radial_embedding": emb.view(x.shape[0], -1)},
+        emb = emb.view(x.shape[0], -1)
+        if getattr(x, "_e3b_edge_length", False):
+            # a function of the edge length only: the interaction blocks may evaluate their radial MLPs once per
+            # undirected edge of a symmetric graph (e3b200.interaction.undirected); any other provenance does not get the tag
+            emb._e3b_length_only = True
+        return ({"radial_embedding": emb},
                 {"radial_embedding": (attrs["input"][0], self.irreps_out["radial_embedding"])})
 
 

@@ -220,6 +220,7 @@ class _RadialHidden(torch.autograd.Function):
 
 
 SHARED_W = __import__("os").environ.get("E3B_SHARED_W", "1") != "0"
+SHARED_CALLS = 0          # forward passes of a block that took the shared-weight-row path (tests)
 
 
 class _Undirected:
@@ -229,7 +230,8 @@ class _Undirected:
 
 
 def undirected(er, edge_index, csr):
-    """The radial embedding is a function of the edge LENGTH, so the two directions of an edge of the radius graph have
+    """The radial embedding (tagged `_e3b_length_only` by RadialBasisEncoding when its input is the edge length computed
+    by computeEdgeVector) is a function of the edge LENGTH, so the two directions of an edge of the radius graph have
     bit-identical rows: everything downstream of it that does not see the direction (the whole radial MLP, i.e. the
     per-edge weights) is evaluated once per undirected edge.  Built once per forward pass, remembered on `er`."""
     u = getattr(er, "_e3b_und", None)
@@ -580,9 +582,12 @@ def interaction(fi, x, attrs, er, Y, csr, group=None, edge_index=None):
     params = fi._block_params()
     E = er.shape[0]
     und = None
-    if (SHARED_W and not ops.DETERMINISTIC and edge_index is not None and not fi.mp.training and E > 0 and E % 2 == 0 and csr.out_eid is None
+    if (SHARED_W and not ops.DETERMINISTIC and getattr(er, "_e3b_length_only", False) and edge_index is not None
+            and not fi.mp.training and E > 0 and E % 2 == 0 and csr.out_eid is None
             and csr.in_eid is not None and fi.conv.tp.plan.specialized and fi.structure.uniform_mul in (32, 64)
             and fi.conv.fc.n_layers > 1 and fi.hs[-2] % 4 == 0):
+        global SHARED_CALLS
+        SHARED_CALLS += 1
         und = undirected(er, edge_index, csr)
     src = und.er_u if und is not None else er
     h_last = radial_hidden(src, fi, group) if fi.conv.fc.n_layers > 1 else er

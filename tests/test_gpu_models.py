@@ -160,6 +160,37 @@ def test_bucketed_evaluator_distinct_batches():
     assert harness.rel_err(got["forces"], eager["forces"]) < 1e-6
 
 
+def test_shared_weight_rows_only_for_length_only_radial_embeddings():
+    """the one-radial-MLP-per-undirected-edge path is taken when edge_radial provably depends on the edge length only
+    (tag set by computeEdgeVector -> RadialBasisEncoding), equals the per-directed-edge path, and is NOT taken otherwise"""
+    from e3b200 import interaction
+
+    meta = {"config": "config_energy_force", "seed": 5}
+    model = product_harness.build_product(meta, torch.float32, DEV)
+    inputs = synthetic.qm9_like(12, seed=31)
+    n0 = interaction.SHARED_CALLS
+    shared = product_harness.run_product(model, inputs, torch.float32, DEV, pre_edge={"r_max": 5.0})
+    n_blocks = interaction.SHARED_CALLS - n0
+    assert n_blocks >= 4                                      # every full interaction block of the network
+    interaction.SHARED_W = False
+    try:
+        n1 = interaction.SHARED_CALLS
+        plain = product_harness.run_product(model, inputs, torch.float32, DEV, pre_edge={"r_max": 5.0})
+        assert interaction.SHARED_CALLS == n1
+    finally:
+        interaction.SHARED_W = True
+    assert torch.equal(shared["energy"], plain["energy"])     # bit-identical weights -> bit-identical forward
+    assert harness.rel_err(shared["forces"], plain["forces"]) < 2e-6
+    # the diffusion model's edge_radial is a concatenation with bond embeddings: no tag, no sharing
+    meta = {"config": "config_diffusion", "seed": 4, "spec": ""}
+    dm = product_harness.build_product(meta, torch.float32, DEV)
+    d = synthetic.diffusion_like(4, seed=2)
+    n2 = interaction.SHARED_CALLS
+    with torch.no_grad():
+        product_harness.run_product(dm, {k: v for k, v in d.items() if k != "edge_index"}, torch.float32, DEV, edge_index=d["edge_index"])
+    assert interaction.SHARED_CALLS == n2
+
+
 def test_graphed_evaluator_given_topology():
     """batches that bring their edge list (config_diffusion: complete graphs + bond types + t): the whole score evaluation is
     one captured graph per input shape, replays honour new inputs"""
