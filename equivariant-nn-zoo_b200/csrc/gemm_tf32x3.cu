@@ -54,8 +54,7 @@ struct Problem {
   int32_t cta_begin;     // first CTA (blockIdx.x) of this problem
   uint64_t a_mul;        // ceil(2^40 / a_d): r / a_d == (r * a_mul) >> 40 for r < 2^31, a_d < 512
   uint64_t c_mul;        // the same for c_d
-  int32_t dbg;           // E3B_GEMM_DEBUG bisection bits: 1 skip A load+convert, 2 skip MMA, 4 skip B loads, 8 skip stores,
-                         // 16 skip the TMEM read-out of the epilogue, 32 skip the converters' copy wait + group barrier, 64 single issuer
+  int32_t dbg;           // E3B_GEMM_DEBUG bisection bits: 1 skip A load+convert, 2 skip MMA, 4 skip B loads, 8 skip stores
 };
 struct Batch {
   Problem pr[MAXG];
@@ -272,10 +271,6 @@ __device__ __forceinline__ void epilogue_role(const EpiCtx& c) {
 #pragma unroll
       for (int cb = 0; cb < HB; cb += 32) {
         float v[32];
-        if (P.dbg & 16) {
-#pragma unroll
-          for (int i = 0; i < 32; ++i) v[i] = 0.f;
-        } else
         tmem_ld32(t_lane + buf * BN + (uint32_t)cb, v);
         if (MULTI) {
 #pragma unroll
@@ -485,11 +480,9 @@ __global__ void __launch_bounds__(NTHREADS, 1) gemm_tf32x3_kernel(const __grid_c
       for (int j = grp; j < total; j += NG) {
         const int st = j % SA;
         const uint32_t par = (((uint32_t)j / SA) & 1u) ^ 1u;      // first pass through the ring is free
-        if (!(P.dbg & 32)) {
         cp_async_wait<PR - 2>();                 // this thread's copies of job j have landed ...
         if (grp == 0) asm volatile("bar.sync 1, 128;" ::: "memory");   // ... and the group's; the group is done
         else asm volatile("bar.sync 2, 128;" ::: "memory");            // reading its previous job
-        }
         issue();                                 // the group's job PR - 1 ahead reuses the slot just released
         mbar_wait(&a_empty[st], par);
         if (!(P.dbg & 1)) {
@@ -532,7 +525,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) gemm_tf32x3_kernel(const __grid_c
       }
     } else if (warp == 17 || warp == 18) {
       // =============================== MMA issuer ===============================
-      const bool dual = MULTI && !resident && !(P.dbg & 64);       // every stage is consumed by exactly one chain -> chains can alternate
+      const bool dual = MULTI && !resident;       // every stage is consumed by exactly one chain -> chains can alternate
       const uint32_t mi = warp - 17;
       if (mi == 0 || dual) {
       // The whole warp walks the tiles (uniform control flow, so addresses and descriptors live in
