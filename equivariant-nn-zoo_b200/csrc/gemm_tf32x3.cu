@@ -245,7 +245,9 @@ __device__ __forceinline__ void epilogue_role(const EpiCtx& c) {
       const int row = m * BM + q * 32 + lane;
       row_ok = row < g.M;
       if (row_ok && !DENSE) {
-        c_row = g.C + (int64_t)(row / g.c_d) * g.c_s1 + (int64_t)(row % g.c_d) * g.c_s2;
+        int cq = row / g.c_d;
+        if (g.row_map) { const int mq = __ldg(g.row_map + cq); row_ok = mq >= 0; cq = row_ok ? mq : 0; }
+        c_row = g.C + (int64_t)cq * g.c_s1 + (int64_t)(row % g.c_d) * g.c_s2;
         if (EPI == 3) h_row = g.H + (int64_t)row * g.h_ld;
       }
       if (EPI == 1) {
@@ -304,9 +306,13 @@ __device__ __forceinline__ void epilogue_role(const EpiCtx& c) {
                 o.z = epi_apply<EPI>(o.z, h.z, cst); o.w = epi_apply<EPI>(o.w, h.w, cst);
                 const int r = r_base + 4 * i;            // affine row addressing (irreps blocks written in place)
                 const int rq = (int)(((uint64_t)(uint32_t)r * P.c_mul) >> 40);
-                float4* d4 = reinterpret_cast<float4*>(g.C + (int64_t)rq * g.c_s1 + (int64_t)(r - rq * g.c_d) * g.c_s2 + col);
-                if (accumulate) { const float4 old = *d4; o.x += old.x; o.y += old.y; o.z += old.z; o.w += old.w; }
-                *d4 = o;
+                int aq = rq;                                // grouped rows: virtual -> actual row group, < 0 = padding
+                if (g.row_map) aq = __ldg(g.row_map + rq);
+                if (aq >= 0) {
+                  float4* d4 = reinterpret_cast<float4*>(g.C + (int64_t)aq * g.c_s1 + (int64_t)(r - rq * g.c_d) * g.c_s2 + col);
+                  if (accumulate) { const float4 old = *d4; o.x += old.x; o.y += old.y; o.z += old.z; o.w += old.w; }
+                  *d4 = o;
+                }
               }
             }
           }
@@ -442,9 +448,11 @@ __global__ void __launch_bounds__(NTHREADS, 1) gemm_tf32x3_kernel(const __grid_c
         for (int i = 0; i < 8; ++i) {
           const int r = m_tile * BM + row0 + 16 * i;
           const int q = (int)(((uint64_t)(uint32_t)r * P.a_mul) >> 40);
-          roff[i] = (int64_t)q * g.a_s1 + (int64_t)(r - q * g.a_d) * g.a_s2;
-          rbytes[i] = r < g.M ? 16u : 0u;
-          if (r >= g.M) roff[i] = 0;
+          int aq = q;                                     // grouped rows: virtual -> actual row group, < 0 = padding
+          if (g.row_map) aq = r < g.M ? __ldg(g.row_map + q) : -1;
+          const bool ok = r < g.M && aq >= 0;
+          roff[i] = ok ? (int64_t)aq * g.a_s1 + (int64_t)(r - q * g.a_d) * g.a_s2 : 0;
+          rbytes[i] = ok ? 16u : 0u;
         }
       };
       int i_t = t0, i_kc = 0, i_slot = 0, i_job = 0;      // (i_t, i_kc) = coordinates of global job i_job
@@ -512,14 +520,21 @@ __global__ void __launch_bounds__(NTHREADS, 1) gemm_tf32x3_kernel(const __grid_c
       if (lane == 0) {
         uint32_t it = 0;
         constexpr uint32_t bytes = (uint32_t)L::B_STAGE * 4u;
+        const float* b_set = g.B_packed;
+        int m_sel = -1;
         for (int t = t0; t < t1; ++t) {
-          const int n = t % P.n_tiles;
+          const int m = t / P.n_tiles, n = t - m * P.n_tiles;
+          if (g.b_sel && m != m_sel) {                    // a row tile never straddles a block of 128 row groups
+            m_sel = m;
+            const int q0 = (int)(((uint64_t)(uint32_t)(m * BM) * P.a_mul) >> 40);
+            b_set = g.B_packed + (int64_t)__ldg(g.b_sel + (q0 >> 7)) * g.b_set_stride;
+          }
             for (int kc = 0; kc < k_chunks; ++kc, ++it) {
               const int st = it % SB;
               mbar_wait(&b_empty[st], ((it / SB) & 1u) ^ 1u);
               if (P.dbg & 4) { mbar_arrive(&b_full[st]); continue; }
               mbar_expect_tx(&b_full[st], bytes);
-              bulk_g2s(sB + (size_t)st * L::B_STAGE, g.B_packed + ((size_t)n * k_chunks + kc) * L::B_STAGE, bytes, &b_full[st]);
+              bulk_g2s(sB + (size_t)st * L::B_STAGE, b_set + ((size_t)n * k_chunks + kc) * L::B_STAGE, bytes, &b_full[st]);
             }
         }
       }
@@ -621,7 +636,11 @@ __global__ void gemm_pack_kernel(const __grid_constant__ PackBatch pb) {
       if (idx >= pb.begin[i]) gi = i;
     const e3b_gemm_pack_desc& d = pb.d[gi];
     const int BN = pb.bn[gi];
-    const int64_t q = idx - pb.begin[gi];          // float4 slot: [n_tile][k_chunk][c][row]
+    int64_t q = idx - pb.begin[gi];                // float4 slot: [set][n_tile][k_chunk][c][row]
+    const int64_t per_set = (pb.begin[gi + 1] - pb.begin[gi]) / (d.n_sets > 1 ? d.n_sets : 1);
+    const int64_t set = q / per_set;
+    q -= set * per_set;
+    const float* src = d.src + set * d.set_stride;
     const int k_chunks = (d.K + BK - 1) / BK;
     const int row = (int)(q % BN);
     const int c = (int)((q / BN) % 8);
@@ -632,11 +651,11 @@ __global__ void gemm_pack_kernel(const __grid_constant__ PackBatch pb) {
 #pragma unroll
     for (int e = 0; e < 4; ++e) {
       const int k = kc * BK + c * 4 + e;
-      x[e] = (n < d.N && k < d.K && (d.n2_valid <= 0 || (n % d.d) < d.n2_valid)) ? __ldg(d.src + (int64_t)(n / d.d) * d.s1 + (int64_t)(n % d.d) * d.s2 + (int64_t)k * d.sk) : 0.f;
+      x[e] = (n < d.N && k < d.K && (d.n2_valid <= 0 || (n % d.d) < d.n2_valid)) ? __ldg(src + (int64_t)(n / d.d) * d.s1 + (int64_t)(n % d.d) * d.s2 + (int64_t)k * d.sk) : 0.f;
     }
     float4 hi, lo;
     split4(make_float4(x[0], x[1], x[2], x[3]), &hi, &lo);
-    float4* tile = reinterpret_cast<float4*>(d.dst) + ((int64_t)nt * k_chunks + kc) * (2 * BN * 8);
+    float4* tile = reinterpret_cast<float4*>(d.dst) + set * per_set * 2 + ((int64_t)nt * k_chunks + kc) * (2 * BN * 8);
     tile[c * BN + row] = hi;
     tile[BN * 8 + c * BN + row] = lo;
   }
@@ -679,7 +698,7 @@ extern "C" int e3b_gemm_pack(const e3b_gemm_pack_desc* descs, int32_t n, void* s
     if (reinterpret_cast<uintptr_t>(d.dst) & 127) return e3b_fail(E3B_ERR_INVALID, "gemm_pack: dst must be 128-byte aligned");
     pb.d[i] = d;
     pb.bn[i] = tile_n(d.N, d.K);
-    pb.begin[i + 1] = pb.begin[i] + e3b_gemm_packed_floats(d.N, d.K) / 8;   // one float4 slot feeds hi and lo
+    pb.begin[i + 1] = pb.begin[i] + (d.n_sets > 1 ? d.n_sets : 1) * (e3b_gemm_packed_floats(d.N, d.K) / 8);   // one float4 slot feeds hi and lo
   }
   const int64_t total = pb.begin[n];
   const int blocks = (int)((total + 255) / 256 < 148 * 8 ? (total + 255) / 256 : 148 * 8);
@@ -709,6 +728,10 @@ extern "C" int e3b_gemm_run(const e3b_gemm_problem* problems, int32_t n, void* s
     if (p.epilogue == 1 && (!p.aux || (p.V != 16 && p.V != 32) || p.aux_d <= 0 || (p.N % p.V) != 0))
       return e3b_fail(E3B_ERR_INVALID, "gemm_run: reduce epilogue needs aux, V in {16, 32} and N %% V == 0");
     if (p.epilogue == 3 && !p.H) return e3b_fail(E3B_ERR_INVALID, "gemm_run: epilogue 3 needs H");
+    if ((p.row_map || p.b_sel) && (p.a_d != p.c_d || p.epilogue == 3 || p.epilogue == 1))
+      return e3b_fail(E3B_ERR_UNSUPPORTED, "gemm_run: grouped rows need a_d == c_d and epilogue 0 or 2");
+    if (p.b_sel && (!p.row_map || p.b_set_stride <= 0 || (p.b_set_stride & 31)))
+      return e3b_fail(E3B_ERR_INVALID, "gemm_run: b_sel needs row_map and a set stride that keeps the sets 128-byte aligned");
     const int t = tile_n(p.N, p.K);
     const bool mu = p.K > KSEG * BK;
     if (b.n == 0) { bn = t; multi = mu; }

@@ -132,6 +132,8 @@ class OneHotEncoding(Module):
         idx = data["input"].squeeze(-1)
         # the reference hard-codes float32 (D6); follow the default dtype so the fp64 mode works
         one_hot = torch.nn.functional.one_hot(idx, num_classes=self.num_types).to(torch.get_default_dtype())
+        one_hot._e3b_onehot = (idx, self.num_types)     # provenance: whatever is computed row by row from this is a
+                                                        # function of the species (see PointwiseLinear)
         return {"one_hot": one_hot}, {"one_hot": (attrs["input"][0], self.irreps_out["one_hot"])}
 
 

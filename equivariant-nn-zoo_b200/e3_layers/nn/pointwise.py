@@ -15,7 +15,14 @@ class PointwiseLinear(Module):
         self.linear = dense.Linear(self.irreps_in["input"], self.irreps_out["output"], biases=biases)
 
     def forward(self, data, attrs):
-        return ({"output": self.linear(data["input"])},
+        x = data["input"]
+        out = self.linear(x)
+        tag = getattr(x, "_e3b_onehot", None)
+        if tag is not None:
+            # rows of `out` are rows of the table linear(identity): an interaction block that takes `out` as its node
+            # attributes contracts its self-connection weights with the table once per species instead of once per node
+            out._e3b_species = (tag[0], tag[1], self.linear)
+        return ({"output": out},
                 {"output": (attrs["input"][0], self.irreps_out["output"])})
 
 

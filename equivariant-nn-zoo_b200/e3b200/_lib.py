@@ -36,12 +36,13 @@ class GemmProblem(ctypes.Structure):
     _fields_ = [("A", c_vp), ("a_s1", c_i64), ("a_s2", c_i64), ("a_d", c_i32), ("B_packed", c_vp), ("C", c_vp),
                 ("c_s1", c_i64), ("c_s2", c_i64), ("c_s3", c_i64), ("c_d", c_i32), ("aux", c_vp), ("aux_ld", c_i64),
                 ("aux_d", c_i32), ("V", c_i32), ("aux_cols", c_i32), ("H", c_vp), ("h_ld", c_i64), ("M", c_i32), ("N", c_i32), ("K", c_i32),
-                ("epilogue", c_i32), ("accumulate", c_i32), ("alpha", c_f32), ("act_cst", c_f32)]
+                ("epilogue", c_i32), ("accumulate", c_i32), ("alpha", c_f32), ("act_cst", c_f32), ("row_map", c_vp),
+                ("b_sel", c_vp), ("b_set_stride", c_i64)]
 
 
 class GemmPackDesc(ctypes.Structure):
     _fields_ = [("src", c_vp), ("s1", c_i64), ("s2", c_i64), ("sk", c_i64), ("d", c_i32), ("n2_valid", c_i32), ("N", c_i32),
-                ("K", c_i32), ("dst", c_vp)]
+                ("K", c_i32), ("dst", c_vp), ("n_sets", c_i32), ("set_stride", c_i64)]
 
 
 class WgradProblem(ctypes.Structure):
@@ -56,7 +57,7 @@ class PairCriteriaStruct(ctypes.Structure):
                 ("seed", ctypes.c_uint64)]
 
 
-E3B_GEMM_MAX_GROUP = 8
+E3B_GEMM_MAX_GROUP = 16
 E3B_WGRAD_MAX_GROUP = 8
 CELL_GRID_BYTES = 48
 

@@ -134,6 +134,16 @@ class FusedInteraction:
         return out
 
 
+    def sc_sets(self, grp):
+        """self-connection weights contracted with the attribute row of every species (`ops.sc_weight_sets`)"""
+        sc = self.conv.sc
+        return ops.sc_weight_sets(self._cache, [(sc.irreps_in1[i1].mul, sc.irreps_out[o].mul, off) for i1, _, o, off, _ in sc.paths],
+                                  self.V, sc.weight, grp)
+
+
+SPECIES_SC_CALLS = 0      # forward passes of a block whose self-connection took the per-species path (tests)
+
+
 _waves = ops.gemm_waves
 
 
@@ -274,7 +284,7 @@ def radial_hidden(er, fi, group):
 
 class _Interaction(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, x_mi, x_imu, attrs, h_last, Y, fi, csr, und, *params):
+    def forward(ctx, x_mi, x_imu, attrs, h_last, Y, fi, csr, und, grp, *params):
         lib = _lib.load()
         ctx.set_materialize_grads(False)
         conv = fi.conv
@@ -327,12 +337,20 @@ class _Interaction(torch.autograd.Function):
         # (the self-connection writes first: its reducing epilogue stores whole sectors without reading;
         #  the dense epilogue of the linear map then accumulates with coalesced read-modify-writes)
         sc_probs, written = [], set()
+        sets = fi.sc_sets(grp) if grp is not None else None
         for q, (i1, i2, o, off, alpha) in enumerate(sc.paths):
             bi, bo = fi.feat_in[i1], fi.conv_out[o]
-            g = ops.gemm_problem(x_imu, P["sc"][q], cv, N * bi.ir.dim, a_off=fi.x_off[i1],
-                                 a_rows=(fi.Din, bi.mul, bi.ir.dim), c_off=fi.c_off[o],
-                                 c_rows=(fi.Dconv, bo.mul, bo.ir.dim), alpha=alpha, epilogue=1, aux=attrs,
-                                 aux_d=bi.ir.dim, aux_group=fi.Vg)
+            if grp is not None:
+                # attributes = a function of the species: one K = mul GEMM per path with the species' contracted weight
+                # (rows in species order through grp.row_map), 1/V of the flops of the attribute-contraction epilogue
+                g = ops.gemm_problem(x_imu, sets["fwd"][q], cv, grp.n_virtual * bi.ir.dim, a_off=fi.x_off[i1],
+                                     a_rows=(fi.Din, bi.mul, bi.ir.dim), c_off=fi.c_off[o],
+                                     c_rows=(fi.Dconv, bo.mul, bo.ir.dim), alpha=alpha, groups=grp)
+            else:
+                g = ops.gemm_problem(x_imu, P["sc"][q], cv, N * bi.ir.dim, a_off=fi.x_off[i1],
+                                     a_rows=(fi.Din, bi.mul, bi.ir.dim), c_off=fi.c_off[o],
+                                     c_rows=(fi.Dconv, bo.mul, bo.ir.dim), alpha=alpha, epilogue=1, aux=attrs,
+                                     aux_d=bi.ir.dim, aux_group=fi.Vg)
             sc_probs.append((g, o, False))
             written.add(o)
         probs = []
@@ -355,7 +373,7 @@ class _Interaction(torch.autograd.Function):
         with ops.stage("f.gate"):
             check(lib.e3b_gate_imu_fwd(ctypes.byref(fi.gate.desc), 0, ptr(cv), N, ptr(out_mi), ptr(out_imu), stream()))
         count_launch()
-        ctx.fi, ctx.csr, ctx.src_is_imu, ctx.und = fi, csr, src_is_imu, und
+        ctx.fi, ctx.csr, ctx.src_is_imu, ctx.und, ctx.grp = fi, csr, src_is_imu, und, grp
         # parameter gradients are produced whenever a parameter requires them, in training AND in evaluation mode
         # (fine-tuning under model.eval(), gradient diagnostics); the one pass that must not pay for them -- the
         # position gradient of an energy+force evaluation -- is marked by GradientOutput with ops.positions_only
@@ -378,10 +396,10 @@ class _Interaction(torch.autograd.Function):
         need_x = ctx.needs_input_grad[0] or ctx.needs_input_grad[1]
         need_attrs, need_h, need_Y = ctx.needs_input_grad[2], ctx.needs_input_grad[3], ctx.needs_input_grad[4]
         pos_only = ops.positions_only_active()          # parameters never depend on the positions
-        need_params = ctx.want_params and any(ctx.needs_input_grad[8:]) and not pos_only
+        need_params = ctx.want_params and any(ctx.needs_input_grad[9:]) and not pos_only
         need_attrs = need_attrs and ops.needs_grad_now(attrs)
         if g_mi is None and g_imu is None:
-            return (None,) * (8 + len(ctx.needs_input_grad[8:]))
+            return (None,) * len(ctx.needs_input_grad)
         P = fi.packs("bwd")
         # ---- gate
         g_cv = new(N, fi.Dconv)
@@ -472,12 +490,19 @@ class _Interaction(torch.autograd.Function):
                                                c_rows=(fi.Din, bi.mul, bi.ir.dim), alpha=alpha), i, False))
                 written.add(i)
             sc_probs = []
+            grp = ctx.grp
+            sets = fi.sc_sets(grp) if grp is not None else None
             for q, (i1, i2, o, off, alpha) in enumerate(sc.paths):
                 bi, bo = fi.feat_in[i1], fi.conv_out[o]
-                g = ops.gemm_problem(g_cv, P["sc"][q], g_x, N * bi.ir.dim, a_off=fi.c_off[o],
-                                     a_rows=(fi.Dconv, bo.mul, bo.ir.dim), c_off=fi.x_off[i1],
-                                     c_rows=(fi.Din, bi.mul, bi.ir.dim), alpha=alpha, epilogue=1, aux=attrs,
-                                     aux_d=bi.ir.dim, aux_group=fi.Vg)
+                if grp is not None:
+                    g = ops.gemm_problem(g_cv, sets["bwd"][q], g_x, grp.n_virtual * bi.ir.dim, a_off=fi.c_off[o],
+                                         a_rows=(fi.Dconv, bo.mul, bo.ir.dim), c_off=fi.x_off[i1],
+                                         c_rows=(fi.Din, bi.mul, bi.ir.dim), alpha=alpha, groups=grp)
+                else:
+                    g = ops.gemm_problem(g_cv, P["sc"][q], g_x, N * bi.ir.dim, a_off=fi.c_off[o],
+                                         a_rows=(fi.Dconv, bo.mul, bo.ir.dim), c_off=fi.x_off[i1],
+                                         c_rows=(fi.Din, bi.mul, bi.ir.dim), alpha=alpha, epilogue=1, aux=attrs,
+                                         aux_d=bi.ir.dim, aux_group=fi.Vg)
                 sc_probs.append((g, i1, i1 in written))
             if len(written | {t for _, t, _ in sc_probs}) < len(fi.feat_in):
                 g_x.zero_()
@@ -489,18 +514,18 @@ class _Interaction(torch.autograd.Function):
                 for wave in _waves(sc_probs):
                     ops.gemm_run(wave)
         # ---- parameter / attribute gradients (training only): library GEMMs on the saved activations
-        g_params = [None] * len(ctx.needs_input_grad[8:])
+        g_params = [None] * len(ctx.needs_input_grad[9:])
         g_attrs = None
         if need_params or need_attrs:
             gw_rows = gw if und is None else gw.index_select(0, und.canon) + gw.index_select(0, und.rev.long().index_select(0, und.canon))
-            g_params, g_attrs = _param_grads(fi, ctx.needs_input_grad[1:], x_imu, attrs, h_last, gw_rows, mid, g_cv, g_xl, need_attrs)
+            g_params, g_attrs = _param_grads(fi, ctx.needs_input_grad[2:], x_imu, attrs, h_last, gw_rows, mid, g_cv, g_xl, need_attrs)
         g_x_mi = g_x_imu = None
         if need_x:
             if ctx.src_is_imu:
                 g_x_imu = g_x
             else:
                 g_x_mi = g_x if fi.all_scalar_in else ops.layout_convert(g_x, fi.feat_in, False)
-        return (g_x_mi, g_x_imu, g_attrs, g_h, g_Y, None, None, None, *g_params)
+        return (g_x_mi, g_x_imu, g_attrs, g_h, g_Y, None, None, None, None, *g_params)
 
 
 def _param_grads(fi, needs, x_imu, attrs, h_last, gw, mid, g_cv, g_xl, need_attrs):
@@ -591,6 +616,10 @@ def interaction(fi, x, attrs, er, Y, csr, group=None, edge_index=None):
         und = undirected(er, edge_index, csr)
     src = und.er_u if und is not None else er
     h_last = radial_hidden(src, fi, group) if fi.conv.fc.n_layers > 1 else er
+    grp = ops.species_groups_of(attrs)
+    if grp is not None:
+        global SPECIES_SC_CALLS
+        SPECIES_SC_CALLS += 1
     if twin is not None:
-        return _Interaction.apply(None, twin, attrs, h_last, Y, fi, csr, und, *params)
-    return _Interaction.apply(x, None, attrs, h_last, Y, fi, csr, und, *params)
+        return _Interaction.apply(None, twin, attrs, h_last, Y, fi, csr, und, grp, *params)
+    return _Interaction.apply(x, None, attrs, h_last, Y, fi, csr, und, grp, *params)

@@ -2,6 +2,7 @@
 streams, autograd tape); every op below launches hand-written sm_100a kernels through the C ABI
 and raises if the library or a CUDA device is missing."""
 import ctypes
+import os
 
 import torch
 from torch.autograd.function import once_differentiable
@@ -923,16 +924,18 @@ def layout_convert(x, irreps, to_imu):
 class PackedWeight:
     """A weight in the form the tcgen05 GEMM consumes (TF32 hi/lo split, UMMA canonical tiles)."""
 
-    def __init__(self, N, K, device):
+    def __init__(self, N, K, device, n_sets=1):
         lib = _lib.load()
-        self.N, self.K = int(N), int(K)
+        self.N, self.K, self.n_sets = int(N), int(K), int(n_sets)
         self.tile_n = lib.e3b_gemm_tile_n(self.N, self.K)
-        self.buf = torch.empty(lib.e3b_gemm_packed_floats(self.N, self.K), dtype=torch.float32, device=device)
+        self.set_floats = lib.e3b_gemm_packed_floats(self.N, self.K)      # floats of one weight set
+        self.buf = torch.empty(self.n_sets * self.set_floats, dtype=torch.float32, device=device)
 
 
 def gemm_pack(views):
     """views: list of (src fp32 CUDA tensor, element offset, s1, s2, sk, d, n2_valid, N, K): element (n, k),
-    n = n1 * d + n2, is src.flat[offset + n1 * s1 + n2 * s2 + k * sk] (zero for n2 >= n2_valid > 0).
+    n = n1 * d + n2, is src.flat[offset + n1 * s1 + n2 * s2 + k * sk] (zero for n2 >= n2_valid > 0).  Two more entries
+    (n_sets, set_stride) pack n_sets weights of that shape, set i read set_stride elements further (grouped rows).
     -> list of PackedWeight
     (one kernel launch per E3B_GEMM_MAX_GROUP views)."""
     lib = _lib.load()
@@ -940,10 +943,13 @@ def gemm_pack(views):
     for lo in range(0, len(views), _lib.E3B_GEMM_MAX_GROUP):
         chunk = views[lo:lo + _lib.E3B_GEMM_MAX_GROUP]
         descs = (_lib.GemmPackDesc * len(chunk))()
-        for i, (src, off, s1, s2, sk, d, n2_valid, N, K) in enumerate(chunk):
+        for i, view in enumerate(chunk):
+            src, off, s1, s2, sk, d, n2_valid, N, K = view[:9]
+            n_sets, set_stride = view[9:] if len(view) > 9 else (1, 0)
             require_cuda(src)
             assert src.dtype == torch.float32
-            pw = PackedWeight(N, K, src.device)
+            pw = PackedWeight(N, K, src.device, n_sets)
+            descs[i].n_sets, descs[i].set_stride = n_sets, set_stride
             out.append(pw)
             descs[i].src, descs[i].dst = src.data_ptr() + 4 * off, pw.buf.data_ptr()
             descs[i].s1, descs[i].s2, descs[i].sk, descs[i].d, descs[i].N, descs[i].K = s1, s2, sk, d, N, K
@@ -954,10 +960,12 @@ def gemm_pack(views):
 
 
 def gemm_problem(A, Bp, C, M, a_off=0, a_rows=None, c_off=0, c_rows=None, c_col_stride=1, alpha=1.0, epilogue=0,
-                 accumulate=False, aux=None, aux_d=1, aux_group=None, H=None, act_cst=1.0):
+                 accumulate=False, aux=None, aux_d=1, aux_group=None, H=None, act_cst=1.0, groups=None):
     """One problem of a grouped launch: C[r, n] = epilogue(sum_k A[r, k] B[n, k]).  A / C are fp32 CUDA
     tensors used as raw storage (element offsets a_off / c_off); ``a_rows`` / ``c_rows`` = (s1, s2, d)
-    give the affine row addressing base + (r // d) * s1 + (r % d) * s2 (default: dense rows)."""
+    give the affine row addressing base + (r // d) * s1 + (r % d) * s2 (default: dense rows).  ``groups`` (a `RowGroups`):
+    M counts VIRTUAL rows, row group r // d stands for the actual group groups.row_map[r // d] of A and C and uses the
+    weight set groups.b_sel[(r // d) >> 7] of a PackedWeight with n_sets > 1."""
     N, K = Bp.N, Bp.K
     g = _lib.GemmProblem()
     a_s1, a_s2, a_d = a_rows if a_rows is not None else (K, 0, 1)
@@ -979,7 +987,85 @@ def gemm_problem(A, Bp, C, M, a_off=0, a_rows=None, c_off=0, c_rows=None, c_col_
         g.H, g.h_ld = None, 0
     g.M, g.N, g.K = M, N, K
     g.epilogue, g.accumulate, g.alpha, g.act_cst = epilogue, int(bool(accumulate)), float(alpha), float(act_cst)
+    if groups is not None:
+        assert Bp.n_sets == groups.n_sets and a_d == c_d
+        g.row_map, g.b_sel, g.b_set_stride = groups.row_map.data_ptr(), groups.b_sel.data_ptr(), Bp.set_floats
+    else:
+        g.row_map, g.b_sel, g.b_set_stride = None, None, 0
     return g
+
+
+class RowGroups:
+    """Rows (nodes) of a grouped GEMM in VIRTUAL order: sorted by weight set (species), every set padded to a multiple
+    of 128 rows.  row_map [n_virtual] int32: virtual -> actual row (-1 = padding); b_sel [n_virtual / 128] int32: the
+    weight set of every block; table [n_sets, V]: the attribute row of every set; params: what `table` depends on."""
+    __slots__ = ("row_map", "b_sel", "n_virtual", "n_sets", "table", "params")
+
+
+def species_row_groups(idx, n_sets):
+    """idx [N] int64 in [0, n_sets) -> RowGroups (table / params left to the caller).  Static shapes, no host
+    synchronisation: n_virtual = 128 * (ceil(N / 128) + n_sets) bounds every distribution of the rows over the sets."""
+    N, dev = idx.shape[0], idx.device
+    NB = (N + 127) // 128 + n_sets
+    # [S, N] with the scan along the CONTIGUOUS dimension (torch's outer-dimension scan walks the rows one by one: 3 ms)
+    member = (idx.view(1, -1) == torch.arange(n_sets, device=dev).view(-1, 1)).to(torch.int32)
+    seen = torch.cumsum(member, 1)                                          # rows of set s among the first n + 1
+    blocks = (seen[:, -1].long() + 127) // 128 if N else torch.zeros(n_sets, dtype=torch.int64, device=dev)
+    bend = torch.cumsum(blocks, 0)
+    rank = seen.gather(0, idx.view(1, -1)).view(-1).long() - 1              # position among the rows of the same set
+    slot = (bend - blocks).index_select(0, idx) * 128 + rank
+    g = RowGroups()
+    g.row_map = torch.full((NB * 128,), -1, dtype=torch.int32, device=dev)
+    g.row_map.scatter_(0, slot, torch.arange(N, dtype=torch.int32, device=dev))
+    g.b_sel = torch.searchsorted(bend, torch.arange(NB, device=dev), right=True).clamp_(max=n_sets - 1).to(torch.int32)
+    g.n_virtual, g.n_sets, g.table, g.params = NB * 128, n_sets, None, ()
+    return g
+
+
+SPECIES_SC = os.environ.get("E3B_SPECIES_SC", "1") != "0"
+
+
+def species_groups_of(attrs):
+    """`RowGroups` of the nodes by species when the node attributes are a function of the species alone (tagged
+    `_e3b_species` by PointwiseLinear applied to the output of OneHotEncoding: the reference's embedCategorial,
+    configs/layer_configs.py:8-30), else None.  Built once per forward pass, remembered on the tensor."""
+    sp = getattr(attrs, "_e3b_species", None)
+    if sp is None or not SPECIES_SC or not attrs.is_cuda or attrs.dtype != torch.float32:
+        return None
+    grp = getattr(attrs, "_e3b_groups", None)
+    if grp is None:
+        idx, S, lin = sp
+        grp = species_row_groups(idx, S)
+        with torch.no_grad():
+            grp.table = lin(torch.eye(S, dtype=attrs.dtype, device=attrs.device)).contiguous()
+        grp.params = tuple(lin.parameters())
+        attrs._e3b_groups = grp
+    return grp
+
+
+def sc_weight_sets(cache, paths, V, W, grp):
+    """Self-connection weights W[u, v, w] (reference nn/message_passing.py:81-87, e3nn FullyConnectedTensorProduct with
+    scalar attributes) contracted with the attribute row of every species, W_eff[s][u, w] = sum_v table[s, v] W[u, v, w],
+    packed as grp.n_sets weight sets per path for both directions of the map: {'fwd': [PackedWeight per path] (rows w,
+    K = u), 'bwd': [...] (rows u, K = w)}.  `paths`: [(mul_in, mul_out, offset in W)]; `cache`: a dict of the caller,
+    the entry is recomputed only when W or a parameter behind the table changed."""
+    S = grp.n_sets
+    key = (WEIGHTS_EPOCH, W.data_ptr(), W._version) + tuple((p.data_ptr(), p._version) for p in grp.params)
+    hit = cache.get("sets")
+    if hit is not None and hit[0] == key:
+        return hit[1]
+    with torch.no_grad():
+        parts, fwd, bwd, o = [], [], [], 0
+        for m1, mo, off in paths:
+            Wq = W[off:off + m1 * V * mo].view(m1, V, mo)
+            parts.append(torch.einsum("sv,uvw->suw", grp.table, Wq).reshape(-1))       # [s, u, w]
+            fwd.append((o, 1, 0, mo, 1, 0, mo, m1, S, m1 * mo))
+            bwd.append((o, mo, 0, 1, 1, 0, m1, mo, S, m1 * mo))
+            o += S * m1 * mo
+        flat = torch.cat(parts)
+        out = {"fwd": gemm_pack([(flat,) + v for v in fwd]), "bwd": gemm_pack([(flat,) + v for v in bwd])}
+    cache["sets"] = (key, out)
+    return out
 
 
 def gemm_run(problems):
@@ -1190,29 +1276,38 @@ def k_sc(spec, src, attrs, W, to_out):
     the attribute contraction in the epilogue; imu layouts."""
     require_cuda(src, attrs, W)
     N, V, Vg = src.shape[0], spec.V, spec.Vg
-    views = []
-    for i, o, off, alpha in spec.paths:
-        m1, mo = spec.irreps_in[i].mul, spec.irreps_out[o].mul
-        if V:
-            views.append((W, off, 1, mo, V * mo, Vg, V, mo * Vg, m1) if to_out else (W, off, V * mo, mo, 1, Vg, V, m1 * Vg, mo))
-        else:
-            views.append((W, off, 1, 0, mo, 1, 0, mo, m1) if to_out else (W, off, mo, 0, 1, 1, 0, m1, mo))
-    packs = gemm_pack(views)
+    grp = species_groups_of(attrs) if V else None
+    if grp is not None:
+        # attributes = table[species]: one K = mul GEMM per path with the species' contracted weight, rows in species order
+        if not hasattr(spec, "_set_cache"):
+            spec._set_cache = {}
+        packs = sc_weight_sets(spec._set_cache, [(spec.irreps_in[i].mul, spec.irreps_out[o].mul, off) for i, o, off, _ in spec.paths],
+                               V, W, grp)["fwd" if to_out else "bwd"]
+        extra, rows = dict(groups=grp), grp.n_virtual
+    else:
+        views = []
+        for i, o, off, alpha in spec.paths:
+            m1, mo = spec.irreps_in[i].mul, spec.irreps_out[o].mul
+            if V:
+                views.append((W, off, 1, mo, V * mo, Vg, V, mo * Vg, m1) if to_out else (W, off, V * mo, mo, 1, Vg, V, m1 * Vg, mo))
+            else:
+                views.append((W, off, 1, 0, mo, 1, 0, mo, m1) if to_out else (W, off, mo, 0, 1, 1, 0, m1, mo))
+        packs = gemm_pack(views)
+        extra, rows = (dict(epilogue=1, aux=attrs, aux_group=Vg) if V else {}), N
     D_src, D_dst = (spec.Din, spec.Dout) if to_out else (spec.Dout, spec.Din)
     dst = torch.empty(N, D_dst, dtype=torch.float32, device=src.device)
-    extra = dict(epilogue=1, aux=attrs, aux_group=Vg) if V else {}
     probs, written = [], set()
     for q, (i, o, off, alpha) in enumerate(spec.paths):
         bi, bo = spec.irreps_in[i], spec.irreps_out[o]
         d = bi.ir.dim
-        if V:
+        if V and grp is None:
             extra["aux_d"] = d
         if to_out:
-            g = gemm_problem(src, packs[q], dst, N * d, a_off=spec.x_off[i], a_rows=(D_src, bi.mul, d), c_off=spec.c_off[o],
+            g = gemm_problem(src, packs[q], dst, rows * d, a_off=spec.x_off[i], a_rows=(D_src, bi.mul, d), c_off=spec.c_off[o],
                              c_rows=(D_dst, bo.mul, d), alpha=alpha, **extra)
             tgt = o
         else:
-            g = gemm_problem(src, packs[q], dst, N * d, a_off=spec.c_off[o], a_rows=(D_src, bo.mul, d), c_off=spec.x_off[i],
+            g = gemm_problem(src, packs[q], dst, rows * d, a_off=spec.c_off[o], a_rows=(D_src, bo.mul, d), c_off=spec.x_off[i],
                              c_rows=(D_dst, bi.mul, d), alpha=alpha, **extra)
             tgt = i
         probs.append((g, tgt, False))
@@ -1326,6 +1421,7 @@ class _SC(torch.autograd.Function):
     def forward(ctx, src, a, W, spec, to_out):
         ctx.spec, ctx.to_out = spec, to_out
         ctx.save_for_backward(src, a, W)
+        ctx.species = (getattr(a, "_e3b_species", None), getattr(a, "_e3b_groups", None)) if a is not None else (None, None)
         return k_sc(spec, src, a, W, to_out)
 
     @staticmethod
@@ -1333,6 +1429,8 @@ class _SC(torch.autograd.Function):
         src, a, W = ctx.saved_tensors
         spec = ctx.spec
         h = h.contiguous()
+        if ctx.species[0] is not None and getattr(a, "_e3b_species", None) is None:
+            a._e3b_species, a._e3b_groups = ctx.species           # provenance of the attributes (see species_groups_of)
         g_src = _SC.apply(h, a, W, spec, not ctx.to_out) if ctx.needs_input_grad[0] else None
         want_a = a is not None and ctx.needs_input_grad[1] and needs_grad_now(a)
         want_W = ctx.needs_input_grad[2] and needs_grad_now(W)

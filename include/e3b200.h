@@ -320,7 +320,7 @@ E3B_API int e3b_gate_imu_bwd(const e3b_gate_desc* desc, int dtype, const void* i
  * e3b_gemm_run launches up to E3B_GEMM_MAX_GROUP independent problems (e.g. the irreps blocks
  * of one o3.Linear) as ONE persistent kernel; they must share the tile shape, i.e. agree on
  * (K <= 64) and on (N <= 64 or K > 64)  [e3b_gemm_tile_n returns the column-tile width].     */
-#define E3B_GEMM_MAX_GROUP 8
+#define E3B_GEMM_MAX_GROUP 16
 
 typedef struct {
   const float* A;
@@ -339,6 +339,9 @@ typedef struct {
   int32_t M, N, K;
   int32_t epilogue, accumulate;
   float alpha, act_cst;
+  const int32_t* row_map;  /* grouped rows: virtual row group -> actual row group of A and C, < 0 = padding (or NULL) */
+  const int32_t* b_sel;    /* weight set of every block of 128 virtual row groups (or NULL) */
+  int64_t b_set_stride;    /* floats between consecutive weight sets in B_packed */
 } e3b_gemm_problem;
 
 typedef struct {
@@ -348,6 +351,8 @@ typedef struct {
   int32_t n2_valid;      /* rows with n2 >= n2_valid are zero (0 means all valid): pads a group to V */
   int32_t N, K;
   float* dst;
+  int32_t n_sets;        /* > 1: that many weights of the same shape, set i read from src + i * set_stride and written */
+  int64_t set_stride;    /*      to dst + i * e3b_gemm_packed_floats(N, K) (grouped rows of e3b_gemm_problem)        */
 } e3b_gemm_pack_desc;
 
 E3B_API int e3b_gemm_tile_n(int32_t N, int32_t K);

@@ -123,3 +123,34 @@ def test_gemm_many_row_tiles_long_k():
     C = torch.empty(M, N, device=DEV)
     ops.gemm_tf32x3(A.to(DEV), B.to(DEV), C, M, N, K)
     assert _rel(C, A.double() @ B.double().T) < 2e-6
+
+
+@pytest.mark.parametrize("d,N,K", [(1, 64, 64), (3, 64, 64), (5, 64, 64), (1, 256, 64), (3, 64, 256), (5, 32, 32)])
+def test_gemm_grouped_rows_weight_sets(d, N, K):
+    """virtual row order by species + one packed weight set per species (the per-species self-connection): every node's
+    d rows times ITS species' weight, written in place; nodes of absent species / padding slots never touch C"""
+    g = torch.Generator().manual_seed(17 * d + N + K)
+    Z, S, D_in, D_out = 1117, 7, 640 if K * d <= 640 else K * d, 1408
+    species = torch.randint(0, S, (Z,), generator=g)
+    species[species == 4] = 2                                    # one species absent
+    X = torch.randn(Z, D_in, generator=g)
+    W = torch.randn(S, N, K, generator=g)                        # set s: B[n, k]
+    a_off, c_off = 64 if D_in >= 64 + K * d else 0, 128
+    xa = X[:, a_off:a_off + d * K].reshape(Z, d, K).double()
+    ref = 0.61 * torch.einsum("zdk,znk->zdn", xa, W.double()[species])          # [z, d, n]
+    grp = ops.species_row_groups(species.to(DEV), S)
+    assert grp.n_virtual == 128 * ((Z + 127) // 128 + S)
+    rm = grp.row_map.cpu()
+    assert sorted(rm[rm >= 0].tolist()) == list(range(Z))
+    Wd = W.to(DEV).contiguous()
+    (Bp,) = ops.gemm_pack([(Wd, 0, K, 0, 1, 1, 0, N, K, S, N * K)])
+    C = torch.full((Z, D_out), 7.0, device=DEV)
+    ops.gemm_run([ops.gemm_problem(X.to(DEV), Bp, C, grp.n_virtual * d, a_off=a_off, a_rows=(D_in, K, d), c_off=c_off,
+                                   c_rows=(D_out, N, d), alpha=0.61, groups=grp)])
+    out = C[:, c_off:c_off + d * N].reshape(Z, d, N)
+    assert _rel(out, ref) < 2e-6
+    assert bool((C[:, :c_off] == 7.0).all()) and bool((C[:, c_off + d * N:] == 7.0).all())
+    # accumulate into what C holds
+    ops.gemm_run([ops.gemm_problem(X.to(DEV), Bp, C, grp.n_virtual * d, a_off=a_off, a_rows=(D_in, K, d), c_off=c_off,
+                                   c_rows=(D_out, N, d), alpha=0.61, groups=grp, accumulate=True)])
+    assert _rel(C[:, c_off:c_off + d * N].reshape(Z, d, N), 2 * ref) < 2e-6

@@ -294,3 +294,37 @@ def test_ragged_batch_with_isolated_atoms():
     # the same batch through the second-order (training) mode
     tr = product_harness.run_product(model.train(), inputs, torch.float32, DEV, pre_edge={"r_max": 5.0})
     assert harness.rel_err(tr["forces"], ref["forces"]) < 1e-5
+
+
+def test_species_self_connection_matches_attribute_contraction():
+    """node_attrs = PointwiseLinear(one-hot species) (reference embedCategorial, configs/layer_configs.py:8-30) are a
+    function of the species: the self-connection then runs as one K = mul GEMM per path with the weights contracted per
+    species (rows in species order, `ops.species_row_groups`) instead of the attribute-contraction epilogue.  Same
+    numbers as the attribute path (fp32 rounding), in evaluation and in the second-order training mode, and not taken
+    when the attributes are not tagged."""
+    from e3b200 import interaction, ops
+
+    meta = {"config": "config_energy_force", "seed": 9}
+    model = product_harness.build_product(meta, torch.float32, DEV)
+    inputs = synthetic.qm9_like(30, seed=13)
+    n0 = interaction.SPECIES_SC_CALLS
+    fast = product_harness.run_product(model, inputs, torch.float32, DEV, pre_edge={"r_max": 5.0})
+    assert interaction.SPECIES_SC_CALLS - n0 >= 5              # every interaction block
+    ops.SPECIES_SC = False
+    try:
+        n1 = interaction.SPECIES_SC_CALLS
+        plain = product_harness.run_product(model, inputs, torch.float32, DEV, pre_edge={"r_max": 5.0})
+        assert interaction.SPECIES_SC_CALLS == n1
+        tr_plain = product_harness.run_product(model.train(), inputs, torch.float32, DEV, pre_edge={"r_max": 5.0})
+    finally:
+        ops.SPECIES_SC = True
+    tr_fast = product_harness.run_product(model.train(), inputs, torch.float32, DEV, pre_edge={"r_max": 5.0})
+    model.eval()
+    assert harness.rel_err(fast["energy"], plain["energy"]) < 2e-6
+    assert harness.rel_err(fast["forces"], plain["forces"]) < 2e-6
+    assert harness.rel_err(tr_fast["forces"], tr_plain["forces"]) < 2e-6
+    oracle = harness.build_oracle(meta, torch.float64)
+    ref = harness.run_oracle(oracle, inputs, torch.float64, pre_edge={"r_max": 5.0})
+    assert harness.rel_err(fast["energy"], ref["energy"]) < 1e-5
+    assert harness.rel_err(fast["forces"], ref["forces"]) < 1e-5
+    assert harness.rel_err(tr_fast["forces"], ref["forces"]) < 1e-5
