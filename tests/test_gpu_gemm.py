@@ -154,3 +154,24 @@ def test_gemm_grouped_rows_weight_sets(d, N, K):
     ops.gemm_run([ops.gemm_problem(X.to(DEV), Bp, C, grp.n_virtual * d, a_off=a_off, a_rows=(D_in, K, d), c_off=c_off,
                                    c_rows=(D_out, N, d), alpha=0.61, groups=grp, accumulate=True)])
     assert _rel(C[:, c_off:c_off + d * N].reshape(Z, d, N), 2 * ref) < 2e-6
+
+
+@pytest.mark.parametrize("M,N,K", [(120037, 64, 192), (60000, 128, 288), (113665, 64, 1920)])
+def test_gemm_long_k_many_row_tiles(M, N, K):
+    """K-long problems with several row tiles per CTA (the streaming A ring, both MMA issuers, chained accumulators):
+    plain, accumulate and the activation-derivative epilogue, odd tile count, ragged last tile"""
+    g = torch.Generator(device=DEV).manual_seed(M + N + K)
+    A = torch.randn(M, K, generator=g, device=DEV)
+    B = torch.randn(N, K, generator=g, device=DEV)
+    ref = (0.5 * (A.double() @ B.double().T)).cpu()
+    C = torch.full((M, N), float("nan"), device=DEV)
+    ops.gemm_tf32x3(A, B, C, M, N, K, alpha=0.5)
+    assert _rel(C, ref) < 2e-6
+    ops.gemm_tf32x3(A, B, C, M, N, K, alpha=0.5, accumulate=True)
+    assert _rel(C, 2 * ref) < 2e-6
+    cst = 1.3
+    z = torch.randn(M, N, generator=g, device=DEV)
+    H = cst * (torch.nn.functional.softplus(z) - 0.6931471805599453)
+    ops.gemm_tf32x3(A, B, C, M, N, K, alpha=0.5, epilogue=3, H=H, act_cst=cst)
+    ref3 = ref * (cst * torch.sigmoid(z.double())).cpu()
+    assert _rel(C, ref3) < 4e-6
