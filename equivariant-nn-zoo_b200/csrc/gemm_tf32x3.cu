@@ -26,6 +26,7 @@
 // The tensor core accumulates with truncation, so an unbroken chain over a long K drifts
 // (1.5e-5 at K = 1920, measured): chains are cut every 64 floats of K and the partial sums are
 // added in fp32 registers by the epilogue warps while the next chain runs in the other buffer.
+#include <cuda.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdlib.h>
@@ -54,12 +55,20 @@ struct Problem {
   int32_t cta_begin;     // first CTA (blockIdx.x) of this problem
   uint64_t a_mul;        // ceil(2^40 / a_d): r / a_d == (r * a_mul) >> 40 for r < 2^31, a_d < 512
   uint64_t c_mul;        // the same for c_d
+  int32_t tma;           // the A tile is fetched by TMA tensor copies (plain row-major A streamed along a long K): one
+                         // instruction per 128 x 32 chunk into a 128-byte-swizzled slot instead of 2048 16-byte copies
+                         // issued by the converter threads, and up to RS chunks in flight per SM
   int32_t dbg;           // E3B_GEMM_DEBUG bisection bits: 1 skip A load+convert, 2 skip MMA, 4 skip B loads, 8 skip stores
 };
 struct Batch {
   Problem pr[MAXG];
   int32_t n;
 };
+struct TmapBatch {
+  alignas(64) CUtensorMap a[MAXG];   // A of problem i as a 2-D tensor {K, M}, box {32, 128}, 128-byte swizzle (when pr[i].tma)
+};
+constexpr int RS = 6;                // TMA mode: 16 KB slots of the raw ring
+constexpr uint32_t RAW_SLOT_BYTES = BM * BK * 4;
 
 __device__ __forceinline__ uint32_t smem_addr(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
@@ -121,6 +130,15 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
 __device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
   asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
                    smem_addr(dst)), "l"(src), "r"(bytes), "r"(smem_addr(bar)) : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const void* tmap, int32_t c0, int32_t c1, uint64_t* bar) {
+  asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+               ::"r"(dst), "l"(reinterpret_cast<uint64_t>(tmap)), "r"(smem_addr(bar)), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ float4 lds128(uint32_t addr) {
+  float4 v;
+  asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr));
+  return v;
 }
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
@@ -193,7 +211,7 @@ struct Smem {
   static constexpr int RAW_ROW = BK + 4;           // padded row (144 B): conflict-free row-per-lane reads
   static constexpr int RAW_STAGE = BM * RAW_ROW;
   static constexpr int EPI_STAGE = 32 * 36;        // per epilogue warp: 32 rows x (32 + 4 pad) floats
-  static constexpr size_t BYTES = (size_t)(SB * B_STAGE + PRAW * RAW_STAGE + 8 * EPI_STAGE) * 4 + 128 /*align slack*/;
+  static constexpr size_t BYTES = (size_t)(SB * B_STAGE + PRAW * RAW_STAGE + 8 * EPI_STAGE) * 4 + 1024 /*align slack*/;
 };
 
 struct EpiCtx {
@@ -373,15 +391,19 @@ __device__ __forceinline__ void epilogue_role(const EpiCtx& c) {
 // every role repeats the same walk over this CTA's tile range [t0, t1)
 // TMEM map (512 columns): [NACC accumulators of BN columns][SA stages of A: 32 hi | 32 lo columns]
 template <int BN, bool MULTI, int NACC, int SA, int PRAW, int SB>
-__global__ void __launch_bounds__(NTHREADS, 1) gemm_tf32x3_kernel(const __grid_constant__ Batch batch) {
+__global__ void __launch_bounds__(NTHREADS, 1) gemm_tf32x3_kernel(const __grid_constant__ Batch batch,
+                                                                  const __grid_constant__ TmapBatch tmaps) {
   using L = Smem<BN, PRAW, SB>;
   static_assert(NACC * BN + SA * A_COLS <= 512 && PRAW >= 4 && PRAW % 2 == 0, "TMEM / ring configuration");
+  static_assert(!MULTI || ((size_t)PRAW * L::RAW_STAGE * 4 >= (size_t)RS * RAW_SLOT_BYTES && (SB * L::B_STAGE * 4) % 1024 == 0),
+                "TMA mode: RS swizzled 16 KB slots, 1024-byte aligned, inside the raw ring");
   extern __shared__ unsigned char smem_dyn[];
-  float* smem = reinterpret_cast<float*>((reinterpret_cast<uintptr_t>(smem_dyn) + 127) & ~(uintptr_t)127);
+  float* smem = reinterpret_cast<float*>((reinterpret_cast<uintptr_t>(smem_dyn) + 1023) & ~(uintptr_t)1023);
   float* sB = smem;                                   // [SB][hi|lo][c(8)][row(BN)][4]
   float* sRaw = sB + SB * L::B_STAGE;                 // [PRAW][row(128)][36]
   float* sEpi = sRaw + PRAW * L::RAW_STAGE;           // [8 warps][32 rows][36]
   __shared__ uint64_t a_full[SA], a_empty[SA], b_full[SB], b_empty[SB], acc_full[NACC], acc_empty[NACC];
+  __shared__ uint64_t raw_full[RS], raw_empty[RS];
   __shared__ uint32_t tmem_base_smem;
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -398,6 +420,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) gemm_tf32x3_kernel(const __grid_c
   const int t0 = (int)((int64_t)local * n_all / P.n_ctas), t1 = (int)((int64_t)(local + 1) * n_all / P.n_ctas);
   const int k_chunks = P.k_chunks;
   const bool resident = k_chunks <= SA;
+  const bool tma = MULTI && P.tma != 0;               // host: only with a streaming A ring (!resident)
 
   if (warp == 17) {  // TMEM allocation is warp-collective; the same warp frees it
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_addr(&tmem_base_smem)), "r"(512u) : "memory");
@@ -407,6 +430,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) gemm_tf32x3_kernel(const __grid_c
     for (int s = 0; s < SA; ++s) { mbar_init(&a_full[s], NCVT / 2 / 32); mbar_init(&a_empty[s], 1); }
     for (int s = 0; s < SB; ++s) { mbar_init(&b_full[s], 1); mbar_init(&b_empty[s], 1); }
     for (int s = 0; s < NACC; ++s) { mbar_init(&acc_full[s], 1); mbar_init(&acc_empty[s], NEPI / 32); }
+    for (int s = 0; s < RS; ++s) { mbar_init(&raw_full[s], 1); mbar_init(&raw_empty[s], NCVT / 2 / 32); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   tc_fence_before();
@@ -431,6 +455,43 @@ __global__ void __launch_bounds__(NTHREADS, 1) gemm_tf32x3_kernel(const __grid_c
       const int row0 = 8 * (w >> 1) + (lane & 7);
       const int my_row = 32 * w + lane;
       const uint32_t t_mine = tmem_a0 + ((uint32_t)(32 * w) << 16);
+      if (tma) {
+        // TMA mode: the producer warp fetches chunk j into slot j % RS (rows of 128 B, 16-byte pieces XOR-swizzled
+        // with the row index mod 8, so the row-per-lane reads below are conflict-free without padding)
+        const int total = (t1 - t0) * k_chunks;
+        const uint32_t row_addr = smem_addr(sRaw) + (uint32_t)my_row * 128u;
+        const uint32_t sw = (uint32_t)(lane & 7);
+        const bool skip_a = (P.dbg & 1) != 0;
+#pragma unroll 1
+        for (int j = grp; j < total; j += NG) {
+          const int st = j % SA, rs = j % RS;
+          mbar_wait(&raw_full[rs], ((uint32_t)j / RS) & 1u);
+          float hi[32], lo[32];
+          if (!skip_a) {
+            const uint32_t base = row_addr + (uint32_t)rs * RAW_SLOT_BYTES;
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              float4 h, l;
+              split4_fast(lds128(base + (((uint32_t)i ^ sw) << 4)), &h, &l);
+              hi[4 * i] = h.x; hi[4 * i + 1] = h.y; hi[4 * i + 2] = h.z; hi[4 * i + 3] = h.w;
+              lo[4 * i] = l.x; lo[4 * i + 1] = l.y; lo[4 * i + 2] = l.z; lo[4 * i + 3] = l.w;
+            }
+          }
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&raw_empty[rs]);       // the slot is in registers: the producer may refill it
+          mbar_wait(&a_empty[st], (((uint32_t)j / SA) & 1u) ^ 1u);
+          if (!skip_a) {
+            tc_fence_after();
+            const uint32_t ta = t_mine + (uint32_t)st * A_COLS;
+            tmem_st32(ta, hi);
+            tmem_st32(ta + BK, lo);
+            asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+          }
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&a_full[st]);
+        }
+      } else {
       float* raw_ring = sRaw + (size_t)grp * (PRAW / NG) * L::RAW_STAGE;
       constexpr int PR = PRAW / NG;              // raw slots of one group
       static_assert(PR >= 2, "raw ring");
@@ -526,6 +587,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) gemm_tf32x3_kernel(const __grid_c
         if (++slot == PR) slot = 0;
       }
       cp_async_wait<0>();
+      }
     } else if (warp == 16) {
       // =============================== B producer (TMA) ===============================
       if (lane == 0) {
@@ -541,6 +603,15 @@ __global__ void __launch_bounds__(NTHREADS, 1) gemm_tf32x3_kernel(const __grid_c
             b_set = g.B_packed + (int64_t)__ldg(g.b_sel + (q0 >> 7)) * g.b_set_stride;
           }
             for (int kc = 0; kc < k_chunks; ++kc, ++it) {
+              if (tma) {                                    // the A chunk of this job
+                const uint32_t rs = it % RS;
+                mbar_wait(&raw_empty[rs], ((it / RS) & 1u) ^ 1u);
+                if (P.dbg & 1) mbar_arrive(&raw_full[rs]);
+                else {
+                  mbar_expect_tx(&raw_full[rs], RAW_SLOT_BYTES);
+                  tma_load_2d(smem_addr(sRaw) + rs * RAW_SLOT_BYTES, &tmaps.a[gi], kc * BK, m * BM, &raw_full[rs]);
+                }
+              }
               const int st = it % SB;
               mbar_wait(&b_empty[st], ((it / SB) & 1u) ^ 1u);
               if (P.dbg & 4) { mbar_arrive(&b_full[st]); continue; }
@@ -673,7 +744,7 @@ __global__ void gemm_pack_kernel(const __grid_constant__ PackBatch pb) {
 }
 
 template <int BN, bool MULTI, int NACC, int SA, int PRAW, int SB>
-cudaError_t launch(const Batch& b, int ctas, cudaStream_t st) {
+cudaError_t launch(const Batch& b, const TmapBatch& tm, int ctas, cudaStream_t st) {
   using L = Smem<BN, PRAW, SB>;
   static bool attr_set = false;
   if (!attr_set) {
@@ -682,11 +753,39 @@ cudaError_t launch(const Batch& b, int ctas, cudaStream_t st) {
     if (e != cudaSuccess) return e;
     attr_set = true;
   }
-  gemm_tf32x3_kernel<BN, MULTI, NACC, SA, PRAW, SB><<<ctas, NTHREADS, L::BYTES, st>>>(b);
+  gemm_tf32x3_kernel<BN, MULTI, NACC, SA, PRAW, SB><<<ctas, NTHREADS, L::BYTES, st>>>(b, tm);
   return cudaGetLastError();
 }
 
 int tile_n(int N, int K) { return (K <= KSEG * BK && N > 64) ? 128 : 64; }
+
+// cuTensorMapEncodeTiled through the runtime (no link dependency on libcuda)
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+EncodeTiledFn encode_tiled() {
+  static EncodeTiledFn fn = [] {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess ||
+        q != cudaDriverEntryPointSuccess)
+      p = nullptr;
+    return (EncodeTiledFn)p;
+  }();
+  return fn;
+}
+// A [M, K] fp32, row pitch a_s1 floats, as a {K, M} tensor read in boxes of {32, 128} (out-of-range parts read as zero)
+bool make_a_map(CUtensorMap* map, const e3b_gemm_problem& p) {
+  EncodeTiledFn enc = encode_tiled();
+  if (!enc) return false;
+  const cuuint64_t dims[2] = {(cuuint64_t)p.K, (cuuint64_t)p.M};
+  const cuuint64_t strides[1] = {(cuuint64_t)p.a_s1 * 4};
+  const cuuint32_t box[2] = {(cuuint32_t)BK, (cuuint32_t)BM};
+  const cuuint32_t estr[2] = {1, 1};
+  return enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(p.A), dims, strides, box, estr,
+             CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+             CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
 
 }  // namespace
 
@@ -723,6 +822,7 @@ extern "C" int e3b_gemm_run(const e3b_gemm_problem* problems, int32_t n, void* s
   if (n <= 0) return E3B_OK;
   if (!problems || n > MAXG) return e3b_fail(E3B_ERR_INVALID, "gemm_run: 1..%d problems per launch", MAXG);
   Batch b;
+  static TmapBatch tm;            // entries are (re)written for the problems that use them; the launch copies the struct
   b.n = 0;
   int bn = 0;
   bool multi = false;
@@ -759,6 +859,12 @@ extern "C" int e3b_gemm_run(const e3b_gemm_problem* problems, int32_t n, void* s
     P.a_mul = ((1ull << 40) + (uint64_t)p.a_d - 1) / (uint64_t)p.a_d;
     if (p.c_d >= 512) return e3b_fail(E3B_ERR_UNSUPPORTED, "gemm_run: c_d must be < 512");
     P.c_mul = ((1ull << 40) + (uint64_t)p.c_d - 1) / (uint64_t)p.c_d;
+    {
+      // TMA for A: K-long (the A ring streams), plain rows of a row-major matrix, no row map
+      static const int tma_env = [] { const char* v = getenv("E3B_GEMM_TMA"); return v ? atoi(v) : 1; }();
+      P.tma = (tma_env && mu && P.k_chunks > 4 && p.a_d == 1 && !p.row_map && p.a_s1 >= p.K && p.a_s1 < (1ll << 38) &&
+               make_a_map(&tm.a[b.n], p)) ? 1 : 0;
+    }
     work[b.n] = (double)P.m_tiles * P.n_tiles * (P.k_chunks + 2);
     total_work += work[b.n];
     ++b.n;
@@ -798,9 +904,9 @@ extern "C" int e3b_gemm_run(const e3b_gemm_problem* problems, int32_t n, void* s
     ctas += want[i];
   }
   cudaError_t e;
-  if (multi) e = launch<64, true, 4, 4, 6, 4>(b, ctas, (cudaStream_t)stream);
-  else if (bn == 64) e = launch<64, false, 4, 4, 6, 4>(b, ctas, (cudaStream_t)stream);
-  else e = launch<128, false, 2, 4, 4, 3>(b, ctas, (cudaStream_t)stream);
+  if (multi) e = launch<64, true, 4, 4, 6, 4>(b, tm, ctas, (cudaStream_t)stream);
+  else if (bn == 64) e = launch<64, false, 4, 4, 6, 4>(b, tm, ctas, (cudaStream_t)stream);
+  else e = launch<128, false, 2, 4, 4, 3>(b, tm, ctas, (cudaStream_t)stream);
   if (e != cudaSuccess) return e3b_fail(E3B_ERR_CUDA, "gemm_run: %s", cudaGetErrorString(e));
   return E3B_OK;
 }
