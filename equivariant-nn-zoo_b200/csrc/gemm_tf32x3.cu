@@ -58,6 +58,9 @@ struct Problem {
   int32_t tma;           // the A tile is fetched by TMA tensor copies (plain row-major A streamed along a long K): one
                          // instruction per 128 x 32 chunk into a 128-byte-swizzled slot instead of 2048 16-byte copies
                          // issued by the converter threads, and up to RS chunks in flight per SM
+  int32_t tma_c;         // C is a plain row-major matrix written (not accumulated) by epilogue 0 / 2: every epilogue warp
+                         // stages its 32 x 32 block in a swizzled tile and ONE TMA tensor store writes it (the 32 x
+                         // 16-byte stores per lane it replaces bound the [E,64] x [64,1920] launch: 310 us, 162 without)
   int32_t dbg;           // E3B_GEMM_DEBUG bisection bits: 1 skip A load+convert, 2 skip MMA, 4 skip B loads, 8 skip stores
 };
 struct Batch {
@@ -66,6 +69,7 @@ struct Batch {
 };
 struct TmapBatch {
   alignas(64) CUtensorMap a[MAXG];   // A of problem i as a 2-D tensor {K, M}, box {32, 128}, 128-byte swizzle (when pr[i].tma)
+  alignas(64) CUtensorMap c[MAXG];   // C of problem i as {N, M}, box {32, 32}, 128-byte swizzle (when pr[i].tma_c)
 };
 constexpr int RS = 6;                // TMA mode: 16 KB slots of the raw ring
 constexpr uint32_t RAW_SLOT_BYTES = BM * BK * 4;
@@ -134,6 +138,14 @@ __device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t by
 __device__ __forceinline__ void tma_load_2d(uint32_t dst, const void* tmap, int32_t c0, int32_t c1, uint64_t* bar) {
   asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
                ::"r"(dst), "l"(reinterpret_cast<uint64_t>(tmap)), "r"(smem_addr(bar)), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void tma_store_2d(const void* tmap, uint32_t src, int32_t c0, int32_t c1) {
+  asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];"
+               ::"l"(reinterpret_cast<uint64_t>(tmap)), "r"(src), "r"(c0), "r"(c1) : "memory");
+  asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+}
+__device__ __forceinline__ void sts128(uint32_t addr, float4 v) {
+  asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
 }
 __device__ __forceinline__ float4 lds128(uint32_t addr) {
   float4 v;
@@ -210,12 +222,14 @@ struct Smem {
   static constexpr int B_STAGE = 2 * BN * BK;      // floats: hi | lo
   static constexpr int RAW_ROW = BK + 4;           // padded row (144 B): conflict-free row-per-lane reads
   static constexpr int RAW_STAGE = BM * RAW_ROW;
-  static constexpr int EPI_STAGE = 32 * 36;        // per epilogue warp: 32 rows x (32 + 4 pad) floats
+  static constexpr int EPI_STAGE = 32 * 40;        // per epilogue warp: 32 rows x (32 + 4 pad) floats, or a swizzled
+                                                   // 32 x 32 tile for a TMA store (stride kept a multiple of 1024 B)
   static constexpr size_t BYTES = (size_t)(SB * B_STAGE + PRAW * RAW_STAGE + 8 * EPI_STAGE) * 4 + 1024 /*align slack*/;
 };
 
 struct EpiCtx {
   const Problem* P;
+  const CUtensorMap* tmap_c;
   uint64_t* acc_full;
   uint64_t* acc_empty;
   float* stg;            // warp-private staging tile [32][36]
@@ -294,7 +308,21 @@ __device__ __forceinline__ void epilogue_role(const EpiCtx& c) {
         }
         const int nb = n0 + cb;
         if (!last || nb >= g.N || (P.dbg & 8)) continue;
-        if (DENSE) {
+        if (DENSE && EPI != 3 && P.tma_c) {
+          // thread = row: its 32 values go into the swizzled staging tile, one tensor store writes the block
+          // (rows / columns beyond M / N are clipped by the tensor map)
+          if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");   // the previous block has left
+          __syncwarp();
+          const uint32_t srow = smem_addr(c.stg) + (uint32_t)lane * 128u;
+#pragma unroll
+          for (int i = 0; i < 8; ++i)
+            sts128(srow + (((uint32_t)i ^ (uint32_t)(lane & 7)) << 4),
+                   make_float4(epi_apply<EPI>(alpha * v[4 * i], 0.f, cst), epi_apply<EPI>(alpha * v[4 * i + 1], 0.f, cst),
+                               epi_apply<EPI>(alpha * v[4 * i + 2], 0.f, cst), epi_apply<EPI>(alpha * v[4 * i + 3], 0.f, cst)));
+          asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+          __syncwarp();
+          if (lane == 0) tma_store_2d(c.tmap_c, smem_addr(c.stg), nb, m * BM + q * 32);
+        } else if (DENSE) {
           __syncwarp();
 #pragma unroll
           for (int i = 0; i < 8; ++i)
@@ -386,6 +414,8 @@ __device__ __forceinline__ void epilogue_role(const EpiCtx& c) {
       }
     }
   }
+  // tensor stores of this warp must have completed before the CTA's shared memory goes away
+  if (DENSE && EPI != 3 && P.tma_c && lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
 }
 
 // every role repeats the same walk over this CTA's tile range [t0, t1)
@@ -684,7 +714,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) gemm_tf32x3_kernel(const __grid_c
       // =============================== epilogue ===============================
       const bool dense = g.c_s3 == 1 && (g.c_s1 & 3) == 0 && (g.c_s2 & 3) == 0 && (g.N & 3) == 0 &&
                          (reinterpret_cast<uintptr_t>(g.C) & 15) == 0 && (g.epilogue != 3 || (g.h_ld & 3) == 0);
-      EpiCtx c{&P, acc_full, acc_empty, sEpi + warp * L::EPI_STAGE, tmem_base, t0, t1, k_chunks};
+      EpiCtx c{&P, &tmaps.c[gi], acc_full, acc_empty, sEpi + warp * L::EPI_STAGE, tmem_base, t0, t1, k_chunks};
       if (g.epilogue == 1) epilogue_role<BN, MULTI, NACC, 1, false>(c);
       else if (g.epilogue == 0) { if (dense) epilogue_role<BN, MULTI, NACC, 0, true>(c); else epilogue_role<BN, MULTI, NACC, 0, false>(c); }
       else if (g.epilogue == 2) { if (dense) epilogue_role<BN, MULTI, NACC, 2, true>(c); else epilogue_role<BN, MULTI, NACC, 2, false>(c); }
@@ -774,15 +804,16 @@ EncodeTiledFn encode_tiled() {
   }();
   return fn;
 }
-// A [M, K] fp32, row pitch a_s1 floats, as a {K, M} tensor read in boxes of {32, 128} (out-of-range parts read as zero)
-bool make_a_map(CUtensorMap* map, const e3b_gemm_problem& p) {
+// a row-major fp32 matrix [rows, cols] with a row pitch of `pitch` floats as a {cols, rows} tensor accessed in boxes of
+// {32, box_rows} with the 128-byte swizzle (out-of-range parts read as zero / are not written)
+bool make_map(CUtensorMap* map, const float* base, int64_t rows, int64_t cols, int64_t pitch, int box_rows) {
   EncodeTiledFn enc = encode_tiled();
   if (!enc) return false;
-  const cuuint64_t dims[2] = {(cuuint64_t)p.K, (cuuint64_t)p.M};
-  const cuuint64_t strides[1] = {(cuuint64_t)p.a_s1 * 4};
-  const cuuint32_t box[2] = {(cuuint32_t)BK, (cuuint32_t)BM};
+  const cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+  const cuuint64_t strides[1] = {(cuuint64_t)pitch * 4};
+  const cuuint32_t box[2] = {(cuuint32_t)BK, (cuuint32_t)box_rows};
   const cuuint32_t estr[2] = {1, 1};
-  return enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(p.A), dims, strides, box, estr,
+  return enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(base), dims, strides, box, estr,
              CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
              CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
@@ -863,7 +894,12 @@ extern "C" int e3b_gemm_run(const e3b_gemm_problem* problems, int32_t n, void* s
       // TMA for A: K-long (the A ring streams), plain rows of a row-major matrix, no row map
       static const int tma_env = [] { const char* v = getenv("E3B_GEMM_TMA"); return v ? atoi(v) : 1; }();
       P.tma = (tma_env && mu && P.k_chunks > 4 && p.a_d == 1 && !p.row_map && p.a_s1 >= p.K && p.a_s1 < (1ll << 38) &&
-               make_a_map(&tm.a[b.n], p)) ? 1 : 0;
+               make_map(&tm.a[b.n], p.A, p.M, p.K, p.a_s1, BM)) ? 1 : 0;
+      // TMA for C: plain rows of a row-major matrix written by epilogue 0 / 2, large enough to matter
+      const bool dense = p.c_s3 == 1 && (p.c_s1 & 3) == 0 && (p.N & 3) == 0 && (reinterpret_cast<uintptr_t>(p.C) & 15) == 0;
+      P.tma_c = (tma_env && dense && p.c_d == 1 && !p.row_map && !p.accumulate && (p.epilogue == 0 || p.epilogue == 2) &&
+                 p.c_s1 >= p.N && p.c_s1 < (1ll << 38) && (int64_t)p.M * p.N >= (1 << 22) &&
+                 make_map(&tm.c[b.n], p.C, p.M, p.N, p.c_s1, 32)) ? 1 : 0;
     }
     work[b.n] = (double)P.m_tiles * P.n_tiles * (P.k_chunks + 2);
     total_work += work[b.n];

@@ -175,3 +175,25 @@ def test_gemm_long_k_many_row_tiles(M, N, K):
     ops.gemm_tf32x3(A, B, C, M, N, K, alpha=0.5, epilogue=3, H=H, act_cst=cst)
     ref3 = ref * (cst * torch.sigmoid(z.double())).cpu()
     assert _rel(C, ref3) < 4e-6
+
+
+@pytest.mark.parametrize("M,N,K", [(70001, 1920, 64), (150011, 64, 64), (40003, 200, 8)])
+def test_gemm_tensor_store_of_plain_outputs(M, N, K):
+    """large plain row-major outputs of epilogues 0 / 2 leave through TMA tensor stores (one swizzled 32 x 32 block per
+    epilogue warp and column step): ragged last row tile, N not a multiple of 32, untouched neighbours"""
+    g = torch.Generator(device=DEV).manual_seed(M + N + K)
+    A = torch.randn(M, K, generator=g, device=DEV)
+    B = torch.randn(N, K, generator=g, device=DEV)
+    acc = 0.25 * (A.double() @ B.double().T)
+    pitch = N + 8
+    buf = torch.full((M + 1, pitch), 3.0, device=DEV)
+    C = buf[:M, :N]
+    (Bp,) = ops.gemm_pack([(B, 0, K, 0, 1, 1, 0, N, K)])
+    ops.gemm_run([ops.gemm_problem(A, Bp, buf, M, c_rows=(pitch, 0, 1), alpha=0.25)])
+    assert _rel(C, acc.cpu()) < 2e-6
+    assert bool((buf[:M, N:] == 3.0).all()) and bool((buf[M] == 3.0).all())
+    cst = 1.7
+    ops.gemm_run([ops.gemm_problem(A, Bp, buf, M, c_rows=(pitch, 0, 1), alpha=0.25, epilogue=2, act_cst=cst)])
+    ref = cst * (torch.nn.functional.softplus(acc) - 0.6931471805599453)
+    assert _rel(C, ref.cpu()) < 4e-6
+    assert bool((buf[:M, N:] == 3.0).all()) and bool((buf[M] == 3.0).all())
