@@ -306,7 +306,7 @@ def tp_bwd_bytes(E, N, st_mul_dims):
     return E * (8 * W + 8) + N * (24 + 8 * D_in + 4 * D_mid)
 
 
-def training_step_time(model, batches, attrs, n_atoms_list, world, dev, dist, steps=4, warmup=2):
+def training_step_time(model, batches, attrs, n_atoms_list, world, dev, dist, steps=None, warmup=None):
     """One optimiser step of config_energy_force per batch: neighbour list, forward, position gradient WITH
     its graph (second-order mode of GradientOutput), the reference's loss 1e3 MSE(E) + 3e4 MSE(F)
     (config_energy_force.py:30), backward to the parameters with the flat-gradient all-reduce issued bucket by bucket
@@ -314,6 +314,10 @@ def training_step_time(model, batches, attrs, n_atoms_list, world, dev, dist, st
     from e3_layers.data import Batch, computeEdgeIndex
     from e3b200 import optim
 
+    # one untimed pass over every batch of the rotation first: the timed steps then run on shapes the caching allocator has
+    # seen (with 2 warm-up steps the timed region paid cudaMalloc for new shapes on some hosts: 64 vs 96 ms per step)
+    steps = steps or len(batches)
+    warmup = warmup or len(batches)
     model.train()
     state = {k: v.detach().clone() for k, v in model.state_dict().items()}
     opt = optim.FlatAdam(model, lr=1e-4)          # flat parameter / gradient buffers, fused Adam kernel

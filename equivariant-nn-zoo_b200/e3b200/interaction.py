@@ -308,8 +308,37 @@ class _Interaction(torch.autograd.Function):
             written.add(o)
         if len(written) < len(fi.feat_in):
             xl.zero_()
-        with ops.stage("f.linear_1"):
-            for wave in _waves(probs):
+        lin1_waves = _waves(probs)
+        # ---- self-connection into conv (imu); the linear map after the reduction accumulates into it below
+        post, sc = conv.tp.linear, conv.sc
+        cv = new(N, fi.Dconv)
+        # (the self-connection writes first: its reducing epilogue stores whole sectors without reading;
+        #  the dense epilogue of the linear map then accumulates with coalesced read-modify-writes)
+        sc_probs, written = [], set()
+        sets = fi.sc_sets(grp) if grp is not None else None
+        for q, (i1, i2, o, off, alpha) in enumerate(sc.paths):
+            bi, bo = fi.feat_in[i1], fi.conv_out[o]
+            if grp is not None:
+                # attributes = a function of the species: one K = mul GEMM per path with the species' contracted weight
+                # (rows in species order through grp.row_map), 1/V of the flops of the attribute-contraction epilogue
+                g = ops.gemm_problem(x_imu, sets["fwd"][q], cv, grp.n_virtual * bi.ir.dim, a_off=fi.x_off[i1],
+                                     a_rows=(fi.Din, bi.mul, bi.ir.dim), c_off=fi.c_off[o],
+                                     c_rows=(fi.Dconv, bo.mul, bo.ir.dim), alpha=alpha, groups=grp)
+            else:
+                g = ops.gemm_problem(x_imu, P["sc"][q], cv, N * bi.ir.dim, a_off=fi.x_off[i1],
+                                     a_rows=(fi.Din, bi.mul, bi.ir.dim), c_off=fi.c_off[o],
+                                     c_rows=(fi.Dconv, bo.mul, bo.ir.dim), alpha=alpha, epilogue=1, aux=attrs,
+                                     aux_d=bi.ir.dim, aux_group=fi.Vg)
+            sc_probs.append((g, o, False))
+            written.add(o)
+        if len(written | {o for _, o, _, _ in post.paths}) < len(fi.conv_out):
+            cv.zero_()
+        # linear_1 and the self-connection read the same rows and (per species) have the same K <= 64, N <= 64 shape: their
+        # first waves share one grouped launch
+        sc_waves = _waves(sc_probs)
+        with ops.stage("f.linear_1+self_connection"):
+            ops.gemm_run(lin1_waves[0] + sc_waves[0])
+            for wave in lin1_waves[1:] + sc_waves[1:]:
                 ops.gemm_run(wave)
         # ---- last layer of the radial MLP (the hidden layers are the shared `_RadialHidden` node)
         hs = fi.hs
@@ -333,26 +362,6 @@ class _Interaction(torch.autograd.Function):
         count_launch()
         # ---- post-reduction linear (scaled by 1/sqrt(avg_num_neighbors)) + self-connection, both into conv (imu)
         post, sc = conv.tp.linear, conv.sc
-        cv = new(N, fi.Dconv)
-        # (the self-connection writes first: its reducing epilogue stores whole sectors without reading;
-        #  the dense epilogue of the linear map then accumulates with coalesced read-modify-writes)
-        sc_probs, written = [], set()
-        sets = fi.sc_sets(grp) if grp is not None else None
-        for q, (i1, i2, o, off, alpha) in enumerate(sc.paths):
-            bi, bo = fi.feat_in[i1], fi.conv_out[o]
-            if grp is not None:
-                # attributes = a function of the species: one K = mul GEMM per path with the species' contracted weight
-                # (rows in species order through grp.row_map), 1/V of the flops of the attribute-contraction epilogue
-                g = ops.gemm_problem(x_imu, sets["fwd"][q], cv, grp.n_virtual * bi.ir.dim, a_off=fi.x_off[i1],
-                                     a_rows=(fi.Din, bi.mul, bi.ir.dim), c_off=fi.c_off[o],
-                                     c_rows=(fi.Dconv, bo.mul, bo.ir.dim), alpha=alpha, groups=grp)
-            else:
-                g = ops.gemm_problem(x_imu, P["sc"][q], cv, N * bi.ir.dim, a_off=fi.x_off[i1],
-                                     a_rows=(fi.Din, bi.mul, bi.ir.dim), c_off=fi.c_off[o],
-                                     c_rows=(fi.Dconv, bo.mul, bo.ir.dim), alpha=alpha, epilogue=1, aux=attrs,
-                                     aux_d=bi.ir.dim, aux_group=fi.Vg)
-            sc_probs.append((g, o, False))
-            written.add(o)
         probs = []
         for q, (i, o, off, alpha) in enumerate(post.paths):
             bi, bo = fi.mid[i], fi.conv_out[o]
@@ -360,11 +369,6 @@ class _Interaction(torch.autograd.Function):
                                            a_rows=(fi.Dmid, bi.mul, bi.ir.dim), c_off=fi.c_off[o],
                                            c_rows=(fi.Dconv, bo.mul, bo.ir.dim), alpha=alpha * fi.inv_sqrt_avg),
                           o, o in written))
-        if len(written | {o for _, o, _ in probs}) < len(fi.conv_out):
-            cv.zero_()
-        with ops.stage("f.self_connection"):
-            for wave in _waves(sc_probs):
-                ops.gemm_run(wave)
         with ops.stage("f.post_linear"):
             for wave in _waves(probs):
                 ops.gemm_run(wave)

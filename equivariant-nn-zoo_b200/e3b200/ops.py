@@ -1292,7 +1292,19 @@ def k_sc(spec, src, attrs, W, to_out):
                 views.append((W, off, 1, mo, V * mo, Vg, V, mo * Vg, m1) if to_out else (W, off, V * mo, mo, 1, Vg, V, m1 * Vg, mo))
             else:
                 views.append((W, off, 1, 0, mo, 1, 0, mo, m1) if to_out else (W, off, mo, 0, 1, 1, 0, m1, mo))
-        packs = gemm_pack(views)
+        # a parameter is packed once per version and direction (forward, backward and the second-order passes of a training
+        # step all see the same weights); anything else (a cotangent standing in for W) is packed on the spot
+        packs = None
+        if isinstance(W, torch.nn.Parameter):
+            cache = spec.__dict__.setdefault("_pack_cache", {})
+            key = (WEIGHTS_EPOCH, W.data_ptr(), W._version)
+            hit = cache.get(to_out)
+            if hit is not None and hit[0] == key:
+                packs = hit[1]
+        if packs is None:
+            packs = gemm_pack(views)
+            if isinstance(W, torch.nn.Parameter):
+                cache[to_out] = (key, packs)
         extra, rows = (dict(epilogue=1, aux=attrs, aux_group=Vg) if V else {}), N
     D_src, D_dst = (spec.Din, spec.Dout) if to_out else (spec.Dout, spec.Din)
     dst = torch.empty(N, D_dst, dtype=torch.float32, device=src.device)
