@@ -446,7 +446,12 @@ __global__ void __launch_bounds__(NTHREADS, 1) gemm_tf32x3_kernel(const __grid_c
   const Problem& P = batch.pr[gi];
   const e3b_gemm_problem& g = P.p;
   const int local = (int)blockIdx.x - P.cta_begin;
-  const int n_all = P.m_tiles * P.n_tiles;
+  int m_tiles = P.m_tiles;
+  if (g.n_blocks) {                                   // grouped rows: only the blocks of 128 row groups in use (a_d tiles each)
+    const int used = __ldg(g.n_blocks) * g.a_d;
+    m_tiles = used < m_tiles ? used : m_tiles;
+  }
+  const int n_all = m_tiles * P.n_tiles;
   const int t0 = (int)((int64_t)local * n_all / P.n_ctas), t1 = (int)((int64_t)(local + 1) * n_all / P.n_ctas);
   const int k_chunks = P.k_chunks;
   const bool resident = k_chunks <= SA;

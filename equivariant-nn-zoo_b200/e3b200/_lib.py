@@ -37,7 +37,7 @@ class GemmProblem(ctypes.Structure):
                 ("c_s1", c_i64), ("c_s2", c_i64), ("c_s3", c_i64), ("c_d", c_i32), ("aux", c_vp), ("aux_ld", c_i64),
                 ("aux_d", c_i32), ("V", c_i32), ("aux_cols", c_i32), ("H", c_vp), ("h_ld", c_i64), ("M", c_i32), ("N", c_i32), ("K", c_i32),
                 ("epilogue", c_i32), ("accumulate", c_i32), ("alpha", c_f32), ("act_cst", c_f32), ("row_map", c_vp),
-                ("b_sel", c_vp), ("b_set_stride", c_i64)]
+                ("b_sel", c_vp), ("n_blocks", c_vp), ("b_set_stride", c_i64)]
 
 
 class GemmPackDesc(ctypes.Structure):

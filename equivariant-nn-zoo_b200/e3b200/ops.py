@@ -990,16 +990,18 @@ def gemm_problem(A, Bp, C, M, a_off=0, a_rows=None, c_off=0, c_rows=None, c_col_
     if groups is not None:
         assert Bp.n_sets == groups.n_sets and a_d == c_d
         g.row_map, g.b_sel, g.b_set_stride = groups.row_map.data_ptr(), groups.b_sel.data_ptr(), Bp.set_floats
+        g.n_blocks = groups.n_blocks.data_ptr()
     else:
-        g.row_map, g.b_sel, g.b_set_stride = None, None, 0
+        g.row_map, g.b_sel, g.b_set_stride, g.n_blocks = None, None, 0, None
     return g
 
 
 class RowGroups:
     """Rows (nodes) of a grouped GEMM in VIRTUAL order: sorted by weight set (species), every set padded to a multiple
     of 128 rows.  row_map [n_virtual] int32: virtual -> actual row (-1 = padding); b_sel [n_virtual / 128] int32: the
-    weight set of every block; table [n_sets, V]: the attribute row of every set; params: what `table` depends on."""
-    __slots__ = ("row_map", "b_sel", "n_virtual", "n_sets", "table", "params")
+    weight set of every block; n_blocks [1] int32: blocks in use (the kernel skips the rest of the static bound n_virtual);
+    table [n_sets, V]: the attribute row of every set; params: what `table` depends on."""
+    __slots__ = ("row_map", "b_sel", "n_blocks", "n_virtual", "n_sets", "table", "params")
 
 
 def species_row_groups(idx, n_sets):
@@ -1018,6 +1020,7 @@ def species_row_groups(idx, n_sets):
     g.row_map = torch.full((NB * 128,), -1, dtype=torch.int32, device=dev)
     g.row_map.scatter_(0, slot, torch.arange(N, dtype=torch.int32, device=dev))
     g.b_sel = torch.searchsorted(bend, torch.arange(NB, device=dev), right=True).clamp_(max=n_sets - 1).to(torch.int32)
+    g.n_blocks = bend[-1:].to(torch.int32)
     g.n_virtual, g.n_sets, g.table, g.params = NB * 128, n_sets, None, ()
     return g
 

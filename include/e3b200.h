@@ -341,6 +341,8 @@ typedef struct {
   float alpha, act_cst;
   const int32_t* row_map;  /* grouped rows: virtual row group -> actual row group of A and C, < 0 = padding (or NULL) */
   const int32_t* b_sel;    /* weight set of every block of 128 virtual row groups (or NULL) */
+  const int32_t* n_blocks; /* device scalar (or NULL): blocks of 128 virtual row groups actually in use; row tiles past
+                              them are skipped (M, a static bound, keeps the launch shape independent of the batch) */
   int64_t b_set_stride;    /* floats between consecutive weight sets in B_packed */
 } e3b_gemm_problem;
 

@@ -25,3 +25,6 @@ def test_species_row_groups(N, S):
     same = species[1:] == species[:-1]
     assert bool((rm[slots][1:][same] > rm[slots][:-1][same]).all())     # stable inside a species
     assert int(grp.b_sel.min()) >= 0 and int(grp.b_sel.max()) < S
+    used = int(grp.n_blocks)                                            # the kernel stops after the blocks in use
+    assert grp.n_blocks.dtype == torch.int32 and used == int(slots.max()) // 128 + 1
+    assert bool((rm[used * 128:] < 0).all())
