@@ -1437,6 +1437,7 @@ template <typename T, bool BWD>
 __global__ void __launch_bounds__(256) gate_imu_kernel(const __grid_constant__ GateLayout L, const T* __restrict__ in,
                                                        const T* __restrict__ g_mi, const T* __restrict__ g_imu, int64_t n,
                                                        T* __restrict__ out_mi, T* __restrict__ out_imu, T* __restrict__ gin) {
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");   // lets a dependent launch set itself up while this grid drains
   const int n_items = L.n_scalars + L.n_gates;
   for (int64_t row = blockIdx.x; row < n; row += gridDim.x) {
     const T* xin = in + row * L.in_dim;

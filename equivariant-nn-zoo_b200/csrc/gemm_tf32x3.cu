@@ -446,16 +446,14 @@ __global__ void __launch_bounds__(NTHREADS, 1) gemm_tf32x3_kernel(const __grid_c
   const Problem& P = batch.pr[gi];
   const e3b_gemm_problem& g = P.p;
   const int local = (int)blockIdx.x - P.cta_begin;
-  int m_tiles = P.m_tiles;
-  if (g.n_blocks) {                                   // grouped rows: only the blocks of 128 row groups in use (a_d tiles each)
-    const int used = __ldg(g.n_blocks) * g.a_d;
-    m_tiles = used < m_tiles ? used : m_tiles;
-  }
-  const int n_all = m_tiles * P.n_tiles;
-  const int t0 = (int)((int64_t)local * n_all / P.n_ctas), t1 = (int)((int64_t)(local + 1) * n_all / P.n_ctas);
   const int k_chunks = P.k_chunks;
   const bool resident = k_chunks <= SA;
   const bool tma = MULTI && P.tma != 0;               // host: only with a streaming A ring (!resident)
+  // Programmatic dependent launch: the next kernel of the stream may be scheduled as soon as every CTA of this one has
+  // passed this point (it waits for our completion before touching memory), and this kernel's own set-up below -- tensor
+  // memory allocation, barrier initialisation -- runs while the previous kernel drains; nothing a predecessor wrote is
+  // read before griddepcontrol.wait.
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
 
   if (warp == 17) {  // TMEM allocation is warp-collective; the same warp frees it
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_addr(&tmem_base_smem)), "r"(512u) : "memory");
@@ -473,6 +471,14 @@ __global__ void __launch_bounds__(NTHREADS, 1) gemm_tf32x3_kernel(const __grid_c
   tc_fence_after();
   const uint32_t tmem_base = tmem_base_smem;
   const uint32_t tmem_a0 = tmem_base + NACC * BN;     // first A stage
+  asm volatile("griddepcontrol.wait;" ::: "memory");  // everything launched before this kernel has completed
+  int m_tiles = P.m_tiles;
+  if (g.n_blocks) {                                   // grouped rows: only the blocks of 128 row groups in use (a_d tiles each)
+    const int used = __ldg(g.n_blocks) * g.a_d;
+    m_tiles = used < m_tiles ? used : m_tiles;
+  }
+  const int n_all = m_tiles * P.n_tiles;
+  const int t0 = (int)((int64_t)local * n_all / P.n_ctas), t1 = (int)((int64_t)(local + 1) * n_all / P.n_ctas);
 
   if (t1 > t0) {
     if (warp >= 8 && warp < 16) {
@@ -788,8 +794,18 @@ cudaError_t launch(const Batch& b, const TmapBatch& tm, int ctas, cudaStream_t s
     if (e != cudaSuccess) return e;
     attr_set = true;
   }
-  gemm_tf32x3_kernel<BN, MULTI, NACC, SA, PRAW, SB><<<ctas, NTHREADS, L::BYTES, st>>>(b, tm);
-  return cudaGetLastError();
+  static const int pdl = [] { const char* v = getenv("E3B_PDL"); return v ? atoi(v) : 1; }();
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3((unsigned)ctas);
+  cfg.blockDim = dim3(NTHREADS);
+  cfg.dynamicSmemBytes = L::BYTES;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = pdl ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, gemm_tf32x3_kernel<BN, MULTI, NACC, SA, PRAW, SB>, b, tm);
 }
 
 int tile_n(int N, int K) { return (K <= KSEG * BK && N > 64) ? 128 : 64; }

@@ -271,6 +271,7 @@ def emit_structure(E, sid, st):
     E("#ifdef __CUDACC__")
     E(f"template <int MUL> __global__ void __launch_bounds__(32 * {G} * (MUL / 32)) tpfp_S{sid}(const TpArgs<float> a) {{")
     E("  typedef float T;")
+    E("  asm volatile(\"griddepcontrol.launch_dependents;\" ::: \"memory\");   // a dependent launch (the tcgen05 GEMM that follows) may set itself up while this grid drains")
     E(f"  constexpr int G = {G}, ROW_W = {n_paths} * MUL, ROW_X = {xdim} * MUL, STAGE = ROW_W + ROW_X, SH_DIM = {sdim};")
     E("  constexpr int NT = 32 * G * (MUL / 32);")
     E("  extern __shared__ __align__(128) unsigned char tpp_smem[];")
@@ -379,6 +380,7 @@ def emit_structure(E, sid, st):
     # partials are stored directly (fire-and-forget)
     E(f"template <int MUL> __global__ void __launch_bounds__(32 * {G} * (MUL / 32)) tpbp_S{sid}(const TpArgs<float> a) {{")
     E("  typedef float T;")
+    E("  asm volatile(\"griddepcontrol.launch_dependents;\" ::: \"memory\");   // a dependent launch (the tcgen05 GEMM that follows) may set itself up while this grid drains")
     E(f"  constexpr int G = {G}, ROW_W = {n_paths} * MUL, ROW_X = {xdim} * MUL, STAGE = ROW_W + ROW_X, SH_DIM = {sdim};")
     E("  constexpr int NT = 32 * G * (MUL / 32);")
     E("  constexpr int mul = MUL; constexpr bool active = true;")
