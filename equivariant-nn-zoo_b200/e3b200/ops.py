@@ -3,6 +3,7 @@ streams, autograd tape); every op below launches hand-written sm_100a kernels th
 and raises if the library or a CUDA device is missing."""
 import ctypes
 import os
+import weakref
 
 import torch
 from torch.autograd.function import once_differentiable
@@ -1001,7 +1002,13 @@ class RowGroups:
     of 128 rows.  row_map [n_virtual] int32: virtual -> actual row (-1 = padding); b_sel [n_virtual / 128] int32: the
     weight set of every block; n_blocks [1] int32: blocks in use (the kernel skips the rest of the static bound n_virtual);
     table [n_sets, V]: the attribute row of every set; params: what `table` depends on."""
-    __slots__ = ("row_map", "b_sel", "n_blocks", "n_virtual", "n_sets", "table", "params")
+    __slots__ = ("row_map", "b_sel", "n_blocks", "n_virtual", "n_sets", "table", "params", "idx", "_onehot")
+
+    def onehot(self):
+        """[N, n_sets] float32 membership rows (the expansion operand of the weight-gradient kernel)"""
+        if self._onehot is None:
+            self._onehot = torch.nn.functional.one_hot(self.idx, self.n_sets).to(torch.float32).contiguous()
+        return self._onehot
 
 
 def species_row_groups(idx, n_sets):
@@ -1021,6 +1028,7 @@ def species_row_groups(idx, n_sets):
     g.row_map.scatter_(0, slot, torch.arange(N, dtype=torch.int32, device=dev))
     g.b_sel = torch.searchsorted(bend, torch.arange(NB, device=dev), right=True).clamp_(max=n_sets - 1).to(torch.int32)
     g.n_blocks = bend[-1:].to(torch.int32)
+    g.idx, g._onehot = idx, None
     g.n_virtual, g.n_sets, g.table, g.params = NB * 128, n_sets, None, ()
     return g
 
@@ -1183,13 +1191,28 @@ def k_wgrad(x, g, alpha=1.0):
 FORCE_DENSE_FUNCTION = False       # tests: take this path on CPU tensors too (with the launcher replaced)
 
 
+_DENSE_PACKS = {}
+
+
 def k_dense(x, W, alpha, trans):
     """alpha * x @ (W^T if trans else W); x [M, K] contiguous fp32, W a 2-D fp32 view (any strides)"""
     require_cuda(x, W)
     M, K = x.shape
     N = W.shape[0] if trans else W.shape[1]
     s_n, s_k = (W.stride(0), W.stride(1)) if trans else (W.stride(1), W.stride(0))
-    (Bp,) = gemm_pack([(W, 0, s_n, 0, s_k, 1, 0, N, K)])
+    Bp = None
+    if isinstance(W, torch.nn.Parameter):      # packed once per parameter version and orientation (see k_sc)
+        key = (id(W), trans)
+        hit = _DENSE_PACKS.get(key)
+        ver = (WEIGHTS_EPOCH, W._version, W.data_ptr())
+        if hit is not None and hit[0] == ver and hit[2]() is W:      # the same live parameter object, unchanged
+            Bp = hit[1]
+    if Bp is None:
+        (Bp,) = gemm_pack([(W, 0, s_n, 0, s_k, 1, 0, N, K)])
+        if isinstance(W, torch.nn.Parameter):
+            if len(_DENSE_PACKS) > 256:
+                _DENSE_PACKS.clear()
+            _DENSE_PACKS[key] = (ver, Bp, weakref.ref(W))
     out = torch.empty(M, N, dtype=torch.float32, device=x.device)
     gemm_run([gemm_problem(x, Bp, out, M, alpha=alpha)])
     return out
@@ -1311,25 +1334,48 @@ def k_sc(spec, src, attrs, W, to_out):
         extra, rows = (dict(epilogue=1, aux=attrs, aux_group=Vg) if V else {}), N
     D_src, D_dst = (spec.Din, spec.Dout) if to_out else (spec.Dout, spec.Din)
     dst = torch.empty(N, D_dst, dtype=torch.float32, device=src.device)
-    probs, written = [], set()
-    for q, (i, o, off, alpha) in enumerate(spec.paths):
-        bi, bo = spec.irreps_in[i], spec.irreps_out[o]
-        d = bi.ir.dim
-        if V and grp is None:
-            extra["aux_d"] = d
-        if to_out:
-            g = gemm_problem(src, packs[q], dst, rows * d, a_off=spec.x_off[i], a_rows=(D_src, bi.mul, d), c_off=spec.c_off[o],
-                             c_rows=(D_dst, bo.mul, d), alpha=alpha, **extra)
-            tgt = o
-        else:
-            g = gemm_problem(src, packs[q], dst, rows * d, a_off=spec.c_off[o], a_rows=(D_src, bo.mul, d), c_off=spec.x_off[i],
-                             c_rows=(D_dst, bi.mul, d), alpha=alpha, **extra)
-            tgt = i
-        probs.append((g, tgt, False))
-        written.add(tgt)
-    if len(written) < len(spec.irreps_out if to_out else spec.irreps_in):
+    # The problem descriptors of a (spec, direction, grouped?) combination are built once; a call then only patches the
+    # pointers and the row count (filling ~30 ctypes fields per path was most of the host time of a training step).
+    tkey = (to_out, grp is not None)
+    tcache = spec.__dict__.setdefault("_prob_cache", {})
+    tmpl = tcache.get(tkey)
+    if tmpl is None:
+        probs, written = [], set()
+        meta = []
+        for q, (i, o, off, alpha) in enumerate(spec.paths):
+            bi, bo = spec.irreps_in[i], spec.irreps_out[o]
+            d = bi.ir.dim
+            if V and grp is None:
+                extra["aux_d"] = d
+            if to_out:
+                a_off, c_off, tgt = spec.x_off[i], spec.c_off[o], o
+                g = gemm_problem(src, packs[q], dst, rows * d, a_off=a_off, a_rows=(D_src, bi.mul, d), c_off=c_off,
+                                 c_rows=(D_dst, bo.mul, d), alpha=alpha, **extra)
+            else:
+                a_off, c_off, tgt = spec.c_off[o], spec.x_off[i], i
+                g = gemm_problem(src, packs[q], dst, rows * d, a_off=a_off, a_rows=(D_src, bo.mul, d), c_off=c_off,
+                                 c_rows=(D_dst, bi.mul, d), alpha=alpha, **extra)
+            probs.append((g, tgt, False))
+            meta.append((g, q, 4 * a_off, 4 * c_off, d))
+            written.add(tgt)
+        zero = len(written) < len(spec.irreps_out if to_out else spec.irreps_in)
+        tmpl = (meta, gemm_waves(probs), zero)
+        tcache[tkey] = tmpl
+    else:
+        meta = tmpl[0]
+        sp, dp = src.data_ptr(), dst.data_ptr()
+        ap = attrs.data_ptr() if (V and grp is None) else None
+        if ap is not None:
+            assert attrs.is_contiguous() and attrs.dtype == torch.float32
+        for g, q, a_off, c_off, d in meta:
+            g.A, g.C, g.M, g.B_packed = sp + a_off, dp + c_off, rows * d, packs[q].buf.data_ptr()
+            if ap is not None:
+                g.aux = ap
+            if grp is not None:
+                g.row_map, g.b_sel, g.n_blocks = grp.row_map.data_ptr(), grp.b_sel.data_ptr(), grp.n_blocks.data_ptr()
+    if tmpl[2]:
         dst.zero_()
-    for wave in gemm_waves(probs):
+    for wave in tmpl[1]:
         gemm_run(wave)
     return dst
 
@@ -1457,7 +1503,141 @@ class _SC(torch.autograd.Function):
 
 
 def self_connection(x_imu, attrs, W, spec):
+    grp = species_groups_of(attrs) if (SPECIES_SC and spec.V) else None
+    if grp is not None:
+        return self_connection_species(x_imu, attrs, W, spec, grp)
     return _SC.apply(x_imu.contiguous(), attrs.contiguous(), W.contiguous(), spec, True)
+
+
+def k_scg(spec, src, packs, grp, to_out):
+    """y[z,d,w] = alpha sum_u Weff[s(z)][u,w] src[z,d,u] (to_out) or gx[z,d,u] = alpha sum_w Weff[s(z)][u,w] src[z,d,w]:
+    one grouped-row tcgen05 GEMM per irreps path, `packs` = the species weight sets of that direction"""
+    require_cuda(src)
+    N = src.shape[0]
+    D_src, D_dst = (spec.Din, spec.Dout) if to_out else (spec.Dout, spec.Din)
+    dst = torch.empty(N, D_dst, dtype=torch.float32, device=src.device)
+    tcache = spec.__dict__.setdefault("_prob_cache", {})
+    tmpl = tcache.get(("scg", to_out))
+    if tmpl is None:
+        probs, written, meta = [], set(), []
+        for q, (i, o, off, alpha) in enumerate(spec.paths):
+            bi, bo = spec.irreps_in[i], spec.irreps_out[o]
+            d = bi.ir.dim
+            if to_out:
+                a_off, c_off, tgt, ma, mc = spec.x_off[i], spec.c_off[o], o, bi.mul, bo.mul
+            else:
+                a_off, c_off, tgt, ma, mc = spec.c_off[o], spec.x_off[i], i, bo.mul, bi.mul
+            g = gemm_problem(src, packs[q], dst, grp.n_virtual * d, a_off=a_off, a_rows=(D_src, ma, d), c_off=c_off,
+                             c_rows=(D_dst, mc, d), alpha=alpha, groups=grp)
+            probs.append((g, tgt, False))
+            meta.append((g, q, 4 * a_off, 4 * c_off, d))
+            written.add(tgt)
+        tmpl = (meta, gemm_waves(probs), len(written) < len(spec.irreps_out if to_out else spec.irreps_in))
+        tcache[("scg", to_out)] = tmpl
+    else:
+        sp, dp = src.data_ptr(), dst.data_ptr()
+        rm, bs, nb = grp.row_map.data_ptr(), grp.b_sel.data_ptr(), grp.n_blocks.data_ptr()
+        for g, q, a_off, c_off, d in tmpl[0]:
+            g.A, g.C, g.M, g.B_packed = sp + a_off, dp + c_off, grp.n_virtual * d, packs[q].buf.data_ptr()
+            g.row_map, g.b_sel, g.n_blocks = rm, bs, nb
+    if tmpl[2]:
+        dst.zero_()
+    for wave in tmpl[1]:
+        gemm_run(wave)
+    return dst
+
+
+def _scg_layout(spec, S):
+    """offsets of the per-path blocks [S, mul_in, mul_out] inside the flat species weight"""
+    offs, o = [], 0
+    for i, oo, _, _ in spec.paths:
+        offs.append(o)
+        o += S * spec.irreps_in[i].mul * spec.irreps_out[oo].mul
+    return offs, o
+
+
+def _scg_weight_grad(spec, x, g, grp):
+    """dWeff[s][u,w] = alpha sum_{z of species s, d} x[z,d,u] g[z,d,w] per path.  No graph being recorded: the split-K
+    tcgen05 kernel with the one-hot species rows as the expansion operand, written straight into the flat layout;
+    otherwise plain torch contractions (differentiable again)."""
+    S = grp.n_sets
+    offs, total = _scg_layout(spec, S)
+    N = x.shape[0]
+    if not torch.is_grad_enabled() and wgrad_supported(x, g) and x.is_contiguous() and g.is_contiguous():
+        out = torch.empty(total, dtype=torch.float32, device=x.device)
+        onehot = grp.onehot()
+        probs = []
+        for (i, o, _, alpha), off in zip(spec.paths, offs):
+            bi, bo = spec.irreps_in[i], spec.irreps_out[o]
+            d = bi.ir.dim
+            probs.append(wgrad_problem(x, g, out, N * d, bi.mul, bo.mul, a_off=spec.x_off[i], a_rows=(spec.Din, bi.mul, d),
+                                       b_off=spec.c_off[o], b_rows=(spec.Dout, bo.mul, d), aux=onehot, aux_d=d, c_off=off,
+                                       c_rows=(bi.mul * bo.mul, bo.mul, bi.mul), alpha=alpha))
+        wgrad_run(probs, x.device)
+        return out
+    onehot = grp.onehot().to(x.dtype)
+    pieces = []
+    for i, o, _, alpha in spec.paths:
+        bi, bo = spec.irreps_in[i], spec.irreps_out[o]
+        xb = x[:, spec.x_off[i]:spec.x_off[i] + bi.dim].reshape(N, bi.ir.dim, bi.mul)
+        gb = g[:, spec.c_off[o]:spec.c_off[o] + bo.dim].reshape(N, bi.ir.dim, bo.mul)
+        t = torch.bmm(xb.transpose(1, 2), gb).reshape(N, bi.mul * bo.mul)               # [z, (u, w)]
+        pieces.append((alpha * (onehot.t() @ t)).reshape(-1))                            # [s, u, w]
+    return torch.cat(pieces)
+
+
+class _SCG(torch.autograd.Function):
+    """The self-connection when the node attributes are a function of the species (reference embedCategorial,
+    configs/layer_configs.py:8-30): y = S(x, Weff) with Weff[s] = sum_v table[s, v] W[:, v, :] contracted OUTSIDE this node
+    by differentiable torch ops on [S, ...] tensors, so what is left here is bilinear in (x, Weff) and per-node work never
+    sees the attribute index: no [z, mul_in * mul_out] intermediates, no attribute-gradient GEMMs.  to_out False: the
+    adjoint map in x (gx = Sx(g, Weff)); each is the other's backward plus the reduction `_scg_weight_grad`."""
+
+    @staticmethod
+    def forward(ctx, src, Weff, spec, grp, to_out):
+        ctx.spec, ctx.grp, ctx.to_out = spec, grp, to_out
+        packs = getattr(Weff, "_e3b_sets", None)
+        if packs is None:
+            S = grp.n_sets
+            offs, _ = _scg_layout(spec, S)
+            fwd, bwd = [], []
+            for (i, o, _, _), off in zip(spec.paths, offs):
+                m1, mo = spec.irreps_in[i].mul, spec.irreps_out[o].mul
+                fwd.append((Weff, off, 1, 0, mo, 1, 0, mo, m1, S, m1 * mo))
+                bwd.append((Weff, off, mo, 0, 1, 1, 0, m1, mo, S, m1 * mo))
+            packs = {True: gemm_pack(fwd), False: gemm_pack(bwd)}
+            Weff._e3b_sets = packs
+        ctx.packs = packs
+        ctx.save_for_backward(src, Weff)
+        return k_scg(spec, src, packs[to_out], grp, to_out)
+
+    @staticmethod
+    def backward(ctx, h):
+        src, Weff = ctx.saved_tensors
+        spec, grp = ctx.spec, ctx.grp
+        h = h.contiguous()
+        if getattr(Weff, "_e3b_sets", None) is None:
+            Weff._e3b_sets = ctx.packs
+        g_src = _SCG.apply(h, Weff, spec, grp, not ctx.to_out) if ctx.needs_input_grad[0] else None
+        gW = None
+        if ctx.needs_input_grad[1] and needs_grad_now(Weff):
+            x, g = (src, h) if ctx.to_out else (h, src)
+            gW = _scg_weight_grad(spec, x, g, grp)
+        return g_src, gW, None, None, None
+
+
+def self_connection_species(x_imu, attrs, W, spec, grp):
+    """`self_connection` for attributes = table[species]: the weights are contracted with the table per species by torch
+    (tiny, differentiable: gradients reach W and the embedding behind the table), the per-node work is `_SCG`"""
+    idx, S, lin = attrs._e3b_species
+    table = lin(torch.eye(S, dtype=x_imu.dtype, device=x_imu.device))                  # [S, V], tracked
+    V = spec.V
+    blocks = []
+    for i, o, off, _ in spec.paths:
+        m1, mo = spec.irreps_in[i].mul, spec.irreps_out[o].mul
+        blocks.append(torch.einsum("sv,uvw->suw", table, W[off:off + m1 * V * mo].view(m1, V, mo)).reshape(-1))
+    Weff = torch.cat(blocks)
+    return _SCG.apply(x_imu.contiguous(), Weff, spec, grp, True)
 
 
 def block_linear(x_imu, W, spec):
