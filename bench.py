@@ -548,12 +548,13 @@ def run_ours(args, wl):
         return rows, alg, tt
 
     roof = roof_bwd = None
+    traffic_bwd = None
     f = kernel_roofline("fwd", tp_bytes)
     if f:
         rows, alg, tt = f
         _, n_paths, mul, x_dim, y_dim, N0, E0 = rows[0][1]
         ach = alg / (tt * 1e-3) / 1e9
-        traffic = None     # dram bytes per launch of the same kernel from the committed ncu --set full capture
+        traffic = None     # dram bytes per launch of the same kernels from the committed ncu --set full capture
         for name in ("r2_tpfp_traffic.json",):
             tpath = os.path.join(ROOT, "profiles", name)
             if traffic is None and wl.name == "W2" and os.path.exists(tpath):
@@ -561,6 +562,10 @@ def run_ours(args, wl):
                     tj = json.load(fh)
                 if (tj.get("n_edges"), tj.get("n_nodes")) in {(tag[6], tag[5]) for _, tag in rows}:
                     traffic = tj["traffic_bytes_per_launch"]
+                    bw = tj.get("backward_tpbp_S3")
+                    if bw:
+                        traffic_bwd = bw["dram_bytes_read"] + bw["dram_bytes_write"]
+        all_fwd = sum(s.elapsed_time(e) for tag, s, e in timing if tag[0] == "fwd")
         roof = {"kernel": f"tpfp (fused gather + uvu CG tensor product + segmented sum, {n_paths} paths, mul {mul})",
                 "note": "algorithmic bytes = SURVEY 8d per directed edge (one weight row per edge); since round 2 the two directions of "
                         "an undirected edge read ONE shared weight row (the second read mostly hits L2), so `traffic` (ncu DRAM bytes) "
@@ -568,15 +573,21 @@ def run_ours(args, wl):
                 "bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": traffic,
                 "peak_source": peak_src, "timing": timing_how,
                 "algorithmic_bytes_per_launch": alg / len(rows), "avg_launch_ms": tt / len(rows),
-                "launches_timed": len(rows), "edges_per_s": sum(tag[6] for _, tag in rows) / (tt * 1e-3)}
+                "launches_timed": len(rows), "edges_per_s": sum(tag[6] for _, tag in rows) / (tt * 1e-3),
+                "share_of_step": all_fwd / ms if ms else None}
     b = kernel_roofline("bwd", tp_bwd_bytes)
     if b:
         rows, alg, tt = b
         seg = sum(s.elapsed_time(e) for tag, s, e in timing if tag[0] == "stage" and tag[1] == "b.segment_sum")
         n_seg = sum(1 for tag, s, e in timing if tag[0] == "stage" and tag[1] == "b.segment_sum")
         ach = alg / (tt * 1e-3) / 1e9
+        all_bwd = sum(s.elapsed_time(e) for tag, s, e in timing if tag[0] == "bwd")
         roof_bwd = {"kernel": f"tpbp (backward of the same kernel: dw, dx, dY; {rows[0][1][1]} paths, mul {rows[0][1][2]})",
-                    "bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": None,
+                    "note": "the single most expensive kernel of the step (share_of_step: all its launches / step time); "
+                            "bound by instruction issue (ncu: issue slots 73 % busy), not by HBM",
+                    "bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
+                    "traffic": traffic_bwd if roof is not None and roof.get("traffic") else None,
+                    "share_of_step": all_bwd / ms if ms else None,
                     "algorithmic_bytes_per_launch": alg / len(rows), "avg_launch_ms": tt / len(rows),
                     "launches_timed": len(rows),
                     "segment_sum_ms_per_step_all_layers": seg / args.steps if n_seg else 0.0}

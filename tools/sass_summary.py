@@ -1,6 +1,7 @@
 #!/usr/bin/env python3
 """SASS evidence for the shipped library: per kernel, the counts of the Blackwell-specific mnemonics (UTCHMMA = tcgen05.mma,
-LDTM / STTM = tcgen05.ld / st, UBLKCP = TMA bulk copy, UBLKRED = TMA bulk reduce-add, LDGSTS = cp.async, SYNCS = mbarrier, UTCBAR = tcgen05.commit) and of
+LDTM / STTM = tcgen05.ld / st, UTMALDG / UTMASTG = TMA tensor load / store (cp.async.bulk.tensor), ACQBULK / PREEXIT =
+griddepcontrol.wait / launch_dependents (programmatic dependent launch), UBLKCP = TMA bulk copy, UBLKRED = TMA bulk reduce-add, LDGSTS = cp.async, SYNCS = mbarrier, UTCBAR = tcgen05.commit) and of
 atomics (ATOMS = shared memory, ATOMG / REDG = global: only the CSR / cell-list cursors and the layer-norm weight gradient), plus a short excerpt around the first tensor-core instruction of the GEMM kernels.
   python tools/sass_summary.py > profiles/r2_sass_summary.txt"""
 import os
@@ -21,7 +22,8 @@ for line in sass.splitlines():
         kernels[cur].append(line)
 demangle = subprocess.run(["c++filt"], input="\n".join(kernels), capture_output=True, text=True).stdout.splitlines()
 names = dict(zip(kernels, demangle))
-KEYS = ["UTCHMMA", "LDTM", "STTM", "UTCBAR", "UBLKCP", "UBLKRED", "LDGSTS", "SYNCS", "ATOMS", "ATOMG", "REDG"]
+KEYS = ["UTCHMMA", "LDTM", "STTM", "UTCBAR", "UTMALDG", "UTMASTG", "UBLKCP", "UBLKRED", "LDGSTS", "SYNCS", "ACQBULK", "PREEXIT",
+        "ATOMS", "ATOMG", "REDG"]
 PAT = {"ATOMS": r"\bATOMS", "ATOMG": r"\bATOM(G|\.)", "REDG": r"\bRED(G|\.)"}
 print("# cuobjdump -sass equivariant-nn-zoo_b200/lib/libe3b200.so -- mnemonic counts per kernel (sm_100a)")
 print("# %-78s %s" % ("kernel", " ".join("%7s" % k for k in KEYS)))
