@@ -101,6 +101,10 @@ class Linear(nn.Module):
         if (ops.second_order_active() and self.paths and self._spec.ok and z > 0
                 and ((x.is_cuda and x.dtype == torch.float32) or ops.FORCE_DENSE_FUNCTION)):
             return self._forward_node(x)
+        if x.is_cuda and x.requires_grad and self.in_layout == "mul_ir" and not ops.second_order_active():
+            live = sorted({i for i, _, _, _ in self.paths})
+            if 0 < len(live) < len(self.irreps_in):
+                x = ops.tag_live_blocks(x, live, self.irreps_in)      # the gradient of the other blocks is exactly zero
         acc = [None] * len(self.irreps_out)
         for i, o, off, alpha in self.paths:
             mi, mo = self.irreps_in[i].mul, self.irreps_out[o].mul

@@ -134,6 +134,46 @@ class FusedInteraction:
         return out
 
 
+    def scalar_only(self):
+        """What the backward pass needs when only the block's first output block -- the 0e scalars -- has a non-zero
+        gradient (the last block under an energy read-out): the tensor-product plan restricted to the paths that produce
+        0e, the columns of those paths in the full weight row, the single path of the post-reduction linear map and of
+        the self-connection that reach that block, and the last radial layer's weight restricted to the live columns.
+        None when the layer does not have that shape."""
+        if "scalar_only" not in self._cache:
+            out = None
+            st, mul = self.structure, self.structure.uniform_mul
+            scal = self.gate.irreps_scalars
+            if (mul in (32, 64) and len(scal) and scal[0].ir.l == 0 and scal[0].ir.p == 1 and self.conv_out[0].ir == scal[0].ir
+                    and self.conv_out[0].mul == scal[0].mul and self.fc.n_layers > 1):
+                from .plan import scalar_output_restriction
+                pr = scalar_output_restriction(st)
+                idx = {(p.i_in, p.i_sh, str(p.ir_out)): q for q, p in enumerate(st.paths)}
+                cols = [idx[(p.i_in, p.i_sh, str(p.ir_out))] for p in pr.paths]
+                i0 = next((i for i, b in enumerate(self.mid) if b.ir.l == 0 and b.ir.p == 1), None)
+                post_q = [q for q, (i, o, _, _) in enumerate(self.conv.tp.linear.paths) if i == i0 and o == 0]
+                plan = ops.TPPlan(pr) if pr.paths else None
+                if (plan is not None and plan.specialized and i0 is not None and len(post_q) == 1
+                        and self.mid[i0].mul == len(pr.paths) * mul and plan.x_dim == self.conv.tp.plan.x_dim):
+                    out = {"plan": plan, "cols": cols, "post_q": post_q[0], "mid_block": i0,
+                           "sc_q": [q for q, (_, _, o, _, _) in enumerate(self.conv.sc.paths) if o == 0]}
+            self._cache["scalar_only"] = out
+        return self._cache["scalar_only"]
+
+    def scalar_only_fc(self, so):
+        """packed (backward role) last radial layer restricted to the live weight columns, per parameter version"""
+        W = getattr(self.conv.fc, f"layer{self.conv.fc.n_layers - 1}").weight
+        key = (ops.WEIGHTS_EPOCH, W.data_ptr(), W._version)
+        hit = self._cache.get("scalar_only_fc")
+        if hit is None or hit[0] != key:
+            mul = self.structure.uniform_mul
+            with torch.no_grad():
+                Wl = torch.cat([W[:, c * mul:(c + 1) * mul] for c in so["cols"]], 1).contiguous()      # [h, live]
+            hi, ho = Wl.shape
+            hit = (key, ops.gemm_pack([(Wl, 0, ho, 0, 1, 1, 0, hi, ho)])[0])
+            self._cache["scalar_only_fc"] = hit
+        return hit[1]
+
     def sc_sets(self, grp):
         """self-connection weights contracted with the attribute row of every species (`ops.sc_weight_sets`)"""
         sc = self.conv.sc
@@ -142,6 +182,8 @@ class FusedInteraction:
 
 
 SPECIES_SC_CALLS = 0      # forward passes of a block whose self-connection took the per-species path (tests)
+SCALAR_ONLY = __import__("os").environ.get("E3B_SCALAR_ONLY", "1") != "0"
+SCALAR_ONLY_CALLS = 0     # backward passes of a block restricted to the paths that reach its 0e scalars (tests)
 
 
 _waves = ops.gemm_waves
@@ -405,6 +447,16 @@ class _Interaction(torch.autograd.Function):
         if g_mi is None and g_imu is None:
             return (None,) * len(ctx.needs_input_grad)
         P = fi.packs("bwd")
+        # Only the 0e scalars of the output have a non-zero gradient (tag set by the read-out's linear map, see
+        # ops.tag_live_blocks): every path of the block that does not reach them contributes exactly zero.
+        so = None
+        live = getattr(g_mi, "_e3b_live_blocks", None) if g_mi is not None else None
+        if (SCALAR_ONLY and live is not None and g_imu is None and not need_params and not need_attrs and E > 0
+                and live == ((0,), str(fi.gate.irreps_out)) and conv.tp.plan.specialized):
+            so = fi.scalar_only()
+        if so is not None:
+            global SCALAR_ONLY_CALLS
+            SCALAR_ONLY_CALLS += 1
         # ---- gate
         g_cv = new(N, fi.Dconv)
         with ops.stage("b.gate"):
@@ -413,17 +465,25 @@ class _Interaction(torch.autograd.Function):
         count_launch()
         # ---- post linear, transposed: g_mid[z, k, kk] = alpha sum_w W[kk, w] g_cv[z, k, w]
         post, sc, lin1 = conv.tp.linear, conv.sc, conv.linear_1
-        plan = conv.tp.plan
+        plan = conv.tp.plan if so is None else so["plan"]
         g_mid = new(N, plan.y_dim)
         probs, written = [], set()
         for q, (i, o, off, alpha) in enumerate(post.paths):
             bi, bo = fi.mid[i], fi.conv_out[o]
+            if so is not None:
+                if q == so["post_q"]:      # the restricted intermediate is exactly the 0e block of the full one
+                    probs.append((ops.gemm_problem(g_cv, P["post"][q], g_mid, N, a_off=fi.c_off[o], a_rows=(fi.Dconv, bo.mul, 1),
+                                                   c_off=0, c_rows=(plan.y_dim, bi.mul, 1), alpha=alpha * fi.inv_sqrt_avg), 0, False))
+                continue
             probs.append((ops.gemm_problem(g_cv, P["post"][q], g_mid, N * bi.ir.dim, a_off=fi.c_off[o],
                                            a_rows=(fi.Dconv, bo.mul, bo.ir.dim), c_off=fi.m_off[i],
                                            c_rows=(fi.Dmid, bi.mul, bi.ir.dim), alpha=alpha * fi.inv_sqrt_avg), i, False))
             written.add(i)
-        if len(written) < len(fi.mid):
+        if so is None and len(written) < len(fi.mid):
             g_mid.zero_()
+        if so is not None:
+            mul = fi.structure.uniform_mul
+            w = torch.cat([w[:, c * mul:(c + 1) * mul] for c in so["cols"]], 1)      # weight columns of the live paths
         with ops.stage("b.post_linear"):
             for wave in _waves(probs):
                 ops.gemm_run(wave)
@@ -460,11 +520,12 @@ class _Interaction(torch.autograd.Function):
         # multiplied by the activation derivative at h_last (epilogue 3), see `_RadialHidden`
         hs = fi.hs
         n_fc = conv.fc.n_layers
+        fc_last = P["fc"][n_fc - 1] if so is None else fi.scalar_only_fc(so)
         g_h = None
         if need_h and und is None:
             g_h = new(E, hs[-2])
             with ops.stage("b.mlp_last"):
-                ops.gemm_run([ops.gemm_problem(gw, P["fc"][n_fc - 1], g_h, E, alpha=1.0 / math.sqrt(hs[-2]),
+                ops.gemm_run([ops.gemm_problem(gw, fc_last, g_h, E, alpha=1.0 / math.sqrt(hs[-2]),
                                                epilogue=3 if n_fc > 1 else 0, H=h_last if n_fc > 1 else None,
                                                act_cst=conv.fc.cst)])
         elif need_h:
@@ -472,7 +533,7 @@ class _Interaction(torch.autograd.Function):
             # undirected edge are folded afterwards on the small [E, 64] result, with the activation derivative in the same pass
             g_dir = new(E, hs[-2])
             with ops.stage("b.mlp_last"):
-                ops.gemm_run([ops.gemm_problem(gw, P["fc"][n_fc - 1], g_dir, E, alpha=1.0 / math.sqrt(hs[-2]), epilogue=0)])
+                ops.gemm_run([ops.gemm_problem(gw, fc_last, g_dir, E, alpha=1.0 / math.sqrt(hs[-2]), epilogue=0)])
                 g_h = new(Ew, hs[-2])
                 check(lib.e3b_pair_sum_act(ptr(g_dir), ptr(und.canon), ptr(und.rev), ptr(h_last), float(conv.fc.cst), Ew,
                                            hs[-2], ptr(g_h), stream()))
@@ -498,6 +559,8 @@ class _Interaction(torch.autograd.Function):
             sets = fi.sc_sets(grp) if grp is not None else None
             for q, (i1, i2, o, off, alpha) in enumerate(sc.paths):
                 bi, bo = fi.feat_in[i1], fi.conv_out[o]
+                if so is not None and q not in so["sc_q"]:
+                    continue                                     # the gradient of that output block is zero
                 if grp is not None:
                     g = ops.gemm_problem(g_cv, sets["bwd"][q], g_x, grp.n_virtual * bi.ir.dim, a_off=fi.c_off[o],
                                          a_rows=(fi.Dconv, bo.mul, bo.ir.dim), c_off=fi.x_off[i1],

@@ -1640,6 +1640,29 @@ def self_connection_species(x_imu, attrs, W, spec, grp):
     return _SCG.apply(x_imu.contiguous(), Weff, spec, grp, True)
 
 
+class _LiveBlocks(torch.autograd.Function):
+    """identity whose backward tags the gradient: "columns outside these irreps blocks are exactly zero" """
+
+    @staticmethod
+    def forward(ctx, x, tag):
+        ctx.tag = tag
+        return x.view_as(x)
+
+    @staticmethod
+    def backward(ctx, g):
+        g._e3b_live_blocks = ctx.tag
+        return g, None
+
+
+def tag_live_blocks(x, live, irreps):
+    """x unchanged; in the backward pass the gradient that reaches x's producer carries `_e3b_live_blocks = (live block
+    indices, irreps)`.  Used by a per-irrep linear map that reads only some blocks of its input (an energy read-out reads
+    the 0e scalars, reference addEnergyOutput, configs/layer_configs.py:101-113): the last interaction block then skips
+    every path that cannot reach them (interaction.FusedInteraction.scalar_only).  The tag survives only if this map is
+    the sole consumer of x (autograd sums gradients of several consumers into a fresh tensor)."""
+    return _LiveBlocks.apply(x, (tuple(live), str(irreps)))
+
+
 def block_linear(x_imu, W, spec):
     """per-irrep linear map (spec.V == 0) as one bilinear node: imu rows in, imu rows out"""
     return _SC.apply(x_imu.contiguous(), None, W.contiguous(), spec, True)

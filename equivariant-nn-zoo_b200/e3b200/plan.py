@@ -98,13 +98,25 @@ def reference_structures(l_max_features, sh="1x0e+1x1o+1x2e", n_layers=6):
     return out
 
 
+def scalar_output_restriction(st):
+    """`st` restricted to the paths that produce 0e: what the backward pass of the LAST interaction block needs when the
+    only consumer of its output is a head that reads the 0e scalars (an energy read-out: reference addEnergyOutput,
+    configs/layer_configs.py:101-113) -- the gradient of every other output block is exactly zero there."""
+    return TPStructure(st.irreps_in, st.irreps_sh, Irreps([(st.irreps_in[0].mul, "0e")]))
+
+
 def generated_structures():
-    """The list (in order) of structures csrc/gen_tp.py emits unrolled kernels for."""
+    """The list (in order) of structures csrc/gen_tp.py emits unrolled kernels for: the reference's layer structures for
+    l_max 2 and 3, then their restrictions to the 0e output (appended, so the numbering of the former is stable)."""
     out = []
     for lm in (2, 3):
         for st in reference_structures(lm):
             if all(st.key() != s.key() for s in out):
                 out.append(st)
+    for st in list(out):
+        pr = scalar_output_restriction(st)
+        if pr.paths and all(pr.key() != s.key() for s in out):
+            out.append(pr)
     return out
 
 

@@ -328,3 +328,51 @@ def test_species_self_connection_matches_attribute_contraction():
     assert harness.rel_err(fast["energy"], ref["energy"]) < 1e-5
     assert harness.rel_err(fast["forces"], ref["forces"]) < 1e-5
     assert harness.rel_err(tr_fast["forces"], ref["forces"]) < 1e-5
+
+
+def test_last_block_backward_restricted_to_scalar_paths():
+    """An energy read-out consumes only the 0e scalars of the last interaction block: its linear map tags the gradient
+    (`ops.tag_live_blocks`) and the block's backward runs the tensor-product plan restricted to the 3 paths that reach 0e
+    (of 30), the matching column slice of the last radial layer and one path each of the post-reduction linear map and
+    the self-connection.  Forces equal the unrestricted backward to fp32 rounding and the fp64 oracle to 1e-5; the
+    restriction is not taken when something else also consumes the block's output."""
+    from e3b200 import interaction
+
+    meta = {"config": "config_energy_force", "seed": 11}
+    model = product_harness.build_product(meta, torch.float32, DEV)
+    inputs = synthetic.qm9_like(24, seed=17)
+    n0 = interaction.SCALAR_ONLY_CALLS
+    fast = product_harness.run_product(model, inputs, torch.float32, DEV, pre_edge={"r_max": 5.0})
+    assert interaction.SCALAR_ONLY_CALLS - n0 == 1                # exactly the last block
+    interaction.SCALAR_ONLY = False
+    try:
+        full = product_harness.run_product(model, inputs, torch.float32, DEV, pre_edge={"r_max": 5.0})
+        assert interaction.SCALAR_ONLY_CALLS - n0 == 1
+    finally:
+        interaction.SCALAR_ONLY = True
+    assert torch.equal(fast["energy"], full["energy"])
+    assert harness.rel_err(fast["forces"], full["forces"]) < 2e-6
+    oracle = harness.build_oracle(meta, torch.float64)
+    ref = harness.run_oracle(oracle, inputs, torch.float64, pre_edge={"r_max": 5.0})
+    assert harness.rel_err(fast["forces"], ref["forces"]) < 1e-5
+    # a second consumer of the last block's features: autograd sums two gradients, the tag is gone, full backward
+    from e3_layers.data import Batch, computeEdgeIndex
+    data = harness.cast_inputs(inputs, torch.float32, DEV)
+    batch = Batch(harness.attrs_for(data), **data)
+    d, a = computeEdgeIndex(batch.data, batch.attrs, r_max=5.0)
+    batch.update(d)
+    batch.attrs.update(a)
+    batch = Batch(batch.attrs, **batch.data)
+    batch["pos"].requires_grad_(True)
+    out = model.func(batch) if hasattr(model, "func") else None
+    if out is not None:
+        n1 = interaction.SCALAR_ONLY_CALLS
+        y = out["energy"].sum() + 1e-3 * out["node_features"].pow(2).sum()
+        from e3b200 import ops
+        with ops.positions_only(batch["pos"]):
+            (g,) = torch.autograd.grad(y, batch["pos"], retain_graph=True)
+        assert interaction.SCALAR_ONLY_CALLS == n1 and bool(torch.isfinite(g).all())
+        with ops.positions_only(batch["pos"]):                    # the read-out alone: restricted again
+            (g2,) = torch.autograd.grad(out["energy"].sum(), batch["pos"])
+        assert interaction.SCALAR_ONLY_CALLS == n1 + 1
+        assert harness.rel_err(-g2, fast["forces"]) < 2e-6
