@@ -134,44 +134,65 @@ class FusedInteraction:
         return out
 
 
-    def scalar_only(self):
-        """What the backward pass needs when only the block's first output block -- the 0e scalars -- has a non-zero
-        gradient (the last block under an energy read-out): the tensor-product plan restricted to the paths that produce
-        0e, the columns of those paths in the full weight row, the single path of the post-reduction linear map and of
-        the self-connection that reach that block, and the last radial layer's weight restricted to the live columns.
-        None when the layer does not have that shape."""
-        if "scalar_only" not in self._cache:
+    def restricted(self, live):
+        """What the backward pass needs when only the output blocks `live` (indices into the gate's output irreps) have a
+        non-zero gradient -- the last block under an energy read-out (live = the 0e scalars: 3 of 30 paths) and the block
+        before it (live = the inputs of those paths: 0e, 1o, 2e, 15 of 30 paths): the tensor-product plan restricted to
+        the paths whose output irrep is still needed, their columns in the full weight row, the problems of the
+        post-reduction linear map (with their offsets in the restricted intermediate) and of the self-connection that reach
+        live blocks, and the input blocks that receive a gradient (the tag handed to the block before).  None when the
+        layer does not have that shape or the restriction saves less than 40 % of the paths."""
+        key = ("restricted", tuple(live))
+        if key not in self._cache:
             out = None
             st, mul = self.structure, self.structure.uniform_mul
-            scal = self.gate.irreps_scalars
-            if (mul in (32, 64) and len(scal) and scal[0].ir.l == 0 and scal[0].ir.p == 1 and self.conv_out[0].ir == scal[0].ir
-                    and self.conv_out[0].mul == scal[0].mul and self.fc.n_layers > 1):
-                from .plan import scalar_output_restriction
-                pr = scalar_output_restriction(st)
-                idx = {(p.i_in, p.i_sh, str(p.ir_out)): q for q, p in enumerate(st.paths)}
-                cols = [idx[(p.i_in, p.i_sh, str(p.ir_out))] for p in pr.paths]
-                i0 = next((i for i, b in enumerate(self.mid) if b.ir.l == 0 and b.ir.p == 1), None)
-                post_q = [q for q, (i, o, _, _) in enumerate(self.conv.tp.linear.paths) if i == i0 and o == 0]
-                plan = ops.TPPlan(pr) if pr.paths else None
-                if (plan is not None and plan.specialized and i0 is not None and len(post_q) == 1
-                        and self.mid[i0].mul == len(pr.paths) * mul and plan.x_dim == self.conv.tp.plan.x_dim):
-                    out = {"plan": plan, "cols": cols, "post_q": post_q[0], "mid_block": i0,
-                           "sc_q": [q for q, (_, _, o, _, _) in enumerate(self.conv.sc.paths) if o == 0]}
-            self._cache["scalar_only"] = out
-        return self._cache["scalar_only"]
+            gate = self.gate
+            n_s, n_g = len(gate.irreps_scalars), len(gate.irreps_gated)
+            if (mul in (32, 64) and self.fc.n_layers > 1 and len(self.conv_out) == n_s + (1 if n_g else 0) + n_g
+                    and all(0 <= b < n_s + n_g for b in live)):
+                from .plan import output_restriction
+                C = {b for b in live if b < n_s} | {n_s + 1 + (b - n_s) for b in live if b >= n_s}
+                if any(b >= n_s for b in live):
+                    C.add(n_s)                                    # the gates of the live gated blocks
+                need = []
+                for c in sorted(C):
+                    if all(str(self.conv_out[c].ir) != str(ir) for ir in need):
+                        need.append(self.conv_out[c].ir)
+                pr = output_restriction(st, need)
+                if pr.paths and len(pr.paths) <= 0.6 * len(st.paths):
+                    plan = ops.TPPlan(pr)
+                    idx = {(p.i_in, p.i_sh, str(p.ir_out)): q for q, p in enumerate(st.paths)}
+                    cols = [idx[(p.i_in, p.i_sh, str(p.ir_out))] for p in pr.paths]
+                    pmid = pr.irreps_mid.simplify()
+                    p_off, _ = _offsets(pmid)
+                    where = {str(b.ir): (k, b.mul) for k, b in enumerate(pmid)}
+                    post, ok = {}, plan.specialized and plan.x_dim == self.conv.tp.plan.x_dim
+                    for q, (i, o, _, _) in enumerate(self.conv.tp.linear.paths):
+                        hit = where.get(str(self.mid[i].ir))
+                        if o in C and hit is not None:
+                            ok = ok and hit[1] == self.mid[i].mul  # every path into a needed irrep is kept
+                            post[q] = (hit[0], p_off[hit[0]])
+                    sc_q = [q for q, (_, _, o, _, _) in enumerate(self.conv.sc.paths) if o in C]
+                    sup = sorted({p.i_in for p in pr.paths} | {self.conv.sc.paths[q][0] for q in sc_q})
+                    if ok and post:
+                        out = {"plan": plan, "cols": cols, "post": post, "n_mid": len(pmid), "sc_q": sc_q,
+                               "sup": tuple(sup) if len(sup) < len(self.feat_in) else None}
+            self._cache[key] = out
+        return self._cache[key]
 
-    def scalar_only_fc(self, so):
+    def restricted_fc(self, so):
         """packed (backward role) last radial layer restricted to the live weight columns, per parameter version"""
         W = getattr(self.conv.fc, f"layer{self.conv.fc.n_layers - 1}").weight
         key = (ops.WEIGHTS_EPOCH, W.data_ptr(), W._version)
-        hit = self._cache.get("scalar_only_fc")
+        ckey = ("restricted_fc", tuple(so["cols"]))
+        hit = self._cache.get(ckey)
         if hit is None or hit[0] != key:
             mul = self.structure.uniform_mul
             with torch.no_grad():
                 Wl = torch.cat([W[:, c * mul:(c + 1) * mul] for c in so["cols"]], 1).contiguous()      # [h, live]
             hi, ho = Wl.shape
             hit = (key, ops.gemm_pack([(Wl, 0, ho, 0, 1, 1, 0, hi, ho)])[0])
-            self._cache["scalar_only_fc"] = hit
+            self._cache[ckey] = hit
         return hit[1]
 
     def sc_sets(self, grp):
@@ -450,10 +471,11 @@ class _Interaction(torch.autograd.Function):
         # Only the 0e scalars of the output have a non-zero gradient (tag set by the read-out's linear map, see
         # ops.tag_live_blocks): every path of the block that does not reach them contributes exactly zero.
         so = None
-        live = getattr(g_mi, "_e3b_live_blocks", None) if g_mi is not None else None
-        if (SCALAR_ONLY and live is not None and g_imu is None and not need_params and not need_attrs and E > 0
-                and live == ((0,), str(fi.gate.irreps_out)) and conv.tp.plan.specialized):
-            so = fi.scalar_only()
+        g_only = g_mi if g_imu is None else (g_imu if g_mi is None else None)      # a tag counts only on the sole gradient
+        live = getattr(g_only, "_e3b_live_blocks", None) if g_only is not None else None
+        if (SCALAR_ONLY and live is not None and not need_params and not need_attrs and E > 0
+                and live[1] == str(fi.gate.irreps_out) and conv.tp.plan.specialized):
+            so = fi.restricted(live[0])
         if so is not None:
             global SCALAR_ONLY_CALLS
             SCALAR_ONLY_CALLS += 1
@@ -471,15 +493,19 @@ class _Interaction(torch.autograd.Function):
         for q, (i, o, off, alpha) in enumerate(post.paths):
             bi, bo = fi.mid[i], fi.conv_out[o]
             if so is not None:
-                if q == so["post_q"]:      # the restricted intermediate is exactly the 0e block of the full one
-                    probs.append((ops.gemm_problem(g_cv, P["post"][q], g_mid, N, a_off=fi.c_off[o], a_rows=(fi.Dconv, bo.mul, 1),
-                                                   c_off=0, c_rows=(plan.y_dim, bi.mul, 1), alpha=alpha * fi.inv_sqrt_avg), 0, False))
+                hit = so["post"].get(q)    # a block of the restricted intermediate has the layout of the same irrep's full block
+                if hit is not None:
+                    probs.append((ops.gemm_problem(g_cv, P["post"][q], g_mid, N * bi.ir.dim, a_off=fi.c_off[o],
+                                                   a_rows=(fi.Dconv, bo.mul, bo.ir.dim), c_off=hit[1],
+                                                   c_rows=(plan.y_dim, bi.mul, bi.ir.dim), alpha=alpha * fi.inv_sqrt_avg),
+                                  hit[0], False))
+                    written.add(hit[0])
                 continue
             probs.append((ops.gemm_problem(g_cv, P["post"][q], g_mid, N * bi.ir.dim, a_off=fi.c_off[o],
                                            a_rows=(fi.Dconv, bo.mul, bo.ir.dim), c_off=fi.m_off[i],
                                            c_rows=(fi.Dmid, bi.mul, bi.ir.dim), alpha=alpha * fi.inv_sqrt_avg), i, False))
             written.add(i)
-        if so is None and len(written) < len(fi.mid):
+        if len(written) < (len(fi.mid) if so is None else so["n_mid"]):
             g_mid.zero_()
         if so is not None:
             mul = fi.structure.uniform_mul
@@ -520,7 +546,7 @@ class _Interaction(torch.autograd.Function):
         # multiplied by the activation derivative at h_last (epilogue 3), see `_RadialHidden`
         hs = fi.hs
         n_fc = conv.fc.n_layers
-        fc_last = P["fc"][n_fc - 1] if so is None else fi.scalar_only_fc(so)
+        fc_last = P["fc"][n_fc - 1] if so is None else fi.restricted_fc(so)
         g_h = None
         if need_h and und is None:
             g_h = new(E, hs[-2])
@@ -592,6 +618,9 @@ class _Interaction(torch.autograd.Function):
                 g_x_imu = g_x
             else:
                 g_x_mi = g_x if fi.all_scalar_in else ops.layout_convert(g_x, fi.feat_in, False)
+            if so is not None and so["sup"] is not None:
+                # only these input blocks received anything: the block before this one may restrict its backward as well
+                (g_x_imu if g_x_imu is not None else g_x_mi)._e3b_live_blocks = (so["sup"], str(fi.feat_in))
         return (g_x_mi, g_x_imu, g_attrs, g_h, g_Y, None, None, None, None, *g_params)
 
 

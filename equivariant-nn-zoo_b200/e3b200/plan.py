@@ -105,6 +105,17 @@ def scalar_output_restriction(st):
     return TPStructure(st.irreps_in, st.irreps_sh, Irreps([(st.irreps_in[0].mul, "0e")]))
 
 
+def output_restriction(st, irs):
+    """`st` restricted to the paths whose output irrep is one of `irs` (any order)"""
+    keep = [b for b in st.irreps_out if any(b.ir == ir for ir in irs)]
+    seen, uniq = set(), []
+    for b in keep:
+        if str(b.ir) not in seen:
+            seen.add(str(b.ir))
+            uniq.append((st.irreps_in[0].mul, b.ir))
+    return TPStructure(st.irreps_in, st.irreps_sh, Irreps(uniq))
+
+
 def generated_structures():
     """The list (in order) of structures csrc/gen_tp.py emits unrolled kernels for: the reference's layer structures for
     l_max 2 and 3, then their restrictions to the 0e output (appended, so the numbering of the former is stable)."""
@@ -113,9 +124,16 @@ def generated_structures():
         for st in reference_structures(lm):
             if all(st.key() != s.key() for s in out):
                 out.append(st)
-    for st in list(out):
+    base = list(out)
+    for st in base:
         pr = scalar_output_restriction(st)
         if pr.paths and all(pr.key() != s.key() for s in out):
+            out.append(pr)
+    # one block earlier the live outputs are the inputs of those paths: 0e, 1o, 2e (interaction.FusedInteraction.restricted)
+    nat = Irreps("1x0e+1x1o+1x2e")
+    for st in base:
+        pr = output_restriction(st, [b.ir for b in nat])
+        if pr.paths and len(pr.paths) < len(st.paths) and all(pr.key() != s.key() for s in out):
             out.append(pr)
     return out
 
