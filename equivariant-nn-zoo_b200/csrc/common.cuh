@@ -35,12 +35,17 @@ template <typename T> __device__ __forceinline__ T warp_sum(T v) {
 #define TPP_STAGES 3     // shared-memory ring depth of the pipelined forward kernel
 #define TPP_MAXSEG 256   // edges of one destination segment staged per index chunk
 #define TPP_GXBUF 3      // staging rows of the backward kernel's node-reduction mode (TMA reduce-add in flight)
+#define TPP2_MAXSEG 128  // the same for the paired kernels, whose ring depth is a launch parameter (TpArgs::n_stages)
+#define TPP2_LAG 1      // the producer refills the stage of the edge this many behind the one its own warp consumes
 
 #if defined(__CUDACC__) && !defined(E3B_HOST_EMU)
 // ---- mbarrier + TMA bulk-copy primitives (sm_90+; SASS: SYNCS / UBLKCP) ---------------------
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
 __device__ __forceinline__ void fence_mbar_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
 __device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
@@ -76,6 +81,45 @@ template <int N> __device__ __forceinline__ void bulk_wait_read() { asm volatile
 __device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 bool e3b_tp_pipelined_enabled();
+bool e3b_tp_paired_enabled(bool preferred);
+bool e3b_tp_paired_fwd_enabled(bool preferred);
+int e3b_tp_stages(int bwd, size_t per_stage_bytes, size_t fixed_bytes);
+// ---- two channels per thread: packed fp32 pairs (sm_100 FFMA2 / FMUL2; a scalar or an immediate broadcasts to both halves,
+// so Clebsch-Gordan literals and the spherical harmonics of the edge need no register pairs)
+struct __align__(8) F2 {
+  float2 v;
+  __device__ __forceinline__ F2() {}
+  __device__ __forceinline__ explicit F2(float s) : v(make_float2(s, s)) {}
+  __device__ __forceinline__ explicit F2(float2 t) : v(t) {}
+};
+__device__ __forceinline__ F2 operator*(F2 a, F2 b) { return F2(__fmul2_rn(a.v, b.v)); }
+__device__ __forceinline__ F2 fma_(F2 a, F2 b, F2 c) { return F2(__ffma2_rn(a.v, b.v, c.v)); }
+__device__ __forceinline__ void red_add_f32x2(F2* p, F2 v) {   // fire-and-forget L2 reduction of a channel pair (sm_90+)
+  asm volatile("red.global.add.v2.f32 [%0], {%1, %2};" ::"l"(p), "f"(v.v.x), "f"(v.v.y) : "memory");
+}
+__device__ __forceinline__ F2 ldg(const F2* p) { return F2(__ldg(reinterpret_cast<const float2*>(p))); }
+#define E3B_GSH_STORE2(ptr, idx, val) do { const float r_ = warp_sum((val).v.x + (val).v.y); if (lane == 0) (ptr)[idx] = r_; } while (0)
+// sums over the 32 lanes of NINE values per lane (the d/dY partials of one edge, sh_dim = 9) and their store: a halving butterfly
+// (after the exchange over lane bit b a lane keeps half of its values) takes 14 shuffles instead of 45; lane 4 i ends up with the
+// total of value i (i < 8), the ninth value goes through the plain butterfly.  NOT inlined: the unrolled edge loops of the
+// warps of a kernel compete for the 32 KB instruction cache of the SM, one copy serves them all.
+static __device__ __noinline__ void gsh_reduce_store9(float* __restrict__ row, int lane, float r0, float r1, float r2, float r3, float r4,
+                                               float r5, float r6, float r7, float r8) {
+  const float r[9] = {r0, r1, r2, r3, r4, r5, r6, r7, r8};
+  const bool b4 = lane & 16, b3 = lane & 8, b2 = lane & 4;
+  float t[4], s2[2];
+#pragma unroll
+  for (int k = 0; k < 4; ++k) t[k] = (b4 ? r[k + 4] : r[k]) + __shfl_xor_sync(0xffffffffu, b4 ? r[k] : r[k + 4], 16);
+#pragma unroll
+  for (int k = 0; k < 2; ++k) s2[k] = (b3 ? t[k + 2] : t[k]) + __shfl_xor_sync(0xffffffffu, b3 ? t[k] : t[k + 2], 8);
+  float q = (b2 ? s2[1] : s2[0]) + __shfl_xor_sync(0xffffffffu, b2 ? s2[0] : s2[1], 4);
+  q += __shfl_xor_sync(0xffffffffu, q, 2);
+  q += __shfl_xor_sync(0xffffffffu, q, 1);
+  const float s8 = warp_sum(r[8]);
+  if ((lane & 3) == 0) row[(lane >> 4) * 4 + ((lane >> 3) & 1) * 2 + ((lane >> 2) & 1)] = q;
+  if (lane == 1) row[8] = s8;
+}
+#define E3B_GSH_ZERO2(ptr, idx) do { if (lane == 0) (ptr)[idx] = 0.f; } while (0)
 #endif
 
 // Arguments of the tensor-product convolution kernels.  Dims are in scalars per row.
@@ -98,4 +142,5 @@ struct TpArgs {
   int64_t n_nodes;
   int64_t x_dim, sh_dim, w_dim, y_dim;
   int32_t mul, n_chunks, n_part;
+  int32_t n_stages;       // paired pipelined kernels: depth of the shared-memory ring
 };

@@ -1089,6 +1089,7 @@ static TpArgs<T> make_args(const e3b_tp_plan* p, int64_t n_nodes, const void* x,
   a.mul = p->desc.mul;
   a.n_chunks = (p->desc.mul + 31) / 32;
   a.n_part = p->gen ? p->gen->n_groups * a.n_chunks : 1;
+  a.n_stages = 0;
   return a;
 }
 

@@ -19,6 +19,7 @@ from e3b200 import cg  # noqa: E402
 from e3b200.plan import generated_structures  # noqa: E402
 
 MAX_ACC_PER_GROUP = 56  # accumulator registers per thread (forward)
+PAIRED_MAX_ACC = 30     # output components per group of the paired backward kernels (two registers each)
 
 
 def lit(v):
@@ -29,9 +30,10 @@ def coef(l1, l2, l3):
     return sqrt(2 * l3 + 1) * cg.w3j(l1, l2, l3)
 
 
-def make_groups(st):
-    """Partition input blocks into groups with <= MAX_ACC_PER_GROUP output components, keeping
+def make_groups(st, max_acc=None):
+    """Partition input blocks into groups with <= max_acc (default MAX_ACC_PER_GROUP) output components, keeping
     blocks whole and balancing the FMA count.  Returns list of lists of input-block indices."""
+    MAX_ACC_PER_GROUP = max_acc or globals()["MAX_ACC_PER_GROUP"]
     n_in = len(st.irreps_in)
     acc = [sum(p.ir_out.dim for p in st.paths if p.i_in == b) for b in range(n_in)]
     work = [sum((abs(coef(st.irreps_in[p.i_in].ir.l, st.irreps_sh[p.i_sh].ir.l, p.ir_out.l)) > 0).sum()
@@ -86,7 +88,7 @@ def emit_structure(E, sid, st):
                     out.append((b, s, ps))
         return out
 
-    def emit_bwd_body(blocks, xl, wl, yl, stage_gx=False):
+    def emit_bwd_body(blocks, xl, wl, yl, stage_gx=False, paired=False):
             used_s = sorted({s for (b, s, ps) in pairs_of(blocks)})
             for s in used_s:
                 for j in range(st.irreps_sh[s].ir.dim):
@@ -135,23 +137,38 @@ def emit_structure(E, sid, st):
                         E(f"      gY_{s}_{j} = fma_(gxy_{i}_{j}, x_{b}_{i}, gY_{s}_{j});")
                     E("    }")
                 E("    if (a.gx_edge != nullptr && active) {")
-                E("      T* __restrict__ gxr = a.gx_edge + eid * x_dim + u;")
+                if paired:
+                    E("      T* __restrict__ gxr = reinterpret_cast<T*>(a.gx_edge + eid * ROW_X) + u;")
+                else:
+                    E("      T* __restrict__ gxr = a.gx_edge + eid * x_dim + u;")
                 for i in range(d1):
                     E(f"      gxr[{xoff[b] + i} * mul] = gx_{b}_{i};")
                 E("    }")
-                if stage_gx:     # node-reduction mode: the edge's gradient row is staged in shared memory for one TMA reduce-add
+                if stage_gx and paired:   # node-reduction mode, paired kernels: 8-byte vector reductions straight from registers
+                    E("    if (a.gx_node != nullptr) {")
+                    for i in range(d1):
+                        E(f"      red_add_f32x2(gxn + {xoff[b] + i} * mul, gx_{b}_{i});")
+                    E("    }")
+                elif stage_gx:   # node-reduction mode: the edge's gradient row is staged in shared memory for one TMA reduce-add
                     E("    if (a.gx_node != nullptr) {")
                     for i in range(d1):
                         E(f"      gxs[{xoff[b] + i} * mul + u] = gx_{b}_{i};")
                     E("    }")
             E("    if (a.gsh != nullptr) {")
-            E("      T* __restrict__ gsr = a.gsh + (eid * a.n_part + part) * a.sh_dim;")
-            for s in range(len(st.irreps_sh)):
+            E(f"      {'float' if paired else 'T'}* __restrict__ gsr = a.gsh + (eid * a.n_part + part) * a.sh_dim;")
+            sfx = "2" if paired else ""
+            if paired and sdim == 9:
+                vals = ["0.f"] * 9
+                for s in used_s:
+                    for j in range(st.irreps_sh[s].ir.dim):
+                        vals[soff[s] + j] = f"gY_{s}_{j}.v.x + gY_{s}_{j}.v.y"
+                E("      gsh_reduce_store9(gsr, lane, " + ", ".join(vals) + ");")
+            for s in ([] if paired and sdim == 9 else range(len(st.irreps_sh))):
                 for j in range(st.irreps_sh[s].ir.dim):
                     if s in used_s:
-                        E(f"      E3B_GSH_STORE(gsr, {soff[s] + j}, gY_{s}_{j});")
+                        E(f"      E3B_GSH_STORE{sfx}(gsr, {soff[s] + j}, gY_{s}_{j});")
                     else:
-                        E(f"      E3B_GSH_ZERO(gsr, {soff[s] + j});")
+                        E(f"      E3B_GSH_ZERO{sfx}(gsr, {soff[s] + j});")
             E("    }")
 
 
@@ -464,6 +481,183 @@ def emit_structure(E, sid, st):
     E("  if (a.gx_node != nullptr && tid == 0) bulk_wait_all();   // the staging buffers must outlive the reductions reading them")
     E("}")
     E(f"static size_t tpbp_smem_S{sid}(int mul, bool reduce) {{ return ((tpfp_smem_S{sid}(mul) + 15) & ~(size_t)15) + 16 + (reduce ? (size_t)TPP_GXBUF * {xdim} * mul * 4 : 0); }}")
+    # ---- paired pipelined kernels (multiplicity 64): a thread owns the channels (2 lane, 2 lane + 1) and computes on packed
+    # fp32 pairs (FFMA2 / FMUL2: half the issue slots of the arithmetic, 8-byte shared-memory loads and global stores); the
+    # input blocks are split into more groups (warps) so that the doubled live set still fits the register file.  The warps of
+    # a CTA are DECOUPLED: a stage of the ring has a `full` barrier (TMA bytes) and an `empty` barrier (one arrival per
+    # warp); a warp waits for data only, runs ahead of the others by up to the ring depth, and adds ITS input blocks'
+    # d/dx rows into the source node's row with 8-byte vector reductions (red.global.add.v2.f32) from registers -- no
+    # CTA-wide barrier per edge, no staging.  The lightest warp's lane 0
+    # is the producer: one edge behind itself it waits for `empty` and refills the stage.
+    acc_of = [sum(p.ir_out.dim for p in st.paths if p.i_in == b) for b in range(len(st.irreps_in))]
+    for cap in (PAIRED_MAX_ACC, 36, 42, MAX_ACC_PER_GROUP):
+        groups2 = make_groups(st, max(cap, max(acc_of)))
+        G2 = len(groups2)
+        if G2 <= 2 * G:     # the partial-sum rows of d/dY are laid out for G * 2 warps per node
+            break
+    else:
+        groups2, G2 = groups, G
+    work_of = [sum(int((abs(coef(st.irreps_in[p.i_in].ir.l, st.irreps_sh[p.i_sh].ir.l, p.ir_out.l)) > 0).sum())
+                   for p in st.paths if p.i_in == b) for b in range(len(st.irreps_in))]
+    g_light = min(range(G2), key=lambda g: sum(work_of[b] for b in groups2[g]))   # the warp with the least arithmetic
+
+    def paired_head(name, bwd):
+        E(f"__global__ void __launch_bounds__(32 * {G2}) {name}_S{sid}(const TpArgs<float> a) {{")
+        E("  typedef F2 T;")
+        E("  asm volatile(\"griddepcontrol.launch_dependents;\" ::: \"memory\");")
+        E(f"  constexpr int MUL = 64, G = {G2}, PW = {g_light}, ROW_W = {n_paths} * MUL, ROW_X = {xdim} * MUL, STAGE = ROW_W + ROW_X, SH_DIM = {sdim};")
+        E("  constexpr int NT = 32 * G;")
+        E("  constexpr int mul = MUL / 2;   // row strides below are in channel PAIRS")
+        if bwd:
+            E("  constexpr bool active = true;")
+        E("  extern __shared__ __align__(128) unsigned char tpp_smem[];")
+        E("  float* stages = reinterpret_cast<float*>(tpp_smem);")
+        E("  const uint32_t nst = (uint32_t)a.n_stages;   // ring depth: a launch parameter")
+        E("  int* s_src = reinterpret_cast<int*>(stages + nst * STAGE);")
+        E("  int* s_eid = s_src + TPP2_MAXSEG;")
+        E("  int* s_wid = s_eid + TPP2_MAXSEG;")
+        E("  uint64_t* full = reinterpret_cast<uint64_t*>(s_wid + TPP2_MAXSEG);")
+        E("  uint64_t* empty = full + nst;")
+        E("  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;")
+        E("  const int64_t node = blockIdx.x;")
+        E("  const int group = warp, u = lane;" + (" const int part = warp;" if bwd else ""))
+        E("  if (tid == 0) {")
+        E("    for (uint32_t s = 0; s < nst; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], G); }")
+        E("    fence_mbar_init();")
+        E("  }")
+        E("  const int64_t e0 = a.in_ptr[node], e1 = a.in_ptr[node + 1];")
+        E("  uint32_t it = 0, s = 0, ph = 0;   // running edge counter, ring stage and barrier phase of the edge being consumed")
+
+    def paired_chunk_open():
+        E("    for (int64_t c0 = e0; c0 < e1; c0 += TPP2_MAXSEG) {")
+        E("      const int n = (int)((e1 - c0) < TPP2_MAXSEG ? (e1 - c0) : TPP2_MAXSEG);")
+        E("      __syncthreads();   // every warp is through the previous chunk: all stages free (also orders the barrier init)")
+        E("      for (int i = tid; i < n; i += NT) {")
+        E("        s_src[i] = a.in_nbr[c0 + i];")
+        E("        const int eid_i = a.in_eid ? a.in_eid[c0 + i] : (int)(c0 + i);")
+        E("        s_eid[i] = eid_i;")
+        E("        s_wid[i] = a.w_idx ? a.w_idx[eid_i] : eid_i;")
+        E("      }")
+        E("      __syncthreads();")
+        E("      if (warp == PW && lane == 0) {")
+        E("        const int pre = n < (int)nst ? n : (int)nst;")
+        E("        for (int j = 0; j < pre; ++j) {")
+        E("          uint32_t sj = s + j; if (sj >= nst) sj -= nst;")
+        E("          tpp_issue(stages + sj * STAGE, &full[sj], a.w + (int64_t)s_wid[j] * ROW_W, ROW_W, a.x + (int64_t)s_src[j] * ROW_X, ROW_X);")
+        E("        }")
+        E("      }")
+        E("      uint32_t sl = s, phl = ph;   // stage / phase of the edge TPP2_LAG behind: the one the producer refills")
+        E("      float Ycur = (lane < SH_DIM) ? ldg(a.sh + (int64_t)s_eid[0] * SH_DIM + lane) : 0.f;")
+        E("      for (int i = 0; i < n; ++i, ++it) {")
+        E("        if (i >= TPP2_LAG) {")
+        E("          if (warp == PW && lane == 0 && i - TPP2_LAG + (int)nst < n) {   // refill the stage of edge i - LAG once every warp released it")
+        E("            mbar_wait(&empty[sl], phl);")
+        E("            tpp_issue(stages + sl * STAGE, &full[sl], a.w + (int64_t)s_wid[i - TPP2_LAG + nst] * ROW_W, ROW_W,")
+        E("                      a.x + (int64_t)s_src[i - TPP2_LAG + nst] * ROW_X, ROW_X);")
+        E("          }")
+        E("          if (++sl == nst) { sl = 0; phl ^= 1u; }")
+        E("        }")
+        E("        float Ynext = 0.f;")
+        E("        if (i + 1 < n && lane < SH_DIM) Ynext = ldg(a.sh + (int64_t)s_eid[i + 1] * SH_DIM + lane);")
+        E("        mbar_wait(&full[s], ph);")
+        E("        const T* __restrict__ sw = reinterpret_cast<const T*>(stages + s * STAGE) + u;")
+        E("        const T* __restrict__ sx = sw + ROW_W / 2;")
+
+    def paired_chunk_close():
+        E("        Ycur = Ynext;")
+        E("        __syncwarp();")
+        E("        if (lane == 0) mbar_arrive(&empty[s]);   // this warp is done with the stage")
+        E("        if (++s == nst) { s = 0; ph ^= 1u; }")
+        E("      }")
+        E("    }")
+
+    # ---------------- backward
+    paired_head("tpbp2", True)
+    E(f"  const T* __restrict__ gyr = reinterpret_cast<const T*>(a.gy + node * ({ydim} * MUL)) + u;")
+    E("  switch (group) {")
+    for g, blocks in enumerate(groups2):
+        E(f"  case {g}: {{")
+        for pi, p in enumerate(st.paths):
+            if p.i_in in blocks:
+                for k in range(p.ir_out.dim):
+                    E(f"    const T gy_{pi}_{k} = ldg(gyr + {ybase[p.slot] + k * ykst[p.slot]} * mul);")
+        paired_chunk_open()
+        E("        const int64_t eid = s_eid[i];")
+        E("        T* __restrict__ gwr = reinterpret_cast<T*>(a.gw + eid * ROW_W) + u;")
+        E("        T* __restrict__ gxn = reinterpret_cast<T*>(a.gx_node + (int64_t)s_src[i] * ROW_X) + u;   // d/dx of the SOURCE node (node-reduction mode)")
+        E("        {")
+        emit_bwd_body(blocks, lambda b, i: f"sx[{xoff[b] + i} * mul]", lambda pi: f"sw[{pi} * mul]",
+                      lambda s_, j: f"T(__shfl_sync(0xffffffffu, Ycur, {soff[s_] + j}))", stage_gx=True, paired=True)
+        E("        }")
+        if g == g_light and G2 != 2 * G:
+            E(f"        if (a.gsh != nullptr && lane < SH_DIM)     // partial-sum rows no warp of this kernel owns")
+            E(f"          for (int p = G; p < a.n_part; ++p) a.gsh[(eid * a.n_part + p) * SH_DIM + lane] = 0.f;")
+        paired_chunk_close()
+        E("  } break;")
+    E("  }")
+    E("}")
+    E(f"static const int kPairedGroups_S{sid} = {G2};")
+    # which variant runs by default -- measured per kernel on the W2 step (ncu launch list, paired vs one channel per thread):
+    # backward 3-path structures 133 -> 88 us and 188 -> 171 us, the 15-path restriction of the full block 405 -> 371 us, but the
+    # 15-path second block 327 -> 338 us and 27 paths 609 -> 646 us (the unrolled loops of the 4 warps, 27 KB, no longer fit the 32 KB instruction
+    # cache of the SM: ncu `no_instruction` is the top stall); forward 27 / 30 paths 258 -> 227 us and 260 -> 248 us, smaller
+    # structures unchanged.  E3B_TP_PAIRED_FORCE=1 runs the paired kernels everywhere.
+    E(f"static const bool kPairedBwdOk_S{sid} = {'true' if (n_paths <= 3 or (n_paths == 15 and len(st.irreps_in) == 6)) else 'false'};")
+    E(f"static const bool kPairedFwdOk_S{sid} = {'true' if n_paths >= 20 else 'false'};")
+    E(f"static size_t tpp2_smem_S{sid}(int nst, bool reduce) {{ return (size_t)nst * ({n_paths} + {xdim}) * 64 * 4 + 3 * TPP2_MAXSEG * 4 + (size_t)nst * 16; }}")
+
+    # ---------------- forward
+    paired_head("tpfp2", False)
+    E("  switch (group) {")
+    for g, blocks in enumerate(groups2):
+        E(f"  case {g}: {{")
+        accs = [f"acc_{pi}_{k}" for pi, p in enumerate(st.paths) if p.i_in in blocks for k in range(p.ir_out.dim)]
+        for i in range(0, len(accs), 8):
+            E("    T " + ", ".join(f"{n} = T(0.f)" for n in accs[i:i + 8]) + ";")
+        paired_chunk_open()
+        used_s = sorted({s_ for (b_, s_, ps_) in pairs_of(blocks)})
+        for s_ in used_s:
+            for j in range(st.irreps_sh[s_].ir.dim):
+                E(f"        const T Y_{s_}_{j} = T(__shfl_sync(0xffffffffu, Ycur, {soff[s_] + j}));")
+        for b_ in blocks:
+            for i in range(st.irreps_in[b_].ir.dim):
+                E(f"        const T x_{b_}_{i} = sx[{xoff[b_] + i} * mul];")
+        for (b_, s_, ps) in pairs_of(blocks):
+            l1, l2 = st.irreps_in[b_].ir.l, st.irreps_sh[s_].ir.l
+            need = set()
+            for pi in ps:
+                C = coef(l1, l2, st.paths[pi].ir_out.l)
+                for i in range(2 * l1 + 1):
+                    for j in range(2 * l2 + 1):
+                        if abs(C[i, j]).max() > 0:
+                            need.add((i, j))
+            E("        {")
+            for (i, j) in sorted(need):
+                E(f"          const T xy_{i}_{j} = x_{b_}_{i} * Y_{s_}_{j};")
+            for pi in ps:
+                l3 = st.paths[pi].ir_out.l
+                C = coef(l1, l2, l3)
+                E(f"          {{ const T w_p = sw[{pi} * mul];")
+                for k in range(2 * l3 + 1):
+                    terms = [(i, j, C[i, j, k]) for i in range(2 * l1 + 1) for j in range(2 * l2 + 1) if C[i, j, k] != 0]
+                    if not terms:
+                        continue
+                    i, j, c = terms[0]
+                    expr = f"{lit(c)} * xy_{i}_{j}"
+                    for (i, j, c) in terms[1:]:
+                        expr = f"fma_({lit(c)}, xy_{i}_{j}, {expr})"
+                    E(f"            acc_{pi}_{k} = fma_(w_p, {expr}, acc_{pi}_{k});")
+                E("          }")
+            E("        }")
+        paired_chunk_close()
+        E(f"    T* __restrict__ yo = reinterpret_cast<T*>(a.y + node * ({ydim} * MUL)) + u;")
+        for pi, p in enumerate(st.paths):
+            if p.i_in in blocks:
+                for k in range(p.ir_out.dim):
+                    E(f"    yo[{ybase[p.slot] + k * ykst[p.slot]} * mul] = acc_{pi}_{k};")
+        E("  } break;")
+    E("  }")
+    E("}")
     E("#endif  // __CUDACC__")
     E()
 
@@ -528,7 +722,12 @@ def emit_tables(st_list):
             if kind == "b":
                 E(f"  if ((a.mul == 64 || a.mul == 32) && e3b_tp_pipelined_enabled()) {{")
                 E(f"    const size_t smem = tpbp_smem_S{sid}(a.mul, a.gx_node != nullptr);")
-                E(f"    if (a.mul == 64) {{ if (smem > 48 * 1024) cudaFuncSetAttribute(tpbp_S{sid}<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);")
+                E(f"    if (a.mul == 64 && e3b_tp_paired_enabled(kPairedBwdOk_S{sid})) {{")
+                E(f"      TpArgs<float> a2 = a; a2.n_stages = e3b_tp_stages(1, tpp2_smem_S{sid}(1, a.gx_node != nullptr) - tpp2_smem_S{sid}(0, a.gx_node != nullptr), tpp2_smem_S{sid}(0, a.gx_node != nullptr));")
+                E(f"      const size_t smem2 = tpp2_smem_S{sid}(a2.n_stages, a.gx_node != nullptr);")
+                E(f"      if (smem2 > 48 * 1024) cudaFuncSetAttribute(tpbp2_S{sid}, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2);")
+                E(f"      tpbp2_S{sid}<<<(unsigned)a.n_nodes, 32 * kPairedGroups_S{sid}, smem2, s>>>(a2); }}")
+                E(f"    else if (a.mul == 64) {{ if (smem > 48 * 1024) cudaFuncSetAttribute(tpbp_S{sid}<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);")
                 E(f"      tpbp_S{sid}<64><<<(unsigned)a.n_nodes, 32 * {Gs[sid]} * 2, smem, s>>>(a); }}")
                 E(f"    else {{ if (smem > 48 * 1024) cudaFuncSetAttribute(tpbp_S{sid}<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);")
                 E(f"      tpbp_S{sid}<32><<<(unsigned)a.n_nodes, 32 * {Gs[sid]}, smem, s>>>(a); }}")
@@ -537,7 +736,12 @@ def emit_tables(st_list):
             if kind == "f":
                 E(f"  if ((a.mul == 64 || a.mul == 32) && e3b_tp_pipelined_enabled()) {{")
                 E(f"    const size_t smem = tpfp_smem_S{sid}(a.mul);")
-                E(f"    if (a.mul == 64) {{ if (smem > 48 * 1024) cudaFuncSetAttribute(tpfp_S{sid}<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);")
+                E(f"    if (a.mul == 64 && e3b_tp_paired_fwd_enabled(kPairedFwdOk_S{sid})) {{")
+                E(f"      TpArgs<float> a2 = a; a2.n_stages = e3b_tp_stages(0, tpp2_smem_S{sid}(1, false) - tpp2_smem_S{sid}(0, false), tpp2_smem_S{sid}(0, false));")
+                E(f"      const size_t smem2 = tpp2_smem_S{sid}(a2.n_stages, false);")
+                E(f"      if (smem2 > 48 * 1024) cudaFuncSetAttribute(tpfp2_S{sid}, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2);")
+                E(f"      tpfp2_S{sid}<<<(unsigned)a.n_nodes, 32 * kPairedGroups_S{sid}, smem2, s>>>(a2); }}")
+                E(f"    else if (a.mul == 64) {{ if (smem > 48 * 1024) cudaFuncSetAttribute(tpfp_S{sid}<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);")
                 E(f"      tpfp_S{sid}<64><<<(unsigned)a.n_nodes, 32 * {Gs[sid]} * 2, smem, s>>>(a); }}")
                 E(f"    else {{ if (smem > 48 * 1024) cudaFuncSetAttribute(tpfp_S{sid}<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);")
                 E(f"      tpfp_S{sid}<32><<<(unsigned)a.n_nodes, 32 * {Gs[sid]}, smem, s>>>(a); }}")
@@ -594,6 +798,11 @@ def emit_cg_tables(lmax=3):
 
 def main():
     sts = generated_structures()
+    if os.environ.get("E3B_GEN_ONLY"):      # compile-time experiments on a few structures (the output is not a working table)
+        sts = [sts[int(i)] for i in os.environ["E3B_GEN_ONLY"].split(",")]
+        with open(os.environ.get("E3B_GEN_OUT", "/tmp/tp_generated_only.cuh"), "w") as f:
+            f.write(emit_tables(sts))
+        return
     with open(os.path.join(HERE, "tp_generated.cuh"), "w") as f:
         f.write(emit_tables(sts))
     with open(os.path.join(HERE, "cg_tables.cuh"), "w") as f:

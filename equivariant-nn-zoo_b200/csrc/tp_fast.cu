@@ -9,6 +9,34 @@ bool e3b_tp_pipelined_enabled() {
   return on != 0;
 }
 
+// E3B_TP_PAIRED=0 keeps one channel per thread in the pipelined backward kernels (A/B comparison)
+// (E3B_TP_PAIRED=1: backward only, 2: forward only, default 3: both)
+static int tp_paired_mask() {
+  static const int m = [] { const char* v = getenv("E3B_TP_PAIRED"); return (v && v[0] >= '0' && v[0] <= '3') ? v[0] - '0' : 3; }();
+  return m;
+}
+static bool tp_paired_force() {
+  static const int on = [] { const char* v = getenv("E3B_TP_PAIRED_FORCE"); return (v && v[0] == '1') ? 1 : 0; }();
+  return on != 0;
+}
+// `preferred`: the generator's per-structure choice (measured, see gen_tp.py); E3B_TP_PAIRED_FORCE=1 overrides it
+bool e3b_tp_paired_enabled(bool preferred) { return (tp_paired_mask() & 1) != 0 && (preferred || tp_paired_force()); }
+bool e3b_tp_paired_fwd_enabled(bool preferred) { return (tp_paired_mask() & 2) != 0 && (preferred || tp_paired_force()); }
+
+// Ring depth of the paired kernels: 3 like the one-channel kernels.  Measured at W2: 3 / 4 / 5 stages make no difference at equal
+// CTAs per SM (the kernels are bound by arithmetic and instruction fetch, not by bytes in flight), and a deeper ring only
+// costs occupancy.  E3B_TP_STAGES_B / E3B_TP_STAGES_F override (experiments).
+int e3b_tp_stages(int bwd, size_t per_stage, size_t fixed) {
+  static const int env_b = [] { const char* v = getenv("E3B_TP_STAGES_B"); return v ? atoi(v) : 0; }();
+  static const int env_f = [] { const char* v = getenv("E3B_TP_STAGES_F"); return v ? atoi(v) : 0; }();
+  long n = (bwd ? env_b : env_f);
+  if (n <= 0) n = 3;
+  const long n_max = (long)((227 * 1024 - 64 - fixed) / per_stage);
+  if (n > n_max) n = n_max;
+  if (n < 2) n = 2;
+  return (int)n;
+}
+
 #include "tp_generated.cuh"
 
 const GenEntry* e3b_find_generated(const e3b_tp_desc* d, const int32_t* y_base, const int32_t* y_kstride) {
