@@ -979,7 +979,7 @@ extern "C" int e3b_tp_plan_dims(const e3b_tp_plan* p, int32_t* x_dim, int32_t* s
   if (sh_dim) *sh_dim = (int32_t)p->sh_dim;
   if (w_dim) *w_dim = (int32_t)p->w_dim;
   if (y_dim) *y_dim = (int32_t)p->y_dim;
-  if (n_part_f32) *n_part_f32 = p->gen ? p->gen->n_groups * ((p->desc.mul + 31) / 32) : 1;
+  if (n_part_f32) *n_part_f32 = p->gen ? e3b_gen_bwd_parts(p->gen, p->desc.mul) : 1;
   return E3B_OK;
 }
 
@@ -1088,7 +1088,7 @@ static TpArgs<T> make_args(const e3b_tp_plan* p, int64_t n_nodes, const void* x,
   a.x_dim = p->x_dim; a.sh_dim = p->sh_dim; a.w_dim = p->w_dim; a.y_dim = p->y_dim;
   a.mul = p->desc.mul;
   a.n_chunks = (p->desc.mul + 31) / 32;
-  a.n_part = p->gen ? p->gen->n_groups * a.n_chunks : 1;
+  a.n_part = p->gen ? e3b_gen_bwd_parts(p->gen, p->desc.mul) : 1;
   a.n_stages = 0;
   return a;
 }

@@ -88,7 +88,10 @@ def emit_structure(E, sid, st):
                     out.append((b, s, ps))
         return out
 
-    def emit_bwd_body(blocks, xl, wl, yl, stage_gx=False, paired=False):
+    def emit_bwd_body(blocks, xl, wl, yl, stage_gx=False, paired=False, pmap=None, xmap=None, gyname=None, xbase="0"):
+            pmap = pmap or (lambda pi: pi)
+            xmap = xmap or (lambda b, i: xoff[b] + i)
+            gyname = gyname or (lambda pi, k: f"gy_{pi}_{k}")
             used_s = sorted({s for (b, s, ps) in pairs_of(blocks)})
             for s in used_s:
                 for j in range(st.irreps_sh[s].ir.dim):
@@ -126,28 +129,28 @@ def emit_structure(E, sid, st):
                             expr = f"{lit(c)} * xy_{i}_{j}"
                             for (i, j, c) in terms[1:]:
                                 expr = f"fma_({lit(c)}, xy_{i}_{j}, {expr})"
-                            E(f"        gw_p = fma_(gy_{pi}_{k}, {expr}, gw_p);")
-                            E(f"        {{ const T gt = w_p * gy_{pi}_{k};")
+                            E(f"        gw_p = fma_({gyname(pi, k)}, {expr}, gw_p);")
+                            E(f"        {{ const T gt = w_p * {gyname(pi, k)};")
                             for (i, j, c) in terms:
                                 E(f"          gxy_{i}_{j} = fma_({lit(c)}, gt, gxy_{i}_{j});")
                             E("        }")
-                        E(f"        if (active) gwr[{pi} * mul] = gw_p; }}")
+                        E(f"        if (active) gwr[{pmap(pi)} * mul] = gw_p; }}")
                     for (i, j) in need:
                         E(f"      gx_{b}_{i} = fma_(gxy_{i}_{j}, Y_{s}_{j}, gx_{b}_{i});")
                         E(f"      gY_{s}_{j} = fma_(gxy_{i}_{j}, x_{b}_{i}, gY_{s}_{j});")
                     E("    }")
                 E("    if (a.gx_edge != nullptr && active) {")
                 if paired:
-                    E("      T* __restrict__ gxr = reinterpret_cast<T*>(a.gx_edge + eid * ROW_X) + u;")
+                    E(f"      T* __restrict__ gxr = reinterpret_cast<T*>(a.gx_edge + eid * ROW_X) + {xbase} + u;")
                 else:
                     E("      T* __restrict__ gxr = a.gx_edge + eid * x_dim + u;")
                 for i in range(d1):
-                    E(f"      gxr[{xoff[b] + i} * mul] = gx_{b}_{i};")
+                    E(f"      gxr[{xmap(b, i)} * mul] = gx_{b}_{i};")
                 E("    }")
                 if stage_gx and paired:   # node-reduction mode, paired kernels: 8-byte vector reductions straight from registers
                     E("    if (a.gx_node != nullptr) {")
                     for i in range(d1):
-                        E(f"      red_add_f32x2(gxn + {xoff[b] + i} * mul, gx_{b}_{i});")
+                        E(f"      red_add_f32x2(gxn + {xmap(b, i)} * mul, gx_{b}_{i});")
                     E("    }")
                 elif stage_gx:   # node-reduction mode: the edge's gradient row is staged in shared memory for one TMA reduce-add
                     E("    if (a.gx_node != nullptr) {")
@@ -501,11 +504,13 @@ def emit_structure(E, sid, st):
                    for p in st.paths if p.i_in == b) for b in range(len(st.irreps_in))]
     g_light = min(range(G2), key=lambda g: sum(work_of[b] for b in groups2[g]))   # the warp with the least arithmetic
 
-    def paired_head(name, bwd):
-        E(f"__global__ void __launch_bounds__(32 * {G2}) {name}_S{sid}(const TpArgs<float> a) {{")
+    def paired_head(name, bwd, nwarps=None, pw=None):
+        nwarps = G2 if nwarps is None else nwarps
+        pw = g_light if pw is None else pw
+        E(f"__global__ void __launch_bounds__(32 * {nwarps}) {name}_S{sid}(const TpArgs<float> a) {{")
         E("  typedef F2 T;")
         E("  asm volatile(\"griddepcontrol.launch_dependents;\" ::: \"memory\");")
-        E(f"  constexpr int MUL = 64, G = {G2}, PW = {g_light}, ROW_W = {n_paths} * MUL, ROW_X = {xdim} * MUL, STAGE = ROW_W + ROW_X, SH_DIM = {sdim};")
+        E(f"  constexpr int MUL = 64, G = {nwarps}, PW = {pw}, ROW_W = {n_paths} * MUL, ROW_X = {xdim} * MUL, STAGE = ROW_W + ROW_X, SH_DIM = {sdim};")
         E("  constexpr int NT = 32 * G;")
         E("  constexpr int mul = MUL / 2;   // row strides below are in channel PAIRS")
         if bwd:
@@ -572,37 +577,99 @@ def emit_structure(E, sid, st):
         E("    }")
 
     # ---------------- backward
-    paired_head("tpbp2", True)
-    E(f"  const T* __restrict__ gyr = reinterpret_cast<const T*>(a.gy + node * ({ydim} * MUL)) + u;")
-    E("  switch (group) {")
-    for g, blocks in enumerate(groups2):
-        E(f"  case {g}: {{")
-        for pi, p in enumerate(st.paths):
-            if p.i_in in blocks:
-                for k in range(p.ir_out.dim):
-                    E(f"    const T gy_{pi}_{k} = ldg(gyr + {ybase[p.slot] + k * ykst[p.slot]} * mul);")
-        paired_chunk_open()
-        E("        const int64_t eid = s_eid[i];")
-        E("        T* __restrict__ gwr = reinterpret_cast<T*>(a.gw + eid * ROW_W) + u;")
-        E("        T* __restrict__ gxn = reinterpret_cast<T*>(a.gx_node + (int64_t)s_src[i] * ROW_X) + u;   // d/dx of the SOURCE node (node-reduction mode)")
-        E("        {")
-        emit_bwd_body(blocks, lambda b, i: f"sx[{xoff[b] + i} * mul]", lambda pi: f"sw[{pi} * mul]",
-                      lambda s_, j: f"T(__shfl_sync(0xffffffffu, Ycur, {soff[s_] + j}))", stage_gx=True, paired=True)
-        E("        }")
-        if g == g_light and G2 != 2 * G:
-            E(f"        if (a.gsh != nullptr && lane < SH_DIM)     // partial-sum rows no warp of this kernel owns")
-            E(f"          for (int p = G; p < a.n_part; ++p) a.gsh[(eid * a.n_part + p) * SH_DIM + lane] = 0.f;")
-        paired_chunk_close()
-        E("  } break;")
-    E("  }")
-    E("}")
+    # Class-shared variant: one warp per input block, and blocks of the same l with the same relative path list (the two
+    # parities of an l in the hidden layers) run THE SAME unrolled code with per-warp base offsets -- the hot loops of a
+    # kernel then total ~14 KB instead of 27 KB and stay inside the SM's 32 KB instruction cache (ncu: `no_instruction`
+    # 2.2 -> 0.2 stall cycles per issue).  Needs: every block has paths (contiguous in the weight row, by construction of
+    # the plan) -- the restricted structures keep the group variant.  MEASURED SLOWER than one channel per thread and
+    # therefore not the default (E3B_TP_PAIRED_FORCE=1 runs it): 160-192 threads x 164 registers leave 2 CTAs per SM, and
+    # with one CTA per destination node the start-up chain of a node (in_ptr -> indices -> TMA -> first data) is hidden
+    # only by the other resident CTAs: 27 paths 609 -> 773 us, 15 paths 327 -> 413 us; ring depth 3 -> 8 recovers 5 %.
+    # What it needs next is a persistent CTA over a flattened edge range.
+    blk_paths = [[pi for pi, p in enumerate(st.paths) if p.i_in == b] for b in range(len(st.irreps_in))]
+    sig = [(st.irreps_in[b].ir.l, tuple((st.paths[pi].i_sh, st.paths[pi].ir_out.l) for pi in blk_paths[b])) for b in range(len(st.irreps_in))]
+    class_ok = (all(len(ps) > 0 and ps == list(range(ps[0], ps[0] + len(ps))) for ps in blk_paths)
+                and 2 <= len(st.irreps_in) <= 8 and sdim == 9 and n_paths > 3)
+    if class_ok:
+        order = sorted(range(len(st.irreps_in)), key=lambda b: -work_of[b])      # warp w runs block order[w]: heavy blocks first
+        classes = []
+        for b in order:
+            if sig[b] not in [sig[c] for c in classes]:
+                classes.append(b)                                                # representative block of each class
+        cls_of = [[sig[c] for c in classes].index(sig[b]) for b in order]
+        W3 = len(order)
+        n_gy = [sum(st.paths[pi].ir_out.dim for pi in blk_paths[b]) for b in order]
+        E(f"static __device__ const int kB3Cls_S{sid}[{W3}] = {{" + ", ".join(map(str, cls_of)) + "};")
+        E(f"static __device__ const int kB3Xb_S{sid}[{W3}] = {{" + ", ".join(str(xoff[b]) for b in order) + "};")
+        E(f"static __device__ const int kB3Wb_S{sid}[{W3}] = {{" + ", ".join(str(blk_paths[b][0]) for b in order) + "};")
+        E(f"static __device__ const int kB3Gy_S{sid}[{W3}][{max(n_gy)}] = {{")
+        for b in order:
+            offs = [ybase[st.paths[pi].slot] + k * ykst[st.paths[pi].slot] for pi in blk_paths[b] for k in range(st.paths[pi].ir_out.dim)]
+            E("  {" + ", ".join(map(str, offs + [0] * (max(n_gy) - len(offs)))) + "},")
+        E("};")
+        pw3 = W3 - 1                                                             # the lightest block's warp is the producer
+        paired_head("tpbp2", True, W3, pw3)
+        E(f"  const int xb = kB3Xb_S{sid}[warp] * mul, wb = kB3Wb_S{sid}[warp] * mul;   // this warp's block: offsets in channel pairs")
+        E(f"  const int* __restrict__ go = kB3Gy_S{sid}[warp];")
+        E(f"  const T* __restrict__ gyr = reinterpret_cast<const T*>(a.gy + node * ({ydim} * MUL)) + u;")
+        E(f"  switch (kB3Cls_S{sid}[warp]) {{")
+        for ci, b in enumerate(classes):
+            p0 = blk_paths[b][0]
+            E(f"  case {ci}: {{")
+            j = 0
+            for pi in blk_paths[b]:
+                for k in range(st.paths[pi].ir_out.dim):
+                    E(f"    const T gy_{pi}_{k} = ldg(gyr + go[{j}] * mul);")
+                    j += 1
+            paired_chunk_open()
+            E("        sw += wb; sx += xb;")
+            E("        const int64_t eid = s_eid[i];")
+            E("        T* __restrict__ gwr = reinterpret_cast<T*>(a.gw + eid * ROW_W) + wb + u;")
+            E("        T* __restrict__ gxn = reinterpret_cast<T*>(a.gx_node + (int64_t)s_src[i] * ROW_X) + xb + u;   // d/dx of the SOURCE node (node-reduction mode)")
+            E("        {")
+            emit_bwd_body([b], lambda b_, i: f"sx[{i} * mul]", lambda pi: f"sw[{pi - p0} * mul]",
+                          lambda s_, j_: f"T(__shfl_sync(0xffffffffu, Ycur, {soff[s_] + j_}))", stage_gx=True, paired=True,
+                          pmap=lambda pi: pi - p0, xmap=lambda b_, i: i, xbase="xb")
+            E("        }")
+            paired_chunk_close()
+            E("  } break;")
+        E("  }")
+        E("}")
+        E(f"static const int kPairedBwdWarps_S{sid} = {W3}, kPairedBwdParts_S{sid} = {W3};")
+    else:
+        E(f"static const int kPairedBwdWarps_S{sid} = {G2}, kPairedBwdParts_S{sid} = {2 * G};")
+    if not class_ok:
+        paired_head("tpbp2", True)
+        E(f"  const T* __restrict__ gyr = reinterpret_cast<const T*>(a.gy + node * ({ydim} * MUL)) + u;")
+        E("  switch (group) {")
+        for g, blocks in enumerate(groups2):
+            E(f"  case {g}: {{")
+            for pi, p in enumerate(st.paths):
+                if p.i_in in blocks:
+                    for k in range(p.ir_out.dim):
+                        E(f"    const T gy_{pi}_{k} = ldg(gyr + {ybase[p.slot] + k * ykst[p.slot]} * mul);")
+            paired_chunk_open()
+            E("        const int64_t eid = s_eid[i];")
+            E("        T* __restrict__ gwr = reinterpret_cast<T*>(a.gw + eid * ROW_W) + u;")
+            E("        T* __restrict__ gxn = reinterpret_cast<T*>(a.gx_node + (int64_t)s_src[i] * ROW_X) + u;   // d/dx of the SOURCE node (node-reduction mode)")
+            E("        {")
+            emit_bwd_body(blocks, lambda b, i: f"sx[{xoff[b] + i} * mul]", lambda pi: f"sw[{pi} * mul]",
+                          lambda s_, j: f"T(__shfl_sync(0xffffffffu, Ycur, {soff[s_] + j}))", stage_gx=True, paired=True)
+            E("        }")
+            if g == g_light and G2 != 2 * G:
+                E(f"        if (a.gsh != nullptr && lane < SH_DIM)     // partial-sum rows no warp of this kernel owns")
+                E(f"          for (int p = G; p < a.n_part; ++p) a.gsh[(eid * a.n_part + p) * SH_DIM + lane] = 0.f;")
+            paired_chunk_close()
+            E("  } break;")
+        E("  }")
+        E("}")
     E(f"static const int kPairedGroups_S{sid} = {G2};")
     # which variant runs by default -- measured per kernel on the W2 step (ncu launch list, paired vs one channel per thread):
     # backward 3-path structures 133 -> 88 us and 188 -> 171 us, the 15-path restriction of the full block 405 -> 371 us, but the
     # 15-path second block 327 -> 338 us and 27 paths 609 -> 646 us (the unrolled loops of the 4 warps, 27 KB, no longer fit the 32 KB instruction
     # cache of the SM: ncu `no_instruction` is the top stall); forward 27 / 30 paths 258 -> 227 us and 260 -> 248 us, smaller
     # structures unchanged.  E3B_TP_PAIRED_FORCE=1 runs the paired kernels everywhere.
-    E(f"static const bool kPairedBwdOk_S{sid} = {'true' if (n_paths <= 3 or (n_paths == 15 and len(st.irreps_in) == 6)) else 'false'};")
+    E(f"static const bool kPairedBwdOk_S{sid} = {'true' if (not class_ok and (n_paths <= 3 or (n_paths == 15 and len(st.irreps_in) == 6))) else 'false'};")
     E(f"static const bool kPairedFwdOk_S{sid} = {'true' if n_paths >= 20 else 'false'};")
     E(f"static size_t tpp2_smem_S{sid}(int nst, bool reduce) {{ return (size_t)nst * ({n_paths} + {xdim}) * 64 * 4 + 3 * TPP2_MAXSEG * 4 + (size_t)nst * 16; }}")
 
@@ -726,7 +793,8 @@ def emit_tables(st_list):
                 E(f"      TpArgs<float> a2 = a; a2.n_stages = e3b_tp_stages(1, tpp2_smem_S{sid}(1, a.gx_node != nullptr) - tpp2_smem_S{sid}(0, a.gx_node != nullptr), tpp2_smem_S{sid}(0, a.gx_node != nullptr));")
                 E(f"      const size_t smem2 = tpp2_smem_S{sid}(a2.n_stages, a.gx_node != nullptr);")
                 E(f"      if (smem2 > 48 * 1024) cudaFuncSetAttribute(tpbp2_S{sid}, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2);")
-                E(f"      tpbp2_S{sid}<<<(unsigned)a.n_nodes, 32 * kPairedGroups_S{sid}, smem2, s>>>(a2); }}")
+                E(f"      a2.n_part = kPairedBwdParts_S{sid};")
+                E(f"      tpbp2_S{sid}<<<(unsigned)a.n_nodes, 32 * kPairedBwdWarps_S{sid}, smem2, s>>>(a2); }}")
                 E(f"    else if (a.mul == 64) {{ if (smem > 48 * 1024) cudaFuncSetAttribute(tpbp_S{sid}<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);")
                 E(f"      tpbp_S{sid}<64><<<(unsigned)a.n_nodes, 32 * {Gs[sid]} * 2, smem, s>>>(a); }}")
                 E(f"    else {{ if (smem > 48 * 1024) cudaFuncSetAttribute(tpbp_S{sid}<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);")
@@ -764,7 +832,7 @@ def emit_tables(st_list):
             str(len(st.paths)), arr(p.i_in for p in st.paths), arr(p.i_sh for p in st.paths),
             arr(p.ir_out.l for p in st.paths), arr(p.slot for p in st.paths),
             arr(st.y_layout()[0][p.slot] for p in st.paths), arr(st.y_layout()[1][p.slot] for p in st.paths),
-            str(Gs[sid]), f"launch_tpf_S{sid}", f"launch_tpb_S{sid}"]) + "},")
+            str(Gs[sid]), f"launch_tpf_S{sid}", f"launch_tpb_S{sid}", f"kPairedBwdParts_S{sid}", f"kPairedBwdOk_S{sid}"]) + "},")
     E("};")
     E("#endif  // __CUDACC__")
     return E.text()

@@ -39,6 +39,11 @@ int e3b_tp_stages(int bwd, size_t per_stage, size_t fixed) {
 
 #include "tp_generated.cuh"
 
+int e3b_gen_bwd_parts(const GenEntry* g, int mul) {
+  if (mul == 64 && e3b_tp_pipelined_enabled() && e3b_tp_paired_enabled(g->paired_bwd_ok)) return g->paired_bwd_parts;
+  return g->n_groups * ((mul + 31) / 32);
+}
+
 const GenEntry* e3b_find_generated(const e3b_tp_desc* d, const int32_t* y_base, const int32_t* y_kstride) {
   for (int e = 0; e < kNumGenEntries; ++e) {
     const GenEntry& g = kGenEntries[e];

@@ -180,8 +180,10 @@ class FusedInteraction:
             self._cache[key] = out
         return self._cache[key]
 
-    def restricted_fc(self, so):
-        """packed (backward role) last radial layer restricted to the live weight columns, per parameter version"""
+    def restricted_fc(self, so, role="bwd"):
+        """packed last radial layer restricted to the live weight columns, per parameter version: role 'bwd' for the gradient
+        of the hidden activations, role 'fwd' to RECOMPUTE the live columns of the per-edge weights from the saved hidden
+        activations ([E, 64] x [64, live]: cheaper than gathering them out of the [E, 1920] rows of the forward pass)"""
         W = getattr(self.conv.fc, f"layer{self.conv.fc.n_layers - 1}").weight
         key = (ops.WEIGHTS_EPOCH, W.data_ptr(), W._version)
         ckey = ("restricted_fc", tuple(so["cols"]))
@@ -191,9 +193,10 @@ class FusedInteraction:
             with torch.no_grad():
                 Wl = torch.cat([W[:, c * mul:(c + 1) * mul] for c in so["cols"]], 1).contiguous()      # [h, live]
             hi, ho = Wl.shape
-            hit = (key, ops.gemm_pack([(Wl, 0, ho, 0, 1, 1, 0, hi, ho)])[0])
+            packed = ops.gemm_pack([(Wl, 0, ho, 0, 1, 1, 0, hi, ho), (Wl, 0, 1, 0, ho, 1, 0, ho, hi)])
+            hit = (key, {"bwd": packed[0], "fwd": packed[1]})
             self._cache[ckey] = hit
-        return hit[1]
+        return hit[1][role]
 
     def sc_sets(self, grp):
         """self-connection weights contracted with the attribute row of every species (`ops.sc_weight_sets`)"""
@@ -508,8 +511,15 @@ class _Interaction(torch.autograd.Function):
         if len(written) < (len(fi.mid) if so is None else so["n_mid"]):
             g_mid.zero_()
         if so is not None:
-            mul = fi.structure.uniform_mul
-            w = torch.cat([w[:, c * mul:(c + 1) * mul] for c in so["cols"]], 1)      # weight columns of the live paths
+            # weight columns of the live paths, recomputed from the hidden activations with the column slice of the last
+            # radial layer (same arithmetic as the forward pass; a gather out of the full rows cost 0.20 + 0.05 ms per step)
+            hs_, n_fc_ = fi.hs, conv.fc.n_layers
+            w_live = new(w.shape[0], len(so["cols"]) * fi.structure.uniform_mul)
+            with ops.stage("b.w_live"):
+                ops.gemm_run([ops.gemm_problem(h_last, fi.restricted_fc(so, "fwd"), w_live, w.shape[0],
+                                               a_rows=(h_last.stride(0), 0, 1), alpha=1.0 / math.sqrt(hs_[-2]), epilogue=0,
+                                               act_cst=conv.fc.cst)])
+            w = w_live
         with ops.stage("b.post_linear"):
             for wave in _waves(probs):
                 ops.gemm_run(wave)
