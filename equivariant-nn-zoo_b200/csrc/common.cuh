@@ -17,6 +17,8 @@ static inline float fma_(float a, float b, float c) { return fmaf(a, b, c); }
 static inline double fma_(double a, double b, double c) { return fma(a, b, c); }
 #define E3B_GSH_STORE(ptr, idx, val) do { if (active) (ptr)[idx] += (val); } while (0)
 #define E3B_GSH_ZERO(ptr, idx) do { } while (0)
+#define E3B_GSH_STORE9(ptr, lane, v0, v1, v2, v3, v4, v5, v6, v7, v8) do { if (active) { (ptr)[0] += (v0); (ptr)[1] += (v1); \
+  (ptr)[2] += (v2); (ptr)[3] += (v3); (ptr)[4] += (v4); (ptr)[5] += (v5); (ptr)[6] += (v6); (ptr)[7] += (v7); (ptr)[8] += (v8); } } while (0)
 #else
 #include <cuda_runtime.h>
 template <typename T> __device__ __forceinline__ T ldg(const T* p) { return __ldg(p); }
@@ -29,6 +31,7 @@ template <typename T> __device__ __forceinline__ T warp_sum(T v) {
 }
 #define E3B_GSH_STORE(ptr, idx, val) do { const T r_ = warp_sum(val); if (lane == 0) (ptr)[idx] = r_; } while (0)
 #define E3B_GSH_ZERO(ptr, idx) do { if (lane == 0) (ptr)[idx] = T(0); } while (0)
+#define E3B_GSH_STORE9(ptr, lane, ...) gsh_reduce_store9(ptr, lane, __VA_ARGS__)
 #endif
 
 #define TP_THREADS 128
@@ -83,6 +86,7 @@ __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.
 bool e3b_tp_pipelined_enabled();
 bool e3b_tp_paired_enabled(bool preferred);
 bool e3b_tp_paired_fwd_enabled(bool preferred);
+bool e3b_tp_decoupled_enabled();
 int e3b_tp_stages(int bwd, size_t per_stage_bytes, size_t fixed_bytes);
 // ---- two channels per thread: packed fp32 pairs (sm_100 FFMA2 / FMUL2; a scalar or an immediate broadcasts to both halves,
 // so Clebsch-Gordan literals and the spherical harmonics of the edge need no register pairs)
@@ -94,9 +98,14 @@ struct __align__(8) F2 {
 };
 __device__ __forceinline__ F2 operator*(F2 a, F2 b) { return F2(__fmul2_rn(a.v, b.v)); }
 __device__ __forceinline__ F2 fma_(F2 a, F2 b, F2 c) { return F2(__ffma2_rn(a.v, b.v, c.v)); }
-__device__ __forceinline__ void red_add_f32x2(F2* p, F2 v) {   // fire-and-forget L2 reduction of a channel pair (sm_90+)
+__device__ __forceinline__ void red_add(F2* p, F2 v) {   // fire-and-forget L2 reduction of a channel pair (sm_90+)
   asm volatile("red.global.add.v2.f32 [%0], {%1, %2};" ::"l"(p), "f"(v.v.x), "f"(v.v.y) : "memory");
 }
+__device__ __forceinline__ void red_add(float* p, float v) {
+  asm volatile("red.global.add.f32 [%0], %1;" ::"l"(p), "f"(v) : "memory");
+}
+__device__ __forceinline__ float pair_sum(F2 v) { return v.v.x + v.v.y; }
+__device__ __forceinline__ float pair_sum(float v) { return v; }
 __device__ __forceinline__ F2 ldg(const F2* p) { return F2(__ldg(reinterpret_cast<const float2*>(p))); }
 #define E3B_GSH_STORE2(ptr, idx, val) do { const float r_ = warp_sum((val).v.x + (val).v.y); if (lane == 0) (ptr)[idx] = r_; } while (0)
 // sums over the 32 lanes of NINE values per lane (the d/dY partials of one edge, sh_dim = 9) and their store: a halving butterfly

@@ -150,7 +150,7 @@ def emit_structure(E, sid, st):
                 if stage_gx and paired:   # node-reduction mode, paired kernels: 8-byte vector reductions straight from registers
                     E("    if (a.gx_node != nullptr) {")
                     for i in range(d1):
-                        E(f"      red_add_f32x2(gxn + {xmap(b, i)} * mul, gx_{b}_{i});")
+                        E(f"      red_add(gxn + {xmap(b, i)} * mul, gx_{b}_{i});")
                     E("    }")
                 elif stage_gx:   # node-reduction mode: the edge's gradient row is staged in shared memory for one TMA reduce-add
                     E("    if (a.gx_node != nullptr) {")
@@ -164,9 +164,15 @@ def emit_structure(E, sid, st):
                 vals = ["0.f"] * 9
                 for s in used_s:
                     for j in range(st.irreps_sh[s].ir.dim):
-                        vals[soff[s] + j] = f"gY_{s}_{j}.v.x + gY_{s}_{j}.v.y"
+                        vals[soff[s] + j] = f"pair_sum(gY_{s}_{j})"
                 E("      gsh_reduce_store9(gsr, lane, " + ", ".join(vals) + ");")
-            for s in ([] if paired and sdim == 9 else range(len(st.irreps_sh))):
+            if not paired and sdim == 9:      # one channel per thread: the same halving butterfly (host emulation: plain sums)
+                vals = ["T(0)"] * 9
+                for s in used_s:
+                    for j in range(st.irreps_sh[s].ir.dim):
+                        vals[soff[s] + j] = f"gY_{s}_{j}"
+                E("      E3B_GSH_STORE9(gsr, lane, " + ", ".join(vals) + ");")
+            for s in ([] if sdim == 9 else range(len(st.irreps_sh))):
                 for j in range(st.irreps_sh[s].ir.dim):
                     if s in used_s:
                         E(f"      E3B_GSH_STORE{sfx}(gsr, {soff[s] + j}, gY_{s}_{j});")
@@ -504,15 +510,15 @@ def emit_structure(E, sid, st):
                    for p in st.paths if p.i_in == b) for b in range(len(st.irreps_in))]
     g_light = min(range(G2), key=lambda g: sum(work_of[b] for b in groups2[g]))   # the warp with the least arithmetic
 
-    def paired_head(name, bwd, nwarps=None, pw=None):
+    def paired_head(name, bwd, nwarps=None, pw=None, pair=True, ngroups=None):
         nwarps = G2 if nwarps is None else nwarps
         pw = g_light if pw is None else pw
         E(f"__global__ void __launch_bounds__(32 * {nwarps}) {name}_S{sid}(const TpArgs<float> a) {{")
-        E("  typedef F2 T;")
+        E("  typedef F2 T;" if pair else "  typedef float T;")
         E("  asm volatile(\"griddepcontrol.launch_dependents;\" ::: \"memory\");")
         E(f"  constexpr int MUL = 64, G = {nwarps}, PW = {pw}, ROW_W = {n_paths} * MUL, ROW_X = {xdim} * MUL, STAGE = ROW_W + ROW_X, SH_DIM = {sdim};")
         E("  constexpr int NT = 32 * G;")
-        E("  constexpr int mul = MUL / 2;   // row strides below are in channel PAIRS")
+        E("  constexpr int mul = MUL / 2;   // row strides below are in channel PAIRS" if pair else "  constexpr int mul = MUL;")
         if bwd:
             E("  constexpr bool active = true;")
         E("  extern __shared__ __align__(128) unsigned char tpp_smem[];")
@@ -525,7 +531,10 @@ def emit_structure(E, sid, st):
         E("  uint64_t* empty = full + nst;")
         E("  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;")
         E("  const int64_t node = blockIdx.x;")
-        E("  const int group = warp, u = lane;" + (" const int part = warp;" if bwd else ""))
+        if pair:
+            E("  const int group = warp, u = lane;" + (" const int part = warp;" if bwd else ""))
+        else:
+            E(f"  const int chunk = warp / {ngroups}, group = warp - chunk * {ngroups}, u = chunk * 32 + lane;" + (" const int part = warp;" if bwd else ""))
         E("  if (tid == 0) {")
         E("    for (uint32_t s = 0; s < nst; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], G); }")
         E("    fence_mbar_init();")
@@ -533,7 +542,7 @@ def emit_structure(E, sid, st):
         E("  const int64_t e0 = a.in_ptr[node], e1 = a.in_ptr[node + 1];")
         E("  uint32_t it = 0, s = 0, ph = 0;   // running edge counter, ring stage and barrier phase of the edge being consumed")
 
-    def paired_chunk_open():
+    def paired_chunk_open(pair=True):
         E("    for (int64_t c0 = e0; c0 < e1; c0 += TPP2_MAXSEG) {")
         E("      const int n = (int)((e1 - c0) < TPP2_MAXSEG ? (e1 - c0) : TPP2_MAXSEG);")
         E("      __syncthreads();   // every warp is through the previous chunk: all stages free (also orders the barrier init)")
@@ -566,7 +575,7 @@ def emit_structure(E, sid, st):
         E("        if (i + 1 < n && lane < SH_DIM) Ynext = ldg(a.sh + (int64_t)s_eid[i + 1] * SH_DIM + lane);")
         E("        mbar_wait(&full[s], ph);")
         E("        const T* __restrict__ sw = reinterpret_cast<const T*>(stages + s * STAGE) + u;")
-        E("        const T* __restrict__ sx = sw + ROW_W / 2;")
+        E("        const T* __restrict__ sx = sw + ROW_W / 2;" if pair else "        const T* __restrict__ sx = sw + ROW_W;")
 
     def paired_chunk_close():
         E("        Ycur = Ynext;")
@@ -672,6 +681,32 @@ def emit_structure(E, sid, st):
     E(f"static const bool kPairedBwdOk_S{sid} = {'true' if (not class_ok and (n_paths <= 3 or (n_paths == 15 and len(st.irreps_in) == 6))) else 'false'};")
     E(f"static const bool kPairedFwdOk_S{sid} = {'true' if n_paths >= 20 else 'false'};")
     E(f"static size_t tpp2_smem_S{sid}(int nst, bool reduce) {{ return (size_t)nst * ({n_paths} + {xdim}) * 64 * 4 + 3 * TPP2_MAXSEG * 4 + (size_t)nst * 16; }}")
+
+    # ---------------- backward, one channel per thread, with the decoupled pipeline of the paired kernels (no CTA barrier per
+    # edge, d/dx by fire-and-forget reductions from registers instead of the staged TMA reduce-add): the default for the
+    # structures whose paired variant is slower
+    pw1 = min(range(G), key=lambda g: sum(work_of[b] for b in groups[g]))
+    paired_head("tpbp1d", True, 2 * G, pw1, pair=False, ngroups=G)
+    E(f"  const T* __restrict__ gyr = a.gy + node * ({ydim} * MUL) + u;")
+    E("  switch (group) {")
+    for g, blocks in enumerate(groups):
+        E(f"  case {g}: {{")
+        for pi, p in enumerate(st.paths):
+            if p.i_in in blocks:
+                for k in range(p.ir_out.dim):
+                    E(f"    const T gy_{pi}_{k} = ldg(gyr + {ybase[p.slot] + k * ykst[p.slot]} * mul);")
+        paired_chunk_open(pair=False)
+        E("        const int64_t eid = s_eid[i];")
+        E("        T* __restrict__ gwr = a.gw + eid * ROW_W + u;")
+        E("        T* __restrict__ gxn = a.gx_node + (int64_t)s_src[i] * ROW_X + u;   // d/dx of the SOURCE node (node-reduction mode)")
+        E("        {")
+        emit_bwd_body(blocks, lambda b, i: f"sx[{xoff[b] + i} * mul]", lambda pi: f"sw[{pi} * mul]",
+                      lambda s_, j: f"__shfl_sync(0xffffffffu, Ycur, {soff[s_] + j})", stage_gx=True, paired=True)
+        E("        }")
+        paired_chunk_close()
+        E("  } break;")
+    E("  }")
+    E("}")
 
     # ---------------- forward
     paired_head("tpfp2", False)
@@ -795,6 +830,11 @@ def emit_tables(st_list):
                 E(f"      if (smem2 > 48 * 1024) cudaFuncSetAttribute(tpbp2_S{sid}, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2);")
                 E(f"      a2.n_part = kPairedBwdParts_S{sid};")
                 E(f"      tpbp2_S{sid}<<<(unsigned)a.n_nodes, 32 * kPairedBwdWarps_S{sid}, smem2, s>>>(a2); }}")
+                E(f"    else if (a.mul == 64 && e3b_tp_decoupled_enabled()) {{")
+                E(f"      TpArgs<float> a2 = a; a2.n_stages = e3b_tp_stages(1, tpp2_smem_S{sid}(1, false) - tpp2_smem_S{sid}(0, false), tpp2_smem_S{sid}(0, false));")
+                E(f"      const size_t smem2 = tpp2_smem_S{sid}(a2.n_stages, false);")
+                E(f"      if (smem2 > 48 * 1024) cudaFuncSetAttribute(tpbp1d_S{sid}, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2);")
+                E(f"      tpbp1d_S{sid}<<<(unsigned)a.n_nodes, 32 * {Gs[sid]} * 2, smem2, s>>>(a2); }}")
                 E(f"    else if (a.mul == 64) {{ if (smem > 48 * 1024) cudaFuncSetAttribute(tpbp_S{sid}<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);")
                 E(f"      tpbp_S{sid}<64><<<(unsigned)a.n_nodes, 32 * {Gs[sid]} * 2, smem, s>>>(a); }}")
                 E(f"    else {{ if (smem > 48 * 1024) cudaFuncSetAttribute(tpbp_S{sid}<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);")

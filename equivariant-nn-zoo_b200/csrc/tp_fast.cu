@@ -15,6 +15,11 @@ static int tp_paired_mask() {
   static const int m = [] { const char* v = getenv("E3B_TP_PAIRED"); return (v && v[0] >= '0' && v[0] <= '3') ? v[0] - '0' : 3; }();
   return m;
 }
+// E3B_TP_DECOUPLED=0: the one-channel-per-thread backward keeps its CTA barrier per edge and the staged TMA reduce-add (A/B)
+bool e3b_tp_decoupled_enabled() {
+  static const int on = [] { const char* v = getenv("E3B_TP_DECOUPLED"); return (v && v[0] == '0') ? 0 : 1; }();
+  return on != 0;
+}
 static bool tp_paired_force() {
   static const int on = [] { const char* v = getenv("E3B_TP_PAIRED_FORCE"); return (v && v[0] == '1') ? 1 : 0; }();
   return on != 0;
