@@ -569,7 +569,8 @@ def run_ours(args, wl):
         roof = {"kernel": f"tpfp (fused gather + uvu CG tensor product + segmented sum, {n_paths} paths, mul {mul})",
                 "note": "algorithmic bytes = SURVEY 8d per directed edge (one weight row per edge); since round 2 the two directions of "
                         "an undirected edge read ONE shared weight row (the second read mostly hits L2), so `traffic` (ncu DRAM bytes) "
-                        "is below the algorithmic figure and `frac` can exceed what HBM alone would allow",
+                        "is below the algorithmic figure and `frac` can exceed what HBM alone would allow; the paired (FFMA2) kernel is "
+                        "bound by the FMA pipe (ncu profiles/r2_ncu_tpfp2_S3.txt: packed instructions occupy it two cycles, ~77 % busy)",
                 "bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": traffic,
                 "peak_source": peak_src, "timing": timing_how,
                 "algorithmic_bytes_per_launch": alg / len(rows), "avg_launch_ms": tt / len(rows),
@@ -584,7 +585,8 @@ def run_ours(args, wl):
         all_bwd = sum(s.elapsed_time(e) for tag, s, e in timing if tag[0] == "bwd")
         roof_bwd = {"kernel": f"tpbp (backward of the same kernel: dw, dx, dY; {rows[0][1][1]} paths, mul {rows[0][1][2]})",
                     "note": "the single most expensive kernel of the step (share_of_step: all its launches / step time); "
-                            "bound by instruction issue (ncu: issue slots 73 % busy), not by HBM",
+                            "bound by instruction issue (ncu profiles/r2_ncu_tpbp1d_S2.txt: issue slots 72 % busy, FMA pipe 53 %, "
+                            "top stall `not_selected`), not by HBM",
                     "bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
                     "traffic": traffic_bwd if roof is not None and roof.get("traffic") else None,
                     "share_of_step": all_bwd / ms if ms else None,

@@ -2,7 +2,8 @@
 """SASS evidence for the shipped library: per kernel, the counts of the Blackwell-specific mnemonics (UTCHMMA = tcgen05.mma,
 LDTM / STTM = tcgen05.ld / st, UTMALDG / UTMASTG = TMA tensor load / store (cp.async.bulk.tensor), ACQBULK / PREEXIT =
 griddepcontrol.wait / launch_dependents (programmatic dependent launch), UBLKCP = TMA bulk copy, UBLKRED = TMA bulk reduce-add, LDGSTS = cp.async, SYNCS = mbarrier, UTCBAR = tcgen05.commit) and of
-atomics (ATOMS = shared memory, ATOMG / REDG = global: only the CSR / cell-list cursors and the layer-norm weight gradient), plus a short excerpt around the first tensor-core instruction of the GEMM kernels.
+FFMA2 / FMUL2 = packed fp32 pairs (paired tensor-product kernels), and of atomics (ATOMS = shared memory, ATOMG / REDG = global: the CSR / cell-list cursors, the layer-norm weight
+gradient, and the d/dx reductions of the decoupled tensor-product backward kernels -- evaluation mode only, REDG.E.ADD.F32 / .F32x2), plus a short excerpt around the first tensor-core instruction of the GEMM kernels.
   python tools/sass_summary.py > profiles/r2_sass_summary.txt"""
 import os
 import re
@@ -23,7 +24,7 @@ for line in sass.splitlines():
 demangle = subprocess.run(["c++filt"], input="\n".join(kernels), capture_output=True, text=True).stdout.splitlines()
 names = dict(zip(kernels, demangle))
 KEYS = ["UTCHMMA", "LDTM", "STTM", "UTCBAR", "UTMALDG", "UTMASTG", "UBLKCP", "UBLKRED", "LDGSTS", "SYNCS", "ACQBULK", "PREEXIT",
-        "ATOMS", "ATOMG", "REDG"]
+        "FFMA2", "FMUL2", "ATOMS", "ATOMG", "REDG"]
 PAT = {"ATOMS": r"\bATOMS", "ATOMG": r"\bATOM(G|\.)", "REDG": r"\bRED(G|\.)"}
 print("# cuobjdump -sass equivariant-nn-zoo_b200/lib/libe3b200.so -- mnemonic counts per kernel (sm_100a)")
 print("# %-78s %s" % ("kernel", " ".join("%7s" % k for k in KEYS)))
@@ -38,7 +39,7 @@ for k, lines in sorted(kernels.items(), key=lambda kv: names[kv[0]]):
     short = re.sub(r"\(.*", "", short)
     print("  %-78s %s" % (short[:78], " ".join("%7d" % cnt[key] for key in KEYS)))
 print("  %-78s %s" % ("TOTAL", " ".join("%7d" % tot[key] for key in KEYS)))
-for pat in ("gemm_tf32x3_kernel<128", "wgrad_tf32x3_kernel", "tpfp_S3<64>"):
+for pat in ("gemm_tf32x3_kernel<128", "wgrad_tf32x3_kernel", "tpfp_S3<64>", "tpfp2_S3"):
     for k, lines in kernels.items():
         if pat in names[k]:
             idx = next((i for i, ln in enumerate(lines) if "UTCHMMA" in ln or "UBLKCP" in ln), None)
