@@ -19,6 +19,8 @@ from e3b200 import cg  # noqa: E402
 from e3b200.plan import generated_structures  # noqa: E402
 
 MAX_ACC_PER_GROUP = 56  # accumulator registers per thread (forward)
+PAIRED_INFO = {}        # sid -> (d/dY partial rows of the paired backward kernel, selected by default)
+N_PARTS = 4             # translation units the generated kernels are spread over (E3B_TP_PART)
 PAIRED_MAX_ACC = 30     # output components per group of the paired backward kernels (two registers each)
 
 
@@ -678,7 +680,9 @@ def emit_structure(E, sid, st):
     # 15-path second block 327 -> 338 us and 27 paths 609 -> 646 us (the unrolled loops of the 4 warps, 27 KB, no longer fit the 32 KB instruction
     # cache of the SM: ncu `no_instruction` is the top stall); forward 27 / 30 paths 258 -> 227 us and 260 -> 248 us, smaller
     # structures unchanged.  E3B_TP_PAIRED_FORCE=1 runs the paired kernels everywhere.
-    E(f"static const bool kPairedBwdOk_S{sid} = {'true' if (not class_ok and (n_paths <= 3 or (n_paths == 15 and len(st.irreps_in) == 6))) else 'false'};")
+    bwd_ok = not class_ok and (n_paths <= 3 or (n_paths == 15 and len(st.irreps_in) == 6))
+    PAIRED_INFO[sid] = (W3 if class_ok else 2 * G, bwd_ok)
+    E(f"static const bool kPairedBwdOk_S{sid} = {'true' if bwd_ok else 'false'};")
     E(f"static const bool kPairedFwdOk_S{sid} = {'true' if n_paths >= 20 else 'false'};")
     E(f"static size_t tpp2_smem_S{sid}(int nst, bool reduce) {{ return (size_t)nst * ({n_paths} + {xdim}) * 64 * 4 + 3 * TPP2_MAXSEG * 4 + (size_t)nst * 16; }}")
 
@@ -788,16 +792,76 @@ def emit_structure(E, sid, st):
     return G
 
 
+def emit_launchers(E, sid, G_):
+    Gs = {sid: G_}
+    for kind in ("f", "b"):
+        E(f"void launch_tp{kind}_S{sid}(const TpArgs<float>& a, int64_t grid, cudaStream_t s) {{")
+        if kind == "b":
+            E(f"  if ((a.mul == 64 || a.mul == 32) && e3b_tp_pipelined_enabled()) {{")
+            E(f"    const size_t smem = tpbp_smem_S{sid}(a.mul, a.gx_node != nullptr);")
+            E(f"    if (a.mul == 64 && e3b_tp_paired_enabled(kPairedBwdOk_S{sid})) {{")
+            E(f"      TpArgs<float> a2 = a; a2.n_stages = e3b_tp_stages(1, tpp2_smem_S{sid}(1, a.gx_node != nullptr) - tpp2_smem_S{sid}(0, a.gx_node != nullptr), tpp2_smem_S{sid}(0, a.gx_node != nullptr));")
+            E(f"      const size_t smem2 = tpp2_smem_S{sid}(a2.n_stages, a.gx_node != nullptr);")
+            E(f"      if (smem2 > 48 * 1024) cudaFuncSetAttribute(tpbp2_S{sid}, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2);")
+            E(f"      a2.n_part = kPairedBwdParts_S{sid};")
+            E(f"      tpbp2_S{sid}<<<(unsigned)a.n_nodes, 32 * kPairedBwdWarps_S{sid}, smem2, s>>>(a2); }}")
+            E(f"    else if (a.mul == 64 && e3b_tp_decoupled_enabled()) {{")
+            E(f"      TpArgs<float> a2 = a; a2.n_stages = e3b_tp_stages(1, tpp2_smem_S{sid}(1, false) - tpp2_smem_S{sid}(0, false), tpp2_smem_S{sid}(0, false));")
+            E(f"      const size_t smem2 = tpp2_smem_S{sid}(a2.n_stages, false);")
+            E(f"      if (smem2 > 48 * 1024) cudaFuncSetAttribute(tpbp1d_S{sid}, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2);")
+            E(f"      tpbp1d_S{sid}<<<(unsigned)a.n_nodes, 32 * {Gs[sid]} * 2, smem2, s>>>(a2); }}")
+            E(f"    else if (a.mul == 64) {{ if (smem > 48 * 1024) cudaFuncSetAttribute(tpbp_S{sid}<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);")
+            E(f"      tpbp_S{sid}<64><<<(unsigned)a.n_nodes, 32 * {Gs[sid]} * 2, smem, s>>>(a); }}")
+            E(f"    else {{ if (smem > 48 * 1024) cudaFuncSetAttribute(tpbp_S{sid}<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);")
+            E(f"      tpbp_S{sid}<32><<<(unsigned)a.n_nodes, 32 * {Gs[sid]}, smem, s>>>(a); }}")
+            E("    return;")
+            E("  }")
+        if kind == "f":
+            E(f"  if ((a.mul == 64 || a.mul == 32) && e3b_tp_pipelined_enabled()) {{")
+            E(f"    const size_t smem = tpfp_smem_S{sid}(a.mul);")
+            E(f"    if (a.mul == 64 && e3b_tp_paired_fwd_enabled(kPairedFwdOk_S{sid})) {{")
+            E(f"      TpArgs<float> a2 = a; a2.n_stages = e3b_tp_stages(0, tpp2_smem_S{sid}(1, false) - tpp2_smem_S{sid}(0, false), tpp2_smem_S{sid}(0, false));")
+            E(f"      const size_t smem2 = tpp2_smem_S{sid}(a2.n_stages, false);")
+            E(f"      if (smem2 > 48 * 1024) cudaFuncSetAttribute(tpfp2_S{sid}, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2);")
+            E(f"      tpfp2_S{sid}<<<(unsigned)a.n_nodes, 32 * kPairedGroups_S{sid}, smem2, s>>>(a2); }}")
+            E(f"    else if (a.mul == 64) {{ if (smem > 48 * 1024) cudaFuncSetAttribute(tpfp_S{sid}<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);")
+            E(f"      tpfp_S{sid}<64><<<(unsigned)a.n_nodes, 32 * {Gs[sid]} * 2, smem, s>>>(a); }}")
+            E(f"    else {{ if (smem > 48 * 1024) cudaFuncSetAttribute(tpfp_S{sid}<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);")
+            E(f"      tpfp_S{sid}<32><<<(unsigned)a.n_nodes, 32 * {Gs[sid]}, smem, s>>>(a); }}")
+            E("    return;")
+            E("  }")
+        E(f"  if (a.mul == 64) tp{kind}_S{sid}<float, 64><<<(unsigned)grid, TP_THREADS, 0, s>>>(a);")
+        E(f"  else if (a.mul == 32) tp{kind}_S{sid}<float, 32><<<(unsigned)grid, TP_THREADS, 0, s>>>(a);")
+        E(f"  else tp{kind}_S{sid}<float, 0><<<(unsigned)grid, TP_THREADS, 0, s>>>(a);")
+        E("}")
+
+
 def emit_tables(st_list):
     E = Emitter()
     E("// GENERATED by csrc/gen_tp.py -- do not edit.")
     E("#pragma once")
     E()
-    Gs = []
+    Gs, texts = [], []
     for sid, st in enumerate(st_list):
-        E(f"// ---- structure S{sid}: in l={[b.ir.l for b in st.irreps_in]} sh l={[b.ir.l for b in st.irreps_sh]} "
-          f"paths={len(st.paths)} out comps={st.y_layout()[2]}")
-        Gs.append(emit_structure(E, sid, st))
+        sub = Emitter()
+        sub(f"// ---- structure S{sid}: in l={[b.ir.l for b in st.irreps_in]} sh l={[b.ir.l for b in st.irreps_sh]} "
+            f"paths={len(st.paths)} out comps={st.y_layout()[2]}")
+        Gs.append(emit_structure(sub, sid, st))
+        sub("#ifdef __CUDACC__")
+        emit_launchers(sub, sid, Gs[sid])
+        sub("#endif  // __CUDACC__")
+        texts.append(sub.text())
+    # the structures are spread over N_PARTS translation units (tp_fast.cu = part 0, tp_fast_p{k}.cu), balanced by size; a
+    # CUDA compile with E3B_TP_PART defined sees only its part, anything else (host emulation, a single-TU build) sees all
+    part_of, load = {}, [0] * N_PARTS
+    for sid in sorted(range(len(st_list)), key=lambda i: -len(texts[i])):
+        k = min(range(N_PARTS), key=lambda q: load[q])
+        part_of[sid] = k
+        load[k] += len(texts[sid])
+    for sid in range(len(st_list)):
+        E(f"#if !defined(__CUDACC__) || !defined(E3B_TP_PART) || E3B_TP_PART == {part_of[sid]}")
+        E.lines.append(texts[sid].rstrip("\n"))
+        E(f"#endif  // part {part_of[sid]}")
     E("#ifdef E3B_HOST_EMU")
     E("// CPU emulation entry (tests only): runs every (node, channel, group) item serially.")
     E("template <typename T> static int emu_tp(int sid, int bwd, const TpArgs<T>& a) {")
@@ -817,48 +881,9 @@ def emit_tables(st_list):
     E("}")
     E("static const int kEmuGroups[] = {" + ", ".join(str(g) for g in Gs) + "};")
     E("#endif  // E3B_HOST_EMU")
-    E("#ifdef __CUDACC__")
+    E("#if defined(__CUDACC__) && (!defined(E3B_TP_PART) || E3B_TP_PART == 0)")
     for sid in range(len(st_list)):
-        for kind in ("f", "b"):
-            E(f"static void launch_tp{kind}_S{sid}(const TpArgs<float>& a, int64_t grid, cudaStream_t s) {{")
-            if kind == "b":
-                E(f"  if ((a.mul == 64 || a.mul == 32) && e3b_tp_pipelined_enabled()) {{")
-                E(f"    const size_t smem = tpbp_smem_S{sid}(a.mul, a.gx_node != nullptr);")
-                E(f"    if (a.mul == 64 && e3b_tp_paired_enabled(kPairedBwdOk_S{sid})) {{")
-                E(f"      TpArgs<float> a2 = a; a2.n_stages = e3b_tp_stages(1, tpp2_smem_S{sid}(1, a.gx_node != nullptr) - tpp2_smem_S{sid}(0, a.gx_node != nullptr), tpp2_smem_S{sid}(0, a.gx_node != nullptr));")
-                E(f"      const size_t smem2 = tpp2_smem_S{sid}(a2.n_stages, a.gx_node != nullptr);")
-                E(f"      if (smem2 > 48 * 1024) cudaFuncSetAttribute(tpbp2_S{sid}, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2);")
-                E(f"      a2.n_part = kPairedBwdParts_S{sid};")
-                E(f"      tpbp2_S{sid}<<<(unsigned)a.n_nodes, 32 * kPairedBwdWarps_S{sid}, smem2, s>>>(a2); }}")
-                E(f"    else if (a.mul == 64 && e3b_tp_decoupled_enabled()) {{")
-                E(f"      TpArgs<float> a2 = a; a2.n_stages = e3b_tp_stages(1, tpp2_smem_S{sid}(1, false) - tpp2_smem_S{sid}(0, false), tpp2_smem_S{sid}(0, false));")
-                E(f"      const size_t smem2 = tpp2_smem_S{sid}(a2.n_stages, false);")
-                E(f"      if (smem2 > 48 * 1024) cudaFuncSetAttribute(tpbp1d_S{sid}, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2);")
-                E(f"      tpbp1d_S{sid}<<<(unsigned)a.n_nodes, 32 * {Gs[sid]} * 2, smem2, s>>>(a2); }}")
-                E(f"    else if (a.mul == 64) {{ if (smem > 48 * 1024) cudaFuncSetAttribute(tpbp_S{sid}<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);")
-                E(f"      tpbp_S{sid}<64><<<(unsigned)a.n_nodes, 32 * {Gs[sid]} * 2, smem, s>>>(a); }}")
-                E(f"    else {{ if (smem > 48 * 1024) cudaFuncSetAttribute(tpbp_S{sid}<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);")
-                E(f"      tpbp_S{sid}<32><<<(unsigned)a.n_nodes, 32 * {Gs[sid]}, smem, s>>>(a); }}")
-                E("    return;")
-                E("  }")
-            if kind == "f":
-                E(f"  if ((a.mul == 64 || a.mul == 32) && e3b_tp_pipelined_enabled()) {{")
-                E(f"    const size_t smem = tpfp_smem_S{sid}(a.mul);")
-                E(f"    if (a.mul == 64 && e3b_tp_paired_fwd_enabled(kPairedFwdOk_S{sid})) {{")
-                E(f"      TpArgs<float> a2 = a; a2.n_stages = e3b_tp_stages(0, tpp2_smem_S{sid}(1, false) - tpp2_smem_S{sid}(0, false), tpp2_smem_S{sid}(0, false));")
-                E(f"      const size_t smem2 = tpp2_smem_S{sid}(a2.n_stages, false);")
-                E(f"      if (smem2 > 48 * 1024) cudaFuncSetAttribute(tpfp2_S{sid}, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2);")
-                E(f"      tpfp2_S{sid}<<<(unsigned)a.n_nodes, 32 * kPairedGroups_S{sid}, smem2, s>>>(a2); }}")
-                E(f"    else if (a.mul == 64) {{ if (smem > 48 * 1024) cudaFuncSetAttribute(tpfp_S{sid}<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);")
-                E(f"      tpfp_S{sid}<64><<<(unsigned)a.n_nodes, 32 * {Gs[sid]} * 2, smem, s>>>(a); }}")
-                E(f"    else {{ if (smem > 48 * 1024) cudaFuncSetAttribute(tpfp_S{sid}<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);")
-                E(f"      tpfp_S{sid}<32><<<(unsigned)a.n_nodes, 32 * {Gs[sid]}, smem, s>>>(a); }}")
-                E("    return;")
-                E("  }")
-            E(f"  if (a.mul == 64) tp{kind}_S{sid}<float, 64><<<(unsigned)grid, TP_THREADS, 0, s>>>(a);")
-            E(f"  else if (a.mul == 32) tp{kind}_S{sid}<float, 32><<<(unsigned)grid, TP_THREADS, 0, s>>>(a);")
-            E(f"  else tp{kind}_S{sid}<float, 0><<<(unsigned)grid, TP_THREADS, 0, s>>>(a);")
-            E("}")
+        E(f"void launch_tpf_S{sid}(const TpArgs<float>&, int64_t, cudaStream_t); void launch_tpb_S{sid}(const TpArgs<float>&, int64_t, cudaStream_t);")
 
     def arr(v):
         return "{" + ", ".join(str(int(t)) for t in v) + "}"
@@ -872,7 +897,7 @@ def emit_tables(st_list):
             str(len(st.paths)), arr(p.i_in for p in st.paths), arr(p.i_sh for p in st.paths),
             arr(p.ir_out.l for p in st.paths), arr(p.slot for p in st.paths),
             arr(st.y_layout()[0][p.slot] for p in st.paths), arr(st.y_layout()[1][p.slot] for p in st.paths),
-            str(Gs[sid]), f"launch_tpf_S{sid}", f"launch_tpb_S{sid}", f"kPairedBwdParts_S{sid}", f"kPairedBwdOk_S{sid}"]) + "},")
+            str(Gs[sid]), f"launch_tpf_S{sid}", f"launch_tpb_S{sid}", str(PAIRED_INFO[sid][0]), "true" if PAIRED_INFO[sid][1] else "false"]) + "},")
     E("};")
     E("#endif  // __CUDACC__")
     return E.text()

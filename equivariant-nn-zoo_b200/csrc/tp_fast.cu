@@ -42,6 +42,7 @@ int e3b_tp_stages(int bwd, size_t per_stage, size_t fixed) {
   return (int)n;
 }
 
+#define E3B_TP_PART 0   // this translation unit: part 0 of the generated kernels + the table (parts 1.. in tp_fast_p*.cu)
 #include "tp_generated.cuh"
 
 int e3b_gen_bwd_parts(const GenEntry* g, int mul) {

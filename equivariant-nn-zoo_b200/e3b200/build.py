@@ -9,7 +9,7 @@ LIB_DIR = os.path.join(os.path.dirname(PKG), "lib")
 LIB_PATH = os.path.join(LIB_DIR, "libe3b200.so")
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC", "-Xcompiler", "-fvisibility=hidden"]
-SOURCES = ["e3b200.cu", "tp_fast.cu", "gemm_tf32x3.cu", "wgrad_tf32x3.cu"]
+SOURCES = ["e3b200.cu", "tp_fast.cu", "tp_fast_p1.cu", "tp_fast_p2.cu", "tp_fast_p3.cu", "gemm_tf32x3.cu", "wgrad_tf32x3.cu"]
 
 
 def _nvcc():
