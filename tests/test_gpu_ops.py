@@ -156,6 +156,32 @@ def test_tp_conv_kernels(sid, dtype, mul):
     assert rel(gw, gw_ref) < tol
 
 
+@pytest.mark.parametrize("env", [
+    {"E3B_TP_PAIRED": "3", "E3B_TP_PAIRED_FORCE": "1"},      # two channels per thread everywhere (group and class-shared variants)
+    {"E3B_TP_PAIRED": "0", "E3B_TP_DECOUPLED": "0"},         # one channel per thread, CTA barrier per edge, staged TMA reduce-add
+    {"E3B_TP_PAIRED": "0", "E3B_TP_DECOUPLED": "1"},         # one channel per thread, decoupled warps everywhere
+    {"E3B_TP_PIPELINED": "0"},                               # direct-load kernels (no TMA ring)
+], ids=["paired-forced", "coupled", "decoupled", "direct"])
+def test_tp_conv_kernel_variants(env):
+    """The launcher picks ONE variant of the generated kernels per structure (measured defaults, csrc/gen_tp.py); the others stay
+    selectable through environment switches that are read once per process -- so every variant is run against the oracle in a
+    child process: all structures at multiplicity 64, forward + the three gradients, and the model test that exercises the
+    node-reduction mode of the backward kernels."""
+    import os
+    import subprocess
+    import sys
+    here = os.path.dirname(os.path.abspath(__file__))
+    base = [sys.executable, "-m", "pytest", "-x", "-q", "-m", "gpu", "-p", "no:cacheprovider"]
+    targets = [(os.path.join(here, "test_gpu_ops.py"), "test_tp_conv_kernels and dtype1-64")]
+    if "E3B_TP_PIPELINED" not in env:      # the model path shares weight rows between the two directions of an edge: pipelined kernels only
+        targets.append((os.path.join(here, "test_gpu_models.py"), "w1_batch or restricted or in_kernel_node_reduction"))
+    for target, select in targets:
+        out = subprocess.run(base + [target, "-k", select], env={**os.environ, **env}, cwd=os.path.dirname(here),
+                             capture_output=True, text=True, timeout=600)
+        assert out.returncode == 0, out.stdout[-3000:] + out.stderr[-2000:]
+        assert " passed" in out.stdout
+
+
 def test_tp_conv_generic_matches_generated_fp32():
     """same inputs through the generic (table-driven) and the generated kernels"""
     base = plan.generated_structures()[3]
