@@ -174,7 +174,7 @@ def test_tp_conv_kernel_variants(env):
     base = [sys.executable, "-m", "pytest", "-x", "-q", "-m", "gpu", "-p", "no:cacheprovider"]
     targets = [(os.path.join(here, "test_gpu_ops.py"), "test_tp_conv_kernels and dtype1-64")]
     if "E3B_TP_PIPELINED" not in env:      # the model path shares weight rows between the two directions of an edge: pipelined kernels only
-        targets.append((os.path.join(here, "test_gpu_models.py"), "w1_batch or restricted or in_kernel_node_reduction"))
+        targets.append((os.path.join(here, "test_gpu_models.py"), "restricted or in_kernel_node_reduction"))
     for target, select in targets:
         out = subprocess.run(base + [target, "-k", select], env={**os.environ, **env}, cwd=os.path.dirname(here),
                              capture_output=True, text=True, timeout=600)
