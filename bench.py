@@ -204,8 +204,8 @@ def workload_config(wl, world, n_atoms, n_edges, extra=None):
            "batches": f"{ROTATE} different seeded batches per rank, rotated through the timed steps "
                       "(atoms / edges above: the first one)",
            "parallelism": f"graphs sharded over {world} rank(s), no data-path collective",
-           "l2": "no explicit flush: per-layer per-edge weights are E*W*4 B = %.2f GB >> 126 MB L2, and consecutive steps "
-                 "run different batches" % (n_edges * 1920 * 4 / 1e9)}
+           "l2": "no explicit flush: per-layer per-edge weights are E*W*4 B = %s GB >> 126 MB L2, and consecutive steps "
+                 "run different batches" % ("%.2f" % (n_edges * 1920 * 4 / 1e9) if n_edges is not None else "1.15")}
     if extra:
         cfg.update(extra)
     return cfg
@@ -283,10 +283,23 @@ def run_reference(args, wl):
     cpu, s_per_step = cpu_arm(wl, args.warmup, args.steps, 0.0, args.steps)
     full = wl.host_batch(0)
     unit = wl.metric.split()[-1]
+    full_edges = None          # edge count of the full batch (the `config` of both arms names the same workload)
+    try:
+        if wl.pre_edge is not None:
+            pos, n_nodes = full[wl.pos_key].double(), full["_n_nodes"].reshape(-1).tolist()
+            full_edges, o = 0, 0
+            for n in n_nodes:                       # per graph: ordered pairs i != j within r_max (data/compute_edge.py:56-75)
+                d = torch.cdist(pos[o:o + n], pos[o:o + n])
+                full_edges += int((d < wl.pre_edge["r_max"]).sum()) - n
+                o += n
+        elif "edge_index" in full:
+            full_edges = int(full["edge_index"].shape[1])
+    except Exception:
+        full_edges = None
     line = {"impl": "reference", "metric": wl.metric, "value": cpu["value"], "unit": unit, "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": s_per_step * 1e3,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": workload_config(wl, args.gpus, wl.units(full), None,
+            "config": workload_config(wl, args.gpus, wl.units(full), full_edges,
                                       {"sample": "the CPU arm evaluates a bounded SAMPLE of this workload per step (see "
                                                  "cpu_baseline.sample); throughput is normalised per atom"}),
             "cpu_baseline": cpu,
