@@ -275,6 +275,25 @@ def cpu_arm(wl, warmup, min_reps, budget_s, max_reps):
             "sample": wl.sample_text(inputs, n_edges) + f" x {reps} evaluations"}, dt / reps
 
 
+def host_edge_count(wl, batch):
+    """directed edges of a host batch without the GPU: per graph the ordered pairs i != j within r_max (reference
+    data/compute_edge.py:56-75), or the edge list the batch brings; None if it cannot be told"""
+    try:
+        if wl.pre_edge is not None:
+            pos, n_nodes = batch[wl.pos_key].double(), batch["_n_nodes"].reshape(-1).tolist()
+            total, o = 0, 0
+            for n in n_nodes:
+                d = torch.cdist(pos[o:o + n], pos[o:o + n])
+                total += int((d < wl.pre_edge["r_max"]).sum()) - n
+                o += n
+            return total
+        if "edge_index" in batch:
+            return int(batch["edge_index"].shape[1])
+    except Exception:
+        pass
+    return None
+
+
 def run_reference(args, wl):
     """CPU arm: the oracle port of the reference's path, all host threads, bounded sample."""
     rank = int(os.environ.get("RANK", "0"))
@@ -283,19 +302,7 @@ def run_reference(args, wl):
     cpu, s_per_step = cpu_arm(wl, args.warmup, args.steps, 0.0, args.steps)
     full = wl.host_batch(0)
     unit = wl.metric.split()[-1]
-    full_edges = None          # edge count of the full batch (the `config` of both arms names the same workload)
-    try:
-        if wl.pre_edge is not None:
-            pos, n_nodes = full[wl.pos_key].double(), full["_n_nodes"].reshape(-1).tolist()
-            full_edges, o = 0, 0
-            for n in n_nodes:                       # per graph: ordered pairs i != j within r_max (data/compute_edge.py:56-75)
-                d = torch.cdist(pos[o:o + n], pos[o:o + n])
-                full_edges += int((d < wl.pre_edge["r_max"]).sum()) - n
-                o += n
-        elif "edge_index" in full:
-            full_edges = int(full["edge_index"].shape[1])
-    except Exception:
-        full_edges = None
+    full_edges = host_edge_count(wl, full)     # the `config` of both arms names the same workload
     line = {"impl": "reference", "metric": wl.metric, "value": cpu["value"], "unit": unit, "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": s_per_step * 1e3,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
