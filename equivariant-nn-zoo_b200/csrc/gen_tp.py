@@ -684,7 +684,7 @@ def emit_structure(E, sid, st):
     PAIRED_INFO[sid] = (W3 if class_ok else 2 * G, bwd_ok)
     E(f"static const bool kPairedBwdOk_S{sid} = {'true' if bwd_ok else 'false'};")
     E(f"static const bool kPairedFwdOk_S{sid} = {'true' if n_paths >= 20 else 'false'};")
-    E(f"static size_t tpp2_smem_S{sid}(int nst, bool reduce) {{ return (size_t)nst * ({n_paths} + {xdim}) * 64 * 4 + 3 * TPP2_MAXSEG * 4 + (size_t)nst * 16; }}")
+    E(f"static size_t tpp2_smem_S{sid}(int nst) {{ return (size_t)nst * ({n_paths} + {xdim}) * 64 * 4 + 3 * TPP2_MAXSEG * 4 + (size_t)nst * 16; }}")
 
     # ---------------- backward, one channel per thread, with the decoupled pipeline of the paired kernels (no CTA barrier per
     # edge, d/dx by fire-and-forget reductions from registers instead of the staged TMA reduce-add): the default for the
@@ -793,6 +793,7 @@ def emit_structure(E, sid, st):
 
 
 def emit_launchers(E, sid, G_):
+    """host launchers of structure `sid` (G_ warp groups): pick the kernel variant and its launch geometry"""
     Gs = {sid: G_}
     for kind in ("f", "b"):
         E(f"void launch_tp{kind}_S{sid}(const TpArgs<float>& a, int64_t grid, cudaStream_t s) {{")
@@ -800,14 +801,14 @@ def emit_launchers(E, sid, G_):
             E(f"  if ((a.mul == 64 || a.mul == 32) && e3b_tp_pipelined_enabled()) {{")
             E(f"    const size_t smem = tpbp_smem_S{sid}(a.mul, a.gx_node != nullptr);")
             E(f"    if (a.mul == 64 && e3b_tp_paired_enabled(kPairedBwdOk_S{sid})) {{")
-            E(f"      TpArgs<float> a2 = a; a2.n_stages = e3b_tp_stages(1, tpp2_smem_S{sid}(1, a.gx_node != nullptr) - tpp2_smem_S{sid}(0, a.gx_node != nullptr), tpp2_smem_S{sid}(0, a.gx_node != nullptr));")
-            E(f"      const size_t smem2 = tpp2_smem_S{sid}(a2.n_stages, a.gx_node != nullptr);")
+            E(f"      TpArgs<float> a2 = a; a2.n_stages = e3b_tp_stages(1, tpp2_smem_S{sid}(1) - tpp2_smem_S{sid}(0), tpp2_smem_S{sid}(0));")
+            E(f"      const size_t smem2 = tpp2_smem_S{sid}(a2.n_stages);")
             E(f"      if (smem2 > 48 * 1024) cudaFuncSetAttribute(tpbp2_S{sid}, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2);")
             E(f"      a2.n_part = kPairedBwdParts_S{sid};")
             E(f"      tpbp2_S{sid}<<<(unsigned)a.n_nodes, 32 * kPairedBwdWarps_S{sid}, smem2, s>>>(a2); }}")
             E(f"    else if (a.mul == 64 && e3b_tp_decoupled_enabled()) {{")
-            E(f"      TpArgs<float> a2 = a; a2.n_stages = e3b_tp_stages(1, tpp2_smem_S{sid}(1, false) - tpp2_smem_S{sid}(0, false), tpp2_smem_S{sid}(0, false));")
-            E(f"      const size_t smem2 = tpp2_smem_S{sid}(a2.n_stages, false);")
+            E(f"      TpArgs<float> a2 = a; a2.n_stages = e3b_tp_stages(1, tpp2_smem_S{sid}(1) - tpp2_smem_S{sid}(0), tpp2_smem_S{sid}(0));")
+            E(f"      const size_t smem2 = tpp2_smem_S{sid}(a2.n_stages);")
             E(f"      if (smem2 > 48 * 1024) cudaFuncSetAttribute(tpbp1d_S{sid}, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2);")
             E(f"      tpbp1d_S{sid}<<<(unsigned)a.n_nodes, 32 * {Gs[sid]} * 2, smem2, s>>>(a2); }}")
             E(f"    else if (a.mul == 64) {{ if (smem > 48 * 1024) cudaFuncSetAttribute(tpbp_S{sid}<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);")
@@ -820,8 +821,8 @@ def emit_launchers(E, sid, G_):
             E(f"  if ((a.mul == 64 || a.mul == 32) && e3b_tp_pipelined_enabled()) {{")
             E(f"    const size_t smem = tpfp_smem_S{sid}(a.mul);")
             E(f"    if (a.mul == 64 && e3b_tp_paired_fwd_enabled(kPairedFwdOk_S{sid})) {{")
-            E(f"      TpArgs<float> a2 = a; a2.n_stages = e3b_tp_stages(0, tpp2_smem_S{sid}(1, false) - tpp2_smem_S{sid}(0, false), tpp2_smem_S{sid}(0, false));")
-            E(f"      const size_t smem2 = tpp2_smem_S{sid}(a2.n_stages, false);")
+            E(f"      TpArgs<float> a2 = a; a2.n_stages = e3b_tp_stages(0, tpp2_smem_S{sid}(1) - tpp2_smem_S{sid}(0), tpp2_smem_S{sid}(0));")
+            E(f"      const size_t smem2 = tpp2_smem_S{sid}(a2.n_stages);")
             E(f"      if (smem2 > 48 * 1024) cudaFuncSetAttribute(tpfp2_S{sid}, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2);")
             E(f"      tpfp2_S{sid}<<<(unsigned)a.n_nodes, 32 * kPairedGroups_S{sid}, smem2, s>>>(a2); }}")
             E(f"    else if (a.mul == 64) {{ if (smem > 48 * 1024) cudaFuncSetAttribute(tpfp_S{sid}<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);")
